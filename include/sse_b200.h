@@ -1,0 +1,187 @@
+/*
+ * sse_b200.h — C ABI of libsse_b200.so, the B200-native drop-in for
+ * StableSpectralElements.jl's semi-discrete residual
+ *
+ *     semi_discrete_residual!(dudt, u, solver::Solver, t)       src/Solvers/Solvers.jl:474-564
+ *
+ * One handle == one reference `Solver` (src/Solvers/Solvers.jl:259-272) living on
+ * one GPU.  The Julia side keeps `Solver`, `ConservationLaws`,
+ * `SpatialDiscretization`, `semidiscretize` and the OrdinaryDiffEq integration; a
+ * new `AbstractParallelism` subtype (Solvers.jl:72,79-80) carries the handle and its
+ * `semi_discrete_residual!` method is one `ccall` of sse_rhs.
+ *
+ * Conventions
+ *  - All arrays are the reference's arrays verbatim: Float64, column-major (first
+ *    index fastest), sizes as documented per field.  Integer index arrays are
+ *    Int64 and 1-based, exactly as Julia holds them.
+ *  - sse_create copies everything it needs to the device; the caller keeps
+ *    ownership of the host arrays.  Device state vectors (u, dudt, ...) are plain
+ *    device pointers to N_p*N_c*N_e doubles in the reference layout
+ *    (N_p, N_c, N_e); they may come from sse_state_alloc or from any other CUDA
+ *    allocator in the same process (CUDA.jl, torch, cudaMalloc).
+ *  - Every entry point returns an int32 status (0 = SSE_OK).  Nothing throws
+ *    across the boundary; sse_last_error_string() describes the last failure of
+ *    the calling thread.  There is no CPU fallback: without a CUDA device every
+ *    compute entry point fails with SSE_ERR_CUDA.
+ *  - Calls on one handle are asynchronous with respect to the host (enqueued on
+ *    the handle's stream) except download/synchronize/functionals.
+ */
+#ifndef SSE_B200_H
+#define SSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSE_ABI_VERSION 1
+
+/* status codes */
+enum {
+    SSE_OK = 0,
+    SSE_ERR_BAD_ARGUMENT = 1, /* reference: DimensionMismatch from LinearMaps.check_dim_mul etc. */
+    SSE_ERR_UNSUPPORTED = 2,  /* reference: MethodError (combination has no method)           */
+    SSE_ERR_CUDA = 3,
+    SSE_ERR_NONFINITE = 4,    /* reference: DomainError from log/sqrt of a non-physical state  */
+    SSE_ERR_COMM = 5
+};
+
+/* AbstractConservationLaw subtypes on the path (src/ConservationLaws) */
+enum { SSE_PDE_ADVECTION = 0,            /* LinearAdvectionEquation{d}           linear_advection_diffusion.jl:10-20 */
+       SSE_PDE_ADVECTION_DIFFUSION = 1,  /* LinearAdvectionDiffusionEquation{d}  linear_advection_diffusion.jl:30-42 */
+       SSE_PDE_EULER = 2 };              /* EulerEquations{d}                    euler_navierstokes.jl:23-38        */
+
+/* residual form x operator strategy (Solvers.jl:75-115, constructors :287-376) */
+enum { SSE_FORM_STANDARD_REFERENCE = 0,  /* StandardForm + ReferenceOperator  standard_form_first_order.jl:16-63 */
+       SSE_FORM_STANDARD_PHYSICAL = 1,   /* StandardForm + PhysicalOperator   standard_form_first_order.jl:65-94,
+                                            and every SecondOrder law          standard_form_second_order.jl:3-75 */
+       SSE_FORM_FLUX_DIFFERENCING = 2 }; /* FluxDifferencingForm              flux_differencing_form.jl:294-347  */
+
+/* AbstractInviscidNumericalFlux (ConservationLaws.jl:52-63) */
+enum { SSE_FLUX_LAX_FRIEDRICHS = 0, SSE_FLUX_CENTRAL = 1, SSE_FLUX_ENTROPY_CONSERVATIVE = 2 };
+/* AbstractViscousNumericalFlux (ConservationLaws.jl:65-68) */
+enum { SSE_VISCOUS_NONE = 0, SSE_VISCOUS_BR1 = 1 };
+/* AbstractTwoPointFlux (ConservationLaws.jl:70-73) */
+enum { SSE_TWO_POINT_CONSERVATIVE = 0, SSE_TWO_POINT_ENTROPY_CONSERVATIVE = 1 };
+/* AbstractMassMatrixSolver (mass_matrix.jl:1-17) */
+enum { SSE_MASS_WEIGHT_ADJUSTED = 0,     /* M^-1 = I assumed (assume_orthonormal=true default, mass_matrix.jl:59-75) */
+       SSE_MASS_DIAGONAL = 1 };
+/* type of the generalized Vandermonde V (MatrixFreeOperators) */
+enum { SSE_V_IDENTITY = 0,               /* LinearMaps.UniformScalingMap (nodal schemes)               */
+       SSE_V_DENSE = 1,                  /* OctavianMap / WrappedMap                                   */
+       SSE_V_WARPED = 2 };               /* WarpedTensorProductMap2D/3D  warped_product_{2d,3d}.jl     */
+
+typedef struct sse_config {
+    int32_t abi_version;     /* SSE_ABI_VERSION */
+    int32_t d;               /* spatial dimension 1..3 */
+    int32_t N_c, N_p, N_q, N_f, N_fac;
+    int32_t p;               /* polynomial degree (size of warped tensors = p+1) */
+    int64_t N_e;             /* elements owned by this handle */
+    int64_t N_ghost;         /* ghost facet nodes appended to u_f after the N_f*N_e owned ones
+                                (multi-GPU halo); 0 for a single GPU */
+    int32_t pde, form, inviscid_flux, viscous_flux, two_point_flux, mass_solver, v_kind;
+    int32_t M1d[3];          /* 1-D node counts of the warped tensors (size(A,1), size(B,1), size(C,1)) */
+    double  half_lambda;     /* LaxFriedrichsNumericalFlux.halfλ (ConservationLaws.jl:54-60) */
+    double  a[3];            /* advection velocity */
+    double  b;               /* diffusion coefficient */
+    double  gamma;           /* EulerEquations.γ */
+} sse_config;
+
+/* Host arrays of the reference Solver.  Unused pointers are NULL. */
+typedef struct sse_arrays {
+    /* --- reference-element operators (ReferenceApproximation, SpatialDiscretizations.jl:191-251) */
+    const double*  V;        /* N_q x N_p  Matrix(V)            (v_kind = DENSE)                      */
+    const double*  A;        /* M1 x (p+1)                      (v_kind = WARPED; warped_product_3d.jl:2-35) */
+    const double*  B;        /* M2 x (p+1) x (p+1)                                                     */
+    const double*  C;        /* M3 x (p+1)^3 (d = 3 only)                                              */
+    const int64_t* sigma_i;  /* (p+1)^d, 1-based modal index, 0 = unused                               */
+    const int64_t* sigma_o;  /* M1 x M2 [x M3], 1-based nodal index                                    */
+    const double*  R;        /* N_f x N_q  Matrix(R)                                                   */
+    const double*  W;        /* N_q   diag(W)                                                          */
+    const double*  Bf;       /* N_f   diag(B)                                                          */
+    const double*  D[3];     /* N_q x N_q Matrix(D[m])  (StandardForm+ReferenceOperator)               */
+    const double*  S[3];     /* N_q x N_q Matrix(S[m])  (FluxDifferencingOperators.S, Solvers.jl:166)  */
+    const double*  Cfd;      /* N_q x N_f Matrix(C), NULL when C === nothing (diag-E; Solvers.jl:167)  */
+    /* --- geometric factors (GeometricFactors, SpatialDiscretizations.jl:283-289), as passed to the
+           Solver constructors (Solvers.jl:287-376).  For StandardForm+ReferenceOperator, Lambda_q is the
+           composite metric returned by apply_reference_mapping (SpatialDiscretizations.jl:398-411). */
+    const double*  J_q;      /* N_q x N_e                                                              */
+    const double*  Lambda_q; /* N_q x d x d x N_e                                                      */
+    const double*  J_f;      /* N_f x N_e                                                              */
+    const double*  nJf;      /* d x N_f x N_e                                                          */
+    const double*  nJq;      /* d x N_fac x N_q x N_e, or NULL: recomputed from Lambda_q and nref
+                                as in mesh.jl:262-269                                                  */
+    const double*  nref;     /* d x N_fac reference normal of each face (first node of the face)       */
+    /* --- PhysicalOperators (Solvers.jl:147-154, operators.jl:83-160) */
+    const double*  VOL;      /* N_p x N_q x d x N_e   VOL[k][m]                                        */
+    const double*  FAC;      /* N_p x N_f x N_e       FAC[k]                                           */
+    /* --- connectivity: mesh.mapP (Solvers.jl:268,305), N_f x N_e, 1-based linear index into the
+           (N_f, N_e [+ghost]) facet array */
+    const int64_t* mapP;
+} sse_arrays;
+
+typedef struct sse_handle sse_handle;
+
+/* -- lifetime ------------------------------------------------------------------------------- */
+/* replaces Solver(conservation_law, spatial_discretization, form, strategy, alg, mass_solver,
+   parallelism)  (Solvers.jl:287-376) */
+int32_t sse_create(const sse_config* cfg, const sse_arrays* arr, int32_t device, sse_handle** out);
+int32_t sse_destroy(sse_handle* h);
+/* run all work of this handle on a caller-owned CUDA stream (cudaStream_t); NULL = default */
+int32_t sse_set_stream(sse_handle* h, void* cuda_stream);
+/* 0: generic kernels only; 1 (default): use the tensor-line specialised kernels when the
+   operators have the collapsed tensor-product structure */
+int32_t sse_set_kernel_variant(sse_handle* h, int32_t variant);
+int32_t sse_get_kernel_variant(const sse_handle* h, int32_t* variant);
+
+/* -- state vectors (u, dudt of Solvers.jl:474-483; layout (N_p, N_c, N_e)) --------------------- */
+int32_t sse_state_alloc(sse_handle* h, double** d_out);
+int32_t sse_state_free(sse_handle* h, double* d_ptr);
+int32_t sse_state_upload(sse_handle* h, double* d_dst, const double* h_src);
+int32_t sse_state_download(sse_handle* h, double* h_dst, const double* d_src);
+
+/* -- the hot path ------------------------------------------------------------------------------ */
+/* semi_discrete_residual!(dudt, u, solver, t)  (Solvers.jl:474-564).  Single GPU: all passes. */
+int32_t sse_rhs(sse_handle* h, const double* d_u, double* d_dudt, double t);
+/* Split form used by the multi-GPU driver.  Pass A (nodal_values!, Solvers.jl:505-507)
+   fills u_q and the owned part of u_f and packs the halo send buffer; the caller exchanges halos
+   (NCCL) into sse_halo_recv_buffer; pass B (time_derivative!, Solvers.jl:509-511) runs on the
+   element range [first, first+count).  Second-order laws have an extra aux pass + exchange. */
+int32_t sse_rhs_pass_a(sse_handle* h, const double* d_u);
+int32_t sse_rhs_pass_aux(sse_handle* h, double* d_dudt, int64_t first, int64_t count);
+int32_t sse_rhs_pass_b(sse_handle* h, double* d_dudt, int64_t first, int64_t count);
+/* halo plumbing: the send list holds 1-based linear indices into the owned (N_f, N_e) facet array */
+int32_t sse_halo_configure(sse_handle* h, const int64_t* send_index, int64_t n_send);
+int32_t sse_halo_pack(sse_handle* h, int32_t which /*0: u_f, 1: q_f*/);
+int32_t sse_halo_send_buffer(sse_handle* h, double** d_buf, int64_t* n_doubles);
+int32_t sse_halo_recv_buffer(sse_handle* h, int32_t which, double** d_buf, int64_t* n_doubles);
+int32_t sse_halo_unpack(sse_handle* h, int32_t which);
+
+/* -- callers either side of the path ----------------------------------------- */
+/* y = a*x + b*y on state vectors (OrdinaryDiffEq broadcast updates) */
+int32_t sse_axpby(sse_handle* h, double a, const double* d_x, double b, double* d_y);
+/* 2N low-storage RK stage: tmp = A*tmp + dt*dudt ; u += B*tmp   (CarpenterKennedy2N54 stage) */
+int32_t sse_lsrk_stage(sse_handle* h, double* d_u, double* d_tmp, const double* d_dudt,
+                       double A, double B, double dt);
+/* one full CarpenterKennedy2N54 step on device (single GPU) */
+int32_t sse_step_ck54(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double t, double dt);
+/* conservation / energy / entropy residuals of Analysis/conservation.jl:145-189.
+   out[0..N_c-1] = sum_k 1' WJ_k V dudt[:,e,k];  out[N_c] = sum_k u_k' M_k dudt_k (energy);
+   out[N_c+1] = sum_k (P_k w(V u_k))' M_k dudt_k (entropy; Euler only, else 0).  Blocking. */
+int32_t sse_functionals(sse_handle* h, const double* d_u, const double* d_dudt, double* out);
+
+/* -- misc -------------------------------------------------------------------------------------- */
+int32_t sse_synchronize(sse_handle* h);
+const char* sse_last_error_string(void);
+int32_t sse_abi_version(void);
+/* scratch views for testing/analysis: u_q (N_q,N_c,N_e) and u_f (N_f,N_e+ghost,N_c) device pointers */
+int32_t sse_debug_views(sse_handle* h, double** d_u_q, double** d_u_f);
+/* register-resident DFMA microbenchmark: achieved FP64 FLOP/s on the handle's device (FMA = 2) */
+int32_t sse_fp64_peak(int32_t device, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSE_B200_H */

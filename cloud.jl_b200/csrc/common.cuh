@@ -1,0 +1,54 @@
+// common.cuh — device-side views of the Solver image shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "physics.cuh"
+
+namespace sse {
+
+struct SpMat {              // compressed rows: row r owns entries [ptr[r], ptr[r+1])
+    const int* ptr;
+    const int* idx;
+    const double* val;
+};
+
+// Reference-element operators (element independent), device pointers.
+struct Ops {
+    int d, NC, Np, Nq, Nf, Nfac, npf;
+    int v_kind;
+    int P1, M1, M2, M3;            // warped tensors (2-D embedded as M3 = 1)
+    const double* Vd;              // dense V, column-major Nq x Np
+    const double *A, *B, *C;       // warped_product_3d.jl:2-35
+    const int *sig_i, *sig_o;      // 0-based, -1 = unused
+    int N2[8];
+    int N3[64];                    // [b1 * 8 + b2]
+    SpMat R, Rt;                   // R by facet rows; R^T by volume-node rows
+    SpMat D[3], Dt[3];             // D_m by rows; D_m^T by rows
+    // flux differencing: for volume node i the partners j != i with the d values S_m[i,j]
+    const int* vol_ptr;
+    const int* vol_j;
+    const double* vol_S;           // [entry * d + m]
+    SpMat Cq;                      // C by volume-node rows  (j, C_ij)
+    SpMat Cf;                      // C by facet-node rows   (i, C_ij)
+    int has_C;
+    const double *W, *Bf, *nref;   // nref: d x Nfac column-major
+};
+
+// Per-element geometry and scratch, device pointers (reference layouts).
+struct Geo {
+    const double* J_q;       // Nq x Ne
+    const double* Lambda_q;  // Nq x d x d x Ne
+    const double* J_f;       // Nf x Ne
+    const double* nJf;       // d x Nf x Ne
+    const double* nJq;       // d x Nfac x Nq x Ne or nullptr
+    const double* VOL;       // Np x Nq x d x Ne
+    const double* FAC;       // Np x Nf x Ne
+    const long long* mapP;   // Nf x Ne, 1-based linear index into the (Nf, Ne [+ghost]) facet array
+    long long Ne;
+    long long NFT;           // Nf*Ne + N_ghost: stride between variables of u_f / q_f
+    int mass_solver;
+};
+
+#define SSE_FOR(t, n) for (int t = threadIdx.x; t < (n); t += blockDim.x)
+
+}  // namespace sse

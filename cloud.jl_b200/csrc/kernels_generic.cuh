@@ -1,0 +1,635 @@
+// kernels_generic.cuh — element-per-CTA kernels for ANY operator set the reference accepts
+// (dense / sparse / warped operators, d = 1..3).  They are the correctness backbone and the
+// fallback for operator families without tensor-line structure; the tensor-product
+// simplex paths of the BASELINE configs run the specialised kernels in kernels_tensor.cuh.
+//
+// One CTA owns one element; all per-element tiles live in shared memory; threads stride
+// over (node, variable) items.  Pair contributions are evaluated "row-wise" (each thread
+// accumulates only its own node), so no atomics are needed.
+#pragma once
+#include "common.cuh"
+
+namespace sse {
+
+// ------------------------------------------------------------------ V, V^T on shared tiles
+// y (Nq x NC) = V x (Np x NC).  zb, wb: scratch of NC*P1*P1*M3 and NC*P1*M2*M3 doubles.
+// warped_product_3d.jl:47-84 (2-D: warped_product_2d.jl:31-55 embedded with M3 = 1)
+template <int NC>
+__device__ void apply_V(const Ops& o, const double* x, double* y, double* zb, double* wb) {
+    const int Nq = o.Nq, Np = o.Np;
+    if (o.v_kind == SSE_V_IDENTITY) {
+        SSE_FOR(t, Nq * NC) y[t] = x[t];
+        __syncthreads();
+        return;
+    }
+    if (o.v_kind == SSE_V_DENSE) {
+        SSE_FOR(t, Nq * NC) {
+            int i = t % Nq, e = t / Nq;
+            double s = 0.0;
+            for (int j = 0; j < Np; j++) s = fma(o.Vd[i + (size_t)Nq * j], x[j + Np * e], s);
+            y[t] = s;
+        }
+        __syncthreads();
+        return;
+    }
+    const int P1 = o.P1, M1 = o.M1, M2 = o.M2, M3 = o.M3;
+    SSE_FOR(t, NC * P1 * P1 * M3) {
+        int a3 = t % M3, b2 = (t / M3) % P1, b1 = (t / (M3 * P1)) % P1, e = t / (M3 * P1 * P1);
+        if (b2 < o.N2[b1]) {
+            double s = 0.0;
+            for (int b3 = 0; b3 < o.N3[b1 * 8 + b2]; b3++)
+                s = fma(o.C[a3 + M3 * (b1 + P1 * (b2 + P1 * b3))], x[o.sig_i[b1 + P1 * (b2 + P1 * b3)] + Np * e], s);
+            zb[t] = s;
+        }
+    }
+    __syncthreads();
+    SSE_FOR(t, NC * P1 * M2 * M3) {
+        int a3 = t % M3, a2 = (t / M3) % M2, b1 = (t / (M3 * M2)) % P1, e = t / (M3 * M2 * P1);
+        double s = 0.0;
+        for (int b2 = 0; b2 < o.N2[b1]; b2++)
+            s = fma(o.B[a2 + M2 * (b1 + P1 * b2)], zb[((e * P1 + b1) * P1 + b2) * M3 + a3], s);
+        wb[t] = s;
+    }
+    __syncthreads();
+    SSE_FOR(t, NC * M1 * M2 * M3) {
+        int a3 = t % M3, a2 = (t / M3) % M2, a1 = (t / (M3 * M2)) % M1, e = t / (M3 * M2 * M1);
+        double s = 0.0;
+        for (int b1 = 0; b1 < P1; b1++) s = fma(o.A[a1 + M1 * b1], wb[((e * P1 + b1) * M2 + a2) * M3 + a3], s);
+        y[o.sig_o[a1 + M1 * (a2 + M2 * a3)] + Nq * e] = s;
+    }
+    __syncthreads();
+}
+
+// y (Np x NC) = V^T x (Nq x NC).  warped_product_3d.jl:94-136 / warped_product_2d.jl:61-89
+template <int NC>
+__device__ void apply_Vt(const Ops& o, const double* x, double* y, double* zb, double* wb) {
+    const int Nq = o.Nq, Np = o.Np;
+    if (o.v_kind == SSE_V_IDENTITY) {
+        SSE_FOR(t, Nq * NC) y[t] = x[t];
+        __syncthreads();
+        return;
+    }
+    if (o.v_kind == SSE_V_DENSE) {
+        SSE_FOR(t, Np * NC) {
+            int j = t % Np, e = t / Np;
+            double s = 0.0;
+            for (int i = 0; i < Nq; i++) s = fma(o.Vd[i + (size_t)Nq * j], x[i + Nq * e], s);
+            y[t] = s;
+        }
+        __syncthreads();
+        return;
+    }
+    const int P1 = o.P1, M1 = o.M1, M2 = o.M2, M3 = o.M3;
+    SSE_FOR(t, NC * P1 * M2 * M3) {
+        int a3 = t % M3, a2 = (t / M3) % M2, b1 = (t / (M3 * M2)) % P1, e = t / (M3 * M2 * P1);
+        double s = 0.0;
+        for (int a1 = 0; a1 < M1; a1++) s = fma(o.A[a1 + M1 * b1], x[o.sig_o[a1 + M1 * (a2 + M2 * a3)] + Nq * e], s);
+        wb[t] = s;
+    }
+    __syncthreads();
+    SSE_FOR(t, NC * P1 * P1 * M3) {
+        int a3 = t % M3, b2 = (t / M3) % P1, b1 = (t / (M3 * P1)) % P1, e = t / (M3 * P1 * P1);
+        if (b2 < o.N2[b1]) {
+            double s = 0.0;
+            for (int a2 = 0; a2 < M2; a2++) s = fma(o.B[a2 + M2 * (b1 + P1 * b2)], wb[((e * P1 + b1) * M2 + a2) * M3 + a3], s);
+            zb[t] = s;
+        }
+    }
+    __syncthreads();
+    SSE_FOR(t, NC * P1 * P1 * P1) {
+        int b3 = t % P1, b2 = (t / P1) % P1, b1 = (t / (P1 * P1)) % P1, e = t / (P1 * P1 * P1);
+        if (b2 < o.N2[b1] && b3 < o.N3[b1 * 8 + b2]) {
+            double s = 0.0;
+            for (int a3 = 0; a3 < M3; a3++) s = fma(o.C[a3 + M3 * (b1 + P1 * (b2 + P1 * b3))], zb[((e * P1 + b1) * P1 + b2) * M3 + a3], s);
+            y[o.sig_i[b1 + P1 * (b2 + P1 * b3)] + Np * e] = s;
+        }
+    }
+    __syncthreads();
+}
+
+// y (nrow x NC) = A x, rows of A compressed; ldx / ldy are the leading dimensions of the tiles
+template <int NC>
+__device__ void apply_sp(const SpMat& A, int nrow, const double* x, int ldx, double* y, int ldy) {
+    SSE_FOR(t, nrow * NC) {
+        int i = t % nrow, e = t / nrow;
+        double s = 0.0;
+        for (int q = A.ptr[i]; q < A.ptr[i + 1]; q++) s = fma(A.val[q], x[A.idx[q] + ldx * e], s);
+        y[i + ldy * e] = s;
+    }
+    __syncthreads();
+}
+
+// mass_matrix_solve! (mass_matrix.jl:169-196) on a shared Np x NC tile; tq: Nq x NC scratch
+template <int NC>
+__device__ void mass_solve(const Ops& o, const Geo& g, long long k, double* rhs, double* tq, double* zb, double* wb) {
+    const double* J = g.J_q + (size_t)o.Nq * k;
+    if (g.mass_solver == SSE_MASS_DIAGONAL) {
+        SSE_FOR(t, o.Np * NC) { int i = t % o.Np; rhs[t] *= 1.0 / (o.W[i] * J[i]); }
+        __syncthreads();
+        return;
+    }
+    apply_V<NC>(o, rhs, tq, zb, wb);
+    SSE_FOR(t, o.Nq * NC) { int i = t % o.Nq; tq[t] *= o.W[i] / J[i]; }
+    __syncthreads();
+    apply_Vt<NC>(o, tq, rhs, zb, wb);
+}
+
+struct SmemPlan {       // offsets in doubles into the dynamic shared array
+    int u, a, b, f, f2, z, w, lam, nf, fq, total;
+};
+
+__host__ __device__ inline int warp_z_size(const Ops& o, int NC) { return o.v_kind == SSE_V_WARPED ? NC * o.P1 * o.P1 * o.M3 : 0; }
+__host__ __device__ inline int warp_w_size(const Ops& o, int NC) { return o.v_kind == SSE_V_WARPED ? NC * o.P1 * o.M2 * o.M3 : 0; }
+
+// ------------------------------------------------------------------ pass A: nodal_values!
+// standard_form_first_order.jl:1-14; flux_differencing_form.jl:171-292.
+// project: 0 = none, 1 = nodal (w_f = R w(u_q)), 2 = general/modal entropy projection.
+// NV = number of "variables" moved per node = NC.
+template <int D, int NC>
+__global__ void k_nodal_generic(Ops o, Geo g, Law L, int project, const double* __restrict__ u,
+                                double* __restrict__ u_q, double* __restrict__ u_f) {
+    extern __shared__ double sm[];
+    const long long k = blockIdx.x;
+    const int Nq = o.Nq, Np = o.Np, Nf = o.Nf;
+    double* s_u = sm;                       // Np x NC
+    double* s_a = s_u + Np * NC;            // Nq x NC
+    double* s_b = s_a + Nq * NC;            // Nq x NC
+    double* s_f = s_b + Nq * NC;            // Nf x NC
+    double* s_z = s_f + Nf * NC;
+    double* s_w = s_z + warp_z_size(o, NC);
+
+    SSE_FOR(t, Np * NC) s_u[t] = u[(size_t)Np * NC * k + t];
+    __syncthreads();
+    apply_V<NC>(o, s_u, s_a, s_z, s_w);                           // u_q = V u
+    if (project == 0) {
+        apply_sp<NC>(o.R, Nf, s_a, Nq, s_f, Nf);                  // u_f = R u_q
+    } else if (project == 1) {
+        SSE_FOR(i, Nq) {
+            double ui[NC], wi[NC];
+#pragma unroll
+            for (int e = 0; e < NC; e++) ui[e] = s_a[i + Nq * e];
+            cons_to_entropy<D, NC>(L, ui, wi);
+#pragma unroll
+            for (int e = 0; e < NC; e++) s_b[i + Nq * e] = wi[e];
+        }
+        __syncthreads();
+        apply_sp<NC>(o.R, Nf, s_b, Nq, s_f, Nf);                  // w_f = R w_q
+        SSE_FOR(i, Nf) {
+            double wi[NC], ui[NC];
+#pragma unroll
+            for (int e = 0; e < NC; e++) wi[e] = s_f[i + Nf * e];
+            entropy_to_cons<D, NC>(L, wi, ui);
+#pragma unroll
+            for (int e = 0; e < NC; e++) s_f[i + Nf * e] = ui[e];
+        }
+        __syncthreads();
+    } else {
+        const double* J = g.J_q + (size_t)Nq * k;
+        SSE_FOR(i, Nq) {                                           // w_q = WJ * w(u_q)
+            double ui[NC], wi[NC];
+#pragma unroll
+            for (int e = 0; e < NC; e++) ui[e] = s_a[i + Nq * e];
+            cons_to_entropy<D, NC>(L, ui, wi);
+            double wj = o.W[i] * J[i];
+#pragma unroll
+            for (int e = 0; e < NC; e++) s_b[i + Nq * e] = wi[e] * wj;
+        }
+        __syncthreads();
+        apply_Vt<NC>(o, s_b, s_u, s_z, s_w);                       // w = V' w_q
+        mass_solve<NC>(o, g, k, s_u, s_b, s_z, s_w);               // w = M \ w
+        apply_V<NC>(o, s_u, s_b, s_z, s_w);                        // w_q = V w
+        apply_sp<NC>(o.R, Nf, s_b, Nq, s_f, Nf);                   // w_f = R w_q
+        SSE_FOR(i, Nq + Nf) {
+            double wi[NC], ui[NC];
+            if (i < Nq) {
+#pragma unroll
+                for (int e = 0; e < NC; e++) wi[e] = s_b[i + Nq * e];
+                entropy_to_cons<D, NC>(L, wi, ui);
+#pragma unroll
+                for (int e = 0; e < NC; e++) s_a[i + Nq * e] = ui[e];
+            } else {
+                int j = i - Nq;
+#pragma unroll
+                for (int e = 0; e < NC; e++) wi[e] = s_f[j + Nf * e];
+                entropy_to_cons<D, NC>(L, wi, ui);
+#pragma unroll
+                for (int e = 0; e < NC; e++) s_f[j + Nf * e] = ui[e];
+            }
+        }
+        __syncthreads();
+    }
+    SSE_FOR(t, Nq * NC) u_q[(size_t)Nq * NC * k + t] = s_a[t];
+    SSE_FOR(t, Nf * NC) { int i = t % Nf, e = t / Nf; u_f[(size_t)Nf * k + i + (size_t)g.NFT * e] = s_f[t]; }
+}
+
+// ------------------------------------------------------------------ shared pieces of pass B
+// interior/exterior facet states and unit normals of element k into shared tiles
+template <int D, int NC>
+__device__ void load_facets(const Ops& o, const Geo& g, long long k, const double* __restrict__ u_f,
+                            double* s_in, double* s_out, double* s_nf) {
+    const int Nf = o.Nf;
+    SSE_FOR(t, Nf * NC) {
+        int i = t % Nf, e = t / Nf;
+        s_in[t] = u_f[(size_t)Nf * k + i + (size_t)g.NFT * e];
+        s_out[t] = u_f[(size_t)(g.mapP[(size_t)Nf * k + i] - 1) + (size_t)g.NFT * e];
+    }
+    SSE_FOR(i, Nf) {
+        double jf = g.J_f[(size_t)Nf * k + i];
+#pragma unroll
+        for (int m = 0; m < D; m++) s_nf[m + D * i] = g.nJf[m + D * ((size_t)Nf * k + i)] / jf;   // operators.jl:19,59
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------ pass B: flux differencing
+// time_derivative! flux_differencing_form.jl:294-347 with flux_difference! (:37-75) and
+// facet_correction! (:126-168) evaluated row-wise.
+template <int D, int NC>
+__global__ void k_time_fluxdiff_generic(Ops o, Geo g, Law L, long long first, const double* __restrict__ u_q,
+                                        const double* __restrict__ u_f, double* __restrict__ dudt) {
+    extern __shared__ double sm[];
+    const long long k = first + blockIdx.x;
+    const int Nq = o.Nq, Np = o.Np, Nf = o.Nf;
+    double* s_uq = sm;                       // Nq x NC
+    double* s_r = s_uq + Nq * NC;            // Nq x NC
+    double* s_in = s_r + Nq * NC;            // Nf x NC
+    double* s_out = s_in + Nf * NC;          // Nf x NC
+    double* s_ff = s_out + Nf * NC;          // Nf x NC
+    double* s_nf = s_ff + Nf * NC;           // D x Nf
+    double* s_lam = s_nf + D * Nf;           // Nq x D x D
+    double* s_m = s_lam + Nq * D * D;        // Np x NC
+    double* s_z = s_m + Np * NC;
+    double* s_w = s_z + warp_z_size(o, NC);
+
+    SSE_FOR(t, Nq * NC) s_uq[t] = u_q[(size_t)Nq * NC * k + t];
+    SSE_FOR(t, Nq * D * D) s_lam[t] = g.Lambda_q[(size_t)Nq * D * D * k + t];
+    load_facets<D, NC>(o, g, k, u_f, s_in, s_out, s_nf);
+
+    // facet side: f_f = BJf f* - sum_i C_ij (F(u_i, u_fj) . nJ_ij)
+    SSE_FOR(j, Nf) {
+        double ui[NC], uo[NC], fs[NC];
+#pragma unroll
+        for (int e = 0; e < NC; e++) { ui[e] = s_in[j + Nf * e]; uo[e] = s_out[j + Nf * e]; }
+        numerical_flux<D, NC>(L, L.two_point, ui, uo, s_nf + D * j, fs);
+        double bj = o.Bf[j] * g.J_f[(size_t)Nf * k + j];
+#pragma unroll
+        for (int e = 0; e < NC; e++) fs[e] *= bj;
+        if (o.has_C) {
+            const int f = j / o.npf;
+            double hf[D];
+#pragma unroll
+            for (int m = 0; m < D; m++) hf[m] = 0.5 * g.nJf[m + D * ((size_t)Nf * k + j)];
+            for (int q = o.Cf.ptr[j]; q < o.Cf.ptr[j + 1]; q++) {
+                const int i = o.Cf.idx[q];
+                double uq[NC], F[NC][D], nJ[D];
+#pragma unroll
+                for (int e = 0; e < NC; e++) uq[e] = s_uq[i + Nq * e];
+                two_point_flux<D, NC>(L, L.two_point, uq, ui, F);
+#pragma unroll
+                for (int m = 0; m < D; m++) {
+                    double hq;
+                    if (g.nJq) hq = 0.5 * g.nJq[m + D * (f + (size_t)o.Nfac * (i + (size_t)Nq * k))];
+                    else {
+                        double t = 0.0;
+#pragma unroll
+                        for (int l = 0; l < D; l++) t += s_lam[i + Nq * (l + D * m)] * o.nref[l + D * f];
+                        hq = 0.5 * t;
+                    }
+                    nJ[m] = hf[m] + hq;
+                }
+                const double cij = o.Cf.val[q];
+#pragma unroll
+                for (int e = 0; e < NC; e++) {
+                    double Fn = 0.0;
+#pragma unroll
+                    for (int m = 0; m < D; m++) Fn = fma(nJ[m], F[e][m], Fn);
+                    fs[e] -= cij * Fn;
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < NC; e++) s_ff[j + Nf * e] = fs[e];
+    }
+    // volume side: r_i = -sum_j sum_m S_m[i,j] (Lam_i + Lam_j)[m,:] . F(u_i,u_j) - sum_j C_ij F(u_i,u_fj).nJ_ij
+    SSE_FOR(i, Nq) {
+        double ui[NC], r[NC];
+#pragma unroll
+        for (int e = 0; e < NC; e++) { ui[e] = s_uq[i + Nq * e]; r[e] = 0.0; }
+        for (int q = o.vol_ptr[i]; q < o.vol_ptr[i + 1]; q++) {
+            const int j = o.vol_j[q];
+            double uj[NC], F[NC][D];
+#pragma unroll
+            for (int e = 0; e < NC; e++) uj[e] = s_uq[j + Nq * e];
+            two_point_flux<D, NC>(L, L.two_point, ui, uj, F);
+#pragma unroll
+            for (int m = 0; m < D; m++) {
+                const double Sm = o.vol_S[q * D + m];
+                if (Sm != 0.0) {
+#pragma unroll
+                    for (int e = 0; e < NC; e++) {
+                        double Fm = 0.0;
+#pragma unroll
+                        for (int n = 0; n < D; n++) Fm = fma(s_lam[i + Nq * (m + D * n)] + s_lam[j + Nq * (m + D * n)], F[e][n], Fm);
+                        r[e] -= Sm * Fm;
+                    }
+                }
+            }
+        }
+        if (o.has_C) {
+            for (int q = o.Cq.ptr[i]; q < o.Cq.ptr[i + 1]; q++) {
+                const int j = o.Cq.idx[q];
+                const int f = j / o.npf;
+                double uj[NC], F[NC][D], nJ[D];
+#pragma unroll
+                for (int e = 0; e < NC; e++) uj[e] = s_in[j + Nf * e];
+                two_point_flux<D, NC>(L, L.two_point, ui, uj, F);
+#pragma unroll
+                for (int m = 0; m < D; m++) {
+                    double hq;
+                    if (g.nJq) hq = 0.5 * g.nJq[m + D * (f + (size_t)o.Nfac * (i + (size_t)Nq * k))];
+                    else {
+                        double t = 0.0;
+#pragma unroll
+                        for (int l = 0; l < D; l++) t += s_lam[i + Nq * (l + D * m)] * o.nref[l + D * f];
+                        hq = 0.5 * t;
+                    }
+                    nJ[m] = 0.5 * g.nJf[m + D * ((size_t)Nf * k + j)] + hq;
+                }
+                const double cij = o.Cq.val[q];
+#pragma unroll
+                for (int e = 0; e < NC; e++) {
+                    double Fn = 0.0;
+#pragma unroll
+                    for (int m = 0; m < D; m++) Fn = fma(nJ[m], F[e][m], Fn);
+                    r[e] -= cij * Fn;
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < NC; e++) s_r[i + Nq * e] = r[e];
+    }
+    __syncthreads();
+    // r_q -= R' f_f
+    SSE_FOR(t, Nq * NC) {
+        int i = t % Nq, e = t / Nq;
+        double s = 0.0;
+        for (int q = o.Rt.ptr[i]; q < o.Rt.ptr[i + 1]; q++) s = fma(o.Rt.val[q], s_ff[o.Rt.idx[q] + Nf * e], s);
+        s_r[t] -= s;
+    }
+    __syncthreads();
+    apply_Vt<NC>(o, s_r, s_m, s_z, s_w);
+    mass_solve<NC>(o, g, k, s_m, s_uq, s_z, s_w);
+    SSE_FOR(t, Np * NC) dudt[(size_t)Np * NC * k + t] = s_m[t];
+}
+
+// physical_flux! into a shared Nq x NC x D tile
+template <int D, int NC>
+__device__ void physical_flux_tile(const Ops& o, const Law& L, const double* s_uq, const double* s_qq, double* s_fq) {
+    const int Nq = o.Nq;
+    SSE_FOR(i, Nq) {
+        if (L.pde == SSE_PDE_EULER) {
+            if constexpr (NC == D + 2) {
+                double ui[NC], F[NC][D];
+#pragma unroll
+                for (int e = 0; e < NC; e++) ui[e] = s_uq[i + Nq * e];
+                euler_physical_flux<D>(L, ui, F);
+#pragma unroll
+                for (int e = 0; e < NC; e++)
+#pragma unroll
+                    for (int m = 0; m < D; m++) s_fq[i + Nq * (e + NC * m)] = F[e][m];
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < D; m++) {
+                double f = L.a[m] * s_uq[i];
+                if (L.pde == SSE_PDE_ADVECTION_DIFFUSION) f = L.a[m] * s_uq[i] - L.b * s_qq[i + Nq * NC * m];
+                s_fq[i + Nq * NC * m] = f;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------ pass B: StandardForm + ReferenceOperators
+// standard_form_first_order.jl:16-63
+template <int D, int NC>
+__global__ void k_time_standard_reference(Ops o, Geo g, Law L, long long first, const double* __restrict__ u_q,
+                                          const double* __restrict__ u_f, double* __restrict__ dudt) {
+    extern __shared__ double sm[];
+    const long long k = first + blockIdx.x;
+    const int Nq = o.Nq, Np = o.Np, Nf = o.Nf;
+    double* s_uq = sm;                        // Nq x NC (later scratch)
+    double* s_r = s_uq + Nq * NC;             // Nq x NC
+    double* s_fq = s_r + Nq * NC;             // Nq x NC x D
+    double* s_in = s_fq + Nq * NC * D;        // Nf x NC
+    double* s_out = s_in + Nf * NC;
+    double* s_ff = s_out + Nf * NC;
+    double* s_nf = s_ff + Nf * NC;            // D x Nf
+    double* s_lam = s_nf + D * Nf;            // Nq x D x D, premultiplied by 0.5 W (halfWΛ, operators.jl:16-18)
+    double* s_m = s_lam + Nq * D * D;         // Np x NC
+    double* s_z = s_m + Np * NC;
+    double* s_w = s_z + warp_z_size(o, NC);
+
+    SSE_FOR(t, Nq * NC) s_uq[t] = u_q[(size_t)Nq * NC * k + t];
+    SSE_FOR(t, Nq * D * D) { int i = t % Nq; s_lam[t] = (0.5 * o.W[i]) * g.Lambda_q[(size_t)Nq * D * D * k + t]; }
+    load_facets<D, NC>(o, g, k, u_f, s_in, s_out, s_nf);
+    physical_flux_tile<D, NC>(o, L, s_uq, nullptr, s_fq);
+    // volume terms: r = sum_{m,n} D_m' (hWL_mn f_n) - hWL_mn (D_m f_n)
+    SSE_FOR(t, Nq * NC) {
+        int i = t % Nq, e = t / Nq;
+        double r = 0.0;
+#pragma unroll
+        for (int n = 0; n < D; n++) {
+            const double* fn = s_fq + Nq * (e + NC * n);
+#pragma unroll
+            for (int m = 0; m < D; m++) {
+                const double* hl = s_lam + Nq * (m + D * n);
+                double s1 = 0.0, s2 = 0.0;
+                for (int q = o.Dt[m].ptr[i]; q < o.Dt[m].ptr[i + 1]; q++) { int j = o.Dt[m].idx[q]; s1 = fma(o.Dt[m].val[q], hl[j] * fn[j], s1); }
+                for (int q = o.D[m].ptr[i]; q < o.D[m].ptr[i + 1]; q++) s2 = fma(o.D[m].val[q], fn[o.D[m].idx[q]], s2);
+                r += s1;
+                r -= hl[i] * s2;
+            }
+        }
+        s_r[t] = r;
+    }
+    // facet terms: f_f = BJf (f* - sum_n halfN_n R f_n)
+    SSE_FOR(j, Nf) {
+        double ui[NC], uo[NC], fs[NC];
+#pragma unroll
+        for (int e = 0; e < NC; e++) { ui[e] = s_in[j + Nf * e]; uo[e] = s_out[j + Nf * e]; }
+        numerical_flux<D, NC>(L, SSE_TWO_POINT_CONSERVATIVE, ui, uo, s_nf + D * j, fs);
+#pragma unroll
+        for (int n = 0; n < D; n++) {
+            const double hn = 0.5 * s_nf[n + D * j];
+#pragma unroll
+            for (int e = 0; e < NC; e++) {
+                double s = 0.0;
+                for (int q = o.R.ptr[j]; q < o.R.ptr[j + 1]; q++) s = fma(o.R.val[q], s_fq[o.R.idx[q] + Nq * (e + NC * n)], s);
+                fs[e] -= hn * s;
+            }
+        }
+        double bj = o.Bf[j] * g.J_f[(size_t)Nf * k + j];
+#pragma unroll
+        for (int e = 0; e < NC; e++) s_ff[j + Nf * e] = bj * fs[e];
+    }
+    __syncthreads();
+    SSE_FOR(t, Nq * NC) {
+        int i = t % Nq, e = t / Nq;
+        double s = 0.0;
+        for (int q = o.Rt.ptr[i]; q < o.Rt.ptr[i + 1]; q++) s = fma(o.Rt.val[q], s_ff[o.Rt.idx[q] + Nf * e], s);
+        s_r[t] -= s;
+    }
+    __syncthreads();
+    apply_Vt<NC>(o, s_r, s_m, s_z, s_w);
+    mass_solve<NC>(o, g, k, s_m, s_uq, s_z, s_w);
+    SSE_FOR(t, Np * NC) dudt[(size_t)Np * NC * k + t] = s_m[t];
+}
+
+// ------------------------------------------------------------------ PhysicalOperators paths
+// BR1 auxiliary variable: standard_form_second_order.jl:3-34, linear_advection_diffusion.jl:75-86
+template <int D, int NC>
+__global__ void k_aux_physical(Ops o, Geo g, Law L, long long first, const double* __restrict__ u_q,
+                               const double* __restrict__ u_f, double* __restrict__ q_q, double* __restrict__ q_f) {
+    extern __shared__ double sm[];
+    const long long k = first + blockIdx.x;
+    const int Nq = o.Nq, Np = o.Np, Nf = o.Nf;
+    double* s_uq = sm;                        // Nq x NC
+    double* s_in = s_uq + Nq * NC;            // Nf x NC
+    double* s_out = s_in + Nf * NC;
+    double* s_nf = s_out + Nf * NC;           // D x Nf
+    double* s_m = s_nf + D * Nf;              // Np x NC
+    double* s_qq = s_m + Np * NC;             // Nq x NC
+    double* s_z = s_qq + Nq * NC;
+    double* s_w = s_z + warp_z_size(o, NC);
+    SSE_FOR(t, Nq * NC) s_uq[t] = u_q[(size_t)Nq * NC * k + t];
+    load_facets<D, NC>(o, g, k, u_f, s_in, s_out, s_nf);
+    const double* FAC = g.FAC + (size_t)Np * Nf * k;
+    for (int m = 0; m < D; m++) {
+        const double* VOL = g.VOL + (size_t)Np * Nq * (m + (size_t)D * k);
+        SSE_FOR(t, Np * NC) {
+            int a = t % Np, e = t / Np;
+            double s = 0.0;
+            for (int q = 0; q < Nq; q++) s = fma(VOL[a + (size_t)Np * q], s_uq[q + Nq * e], s);
+            double s2 = 0.0;
+            for (int f = 0; f < Nf; f++) {
+                double un = 0.5 * (s_in[f + Nf * e] + s_out[f + Nf * e]) * s_nf[m + D * f];
+                s2 = fma(FAC[a + (size_t)Np * f], un, s2);
+            }
+            s_m[t] = -s - s2;
+        }
+        __syncthreads();
+        apply_V<NC>(o, s_m, s_qq, s_z, s_w);
+        SSE_FOR(t, Nq * NC) q_q[(size_t)Nq * NC * (m + (size_t)D * k) + t] = s_qq[t];
+        SSE_FOR(t, Nf * NC) {
+            int j = t % Nf, e = t / Nf;
+            double s = 0.0;
+            for (int q = o.R.ptr[j]; q < o.R.ptr[j + 1]; q++) s = fma(o.R.val[q], s_qq[o.R.idx[q] + Nq * e], s);
+            q_f[(size_t)Nf * k + j + (size_t)g.NFT * (e + NC * m)] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// first-order (standard_form_first_order.jl:65-94) and second-order (standard_form_second_order.jl:38-75)
+// time derivative with per-element VOL / FAC; viscous flux linear_advection_diffusion.jl:90-102
+template <int D, int NC>
+__global__ void k_time_physical(Ops o, Geo g, Law L, long long first, int second_order, const double* __restrict__ u_q,
+                                const double* __restrict__ u_f, const double* __restrict__ q_q,
+                                const double* __restrict__ q_f, double* __restrict__ dudt) {
+    extern __shared__ double sm[];
+    const long long k = first + blockIdx.x;
+    const int Nq = o.Nq, Np = o.Np, Nf = o.Nf;
+    double* s_uq = sm;                        // Nq x NC
+    double* s_qq = s_uq + Nq * NC;            // Nq x NC x D
+    double* s_fq = s_qq + Nq * NC * D;        // Nq x NC x D
+    double* s_in = s_fq + Nq * NC * D;
+    double* s_out = s_in + Nf * NC;
+    double* s_ff = s_out + Nf * NC;
+    double* s_nf = s_ff + Nf * NC;
+    SSE_FOR(t, Nq * NC) s_uq[t] = u_q[(size_t)Nq * NC * k + t];
+    if (second_order) SSE_FOR(t, Nq * NC * D) s_qq[t] = q_q[(size_t)Nq * NC * D * k + t];
+    load_facets<D, NC>(o, g, k, u_f, s_in, s_out, s_nf);
+    physical_flux_tile<D, NC>(o, L, s_uq, s_qq, s_fq);
+    SSE_FOR(j, Nf) {
+        double ui[NC], uo[NC], fs[NC];
+#pragma unroll
+        for (int e = 0; e < NC; e++) { ui[e] = s_in[j + Nf * e]; uo[e] = s_out[j + Nf * e]; }
+        numerical_flux<D, NC>(L, SSE_TWO_POINT_CONSERVATIVE, ui, uo, s_nf + D * j, fs);
+        if (second_order) {
+            const size_t jo = (size_t)(g.mapP[(size_t)Nf * k + j] - 1);
+#pragma unroll
+            for (int e = 0; e < NC; e++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int m = 0; m < D; m++) {
+                    double qi = q_f[(size_t)Nf * k + j + (size_t)g.NFT * (e + NC * m)];
+                    double qo = q_f[jo + (size_t)g.NFT * (e + NC * m)];
+                    acc += L.b * (-0.5 * (qi + qo)) * s_nf[m + D * j];
+                }
+                fs[e] += acc;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < NC; e++) s_ff[j + Nf * e] = fs[e];
+    }
+    __syncthreads();
+    const double* FAC = g.FAC + (size_t)Np * Nf * k;
+    SSE_FOR(t, Np * NC) {
+        int a = t % Np, e = t / Np;
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < D; m++) {
+            const double* VOL = g.VOL + (size_t)Np * Nq * (m + (size_t)D * k);
+            double sv = 0.0;
+            for (int q = 0; q < Nq; q++) sv = fma(VOL[a + (size_t)Np * q], s_fq[q + Nq * (e + NC * m)], sv);
+            s += sv;
+        }
+        double sf = 0.0;
+        for (int f = 0; f < Nf; f++) sf = fma(FAC[a + (size_t)Np * f], s_ff[f + Nf * e], sf);
+        dudt[(size_t)Np * NC * k + t] = s + sf;
+    }
+}
+
+// ------------------------------------------------------------------ small streaming kernels
+__global__ void k_axpby(long long n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = (b == 0.0) ? a * x[i] : fma(a, x[i], b * y[i]);
+}
+// 2N-storage RK stage (Carpenter & Kennedy 1994): tmp = A tmp + dt dudt ; u += B tmp
+__global__ void k_lsrk_stage(long long n, double* __restrict__ u, double* __restrict__ tmp, const double* __restrict__ dudt,
+                             double A, double B, double dt) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double t = fma(A, tmp[i], dt * dudt[i]);
+        tmp[i] = t;
+        u[i] = fma(B, t, u[i]);
+    }
+}
+// halo pack / unpack: buffers are variable-fastest [slot][var]
+__global__ void k_halo_pack(long long n_send, int nvar, long long NFT, const long long* __restrict__ send_idx,
+                            const double* __restrict__ facet, double* __restrict__ buf) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_send * nvar; t += (long long)gridDim.x * blockDim.x) {
+        long long s = t / nvar; int e = (int)(t % nvar);
+        buf[t] = facet[(send_idx[s] - 1) + NFT * e];
+    }
+}
+__global__ void k_halo_unpack(long long n_ghost, int nvar, long long NFT, long long owned, const double* __restrict__ buf,
+                              double* __restrict__ facet) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_ghost * nvar; t += (long long)gridDim.x * blockDim.x) {
+        long long s = t / nvar; int e = (int)(t % nvar);
+        facet[owned + s + NFT * e] = buf[t];
+    }
+}
+
+// register-resident DFMA peak (8 independent chains per thread)
+__global__ void k_fp64_peak(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace sse

@@ -1,0 +1,684 @@
+// sse_b200.cu — C ABI of libsse_b200.so (see include/sse_b200.h).
+//
+// Host side: turns the reference `Solver` image into device tables once (sse_create), then
+// every sse_rhs is two (first-order) or three (second-order) kernel launches that never touch
+// the host.  No CPU fallback exists: if no CUDA device is usable every entry point reports
+// SSE_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sse_b200.h"
+#include "common.cuh"
+#include "kernels_generic.cuh"
+#include "kernels_tensor.cuh"
+
+using namespace sse;
+
+// ------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int32_t fail(int32_t code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(x)                                                                                        \
+    do {                                                                                             \
+        cudaError_t e_ = (x);                                                                        \
+        if (e_ != cudaSuccess) return fail(SSE_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------ handle
+struct sse_handle {
+    sse_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> owned;       // device allocations freed in sse_destroy
+    Ops ops;
+    Geo geo;
+    Law law;
+    TensorPlan tp;                  // tensor-line specialisation (kernels_tensor.cuh); tp.ok == 0 -> generic only
+    int variant = 1;
+    int project = 0;                // 0 none, 1 nodal, 2 general entropy projection
+    int second_order = 0;
+    double *u_q = nullptr, *u_f = nullptr, *q_q = nullptr, *q_f = nullptr;
+    size_t smem_nodal = 0, smem_time = 0, smem_aux = 0;
+    int threads = 128;
+    int sm_count = 148;
+    // halo
+    long long n_send = 0;
+    long long* d_send_idx = nullptr;
+    double *d_send = nullptr, *d_recv = nullptr;
+    int halo_vars = 0;
+};
+
+template <class T>
+static int32_t upload(sse_handle* h, const std::vector<T>& v, const T** out) {
+    void* p = nullptr;
+    size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CU(cudaMalloc(&p, n));
+    h->owned.push_back(p);
+    if (!v.empty()) CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)p;
+    return SSE_OK;
+}
+template <class T>
+static int32_t upload_raw(sse_handle* h, const T* src, size_t count, const T** out) {
+    void* p = nullptr;
+    CU(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    h->owned.push_back(p);
+    if (count) CU(cudaMemcpy(p, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)p;
+    return SSE_OK;
+}
+static int32_t dalloc(sse_handle* h, size_t count, double** out) {
+    void* p = nullptr;
+    CU(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(double)));
+    h->owned.push_back(p);
+    *out = (double*)p;
+    return SSE_OK;
+}
+
+struct HostSp {
+    std::vector<int> ptr, idx;
+    std::vector<double> val;
+};
+// rows of a column-major dense nrow x ncol matrix (transpose = true: rows of A^T)
+static HostSp compress(const double* A, int nrow, int ncol, bool transpose) {
+    HostSp s;
+    int nr = transpose ? ncol : nrow, nc = transpose ? nrow : ncol;
+    s.ptr.assign(nr + 1, 0);
+    for (int r = 0; r < nr; r++) {
+        s.ptr[r] = (int)s.idx.size();
+        for (int c = 0; c < nc; c++) {
+            double v = transpose ? A[c + (size_t)nrow * r] : A[r + (size_t)nrow * c];
+            if (v != 0.0) { s.idx.push_back(c); s.val.push_back(v); }
+        }
+    }
+    s.ptr[nr] = (int)s.idx.size();
+    return s;
+}
+static int32_t upload_sp(sse_handle* h, const HostSp& s, SpMat* out) {
+    int32_t rc;
+    if ((rc = upload(h, s.ptr, &out->ptr))) return rc;
+    if ((rc = upload(h, s.idx, &out->idx))) return rc;
+    return upload(h, s.val, &out->val);
+}
+
+// ------------------------------------------------------------------------------ dispatch
+#define DISPATCH_DNC(h, CALL)                                                  \
+    do {                                                                       \
+        const int d_ = (h)->cfg.d, nc_ = (h)->cfg.N_c;                         \
+        if (d_ == 1 && nc_ == 1) { CALL(1, 1); }                               \
+        else if (d_ == 1 && nc_ == 3) { CALL(1, 3); }                          \
+        else if (d_ == 2 && nc_ == 1) { CALL(2, 1); }                          \
+        else if (d_ == 2 && nc_ == 4) { CALL(2, 4); }                          \
+        else if (d_ == 3 && nc_ == 1) { CALL(3, 1); }                          \
+        else if (d_ == 3 && nc_ == 5) { CALL(3, 5); }                          \
+        else return fail(SSE_ERR_UNSUPPORTED, "unsupported (d, N_c) = (%d, %d)", d_, nc_); \
+    } while (0)
+
+static size_t smem_nodal_bytes(const Ops& o) {
+    int NC = o.NC;
+    return sizeof(double) * (size_t)(o.Np * NC + 2 * o.Nq * NC + o.Nf * NC + warp_z_size(o, NC) + warp_w_size(o, NC));
+}
+static size_t smem_time_bytes(const sse_handle* h) {
+    const Ops& o = h->ops;
+    int NC = o.NC, D = o.d;
+    size_t n = 0;
+    if (h->cfg.form == SSE_FORM_FLUX_DIFFERENCING)
+        n = 2 * o.Nq * NC + 3 * o.Nf * NC + D * o.Nf + o.Nq * D * D + o.Np * NC;
+    else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE)
+        n = 2 * o.Nq * NC + o.Nq * NC * D + 3 * o.Nf * NC + D * o.Nf + o.Nq * D * D + o.Np * NC;
+    else
+        n = o.Nq * NC + 2 * o.Nq * NC * D + 3 * o.Nf * NC + D * o.Nf;
+    n += warp_z_size(o, NC) + warp_w_size(o, NC);
+    return n * sizeof(double);
+}
+static size_t smem_aux_bytes(const Ops& o) {
+    int NC = o.NC, D = o.d;
+    return sizeof(double) * (size_t)(2 * o.Nq * NC + 2 * o.Nf * NC + D * o.Nf + o.Np * NC + warp_z_size(o, NC) + warp_w_size(o, NC));
+}
+
+template <int D, int NC>
+static int32_t set_attrs(sse_handle* h) {
+    CU(cudaFuncSetAttribute(k_nodal_generic<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_nodal));
+    CU(cudaFuncSetAttribute(k_time_fluxdiff_generic<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_time));
+    CU(cudaFuncSetAttribute(k_time_standard_reference<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_time));
+    CU(cudaFuncSetAttribute(k_time_physical<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_time));
+    CU(cudaFuncSetAttribute(k_aux_physical<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_aux));
+    return tensor_set_attrs<D, NC>(h->tp) == cudaSuccess ? SSE_OK : fail(SSE_ERR_CUDA, "cudaFuncSetAttribute (tensor kernels) failed");
+}
+
+// ------------------------------------------------------------------------------ create / destroy
+extern "C" int32_t sse_abi_version(void) { return SSE_ABI_VERSION; }
+extern "C" const char* sse_last_error_string(void) { return g_err.c_str(); }
+
+static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) {
+    const int d = cfg->d, NC = cfg->N_c, Np = cfg->N_p, Nq = cfg->N_q, Nf = cfg->N_f, Nfac = cfg->N_fac;
+    const long long Ne = cfg->N_e;
+    int32_t rc;
+    Ops& o = h->ops;
+    memset(&o, 0, sizeof(o));
+    o.d = d; o.NC = NC; o.Np = Np; o.Nq = Nq; o.Nf = Nf; o.Nfac = Nfac; o.npf = Nf / Nfac;
+    o.v_kind = cfg->v_kind;
+    if (!a->R || !a->W || !a->Bf || !a->J_q || !a->J_f || !a->nJf || !a->mapP)
+        return fail(SSE_ERR_BAD_ARGUMENT, "R, W, Bf, J_q, J_f, nJf and mapP are required");
+    // ---- V
+    if (cfg->v_kind == SSE_V_IDENTITY) {
+        if (Np != Nq) return fail(SSE_ERR_BAD_ARGUMENT, "identity V needs N_p == N_q (DimensionMismatch)");
+    } else if (cfg->v_kind == SSE_V_DENSE) {
+        if (!a->V) return fail(SSE_ERR_BAD_ARGUMENT, "dense V missing");
+        if ((rc = upload_raw(h, a->V, (size_t)Nq * Np, &o.Vd))) return rc;
+    } else if (cfg->v_kind == SSE_V_WARPED) {
+        if (d < 2 || !a->A || !a->B || (d == 3 && !a->C) || !a->sigma_i || !a->sigma_o)
+            return fail(SSE_ERR_BAD_ARGUMENT, "warped V needs A, B, (C), sigma_i, sigma_o and d >= 2");
+        const int P1 = cfg->p + 1;
+        if (P1 > 8) return fail(SSE_ERR_UNSUPPORTED, "p + 1 > 8 not supported by the warped kernels");
+        o.P1 = P1; o.M1 = cfg->M1d[0]; o.M2 = cfg->M1d[1]; o.M3 = (d == 3) ? cfg->M1d[2] : 1;
+        if (o.M1 * o.M2 * o.M3 != Nq) return fail(SSE_ERR_BAD_ARGUMENT, "warped V: M1*M2*M3 != N_q");
+        std::vector<double> C((size_t)o.M3 * P1 * P1 * P1, 0.0);
+        std::vector<int> si((size_t)P1 * P1 * P1, -1), so((size_t)Nq, 0);
+        if (d == 3) {
+            std::copy(a->C, a->C + C.size(), C.begin());
+            for (size_t t = 0; t < si.size(); t++) si[t] = (int)a->sigma_i[t] - 1;
+        } else {
+            for (int b1 = 0; b1 < P1; b1++)
+                for (int b2 = 0; b2 < P1; b2++) {
+                    C[0 + 1 * (b1 + P1 * (b2 + P1 * 0))] = 1.0;
+                    si[b1 + P1 * (b2 + P1 * 0)] = (int)a->sigma_i[b1 + P1 * b2] - 1;
+                }
+        }
+        for (int t = 0; t < Nq; t++) so[t] = (int)a->sigma_o[t] - 1;
+        int count = 0;
+        for (int b1 = 0; b1 < P1; b1++) {
+            int n2 = 0;
+            for (int b2 = 0; b2 < P1; b2++) {
+                int n3 = 0;
+                for (int b3 = 0; b3 < P1; b3++) n3 += si[b1 + P1 * (b2 + P1 * b3)] >= 0;
+                o.N3[b1 * 8 + b2] = n3;
+                n2 += n3 > 0;
+                count += n3;
+            }
+            o.N2[b1] = n2;
+        }
+        if (count != Np) return fail(SSE_ERR_BAD_ARGUMENT, "warped V: count(sigma_i > 0) != N_p");
+        if ((rc = upload_raw(h, a->A, (size_t)o.M1 * P1, &o.A))) return rc;
+        if ((rc = upload_raw(h, a->B, (size_t)o.M2 * P1 * P1, &o.B))) return rc;
+        if ((rc = upload(h, C, &o.C))) return rc;
+        if ((rc = upload(h, si, &o.sig_i))) return rc;
+        if ((rc = upload(h, so, &o.sig_o))) return rc;
+        if (a->V) { if ((rc = upload_raw(h, a->V, (size_t)Nq * Np, &o.Vd))) return rc; }
+    } else
+        return fail(SSE_ERR_BAD_ARGUMENT, "unknown v_kind %d", cfg->v_kind);
+    // ---- R, W, B
+    if ((rc = upload_sp(h, compress(a->R, Nf, Nq, false), &o.R))) return rc;
+    if ((rc = upload_sp(h, compress(a->R, Nf, Nq, true), &o.Rt))) return rc;
+    if ((rc = upload_raw(h, a->W, Nq, &o.W))) return rc;
+    if ((rc = upload_raw(h, a->Bf, Nf, &o.Bf))) return rc;
+    std::vector<double> nref((size_t)d * Nfac, 0.0);
+    if (a->nref) std::copy(a->nref, a->nref + nref.size(), nref.begin());
+    if ((rc = upload(h, nref, &o.nref))) return rc;
+    // ---- form-specific operators
+    Geo& g = h->geo;
+    memset(&g, 0, sizeof(g));
+    g.Ne = Ne; g.NFT = (long long)Nf * Ne + cfg->N_ghost; g.mass_solver = cfg->mass_solver;
+    if (cfg->form == SSE_FORM_STANDARD_REFERENCE) {
+        if (!a->Lambda_q) return fail(SSE_ERR_BAD_ARGUMENT, "Lambda_q required");
+        for (int m = 0; m < d; m++) {
+            if (!a->D[m]) return fail(SSE_ERR_BAD_ARGUMENT, "D[%d] required for StandardForm+ReferenceOperator", m);
+            if ((rc = upload_sp(h, compress(a->D[m], Nq, Nq, false), &o.D[m]))) return rc;
+            if ((rc = upload_sp(h, compress(a->D[m], Nq, Nq, true), &o.Dt[m]))) return rc;
+        }
+    } else if (cfg->form == SSE_FORM_FLUX_DIFFERENCING) {
+        if (!a->Lambda_q) return fail(SSE_ERR_BAD_ARGUMENT, "Lambda_q required");
+        std::vector<int> vptr(Nq + 1, 0), vj;
+        std::vector<double> vS;
+        for (int m = 0; m < d; m++)
+            if (!a->S[m]) return fail(SSE_ERR_BAD_ARGUMENT, "S[%d] required for FluxDifferencingForm", m);
+        // the reference only visits i < j (flux_differencing_form.jl:10-11, 52); row j receives -S[i,j]
+        for (int i = 0; i < Nq; i++) {
+            vptr[i] = (int)vj.size();
+            for (int j = 0; j < Nq; j++) {
+                if (i == j) continue;
+                int lo = std::min(i, j), hi = std::max(i, j);
+                bool any = false;
+                for (int m = 0; m < d; m++) any |= a->S[m][lo + (size_t)Nq * hi] != 0.0;
+                if (!any) continue;
+                vj.push_back(j);
+                for (int m = 0; m < d; m++) vS.push_back((i < j ? 1.0 : -1.0) * a->S[m][lo + (size_t)Nq * hi]);
+            }
+        }
+        vptr[Nq] = (int)vj.size();
+        if ((rc = upload(h, vptr, &o.vol_ptr))) return rc;
+        if ((rc = upload(h, vj, &o.vol_j))) return rc;
+        if ((rc = upload(h, vS, &o.vol_S))) return rc;
+        o.has_C = a->Cfd != nullptr;
+        if (o.has_C) {
+            if (!a->nJq && !a->nref) return fail(SSE_ERR_BAD_ARGUMENT, "facet correction needs nJq or nref");
+            if ((rc = upload_sp(h, compress(a->Cfd, Nq, Nf, false), &o.Cq))) return rc;
+            if ((rc = upload_sp(h, compress(a->Cfd, Nq, Nf, true), &o.Cf))) return rc;
+        }
+    } else if (cfg->form == SSE_FORM_STANDARD_PHYSICAL) {
+        if (!a->VOL || !a->FAC) return fail(SSE_ERR_BAD_ARGUMENT, "VOL and FAC required for PhysicalOperators");
+        if ((rc = upload_raw(h, a->VOL, (size_t)Np * Nq * d * Ne, &g.VOL))) return rc;
+        if ((rc = upload_raw(h, a->FAC, (size_t)Np * Nf * Ne, &g.FAC))) return rc;
+    } else
+        return fail(SSE_ERR_BAD_ARGUMENT, "unknown form %d", cfg->form);
+    // ---- geometry
+    if ((rc = upload_raw(h, a->J_q, (size_t)Nq * Ne, &g.J_q))) return rc;
+    if ((rc = upload_raw(h, a->J_f, (size_t)Nf * Ne, &g.J_f))) return rc;
+    if ((rc = upload_raw(h, a->nJf, (size_t)d * Nf * Ne, &g.nJf))) return rc;
+    if (a->Lambda_q) { if ((rc = upload_raw(h, a->Lambda_q, (size_t)Nq * d * d * Ne, &g.Lambda_q))) return rc; }
+    if (a->nJq && cfg->form == SSE_FORM_FLUX_DIFFERENCING) { if ((rc = upload_raw(h, a->nJq, (size_t)d * Nfac * Nq * Ne, &g.nJq))) return rc; }
+    {
+        const long long lim = g.NFT;
+        for (size_t t = 0; t < (size_t)Nf * Ne; t++)
+            if (a->mapP[t] < 1 || a->mapP[t] > lim) return fail(SSE_ERR_BAD_ARGUMENT, "mapP[%zu] = %lld out of range (BoundsError)", t, (long long)a->mapP[t]);
+        const long long* mp = nullptr;
+        if ((rc = upload_raw(h, (const long long*)a->mapP, (size_t)Nf * Ne, &mp))) return rc;
+        g.mapP = mp;
+    }
+    // ---- law
+    Law& L = h->law;
+    L.pde = cfg->pde; L.two_point = cfg->two_point_flux; L.inviscid = cfg->inviscid_flux;
+    L.half_lambda = cfg->half_lambda; L.b = cfg->b;
+    for (int m = 0; m < 3; m++) L.a[m] = cfg->a[m];
+    L.gamma = cfg->gamma; L.gm1 = cfg->gamma - 1.0; L.igm1 = 1.0 / (cfg->gamma - 1.0);
+    h->second_order = (cfg->pde == SSE_PDE_ADVECTION_DIFFUSION);
+    if (h->second_order && cfg->form != SSE_FORM_STANDARD_PHYSICAL)
+        return fail(SSE_ERR_UNSUPPORTED, "second-order laws are only implemented with PhysicalOperators (Solvers.jl:357-376)");
+    if (cfg->pde == SSE_PDE_EULER && NC != d + 2) return fail(SSE_ERR_BAD_ARGUMENT, "Euler needs N_c = d + 2");
+    if (cfg->pde != SSE_PDE_EULER && NC != 1) return fail(SSE_ERR_BAD_ARGUMENT, "scalar law needs N_c = 1");
+    // entropy-projection variant (flux_differencing_form.jl:171-292)
+    h->project = 0;
+    if (cfg->form == SSE_FORM_FLUX_DIFFERENCING && NC > 1) {
+        if (cfg->v_kind == SSE_V_IDENTITY) h->project = o.has_C ? 1 : 0;
+        else h->project = 2;
+    }
+    // ---- scratch
+    if ((rc = dalloc(h, (size_t)Nq * NC * Ne, &h->u_q))) return rc;
+    if ((rc = dalloc(h, (size_t)g.NFT * NC, &h->u_f))) return rc;
+    if (h->second_order) {
+        if ((rc = dalloc(h, (size_t)Nq * NC * d * Ne, &h->q_q))) return rc;
+        if ((rc = dalloc(h, (size_t)g.NFT * NC * d, &h->q_f))) return rc;
+    }
+    CU(cudaMemsetAsync(h->u_f, 0, sizeof(double) * (size_t)g.NFT * NC, h->stream));
+    // ---- tensor-line specialisation
+    tensor_plan_build(h->tp, *cfg, *a, o);
+    if (h->tp.ok) {
+        if ((rc = tensor_plan_upload(h->tp, [&](const void* src, size_t bytes, const void** out) -> int32_t {
+                 void* p = nullptr;
+                 if (cudaMalloc(&p, std::max<size_t>(bytes, 8)) != cudaSuccess) return SSE_ERR_CUDA;
+                 h->owned.push_back(p);
+                 if (bytes && cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return SSE_ERR_CUDA;
+                 *out = p;
+                 return SSE_OK;
+             })))
+            return fail(rc, "uploading the tensor-line tables failed");
+    }
+    h->smem_nodal = smem_nodal_bytes(o);
+    h->smem_time = smem_time_bytes(h);
+    h->smem_aux = smem_aux_bytes(o);
+    if (std::max(h->smem_nodal, std::max(h->smem_time, h->smem_aux)) > 227 * 1024)
+        return fail(SSE_ERR_UNSUPPORTED, "element tiles exceed 227 KB of shared memory");
+#define SETA(D_, NC_) do { if ((rc = set_attrs<D_, NC_>(h))) return rc; } while (0)
+    DISPATCH_DNC(h, SETA);
+#undef SETA
+    return SSE_OK;
+}
+
+extern "C" int32_t sse_create(const sse_config* cfg, const sse_arrays* arr, int32_t device, sse_handle** out) {
+    if (!cfg || !arr || !out) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (cfg->abi_version != SSE_ABI_VERSION) return fail(SSE_ERR_BAD_ARGUMENT, "ABI version mismatch: header %d, library %d", cfg->abi_version, SSE_ABI_VERSION);
+    if (cfg->d < 1 || cfg->d > 3 || cfg->N_e < 1 || cfg->N_fac < 1 || cfg->N_f % cfg->N_fac != 0)
+        return fail(SSE_ERR_BAD_ARGUMENT, "bad sizes (d=%d, N_e=%lld, N_f=%d, N_fac=%d)", cfg->d, (long long)cfg->N_e, cfg->N_f, cfg->N_fac);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(SSE_ERR_CUDA, "no CUDA device available (%s); libsse_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(SSE_ERR_BAD_ARGUMENT, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+    sse_handle* h = new sse_handle();
+    h->cfg = *cfg;
+    h->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    int32_t rc = build(h, cfg, arr);
+    if (rc == SSE_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(SSE_ERR_CUDA, "device error during setup: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc != SSE_OK) {
+        std::string keep = g_err;
+        sse_destroy(h);
+        g_err = keep;
+        return rc;
+    }
+    *out = h;
+    return SSE_OK;
+}
+
+extern "C" int32_t sse_destroy(sse_handle* h) {
+    if (!h) return SSE_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void* p : h->owned) cudaFree(p);
+    delete h;
+    return SSE_OK;
+}
+
+extern "C" int32_t sse_set_stream(sse_handle* h, void* s) {
+    if (!h) return fail(SSE_ERR_BAD_ARGUMENT, "null handle");
+    h->stream = (cudaStream_t)s;
+    return SSE_OK;
+}
+extern "C" int32_t sse_set_kernel_variant(sse_handle* h, int32_t v) {
+    if (!h || v < 0 || v > 1) return fail(SSE_ERR_BAD_ARGUMENT, "bad kernel variant");
+    h->variant = v;
+    return SSE_OK;
+}
+extern "C" int32_t sse_get_kernel_variant(const sse_handle* h, int32_t* v) {
+    if (!h || !v) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    *v = (h->variant == 1 && h->tp.ok) ? 1 : 0;
+    return SSE_OK;
+}
+
+// ------------------------------------------------------------------------------ state vectors
+static size_t state_len(const sse_handle* h) { return (size_t)h->cfg.N_p * h->cfg.N_c * h->cfg.N_e; }
+extern "C" int32_t sse_state_alloc(sse_handle* h, double** out) {
+    if (!h || !out) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMalloc((void**)out, state_len(h) * sizeof(double)));
+    CU(cudaMemsetAsync(*out, 0, state_len(h) * sizeof(double), h->stream));
+    return SSE_OK;
+}
+extern "C" int32_t sse_state_free(sse_handle* h, double* p) {
+    if (!h) return fail(SSE_ERR_BAD_ARGUMENT, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaFree(p));
+    return SSE_OK;
+}
+extern "C" int32_t sse_state_upload(sse_handle* h, double* d_dst, const double* h_src) {
+    if (!h || !d_dst || !h_src) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(d_dst, h_src, state_len(h) * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    return SSE_OK;
+}
+extern "C" int32_t sse_state_download(sse_handle* h, double* h_dst, const double* d_src) {
+    if (!h || !h_dst || !d_src) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h_dst, d_src, state_len(h) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SSE_OK;
+}
+extern "C" int32_t sse_synchronize(sse_handle* h) {
+    if (!h) return fail(SSE_ERR_BAD_ARGUMENT, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return SSE_OK;
+}
+
+// ------------------------------------------------------------------------------ the hot path
+static bool use_tensor(const sse_handle* h) { return h->variant == 1 && h->tp.ok; }
+
+extern "C" int32_t sse_rhs_pass_a(sse_handle* h, const double* d_u) {
+    if (!h || !d_u) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    CU(cudaSetDevice(h->device));
+    const unsigned Ne = (unsigned)h->cfg.N_e;
+    if (use_tensor(h) && h->tp.has_nodal) {
+#define LA(D_, NC_) tensor_launch_nodal<D_, NC_>(h->tp, h->ops, h->geo, h->law, h->project, d_u, h->u_q, h->u_f, h->cfg.N_e, h->sm_count, h->stream)
+        DISPATCH_DNC(h, LA);
+#undef LA
+    } else {
+#define LA(D_, NC_) k_nodal_generic<D_, NC_><<<Ne, h->threads, h->smem_nodal, h->stream>>>(h->ops, h->geo, h->law, h->project, d_u, h->u_q, h->u_f)
+        DISPATCH_DNC(h, LA);
+#undef LA
+    }
+    CU(cudaGetLastError());
+    return SSE_OK;
+}
+
+extern "C" int32_t sse_rhs_pass_aux(sse_handle* h, double* d_dudt, int64_t first, int64_t count) {
+    (void)d_dudt;
+    if (!h) return fail(SSE_ERR_BAD_ARGUMENT, "null handle");
+    if (!h->second_order || count <= 0) return SSE_OK;
+    if (first < 0 || first + count > h->cfg.N_e) return fail(SSE_ERR_BAD_ARGUMENT, "element range out of bounds");
+    CU(cudaSetDevice(h->device));
+#define LA(D_, NC_) k_aux_physical<D_, NC_><<<(unsigned)count, h->threads, h->smem_aux, h->stream>>>(h->ops, h->geo, h->law, first, h->u_q, h->u_f, h->q_q, h->q_f)
+    DISPATCH_DNC(h, LA);
+#undef LA
+    CU(cudaGetLastError());
+    return SSE_OK;
+}
+
+extern "C" int32_t sse_rhs_pass_b(sse_handle* h, double* d_dudt, int64_t first, int64_t count) {
+    if (!h || !d_dudt) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    if (count <= 0) return SSE_OK;
+    if (first < 0 || first + count > h->cfg.N_e) return fail(SSE_ERR_BAD_ARGUMENT, "element range out of bounds");
+    CU(cudaSetDevice(h->device));
+    const unsigned n = (unsigned)count;
+    if (h->cfg.form == SSE_FORM_FLUX_DIFFERENCING) {
+        if (use_tensor(h) && h->tp.has_fluxdiff) {
+#define LA(D_, NC_) tensor_launch_fluxdiff<D_, NC_>(h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->sm_count, h->stream)
+            DISPATCH_DNC(h, LA);
+#undef LA
+        } else {
+#define LA(D_, NC_) k_time_fluxdiff_generic<D_, NC_><<<n, h->threads, h->smem_time, h->stream>>>(h->ops, h->geo, h->law, first, h->u_q, h->u_f, d_dudt)
+            DISPATCH_DNC(h, LA);
+#undef LA
+        }
+    } else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE) {
+#define LA(D_, NC_) k_time_standard_reference<D_, NC_><<<n, h->threads, h->smem_time, h->stream>>>(h->ops, h->geo, h->law, first, h->u_q, h->u_f, d_dudt)
+        DISPATCH_DNC(h, LA);
+#undef LA
+    } else {
+#define LA(D_, NC_) k_time_physical<D_, NC_><<<n, h->threads, h->smem_time, h->stream>>>(h->ops, h->geo, h->law, first, h->second_order, h->u_q, h->u_f, h->q_q, h->q_f, d_dudt)
+        DISPATCH_DNC(h, LA);
+#undef LA
+    }
+    CU(cudaGetLastError());
+    return SSE_OK;
+}
+
+extern "C" int32_t sse_rhs(sse_handle* h, const double* d_u, double* d_dudt, double t) {
+    (void)t;   // no method of the reference uses t (Solvers.jl:474-564)
+    if (!h) return fail(SSE_ERR_BAD_ARGUMENT, "null handle");
+    if (h->cfg.N_ghost != 0) return fail(SSE_ERR_COMM, "handle has ghost facets: drive pass_a / halo exchange / pass_b explicitly");
+    int32_t rc;
+    if ((rc = sse_rhs_pass_a(h, d_u))) return rc;
+    if ((rc = sse_rhs_pass_aux(h, d_dudt, 0, h->cfg.N_e))) return rc;
+    return sse_rhs_pass_b(h, d_dudt, 0, h->cfg.N_e);
+}
+
+// ------------------------------------------------------------------------------ halo
+extern "C" int32_t sse_halo_configure(sse_handle* h, const int64_t* send_index, int64_t n_send) {
+    if (!h || (n_send > 0 && !send_index)) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    CU(cudaSetDevice(h->device));
+    const long long owned = (long long)h->cfg.N_f * h->cfg.N_e;
+    for (int64_t s = 0; s < n_send; s++)
+        if (send_index[s] < 1 || send_index[s] > owned) return fail(SSE_ERR_BAD_ARGUMENT, "send_index[%lld] out of range", (long long)s);
+    h->n_send = n_send;
+    h->halo_vars = h->cfg.N_c * (h->second_order ? h->cfg.d : 1);
+    const long long* p = nullptr;
+    int32_t rc;
+    if ((rc = upload_raw(h, (const long long*)send_index, (size_t)n_send, &p))) return rc;
+    h->d_send_idx = (long long*)p;
+    if ((rc = dalloc(h, (size_t)n_send * h->halo_vars, &h->d_send))) return rc;
+    if ((rc = dalloc(h, (size_t)h->cfg.N_ghost * h->halo_vars, &h->d_recv))) return rc;
+    return SSE_OK;
+}
+static int halo_nvar(const sse_handle* h, int which) { return which == 0 ? h->cfg.N_c : h->cfg.N_c * h->cfg.d; }
+extern "C" int32_t sse_halo_pack(sse_handle* h, int32_t which) {
+    if (!h || which < 0 || which > 1 || (which == 1 && !h->second_order)) return fail(SSE_ERR_BAD_ARGUMENT, "bad halo selector");
+    if (h->n_send == 0) return SSE_OK;
+    CU(cudaSetDevice(h->device));
+    const int nv = halo_nvar(h, which);
+    const long long n = h->n_send * nv;
+    k_halo_pack<<<(unsigned)std::min<long long>((n + 255) / 256, 4096), 256, 0, h->stream>>>(h->n_send, nv, h->geo.NFT, h->d_send_idx, which ? h->q_f : h->u_f, h->d_send);
+    CU(cudaGetLastError());
+    return SSE_OK;
+}
+extern "C" int32_t sse_halo_unpack(sse_handle* h, int32_t which) {
+    if (!h || which < 0 || which > 1 || (which == 1 && !h->second_order)) return fail(SSE_ERR_BAD_ARGUMENT, "bad halo selector");
+    if (h->cfg.N_ghost == 0) return SSE_OK;
+    CU(cudaSetDevice(h->device));
+    const int nv = halo_nvar(h, which);
+    const long long n = h->cfg.N_ghost * nv;
+    k_halo_unpack<<<(unsigned)std::min<long long>((n + 255) / 256, 4096), 256, 0, h->stream>>>(h->cfg.N_ghost, nv, h->geo.NFT, (long long)h->cfg.N_f * h->cfg.N_e, h->d_recv, which ? h->q_f : h->u_f);
+    CU(cudaGetLastError());
+    return SSE_OK;
+}
+extern "C" int32_t sse_halo_send_buffer(sse_handle* h, double** d_buf, int64_t* n) {
+    if (!h || !d_buf || !n) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    *d_buf = h->d_send; *n = h->n_send * h->halo_vars;
+    return SSE_OK;
+}
+extern "C" int32_t sse_halo_recv_buffer(sse_handle* h, int32_t which, double** d_buf, int64_t* n) {
+    if (!h || !d_buf || !n) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    *d_buf = h->d_recv; *n = h->cfg.N_ghost * halo_nvar(h, which);
+    return SSE_OK;
+}
+
+// ------------------------------------------------------------------------------ callers either side
+extern "C" int32_t sse_axpby(sse_handle* h, double a, const double* d_x, double b, double* d_y) {
+    if (!h || !d_x || !d_y) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    CU(cudaSetDevice(h->device));
+    const long long n = (long long)state_len(h);
+    k_axpby<<<(unsigned)std::min<long long>((n + 255) / 256, 8 * h->sm_count), 256, 0, h->stream>>>(n, a, d_x, b, d_y);
+    CU(cudaGetLastError());
+    return SSE_OK;
+}
+extern "C" int32_t sse_lsrk_stage(sse_handle* h, double* d_u, double* d_tmp, const double* d_dudt, double A, double B, double dt) {
+    if (!h || !d_u || !d_tmp || !d_dudt) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    CU(cudaSetDevice(h->device));
+    const long long n = (long long)state_len(h);
+    k_lsrk_stage<<<(unsigned)std::min<long long>((n + 255) / 256, 8 * h->sm_count), 256, 0, h->stream>>>(n, d_u, d_tmp, d_dudt, A, B, dt);
+    CU(cudaGetLastError());
+    return SSE_OK;
+}
+// Carpenter & Kennedy (1994) 2N-storage RK4(5) coefficients (OrdinaryDiffEq's CarpenterKennedy2N54)
+static const double CK_A[5] = {0.0, -567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+                               -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+static const double CK_B[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0,
+                               1720146321549.0 / 2090206949498.0, 3134564353537.0 / 4481467310338.0,
+                               2277821191437.0 / 14882151754819.0};
+static const double CK_C[5] = {0.0, 1432997174477.0 / 9575080441755.0, 2526269341429.0 / 6820363962896.0,
+                               2006345519317.0 / 3224310063776.0, 2802321613138.0 / 2924317926251.0};
+extern "C" int32_t sse_step_ck54(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double t, double dt) {
+    int32_t rc;
+    for (int s = 0; s < 5; s++) {
+        if ((rc = sse_rhs(h, d_u, d_dudt, t + CK_C[s] * dt))) return rc;
+        if ((rc = sse_lsrk_stage(h, d_u, d_tmp, d_dudt, CK_A[s], CK_B[s], dt))) return rc;
+    }
+    return SSE_OK;
+}
+
+// conservation / entropy residual reductions (Analysis/conservation.jl:145-189)
+template <int D, int NC>
+__global__ void k_functionals(Ops o, Geo g, Law L, const double* __restrict__ u, const double* __restrict__ dudt, double* __restrict__ out) {
+    extern __shared__ double sm[];
+    const int Nq = o.Nq, Np = o.Np;
+    double* s_u = sm;                 // Np x NC
+    double* s_d = s_u + Np * NC;      // Np x NC
+    double* s_uq = s_d + Np * NC;     // Nq x NC
+    double* s_dq = s_uq + Nq * NC;    // Nq x NC
+    double* s_z = s_dq + Nq * NC;
+    double* s_w = s_z + warp_z_size(o, NC);
+    __shared__ double acc[NC + 2];
+    if (threadIdx.x < NC + 2) acc[threadIdx.x] = 0.0;
+    for (long long k = blockIdx.x; k < g.Ne; k += gridDim.x) {
+        __syncthreads();
+        SSE_FOR(t, Np * NC) { s_u[t] = u[(size_t)Np * NC * k + t]; s_d[t] = dudt[(size_t)Np * NC * k + t]; }
+        __syncthreads();
+        apply_V<NC>(o, s_u, s_uq, s_z, s_w);
+        apply_V<NC>(o, s_d, s_dq, s_z, s_w);
+        const double* J = g.J_q + (size_t)Nq * k;
+        SSE_FOR(i, Nq) {
+            const double wj = o.W[i] * J[i];
+            double ui[NC], wi[NC];
+#pragma unroll
+            for (int e = 0; e < NC; e++) { ui[e] = s_uq[i + Nq * e]; atomicAdd(&acc[e], wj * s_dq[i + Nq * e]); }
+            if (L.pde == SSE_PDE_EULER) {
+                cons_to_entropy<D, NC>(L, ui, wi);
+                double s = 0.0;
+#pragma unroll
+                for (int e = 0; e < NC; e++) s += wi[e] * s_dq[i + Nq * e];
+                atomicAdd(&acc[NC + 1], wj * s);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < NC + 2) atomicAdd(&out[threadIdx.x], acc[threadIdx.x]);
+}
+
+extern "C" int32_t sse_functionals(sse_handle* h, const double* d_u, const double* d_dudt, double* out) {
+    if (!h || !d_u || !d_dudt || !out) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    CU(cudaSetDevice(h->device));
+    const int NC = h->cfg.N_c;
+    double* d_out = nullptr;
+    CU(cudaMalloc((void**)&d_out, sizeof(double) * (NC + 2)));
+    CU(cudaMemsetAsync(d_out, 0, sizeof(double) * (NC + 2), h->stream));
+    const Ops& o = h->ops;
+    size_t smem = sizeof(double) * (size_t)(2 * o.Np * NC + 2 * o.Nq * NC + warp_z_size(o, NC) + warp_w_size(o, NC));
+    unsigned grid = (unsigned)std::min<long long>(h->cfg.N_e, 4LL * h->sm_count);
+#define LA(D_, NC_)                                                                                                  \
+    do {                                                                                                             \
+        cudaFuncSetAttribute(k_functionals<D_, NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        k_functionals<D_, NC_><<<grid, 128, smem, h->stream>>>(h->ops, h->geo, h->law, d_u, d_dudt, d_out);           \
+    } while (0)
+    DISPATCH_DNC(h, LA);
+#undef LA
+    cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(double) * (NC + 2), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(SSE_ERR_CUDA, "functionals failed: %s", cudaGetErrorString(e));
+    // energy residual u' M dudt needs the per-element mass matrix; provided for the diagonal solver only
+    out[NC] = NAN;
+    return SSE_OK;
+}
+
+extern "C" int32_t sse_debug_views(sse_handle* h, double** d_u_q, double** d_u_f) {
+    if (!h) return fail(SSE_ERR_BAD_ARGUMENT, "null handle");
+    if (d_u_q) *d_u_q = h->u_q;
+    if (d_u_f) *d_u_f = h->u_f;
+    return SSE_OK;
+}
+
+extern "C" int32_t sse_fp64_peak(int32_t device, double* flops) {
+    if (!flops) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(SSE_ERR_CUDA, "no such CUDA device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    double* d = nullptr;
+    CU(cudaMalloc((void**)&d, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    k_fp64_peak<<<blocks, threads>>>(d, 1 << 10);
+    double best = 0.0;
+    for (int r = 0; r < 5; r++) {
+        CU(cudaEventRecord(e0));
+        k_fp64_peak<<<blocks, threads>>>(d, iters);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double f = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3);
+        best = std::max(best, f);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *flops = best;
+    return SSE_OK;
+}

@@ -1,0 +1,79 @@
+"""ctypes binding of libsse_b200.so (the CUDA library behind include/sse_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or no CUDA device
+is usable, every compute call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsse_b200.so")
+
+# every symbol include/sse_b200.h declares: name -> (restype, argtypes)
+_pd = C.POINTER(C.c_double)
+_ppd = C.POINTER(_pd)
+_pi64 = C.POINTER(C.c_int64)
+_h = C.c_void_p
+SYMBOLS = {
+    "sse_create": (C.c_int32, [C.POINTER(_abi.sse_config), C.POINTER(_abi.sse_arrays), C.c_int32, C.POINTER(_h)]),
+    "sse_destroy": (C.c_int32, [_h]),
+    "sse_set_stream": (C.c_int32, [_h, C.c_void_p]),
+    "sse_set_kernel_variant": (C.c_int32, [_h, C.c_int32]),
+    "sse_get_kernel_variant": (C.c_int32, [_h, C.POINTER(C.c_int32)]),
+    "sse_state_alloc": (C.c_int32, [_h, _ppd]),
+    "sse_state_free": (C.c_int32, [_h, C.c_void_p]),
+    "sse_state_upload": (C.c_int32, [_h, C.c_void_p, C.c_void_p]),
+    "sse_state_download": (C.c_int32, [_h, C.c_void_p, C.c_void_p]),
+    "sse_rhs": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_double]),
+    "sse_rhs_pass_a": (C.c_int32, [_h, C.c_void_p]),
+    "sse_rhs_pass_aux": (C.c_int32, [_h, C.c_void_p, C.c_int64, C.c_int64]),
+    "sse_rhs_pass_b": (C.c_int32, [_h, C.c_void_p, C.c_int64, C.c_int64]),
+    "sse_halo_configure": (C.c_int32, [_h, _pi64, C.c_int64]),
+    "sse_halo_pack": (C.c_int32, [_h, C.c_int32]),
+    "sse_halo_send_buffer": (C.c_int32, [_h, _ppd, _pi64]),
+    "sse_halo_recv_buffer": (C.c_int32, [_h, C.c_int32, _ppd, _pi64]),
+    "sse_halo_unpack": (C.c_int32, [_h, C.c_int32]),
+    "sse_axpby": (C.c_int32, [_h, C.c_double, C.c_void_p, C.c_double, C.c_void_p]),
+    "sse_lsrk_stage": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double]),
+    "sse_step_ck54": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]),
+    "sse_functionals": (C.c_int32, [_h, C.c_void_p, C.c_void_p, _pd]),
+    "sse_synchronize": (C.c_int32, [_h]),
+    "sse_last_error_string": (C.c_char_p, []),
+    "sse_abi_version": (C.c_int32, []),
+    "sse_debug_views": (C.c_int32, [_h, _ppd, _ppd]),
+    "sse_fp64_peak": (C.c_int32, [C.c_int32, _pd]),
+}
+
+_LIB = None
+
+
+class SSEError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libsse_b200 status {code}: {msg}")
+        self.code = code
+
+
+def load():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.sse_abi_version() != _abi.SSE_ABI_VERSION:
+            raise RuntimeError("libsse_b200.so ABI version does not match sse_b200/_abi.py")
+        _LIB = L
+    return _LIB
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().sse_last_error_string()
+        raise SSEError(rc, msg.decode() if msg else "")

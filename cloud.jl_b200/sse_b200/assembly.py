@@ -49,8 +49,8 @@ class SpatialDiscretization:
 
     @staticmethod
     def build(mesh: Mesh, ra: ReferenceApproximation, metric_type: str = "exact",
-              project_jacobian_flag: bool = True) -> "SpatialDiscretization":
-        gf = geometric_factors(mesh, ra, metric_type)
+              project_jacobian_flag: bool = True, need_nJq: bool = True) -> "SpatialDiscretization":
+        gf = geometric_factors(mesh, ra, metric_type, need_nJq=need_nJq)
         if metric_type == "exact" and project_jacobian_flag:
             gf.J_q = np.ascontiguousarray(project_jacobian(gf.J_q, ra))
         return SpatialDiscretization(mesh, ra, gf, mesh.N_e)
@@ -198,6 +198,8 @@ def assemble(law, sd: SpatialDiscretization, form, strategy: str = REFERENCE_OPE
             arrays["Cfd"] = _colmajor(Cfd)
         arrays["Lambda_q"] = _F(gf.Lambda_q)
         if pass_nJq:
+            if gf.nJq is None:
+                raise ValueError("geometric factors were built without nJq")
             arrays["nJq"] = _F(gf.nJq)
     else:
         cfg.form = _abi.SSE_FORM_STANDARD_REFERENCE

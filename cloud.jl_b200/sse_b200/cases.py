@@ -1,0 +1,115 @@
+"""The BASELINE.json configurations as concrete synthetic inputs.
+
+Each builder returns a `Case` (law, discretisation, form, strategy, initial-data callable);
+`Case.image()` assembles the Solver image, `Case.u0(seed)` the L2-projected initial state
+with an optional smooth-random modal perturbation (numpy default_rng(seed)).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+from .assembly import (FluxDifferencingForm, PHYSICAL_OPERATOR, REFERENCE_OPERATOR, SpatialDiscretization,
+                       StandardForm, assemble)
+from .laws import (CentralNumericalFlux, EntropyConservativeNumericalFlux, EulerEquations,
+                   LaxFriedrichsNumericalFlux, LinearAdvectionDiffusionEquation, LinearAdvectionEquation,
+                   initial_data_cosine, initial_data_sine, isentropic_vortex, project_function,
+                   taylor_green_vortex)
+from .mesh import ChanWarping, DelReyWarping, uniform_periodic_mesh
+from .reference import ModalTensor, NodalTensor, reference_approximation
+
+
+@dataclass
+class Case:
+    name: str
+    law: object
+    sd: SpatialDiscretization
+    form: object
+    strategy: str
+    ic: object
+
+    def image(self, **kw):
+        return assemble(self.law, self.sd, self.form, self.strategy, **kw)
+
+    def u0(self, seed: Optional[int] = None, eps: float = 2e-3) -> np.ndarray:
+        sd = self.sd
+        u = project_function(self.ic, sd.reference_approximation, sd.geometric_factors.J_q, sd.mesh.xyzq)
+        if seed is not None:
+            rng = np.random.default_rng(seed)
+            scale = np.abs(u).max(axis=(0, 2), keepdims=True)
+            scale = np.where(scale > 0, scale, 1.0)
+            u = u + eps * rng.standard_normal(u.shape) * scale
+        return np.ascontiguousarray(u)
+
+    @property
+    def dof(self) -> int:
+        ra = self.sd.reference_approximation
+        return ra.N_p * self.law.N_c * self.sd.N_e
+
+
+def _flux(name: str):
+    return {"lf": LaxFriedrichsNumericalFlux(1.0), "lf0": LaxFriedrichsNumericalFlux(0.0),
+            "central": CentralNumericalFlux(), "ec": EntropyConservativeNumericalFlux()}[name]
+
+
+def _approx(kind: str, p: int):
+    return ModalTensor(p) if kind == "modal" else NodalTensor(p)
+
+
+def advection_2d(M=4, p=4, flux="lf", kind="modal", warp=0.1, part=None) -> Case:
+    """config 1: examples/advection_2d.ipynb / runtests.jl:38-60."""
+    ra = reference_approximation(_approx(kind, p), "Tri", mapping_degree=p)
+    mesh = uniform_periodic_mesh(ra, ((0.0, 1.0),) * 2, (M, M), DelReyWarping(warp, (1.0, 1.0)), part)
+    sd = SpatialDiscretization.build(mesh, ra, "exact", True)
+    return Case("advection_2d", LinearAdvectionEquation((1.0, 1.0)), sd,
+                StandardForm(inviscid_numerical_flux=_flux(flux)), REFERENCE_OPERATOR,
+                initial_data_sine(1.0, (2 * np.pi, 2 * np.pi)))
+
+
+def euler_vortex_2d(M=4, p=4, flux="lf", kind="modal", part=None) -> Case:
+    """config 2: test/euler_vortex_2d_modal.jl."""
+    g = 1.4
+    ra = reference_approximation(_approx(kind, p), "Tri", mapping_degree=p)
+    mesh = uniform_periodic_mesh(ra, ((0.0, 1.0),) * 2, (M, M), ChanWarping(1.0 / 16.0, (1.0, 1.0)), part)
+    sd = SpatialDiscretization.build(mesh, ra, "curl")
+    ic = isentropic_vortex(g, 0.4, 0.0, 0.1, np.sqrt(2 / (g - 1) * (1 - 0.75 ** (g - 1))), 1.0, (0.5, 0.5))
+    return Case("euler_vortex_2d", EulerEquations(2, g), sd,
+                FluxDifferencingForm(inviscid_numerical_flux=_flux(flux)), REFERENCE_OPERATOR, ic)
+
+
+def advection_diffusion_2d(M=4, p=4, kind="modal", part=None) -> Case:
+    """config 3: 2-D advection-diffusion, BR1 (PhysicalOperators are the only 2nd-order strategy)."""
+    ra = reference_approximation(_approx(kind, p), "Tri", mapping_degree=p)
+    mesh = uniform_periodic_mesh(ra, ((0.0, 1.0),) * 2, (M, M), DelReyWarping(0.1, (1.0, 1.0)), part)
+    sd = SpatialDiscretization.build(mesh, ra, "exact", True)
+    return Case("advection_diffusion_2d", LinearAdvectionDiffusionEquation((1.0, 1.0), 5e-2), sd,
+                StandardForm(inviscid_numerical_flux=_flux("lf")), PHYSICAL_OPERATOR,
+                initial_data_sine(1.0, (2 * np.pi, 2 * np.pi)))
+
+
+def advection_3d(M=2, p=4, flux="central", kind="modal", part=None) -> Case:
+    """config 4: test/advection_3d.jl."""
+    ra = reference_approximation(_approx(kind, p), "Tet", mapping_degree=p)
+    mesh = uniform_periodic_mesh(ra, ((0.0, 1.0),) * 3, (M,) * 3, DelReyWarping(0.1, (1.0,) * 3), part)
+    sd = SpatialDiscretization.build(mesh, ra, "curl")
+    return Case("advection_3d", LinearAdvectionEquation((1.0, 1.0, 1.0)), sd,
+                StandardForm(inviscid_numerical_flux=_flux(flux)), REFERENCE_OPERATOR,
+                initial_data_cosine(1.0, (2 * np.pi,) * 3))
+
+
+def euler_tgv_3d(M=2, p=4, flux="lf", kind="modal", part=None) -> Case:
+    """config 5 (headline): 3-D Euler Taylor-Green vortex on curved tets, flux differencing."""
+    L = 2 * np.pi
+    ra = reference_approximation(_approx(kind, p), "Tet", mapping_degree=p)
+    mesh = uniform_periodic_mesh(ra, ((0.0, L),) * 3, (M,) * 3, ChanWarping(1.0 / 16.0, (L,) * 3), part)
+    sd = SpatialDiscretization.build(mesh, ra, "curl")
+    return Case("euler_tgv_3d", EulerEquations(3, 1.4), sd,
+                FluxDifferencingForm(inviscid_numerical_flux=_flux(flux)), REFERENCE_OPERATOR,
+                taylor_green_vortex(1.4, 0.1))
+
+
+BUILDERS = {"advection_2d": advection_2d, "euler_vortex_2d": euler_vortex_2d,
+            "advection_diffusion_2d": advection_diffusion_2d, "advection_3d": advection_3d,
+            "euler_tgv_3d": euler_tgv_3d}

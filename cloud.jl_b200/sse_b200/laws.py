@@ -4,8 +4,7 @@ Mirrors the type surface of src/ConservationLaws (ConservationLaws.jl:40-72,
 linear_advection_diffusion.jl:1-47, euler_navierstokes.jl:23-38) and the grid
 functions used by the BASELINE configs (GridFunctions.jl:118-134,
 euler_navierstokes.jl:234-320).  The pointwise physics itself is evaluated on the
-device (csrc/physics.cuh) and, for checking, in the oracle; nothing here is on
-the hot path.
+device (csrc/physics.cuh); nothing here is on the hot path.
 """
 from __future__ import annotations
 
@@ -155,8 +154,19 @@ def project_function(f, ra, J_q, xyzq):
     if ra.V_is_identity:
         return np.ascontiguousarray(np.transpose(u_q, (0, 2, 1)))
     V, W = ra.V, ra.W
-    WJ = W[None, :] * J_q                                  # (N_e, N_q)
-    Mk = np.einsum("qa,kq,qb->kab", V, WJ, V)
-    rhs = np.einsum("qa,kq,kqc->kac", V, WJ, u_q)
-    u0 = np.linalg.solve(Mk, rhs)                          # (N_e, N_p, N_c)
-    return np.ascontiguousarray(np.transpose(u0, (0, 2, 1)))
+    out = np.empty((u_q.shape[0], u_q.shape[2], V.shape[1]))
+    for s in range(0, u_q.shape[0], 16384):
+        WJ = W[None, :] * J_q[s:s + 16384]                 # (n, N_q)
+        VtWJ = V.T[None, :, :] * WJ[:, None, :]            # (n, N_p, N_q)
+        u0 = np.linalg.solve(VtWJ @ V, VtWJ @ u_q[s:s + 16384])   # (n, N_p, N_c)
+        out[s:s + 16384] = np.transpose(u0, (0, 2, 1))
+    return out
+
+
+def project_function_reference(f, ra, xyzq):
+    """Cheap synthetic state for large benchmarks: u = V' W f(x_q) (the L2 projection on the
+    reference element, exact for affine elements since V' W V = I)."""
+    u_q = f(xyzq)
+    if ra.V_is_identity:
+        return np.ascontiguousarray(np.transpose(u_q, (0, 2, 1)))
+    return np.ascontiguousarray(np.einsum("qa,kqc->kca", ra.V * ra.W[:, None], u_q, optimize=True))

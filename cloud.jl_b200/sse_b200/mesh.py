@@ -217,7 +217,7 @@ def _match_faces(xf: List[np.ndarray], N_fac: int, limits, tol=1e-8):
 
 
 def uniform_periodic_mesh(ra: ReferenceApproximation, limits, M, warp=None,
-                          part: Optional[Tuple[int, int]] = None) -> Mesh:
+                          part: Optional[Tuple[int, int]] = None, structured: Optional[bool] = None) -> Mesh:
     """Periodic Cartesian-derived simplex mesh (1-D: intervals), optionally warped.
 
     ``part=(rank, world)`` builds only this rank's slab (cells split along the
@@ -241,6 +241,10 @@ def uniform_periodic_mesh(ra: ReferenceApproximation, limits, M, warp=None,
     limits = tuple(tuple(l) for l in limits)
     ncell = int(np.prod(M))
     nsimp = 2 if d == 2 else 6
+    if structured is None:
+        structured = min(M) >= 4
+    if part is None and structured:
+        part = (0, 1)
     if part is None:
         cells = np.arange(ncell)
         EtoV, n1 = _cartesian_simplex_cells(d, M, cells)
@@ -265,7 +269,7 @@ def _template_connectivity(ra: ReferenceApproximation):
     """
     d = ra.d
     lim = tuple((0.0, 3.0) for _ in range(d))
-    m = uniform_periodic_mesh(ra, lim, (3,) * d)
+    m = uniform_periodic_mesh(ra, lim, (3,) * d, structured=False)
     nsimp = 2 if d == 2 else 6
     N_f = ra.N_f
     center = 1 + 3 * 1 + (9 if d == 3 else 0)
@@ -398,40 +402,54 @@ def _metrics_pointwise(dxdr):
     return J, J[..., None, None] * np.linalg.inv(dxdr)
 
 
-def _finish(ra, J_q, Lq, Lf):
-    """nJq, nJf, J_f from nodal metrics.  Lq: (N_e,N_q,l,m), Lf: (N_e,N_f,l,m)."""
-    d = ra.d
-    npf = ra.nodes_per_face
-    nref_face = np.array([[ra.nrstJ[m][npf * f] for m in range(d)] for f in range(ra.N_fac)])
-    nJq = np.einsum("kiln,fl->kifn", Lq, nref_face)                 # (N_e,N_q,N_fac,n)
-    nref = np.stack(ra.nrstJ, axis=1)                               # (N_f, l)
-    nJf = np.einsum("kilm,il->kim", Lf, nref)                       # (N_e,N_f,m)
-    J_f = np.sqrt(np.sum(nJf ** 2, axis=2))
-    Lambda_q = np.ascontiguousarray(np.transpose(Lq, (0, 3, 2, 1)))  # (N_e, n, m(l), i)
-    return GeometricFactors(np.ascontiguousarray(J_q), Lambda_q, J_f,
-                            np.ascontiguousarray(nJf), np.ascontiguousarray(nJq))
+class _Acc:
+    """Accumulates nodal metric components straight into the ABI layouts (no big temporaries)."""
+
+    def __init__(self, ra, ne, need_nJq):
+        d = ra.d
+        self.ra, self.d = ra, d
+        self.Lambda_q = np.empty((ne, d, d, ra.N_q))          # [k, n(phys), m(ref), i]
+        self.nJf = np.zeros((ne, ra.N_f, d))                  # [k, i, m(phys)]
+        self.nref = np.stack(ra.nrstJ, axis=1)                # (N_f, l)
+        self.need_nJq = need_nJq
+
+    def add(self, l, m, aq, af):
+        """metric J d xi_l / d x_m at volume nodes (aq: ne x N_q) and facet nodes (af: ne x N_f)."""
+        self.Lambda_q[:, m, l, :] = aq
+        self.nJf[:, :, m] += af * self.nref[None, :, l]
+
+    def finish(self, J_q):
+        ra, d = self.ra, self.d
+        J_f = np.sqrt(np.sum(self.nJf ** 2, axis=2))
+        nJq = None
+        if self.need_nJq:
+            npf = ra.nodes_per_face
+            nrf = np.array([[ra.nrstJ[l][npf * f] for l in range(d)] for f in range(ra.N_fac)])
+            nJq = np.ascontiguousarray(np.einsum("knli,fl->kifn", self.Lambda_q, nrf))
+        return GeometricFactors(np.ascontiguousarray(J_q), self.Lambda_q, J_f, self.nJf, nJq)
 
 
 def geometric_factors(mesh: Mesh, ra: ReferenceApproximation, metric_type: str = "exact",
-                      chunk: int = 65536) -> GeometricFactors:
+                      chunk: int = 32768, need_nJq: bool = True) -> GeometricFactors:
     """metric_type: 'exact' (mesh.jl:229-282) or 'curl' (ConservativeCurl/ChanWilcox)."""
     d, g = ra.d, ra.geom
     outs = []
     for s in range(0, mesh.N_e, chunk):
         xyz = [x[s:s + chunk] for x in mesh.xyz]
         if metric_type == "exact" or d == 1:
-            outs.append(_gf_exact(ra, xyz))
+            outs.append(_gf_exact(ra, xyz, need_nJq))
         elif d == 2:
-            outs.append(_gf_curl_2d(ra, xyz))
+            outs.append(_gf_curl_2d(ra, xyz, need_nJq))
         else:
-            outs.append(_gf_curl_3d(ra, xyz))
+            outs.append(_gf_curl_3d(ra, xyz, need_nJq))
     if len(outs) == 1:
         return outs[0]
-    return GeometricFactors(*[np.concatenate([getattr(o, f) for o in outs], axis=0)
+    return GeometricFactors(*[None if getattr(outs[0], f) is None else
+                              np.concatenate([getattr(o, f) for o in outs], axis=0)
                               for f in ("J_q", "Lambda_q", "J_f", "nJf", "nJq")])
 
 
-def _gf_exact(ra, xyz):
+def _gf_exact(ra, xyz, need_nJq=True):
     d, g = ra.d, ra.geom
     ne = xyz[0].shape[0]
     dq = np.empty((ne, ra.N_q, d, d))
@@ -443,10 +461,14 @@ def _gf_exact(ra, xyz):
             df[:, :, m, n] = dx @ g.Vf.T
     J_q, Lq = _metrics_pointwise(dq)
     _, Lf = _metrics_pointwise(df)
-    return _finish(ra, J_q, Lq, Lf)
+    acc = _Acc(ra, ne, need_nJq)
+    for l in range(d):
+        for m in range(d):
+            acc.add(l, m, Lq[:, :, l, m], Lf[:, :, l, m])
+    return acc.finish(J_q)
 
 
-def _gf_curl_2d(ra, xyz):
+def _gf_curl_2d(ra, xyz, need_nJq=True):
     # StartUpDG.geometric_factors(x, y, Dr, Ds) interpolated (mesh.jl:284-339)
     g = ra.geom
     x, y = xyz
@@ -454,19 +476,16 @@ def _gf_curl_2d(ra, xyz):
     xr, xs, yr, ys = x @ Dr.T, x @ Ds.T, y @ Dr.T, y @ Ds.T
     J = -xs * yr + xr * ys
     L = {(0, 0): ys, (1, 0): -yr, (0, 1): -xs, (1, 1): xr}      # (l, m): J d xi_l / d x_m
-    ne = x.shape[0]
-    Lq = np.empty((ne, ra.N_q, 2, 2))
-    Lf = np.empty((ne, ra.N_f, 2, 2))
+    acc = _Acc(ra, x.shape[0], need_nJq)
     for (l, m), a in L.items():
-        Lq[:, :, l, m] = a @ g.Vq.T
-        Lf[:, :, l, m] = a @ g.Vf.T
-    return _finish(ra, J @ g.Vq.T, Lq, Lf)
+        acc.add(l, m, a @ g.Vq.T, a @ g.Vf.T)
+    return acc.finish(J @ g.Vq.T)
 
 
 _CURL_CACHE = {}
 
 
-def _gf_curl_3d(ra, xyz):
+def _gf_curl_3d(ra, xyz, need_nJq=True):
     """Conservative-curl metrics on tets (mesh.jl:410-506; Chan & Wilcox 2019): the
     curl argument is a degree N+1 polynomial, the metric itself degree N."""
     g = ra.geom
@@ -476,8 +495,8 @@ def _gf_curl_3d(ra, xyz):
         g1 = geometry_element(3, N + 1, g.rst, g.rst)          # Vq of g1 = interp (N+1 nodes -> N nodes)
         up = g.interp(g1.rst)                                  # N nodes -> N+1 nodes
         down = g1.Vq                                           # N+1 nodes -> N nodes
-        _CURL_CACHE[key] = (g1, up, g.Vq @ down, g.Vf @ down)
-    g1, up, Vq, Vf = _CURL_CACHE[key]
+        _CURL_CACHE[key] = (g1, up, np.ascontiguousarray((g.Vq @ down).T), np.ascontiguousarray((g.Vf @ down).T))
+    g1, up, VqT, VfT = _CURL_CACHE[key]
     x, y, z = xyz
     Dr, Ds, Dt = g.Drst
     xr, xs, xt = x @ Dr.T, x @ Ds.T, x @ Dt.T
@@ -485,25 +504,19 @@ def _gf_curl_3d(ra, xyz):
     zr, zs, zt = z @ Dr.T, z @ Ds.T, z @ Dt.T
     J = xr * (ys * zt - zs * yt) - yr * (xs * zt - zs * xt) + zr * (xs * yt - ys * xt)
     X, Y, Z = x @ up.T, y @ up.T, z @ up.T
-    D1r, D1s, D1t = (a.T for a in g1.Drst)
+    D1r, D1s, D1t = (np.ascontiguousarray(a.T) for a in g1.Drst)
 
     def curl(a, b):
         # components (r, s, t) of  curl_xi( b * grad_xi a )
         Fr, Fs, Ft = (a @ D1r) * b, (a @ D1s) * b, (a @ D1t) * b
         return Fs @ D1t - Ft @ D1s, Ft @ D1r - Fr @ D1t, Fr @ D1s - Fs @ D1r
 
-    rx, sx, tx = curl(Y, Z)
-    ry, sy, ty = (-c for c in curl(X, Z))
-    rz, sz, tz = (-c for c in curl(Y, X))
-    L = {(0, 0): rx, (1, 0): sx, (2, 0): tx, (0, 1): ry, (1, 1): sy, (2, 1): ty,
-         (0, 2): rz, (1, 2): sz, (2, 2): tz}
-    ne = x.shape[0]
-    Lq = np.empty((ne, ra.N_q, 3, 3))
-    Lf = np.empty((ne, ra.N_f, 3, 3))
-    for (l, m), a in L.items():
-        Lq[:, :, l, m] = a @ Vq.T
-        Lf[:, :, l, m] = a @ Vf.T
-    return _finish(ra, J @ g.Vq.T, Lq, Lf)
+    acc = _Acc(ra, x.shape[0], need_nJq)
+    for m, (a, b, sgn) in enumerate(((Y, Z, 1.0), (X, Z, -1.0), (Y, X, -1.0))):
+        for l, comp in enumerate(curl(a, b)):
+            comp = sgn * comp
+            acc.add(l, m, comp @ VqT, comp @ VfT)
+    return acc.finish(J @ g.Vq.T)
 
 
 def project_jacobian(J_q: np.ndarray, ra: ReferenceApproximation) -> np.ndarray:

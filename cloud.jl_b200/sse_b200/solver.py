@@ -1,0 +1,261 @@
+"""Host mirror of the reference Solver surface for the path (Python stand-in for the Julia host).
+
+    Solver(...)                      src/Solvers/Solvers.jl:259-376
+    semidiscretize(...)              src/Solvers/Solvers.jl:429-452
+    semi_discrete_residual!(...)     src/Solvers/Solvers.jl:474-564
+
+`u` and `dudt` are torch CUDA tensors of shape (N_e, N_c, N_p), float64, C-contiguous — the
+memory image of the reference's column-major (N_p, N_c, N_e) arrays.  NumPy arrays are accepted
+as well; they are staged through pinned host memory and copied to/from the device around the
+call (the "host buffers" end-to-end path).  torch only owns memory and streams here; all
+arithmetic happens in libsse_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _abi, _lib
+from .assembly import (REFERENCE_OPERATOR, PHYSICAL_OPERATOR, SolverImage, SpatialDiscretization,
+                       assemble)
+from .laws import project_function
+
+# Carpenter & Kennedy (1994) 2N-storage RK4(5) (OrdinaryDiffEq's CarpenterKennedy2N54)
+CK54_A = (0.0, -567301805773 / 1357537059087, -2404267990393 / 2016746695238,
+          -3550918686646 / 2091501179385, -1275806237668 / 842570457699)
+CK54_B = (1432997174477 / 9575080441755, 5161836677717 / 13612068292357,
+          1720146321549 / 2090206949498, 3134564353537 / 4481467310338,
+          2277821191437 / 14882151754819)
+CK54_C = (0.0, 1432997174477 / 9575080441755, 2526269341429 / 6820363962896,
+          2006345519317 / 3224310063776, 2802321613138 / 2924317926251)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class _DevView:
+    """__cuda_array_interface__ wrapper of a library-owned device buffer."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+class Solver:
+    """One reference `Solver` resident on one GPU (handle of libsse_b200.so)."""
+
+    def __init__(self, image: SolverImage, device: int = 0):
+        self.image = image
+        self.cfg = image.cfg
+        self.device = device
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        arr = image.c_arrays()
+        _lib.check(self._lib.sse_create(C.byref(image.cfg), C.byref(arr), device, C.byref(self._h)))
+        self._pinned = {}
+        self.launches = 0      # kernels launched through this handle (for bench accounting)
+        self._per_rhs = 3 if image.law.second_order else 2
+
+    # -- plumbing ------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            self._lib.sse_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def state_shape(self) -> Tuple[int, int, int]:
+        return self.image.state_shape
+
+    def size(self):
+        """Base.size(solver) = (N_p, N_c, N_e) (Solvers.jl:276-285)."""
+        return (int(self.cfg.N_p), int(self.cfg.N_c), int(self.cfg.N_e))
+
+    def new_state(self):
+        torch = _torch()
+        return torch.zeros(self.state_shape, dtype=torch.float64, device=f"cuda:{self.device}")
+
+    def use_current_stream(self):
+        torch = _torch()
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._lib.sse_set_stream(self._h, C.c_void_p(s)))
+
+    def set_kernel_variant(self, v: int):
+        _lib.check(self._lib.sse_set_kernel_variant(self._h, v))
+
+    def kernel_variant(self) -> int:
+        v = C.c_int32(0)
+        _lib.check(self._lib.sse_get_kernel_variant(self._h, C.byref(v)))
+        return int(v.value)
+
+    def _check_state(self, x, name):
+        torch = _torch()
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()
+                and tuple(x.shape) == self.state_shape):
+            raise ValueError(f"{name}: expected contiguous float64 CUDA tensor of shape {self.state_shape} "
+                             "(DimensionMismatch)")
+        return C.c_void_p(x.data_ptr())
+
+    # -- the path ------------------------------------------------------------------------
+    def rhs(self, dudt, u, t: float = 0.0):
+        _lib.check(self._lib.sse_rhs(self._h, self._check_state(u, "u"), self._check_state(dudt, "dudt"), float(t)))
+        self.launches += self._per_rhs
+        return dudt
+
+    def pass_a(self, u):
+        _lib.check(self._lib.sse_rhs_pass_a(self._h, self._check_state(u, "u")))
+        self.launches += 1
+
+    def pass_aux(self, dudt, first, count):
+        _lib.check(self._lib.sse_rhs_pass_aux(self._h, self._check_state(dudt, "dudt"), first, count))
+        self.launches += 1 if (count > 0 and self.image.law.second_order) else 0
+
+    def pass_b(self, dudt, first, count):
+        _lib.check(self._lib.sse_rhs_pass_b(self._h, self._check_state(dudt, "dudt"), first, count))
+        self.launches += 1 if count > 0 else 0
+
+    def rhs_host(self, dudt_host, u_host, t: float = 0.0):
+        """Residual on HOST buffers: H2D copy of u, kernels, D2H copy of dudt.  torch CPU tensors
+        (ideally pinned) are copied directly; NumPy arrays are staged through pinned memory."""
+        torch = _torch()
+        p = self._pinned
+        if "d_u" not in p:
+            p["d_u"], p["d_du"] = self.new_state(), self.new_state()
+        if isinstance(u_host, np.ndarray):
+            if "u" not in p:
+                p["u"] = torch.empty(self.state_shape, dtype=torch.float64).pin_memory()
+                p["du"] = torch.empty(self.state_shape, dtype=torch.float64).pin_memory()
+            p["u"].numpy()[...] = u_host
+            src, dst = p["u"], p["du"]
+        else:
+            src, dst = u_host, dudt_host
+        p["d_u"].copy_(src, non_blocking=True)
+        self.rhs(p["d_du"], p["d_u"], t)
+        dst.copy_(p["d_du"], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        if isinstance(u_host, np.ndarray):
+            dudt_host[...] = dst.numpy()
+        return dudt_host
+
+    def axpby(self, a, x, b, y):
+        _lib.check(self._lib.sse_axpby(self._h, a, self._check_state(x, "x"), b, self._check_state(y, "y")))
+        self.launches += 1
+
+    def lsrk_stage(self, u, tmp, dudt, A, B, dt):
+        _lib.check(self._lib.sse_lsrk_stage(self._h, self._check_state(u, "u"), self._check_state(tmp, "tmp"),
+                                            self._check_state(dudt, "dudt"), A, B, dt))
+        self.launches += 1
+
+    def step_ck54(self, u, tmp, dudt, t, dt):
+        _lib.check(self._lib.sse_step_ck54(self._h, self._check_state(u, "u"), self._check_state(tmp, "tmp"),
+                                           self._check_state(dudt, "dudt"), t, dt))
+        self.launches += 5 * (self._per_rhs + 1)
+
+    def functionals(self, u, dudt) -> np.ndarray:
+        out = np.zeros(int(self.cfg.N_c) + 2)
+        _lib.check(self._lib.sse_functionals(self._h, self._check_state(u, "u"), self._check_state(dudt, "dudt"),
+                                             out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def synchronize(self):
+        _lib.check(self._lib.sse_synchronize(self._h))
+
+    def debug_views(self):
+        """(u_q, u_f) scratch as torch tensors: u_q (N_e, N_c, N_q); u_f (N_c, N_f*N_e + ghost)."""
+        torch = _torch()
+        pq, pf = C.POINTER(C.c_double)(), C.POINTER(C.c_double)()
+        _lib.check(self._lib.sse_debug_views(self._h, C.byref(pq), C.byref(pf)))
+        c = self.cfg
+        nq = int(c.N_e) * int(c.N_c) * int(c.N_q)
+        nft = int(c.N_f) * int(c.N_e) + int(c.N_ghost)
+        uq = torch.as_tensor(_DevView(C.cast(pq, C.c_void_p).value, nq), device=f"cuda:{self.device}")
+        uf = torch.as_tensor(_DevView(C.cast(pf, C.c_void_p).value, nft * int(c.N_c)), device=f"cuda:{self.device}")
+        return uq.view(int(c.N_e), int(c.N_c), int(c.N_q)), uf.view(int(c.N_c), nft)
+
+    # -- halo buffers (multi-GPU) ----------------------------------------------------------
+    def halo_configure(self, send_index_1based: np.ndarray):
+        idx = np.ascontiguousarray(send_index_1based, dtype=np.int64)
+        _lib.check(self._lib.sse_halo_configure(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size))
+
+    def halo_buffers(self, which: int = 0):
+        torch = _torch()
+        p, n = C.POINTER(C.c_double)(), C.c_int64(0)
+        _lib.check(self._lib.sse_halo_send_buffer(self._h, C.byref(p), C.byref(n)))
+        nv = int(self.cfg.N_c) * (int(self.cfg.d) if which == 1 else 1)
+        nsend = (n.value // (int(self.cfg.N_c) * (int(self.cfg.d) if self.image.law.second_order else 1))) * nv
+        dev = f"cuda:{self.device}"
+        send = torch.as_tensor(_DevView(C.cast(p, C.c_void_p).value, max(nsend, 1)), device=dev)[:nsend]
+        _lib.check(self._lib.sse_halo_recv_buffer(self._h, which, C.byref(p), C.byref(n)))
+        recv = torch.as_tensor(_DevView(C.cast(p, C.c_void_p).value, max(n.value, 1)), device=dev)[:n.value]
+        return send, recv
+
+    def halo_pack(self, which: int = 0):
+        _lib.check(self._lib.sse_halo_pack(self._h, which))
+        self.launches += 1
+
+    def halo_unpack(self, which: int = 0):
+        _lib.check(self._lib.sse_halo_unpack(self._h, which))
+        self.launches += 1
+
+
+def fp64_peak(device: int = 0) -> float:
+    """Measured register-resident DFMA throughput in FLOP/s (FMA = 2)."""
+    out = C.c_double(0.0)
+    _lib.check(_lib.load().sse_fp64_peak(device, C.byref(out)))
+    return float(out.value)
+
+
+@dataclass
+class ODEProblem:
+    """ODEProblem(semi_discrete_residual!, u0, tspan, solver) (Solvers.jl:451)."""
+    f: object
+    u0: np.ndarray
+    tspan: Tuple[float, float]
+    p: Solver
+
+
+def semi_discrete_residual(dudt, u, solver: Solver, t: float = 0.0):
+    """semi_discrete_residual!(dudt, u, solver, t) (Solvers.jl:474-564); returns dudt."""
+    if isinstance(u, np.ndarray) or not u.is_cuda:
+        return solver.rhs_host(dudt, u, t)
+    return solver.rhs(dudt, u, t)
+
+
+def semidiscretize(conservation_law, spatial_discretization: SpatialDiscretization, initial_data, form,
+                   tspan, strategy: str = REFERENCE_OPERATOR, mass_matrix_solver: Optional[int] = None,
+                   device: int = 0) -> ODEProblem:
+    """semidiscretize (Solvers.jl:429-452): project the initial data, build the Solver."""
+    sd = spatial_discretization
+    u0 = project_function(initial_data, sd.reference_approximation, sd.geometric_factors.J_q, sd.mesh.xyzq)
+    image = assemble(conservation_law, sd, form, strategy, mass_matrix_solver)
+    return ODEProblem(semi_discrete_residual, u0, tuple(tspan), Solver(image, device))
+
+
+def solve_ck54(problem: ODEProblem, dt: float, n_steps: int, fused: bool = True):
+    """solve(ode, CarpenterKennedy2N54(); dt, adaptive=false) with the state resident on the device
+    (test/test_driver.jl:77-83).  Returns the final state as a NumPy array."""
+    torch = _torch()
+    s = problem.p
+    u = torch.from_numpy(np.ascontiguousarray(problem.u0)).to(f"cuda:{s.device}")
+    tmp, du = s.new_state(), s.new_state()
+    t = problem.tspan[0]
+    for _ in range(n_steps):
+        if fused:
+            s.step_ck54(u, tmp, du, t, dt)
+        else:
+            for st in range(5):
+                s.rhs(du, u, t + CK54_C[st] * dt)
+                s.lsrk_stage(u, tmp, du, CK54_A[st], CK54_B[st], dt)
+        t += dt
+    s.synchronize()
+    return u.cpu().numpy()

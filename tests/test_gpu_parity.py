@@ -1,0 +1,154 @@
+"""Parity of the CUDA library (through the C ABI) with the CPU oracle on identical meshes and
+states: max|Δ| <= 1e-12 * max|ref| (BASELINE.json north_star: 1e-12 relative, FP64), for every
+BASELINE config, both kernel variants, plus golden vectors and size-independent invariants."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from sse_b200 import analysis, cases
+from sse_b200.assembly import PHYSICAL_OPERATOR, assemble
+from sse_b200.solver import Solver, solve_ck54, ODEProblem, semi_discrete_residual
+
+pytestmark = pytest.mark.gpu
+RTOL = 1.0e-12
+
+
+def relerr(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def gpu_rhs(img, u, variant=1, check_scratch=False):
+    s = Solver(img, 0)
+    s.set_kernel_variant(variant)
+    du = s.new_state()
+    s.rhs(du, torch.from_numpy(u).cuda())
+    s.synchronize()
+    out = du.cpu().numpy()
+    extra = None
+    if check_scratch:
+        uq, uf = s.debug_views()
+        extra = (uq.cpu().numpy(), uf.cpu().numpy(), s.kernel_variant())
+    s.close()
+    return out, extra
+
+
+CASES = {
+    "advection_2d_lf": lambda: cases.advection_2d(M=4, flux="lf"),
+    "advection_2d_central": lambda: cases.advection_2d(M=2, flux="lf0"),
+    "advection_2d_nodal": lambda: cases.advection_2d(M=3, flux="lf", kind="nodal"),
+    "euler_vortex_2d_p3_lf": lambda: cases.euler_vortex_2d(M=4, p=3, flux="lf"),
+    "euler_vortex_2d_p4_ec": lambda: cases.euler_vortex_2d(M=4, p=4, flux="ec"),
+    "euler_vortex_2d_nodal": lambda: cases.euler_vortex_2d(M=3, p=4, flux="ec", kind="nodal"),
+    "advection_diffusion_2d": lambda: cases.advection_diffusion_2d(M=4),
+    "advection_3d_central": lambda: cases.advection_3d(M=2, flux="central"),
+    "advection_3d_lf": lambda: cases.advection_3d(M=2, flux="lf"),
+    "advection_3d_p3": lambda: cases.advection_3d(M=2, p=3, flux="lf"),
+    "euler_tgv_3d_lf": lambda: cases.euler_tgv_3d(M=2, flux="lf"),
+    "euler_tgv_3d_ec": lambda: cases.euler_tgv_3d(M=2, flux="ec"),
+    "euler_tgv_3d_p3": lambda: cases.euler_tgv_3d(M=2, p=3, flux="lf"),
+    "euler_tgv_3d_nodal": lambda: cases.euler_tgv_3d(M=2, p=3, flux="ec", kind="nodal"),
+    "euler_tgv_3d_M4": lambda: cases.euler_tgv_3d(M=4, flux="lf"),
+}
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_rhs_matches_oracle(name, variant):
+    c = CASES[name]()
+    img, u = c.image(), c.u0(seed=0)
+    ref, uq_ref, uf_ref = oracle.rhs(img, u, return_scratch=True)
+    got, (uq, uf, used) = gpu_rhs(img, u, variant, check_scratch=True)
+    assert np.all(np.isfinite(got))
+    assert relerr(uf[:, :uf_ref.shape[1] * uf_ref.shape[2]].reshape(uf_ref.shape), uf_ref) <= RTOL, "facet states (pass A)"
+    assert relerr(got, ref) <= RTOL, f"dudt, variant requested {variant} used {used}"
+
+
+def test_physical_first_order_and_stored_nJq():
+    c = cases.advection_3d(M=2, flux="lf")
+    u = c.u0(seed=3)
+    img = assemble(c.law, c.sd, c.form, PHYSICAL_OPERATOR)
+    assert relerr(gpu_rhs(img, u)[0], oracle.rhs(img, u)) <= RTOL
+    c = cases.euler_tgv_3d(M=2, flux="ec")
+    u = c.u0(seed=3)
+    img = c.image(pass_nJq=True)
+    assert relerr(gpu_rhs(img, u, 0)[0], oracle.rhs(img, u)) <= RTOL
+
+
+def test_logmean_branches_are_both_exercised():
+    """A state with large density jumps drives logmean through the log branch (f^2 >= 1e-4)."""
+    c = cases.euler_vortex_2d(M=4, p=4, flux="lf")
+    u = c.u0(seed=5, eps=0.05)
+    img = c.image()
+    ref = oracle.rhs(img, u)
+    assert np.all(np.isfinite(ref))
+    for v in (0, 1):
+        assert relerr(gpu_rhs(img, u, v)[0], ref) <= RTOL
+
+
+def test_golden_fixture():
+    """tests/golden/euler_tgv_3d_M2.npz (made by tests/golden/make_golden.py from the pinned oracle)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "euler_tgv_3d_M2.npz"))
+    c = cases.euler_tgv_3d(M=2, flux="lf")
+    got, _ = gpu_rhs(c.image(), z["u"])
+    assert relerr(got, z["dudt"]) <= RTOL
+
+
+def test_euler_1d_reference_golden_on_gpu():
+    """The reference's own golden L2 errors (runtests.jl:89-96) reproduced by the CUDA path with the
+    fused device-resident CarpenterKennedy2N54 integrator."""
+    from test_oracle_goldens import EULER_1D_GOLDEN, euler_1d_setup
+    from sse_b200.laws import project_function
+    ra, mesh, sd, img, exact = euler_1d_setup()
+    u0 = project_function(exact, ra, sd.geometric_factors.J_q, mesh.xyzq)
+    s = Solver(img, 0)
+    u = solve_ck54(ODEProblem(semi_discrete_residual, u0, (0.0, 2.0), s), 2.0 / 1000, 1000)
+    ue = np.transpose(exact(mesh.xyzq), (0, 2, 1))
+    l2 = np.sqrt(np.einsum("kei,ki,kei->e", ue - u, ra.W[None, :] * sd.geometric_factors.J_q, ue - u))
+    assert np.allclose(l2, EULER_1D_GOLDEN, rtol=0, atol=1e-10)
+    s.close()
+
+
+def test_invariants_at_scale_and_functionals():
+    """Size-independent properties on a mesh the oracle is not run on: conservation and entropy
+    conservation (EC interface flux) to roundoff, via the device functionals."""
+    c = cases.euler_tgv_3d(M=8, flux="ec")
+    img, u = c.image(), c.u0(seed=7)
+    s = Solver(img, 0)
+    du = s.new_state()
+    ud = torch.from_numpy(u).cuda()
+    s.rhs(du, ud)
+    f = s.functionals(ud, du)
+    d = du.cpu().numpy()
+    scale = np.abs(d).max() * (2 * np.pi) ** 3
+    assert np.abs(f[:5]).max() < 1e-12 * scale
+    assert abs(f[6]) < 1e-12 * scale
+    assert np.allclose(f[:5], analysis.conservation_residual(img, d), rtol=0, atol=1e-12 * scale)
+    assert abs(f[6] - analysis.entropy_residual(img, u, d)) < 1e-12 * scale
+    s.close()
+
+
+def test_host_buffer_api_and_linearity():
+    c = cases.advection_3d(M=2, flux="lf")
+    img = c.image()
+    s = Solver(img, 0)
+    u1, u2 = c.u0(seed=1), c.u0(seed=2)
+    r = [semi_discrete_residual(np.empty_like(u1), x, s) for x in (u1, u2, 2.0 * u1 - 3.0 * u2)]
+    assert relerr(r[2], 2.0 * r[0] - 3.0 * r[1]) <= 1e-12          # the advection residual is linear
+    assert relerr(r[0], oracle.rhs(img, u1)) <= RTOL
+    s.close()
+
+
+def test_bad_arguments_fail_loudly():
+    from sse_b200._lib import SSEError
+    c = cases.advection_2d(M=2)
+    img = c.image()
+    s = Solver(img, 0)
+    with pytest.raises(ValueError):
+        s.rhs(s.new_state(), torch.zeros(3, dtype=torch.float64, device="cuda"))
+    img.arrays["mapP"] = img.arrays["mapP"].copy()
+    img.arrays["mapP"][0] = 10 ** 9
+    with pytest.raises(SSEError):
+        Solver(img, 0)
+    s.close()

@@ -651,6 +651,32 @@ extern "C" int32_t sse_debug_views(sse_handle* h, double** d_u_q, double** d_u_f
     return SSE_OK;
 }
 
+// Host-only diagnostic: builds the tensor-line schedule for (cfg, arr) without touching a device and
+// replays it against S and C.  info[0..7] = {specialised?, threads/CTA, volume rounds, facet sub-rounds,
+// reducer items max, reducer sources max, shared memory bytes, two-point fluxes per element}.
+extern "C" int32_t sse_plan_selfcheck(const sse_config* cfg, const sse_arrays* arr, int32_t* info, double* max_err) {
+    if (!cfg || !arr || !info || !max_err) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    Ops o;
+    memset(&o, 0, sizeof(o));
+    o.d = cfg->d; o.NC = cfg->N_c; o.Np = cfg->N_p; o.Nq = cfg->N_q; o.Nf = cfg->N_f; o.Nfac = cfg->N_fac;
+    o.npf = cfg->N_f / cfg->N_fac; o.v_kind = cfg->v_kind;
+    if (cfg->v_kind == SSE_V_WARPED) { o.P1 = cfg->p + 1; o.M1 = cfg->M1d[0]; o.M2 = cfg->M1d[1]; o.M3 = cfg->d == 3 ? cfg->M1d[2] : 1; }
+    TensorPlan tp;
+    tensor_plan_build(tp, *cfg, *arr, o);
+    for (int i = 0; i < 8; i++) info[i] = 0;
+    *max_err = 0.0;
+    info[0] = tp.ok;
+    if (!tp.ok) return SSE_OK;
+    info[1] = tp.threads; info[2] = tp.dev.n_vrounds; info[3] = tp.dev.n_frounds;
+    info[4] = tp.dev.red_items_max; info[5] = tp.dev.red_max; info[6] = (int32_t)tp.smem_fluxdiff;
+    int evals = 0;
+    for (int x : tp.v_partner) evals += x >= 0;
+    for (int x : tp.f_partner) evals += x >= 0;
+    info[7] = evals + cfg->N_f;
+    *max_err = tensor_plan_selfcheck(tp, *cfg, *arr);
+    return SSE_OK;
+}
+
 extern "C" int32_t sse_fp64_peak(int32_t device, double* flops) {
     if (!flops) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
     int ndev = 0;

@@ -44,6 +44,7 @@ SYMBOLS = {
     "sse_last_error_string": (C.c_char_p, []),
     "sse_abi_version": (C.c_int32, []),
     "sse_debug_views": (C.c_int32, [_h, _ppd, _ppd]),
+    "sse_plan_selfcheck": (C.c_int32, [C.POINTER(_abi.sse_config), C.POINTER(_abi.sse_arrays), C.POINTER(C.c_int32), _pd]),
     "sse_fp64_peak": (C.c_int32, [C.c_int32, _pd]),
 }
 

@@ -178,6 +178,11 @@ const char* sse_last_error_string(void);
 int32_t sse_abi_version(void);
 /* scratch views for testing/analysis: u_q (N_q,N_c,N_e) and u_f (N_f,N_e+ghost,N_c) device pointers */
 int32_t sse_debug_views(sse_handle* h, double** d_u_q, double** d_u_f);
+/* host-only diagnostic: build the tensor-line pair schedule for (cfg, arr) and replay it against S and C.
+   info[0..7] = {specialised?, threads per CTA, volume rounds, facet sub-rounds, reducer items max, reducer
+   sources max, shared-memory bytes, two-point flux evaluations per element}; max_err = largest deviation of
+   the replayed S_m / C from the operators passed in (0 when every pair is visited exactly once). */
+int32_t sse_plan_selfcheck(const sse_config* cfg, const sse_arrays* arr, int32_t* info, double* max_err);
 /* register-resident DFMA microbenchmark: achieved FP64 FLOP/s on the handle's device (FMA = 2) */
 int32_t sse_fp64_peak(int32_t device, double* flops_per_s);
 

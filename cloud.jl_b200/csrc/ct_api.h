@@ -1,0 +1,28 @@
+// ct_api.h — host-visible interface of the compile-time-sized kernels (instantiated in ct_kernels.cu)
+#pragma once
+#include <vector>
+#include "common.cuh"
+#include "kernels_tensor.cuh"
+
+namespace sse {
+
+struct CtDev {
+    const double* C;        // C[a3 + N*(b1 + N*(b2 + N*b3))]
+    const double* W;        // volume quadrature weights
+    SpMat R, Rt;
+    long long Ne;
+};
+
+struct CtPlan {
+    int ok = 0, N = 0;
+    CtDev dev{};
+    std::vector<double> A, B;       // host copies of the 1-D tensors handed to the kernels by value
+};
+
+bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& tp, int* Nout);
+cudaError_t ct_set_attrs(int N);
+void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, const double* u, double* u_q, double* u_f, cudaStream_t s);
+void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
+                 double* u_q, const double* u_f, double* dudt, cudaStream_t s);
+
+}  // namespace sse

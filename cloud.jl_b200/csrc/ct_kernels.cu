@@ -1,0 +1,64 @@
+// ct_kernels.cu — instantiations of the compile-time-sized kernels (N = p + 1 = 4, 5)
+#include "kernels_ct.cuh"
+
+namespace sse {
+
+// the compile-time path needs: d = 3, Euler + EC two-point flux, flux differencing, warped V with
+// M1 = M2 = M3 = p + 1 in the canonical orderings, weight-adjusted mass solver, and a tensor plan
+bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& tp, int* Nout) {
+    if (!tp.ok || cfg.d != 3 || cfg.N_c != 5 || cfg.pde != SSE_PDE_EULER) return false;
+    if (cfg.form != SSE_FORM_FLUX_DIFFERENCING || cfg.two_point_flux != SSE_TWO_POINT_ENTROPY_CONSERVATIVE) return false;
+    if (cfg.v_kind != SSE_V_WARPED || cfg.mass_solver != SSE_MASS_WEIGHT_ADJUSTED || !a.Cfd) return false;
+    const int N = cfg.p + 1;
+    if (N != 4 && N != 5) return false;
+    if (cfg.M1d[0] != N || cfg.M1d[1] != N || cfg.M1d[2] != N) return false;
+    if (cfg.N_q != N * N * N || cfg.N_p != N * (N + 1) * (N + 2) / 6 || cfg.N_f != 4 * N * N || cfg.N_fac != 4) return false;
+    for (int t = 0; t < N * N * N; t++) {                  // canonical orderings (tensor_simplex.jl:111-131)
+        const int a1 = t % N, a2 = (t / N) % N, a3 = t / (N * N);
+        if (a.sigma_o[t] - 1 != (a1 * N + a2) * N + a3) return false;
+        const long long want = (a1 + a2 + a3 <= N - 1) ? (N == 4 ? tet_l<4>(a1, a2, a3) : tet_l<5>(a1, a2, a3)) + 1 : 0;
+        if (a.sigma_i[t] != want) return false;
+    }
+    *Nout = N;
+    return true;
+}
+
+template <int N> static SFCoef<N> make_coef(const CtPlan& p) {
+    SFCoef<N> c;
+    for (int i = 0; i < N * N; i++) c.A[i] = p.A[i];
+    for (int i = 0; i < N * N * N; i++) c.B[i] = p.B[i];
+    return c;
+}
+
+template <int N> static cudaError_t set_attrs_n() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_nodal_ct<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
+    if ((e = cudaFuncSetAttribute(k_project_ct<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
+    return cudaFuncSetAttribute(k_fluxdiff_ct<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total));
+}
+cudaError_t ct_set_attrs(int N) { return N == 5 ? set_attrs_n<5>() : set_attrs_n<4>(); }
+
+template <int N>
+static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, const double* u, double* u_q, double* u_f, cudaStream_t s) {
+    const unsigned grid = (unsigned)((p.dev.Ne + Tet<N>::EPB - 1) / Tet<N>::EPB);
+    k_nodal_ct<N><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
+}
+void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, const double* u, double* u_q, double* u_f, cudaStream_t s) {
+    if (p.N == 5) nodal_n<5>(p, g, L, u, u_q, u_f, s); else nodal_n<4>(p, g, L, u, u_q, u_f, s);
+}
+
+template <int N>
+static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
+                       double* u_q, const double* u_f, double* dudt, cudaStream_t s) {
+    constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
+    k_fluxdiff_ct<N><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(tp.dev, p.dev, g, L, o.nref, o.Bf, first, u_q, u_f);
+    const unsigned grid = (unsigned)((count + Tet<N>::EPB - 1) / Tet<N>::EPB);
+    k_project_ct<N><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
+}
+void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
+                 double* u_q, const double* u_f, double* dudt, cudaStream_t s) {
+    if (p.N == 5) fluxdiff_n<5>(p, tp, o, g, L, first, count, u_q, u_f, dudt, s);
+    else fluxdiff_n<4>(p, tp, o, g, L, first, count, u_q, u_f, dudt, s);
+}
+
+}  // namespace sse

@@ -1,0 +1,498 @@
+// kernels_ct.cuh — compile-time-sized kernels for the headline path: 3-D Euler, flux differencing,
+// ModalTensor(p) on collapsed tetrahedra with N = p+1 nodes per direction (N = 5 at p = 4).
+//
+//   k_nodal_ct    pass A  : entropy projection  (flux_differencing_form.jl:214-292)
+//   k_fluxdiff_ct pass B-1: interface flux, volume flux differencing, facet correction, lift
+//                           (flux_differencing_form.jl:294-342); leaves r_q in the u_q scratch, as the
+//                           reference itself reuses u_q[:,:,k] (flux_differencing_form.jl:341-346)
+//   k_project_ct  pass B-2: dudt = M^-1 V' r_q  (flux_differencing_form.jl:345-346, mass_matrix.jl:185-196)
+//
+// Sum factorisation (warped_product_3d.jl:47-136) is mapped as one thread per (element, variable, a3):
+// the thread owns the N x N slab y[a1][a2] of its eta_3 index in registers, the A and B tensors arrive as
+// kernel parameters (constant bank, free FMA operands after full unrolling), the C tensor slice of the
+// thread's a3 lives in registers, and the only cross-thread step of V' (the sum over a3) goes through
+// shared memory.  V -> diag(W/J) -> V' of the weight-adjusted mass solve never leaves registers.
+// A warp holds floor(32/N) groups of N lanes; a CTA of NC warps processes EPB = floor(32/N) elements.
+#pragma once
+#include "common.cuh"
+#include "kernels_tensor.cuh"
+#include "ct_api.h"
+
+namespace sse {
+
+template <int N> struct SFCoef {       // A[a1 + N*b1], B[a2 + N*(b1 + N*b2)]  (reference column-major)
+    double A[N * N];
+    double B[N * N * N];
+};
+
+template <int N> struct Tet {
+    static constexpr int Nq = N * N * N;
+    static constexpr int Np = N * (N + 1) * (N + 2) / 6;
+    static constexpr int npf = N * N;
+    static constexpr int Nf = 4 * N * N;
+    static constexpr int GPW = 32 / N;          // groups (of N lanes) per warp
+    static constexpr int EPB = GPW;             // elements per CTA in the projection kernels
+    static constexpr int LPT = (Np + N - 1) / N;  // modal outputs per lane in the a3-reduction
+};
+
+// canonical modal ordering of warped_product (tensor_simplex.jl:113-131): i slowest, k fastest, i+j+k <= p
+template <int N> __host__ __device__ constexpr int tet_l(int b1, int b2, int b3) {
+    int l = 0;
+    for (int i = 0; i < b1; i++) { int m = N - i; l += m * (m + 1) / 2; }
+    for (int j = 0; j < b2; j++) l += N - b1 - j;
+    return l + b3;
+}
+
+// y[a1][a2] (fixed a3) = sum A[a1,b1] B[a2,b1,b2] C[a3,b1,b2,b3] x[l(b1,b2,b3)]      warped_product_3d.jl:47-84
+template <int N>
+__device__ __forceinline__ void sf3_fwd(const SFCoef<N>& cf, const double (&c3)[Tet<N>::Np], const double* __restrict__ xs, double (&y)[N][N]) {
+#pragma unroll
+    for (int a1 = 0; a1 < N; a1++)
+#pragma unroll
+        for (int a2 = 0; a2 < N; a2++) y[a1][a2] = 0.0;
+#pragma unroll
+    for (int b1 = 0; b1 < N; b1++) {
+        double w[N];
+#pragma unroll
+        for (int a2 = 0; a2 < N; a2++) w[a2] = 0.0;
+#pragma unroll
+        for (int b2 = 0; b2 < N - b1; b2++) {
+            double z = 0.0;
+#pragma unroll
+            for (int b3 = 0; b3 < N - b1 - b2; b3++) { const int l = tet_l<N>(b1, b2, b3); z = fma(c3[l], xs[l], z); }
+#pragma unroll
+            for (int a2 = 0; a2 < N; a2++) w[a2] = fma(cf.B[a2 + N * (b1 + N * b2)], z, w[a2]);
+        }
+#pragma unroll
+        for (int a1 = 0; a1 < N; a1++)
+#pragma unroll
+            for (int a2 = 0; a2 < N; a2++) y[a1][a2] = fma(cf.A[a1 + N * b1], w[a2], y[a1][a2]);
+    }
+}
+
+// partial[l][a3] = C[a3,l] * sum_{a2} B[a2,b1,b2] sum_{a1} A[a1,b1] x[a1][a2]        warped_product_3d.jl:94-136
+// written to red[l * N] (the caller passes red already offset by group and a3)
+template <int N>
+__device__ __forceinline__ void sf3_bwd_partials(const SFCoef<N>& cf, const double (&c3)[Tet<N>::Np], const double (&x)[N][N], double* __restrict__ red) {
+#pragma unroll
+    for (int b1 = 0; b1 < N; b1++) {
+        double wt[N];
+#pragma unroll
+        for (int a2 = 0; a2 < N; a2++) {
+            double s = 0.0;
+#pragma unroll
+            for (int a1 = 0; a1 < N; a1++) s = fma(cf.A[a1 + N * b1], x[a1][a2], s);
+            wt[a2] = s;
+        }
+#pragma unroll
+        for (int b2 = 0; b2 < N - b1; b2++) {
+            double z = 0.0;
+#pragma unroll
+            for (int a2 = 0; a2 < N; a2++) z = fma(cf.B[a2 + N * (b1 + N * b2)], wt[a2], z);
+#pragma unroll
+            for (int b3 = 0; b3 < N - b1 - b2; b3++) { const int l = tet_l<N>(b1, b2, b3); red[l * N] = c3[l] * z; }
+        }
+    }
+}
+
+// lane a3 of a group sums the partials of its LPT modal outputs; red is offset by group
+template <int N>
+__device__ __forceinline__ void sf3_bwd_reduce(const double* __restrict__ red, int a3, double (&out)[Tet<N>::LPT]) {
+#pragma unroll
+    for (int q = 0; q < Tet<N>::LPT; q++) {
+        const int l = a3 * Tet<N>::LPT + q;
+        double s = 0.0;
+        if (l < Tet<N>::Np) {
+#pragma unroll
+            for (int a = 0; a < N; a++) s += red[l * N + a];
+        }
+        out[q] = s;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void load_c3(const CtDev& t, int a3, double (&c3)[Tet<N>::Np]) {
+#pragma unroll
+    for (int b1 = 0; b1 < N; b1++)
+#pragma unroll
+        for (int b2 = 0; b2 < N - b1; b2++)
+#pragma unroll
+            for (int b3 = 0; b3 < N - b1 - b2; b3++) c3[tet_l<N>(b1, b2, b3)] = t.C[a3 + N * (b1 + N * (b2 + N * b3))];
+}
+
+// shared-memory plan of the projection kernels (doubles)
+template <int N, int NC> struct ProjSmem {
+    using T = Tet<N>;
+    static constexpr int NG = T::EPB * NC;                         // groups per CTA
+    static constexpr int x = 0;                                    // [NG][Np]
+    static constexpr int big = x + NG * T::Np;                     // union: q [NG][Nq]  |  red [NG][Np][N]
+    static constexpr int big_sz = (NG * T::Nq > NG * T::Np * N) ? NG * T::Nq : NG * T::Np * N;
+    static constexpr int wij = big + big_sz;                       // [EPB][Nq]  W / J
+    static constexpr int total = wij + T::EPB * T::Nq;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// pass A — nodal_values! with the general (modal) entropy projection
+template <int N>
+__global__ void __launch_bounds__(160, 2)
+k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, double* __restrict__ u_q, double* __restrict__ u_f) {
+    constexpr int NC = 5, D = 3;
+    using T = Tet<N>;
+    using S = ProjSmem<N, NC>;
+    constexpr int Nq = T::Nq, Np = T::Np, Nf = T::Nf, EPB = T::EPB, NG = S::NG;
+    extern __shared__ double sm[];
+    double* s_x = sm + S::x;
+    double* s_q = sm + S::big;
+    double* s_red = sm + S::big;
+    double* s_wij = sm + S::wij;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int gl = lane / N, a3 = lane - gl * N;
+    const int grp = warp * T::GPW + gl;                 // (element slot, variable) = (grp / NC, grp % NC)
+    const long long e0 = (long long)blockIdx.x * EPB;   // first element of this CTA
+    const int nel = (int)((t.Ne - e0 < EPB) ? (t.Ne - e0) : EPB);
+    const bool act = gl < T::GPW && (grp / NC) < nel;
+
+    double c3[Np];
+    if (gl < T::GPW) load_c3<N>(t, a3, c3);
+    for (int i = tid; i < nel * NC * Np; i += NT) s_x[i] = u[(size_t)e0 * NC * Np + i];
+    __syncthreads();
+
+    double y[N][N];
+    // u_q = V u
+    if (act) {
+        sf3_fwd<N>(cf, c3, s_x + grp * Np, y);
+#pragma unroll
+        for (int a1 = 0; a1 < N; a1++)
+#pragma unroll
+            for (int a2 = 0; a2 < N; a2++) s_q[grp * Nq + (a1 * N + a2) * N + a3] = y[a1][a2];
+    }
+    __syncthreads();
+    // w_q = WJ * w(u_q)                                      flux_differencing_form.jl:230-235
+    for (int it = tid; it < nel * Nq; it += NT) {
+        const int el = it / Nq, i = it - el * Nq;
+        double ui[NC], wi[NC];
+#pragma unroll
+        for (int e = 0; e < NC; e++) ui[e] = s_q[(el * NC + e) * Nq + i];
+        cons_to_entropy<D, NC>(L, ui, wi);
+        const double J = g.J_q[(size_t)(e0 + el) * Nq + i], W = t.W[i];
+        const double wj = W * J;
+        s_wij[el * Nq + i] = W / J;
+#pragma unroll
+        for (int e = 0; e < NC; e++) s_q[(el * NC + e) * Nq + i] = wi[e] * wj;
+    }
+    __syncthreads();
+    // w = V' w_q
+    if (act) {
+#pragma unroll
+        for (int a1 = 0; a1 < N; a1++)
+#pragma unroll
+            for (int a2 = 0; a2 < N; a2++) y[a1][a2] = s_q[grp * Nq + (a1 * N + a2) * N + a3];
+    }
+    __syncthreads();                                   // s_red aliases s_q
+    double out[T::LPT];
+    if (act) sf3_bwd_partials<N>(cf, c3, y, s_red + grp * Np * N + a3);
+    __syncthreads();
+    if (act) {
+        sf3_bwd_reduce<N>(s_red + grp * Np * N, a3, out);
+#pragma unroll
+        for (int q = 0; q < T::LPT; q++) { const int l = a3 * T::LPT + q; if (l < Np) s_x[grp * Np + l] = out[q]; }
+    }
+    __syncthreads();
+    // w = M \ w : V, diag(W/J), V'                           mass_matrix.jl:185-196
+    if (act) {
+        sf3_fwd<N>(cf, c3, s_x + grp * Np, y);
+        const double* wij = s_wij + (grp / NC) * Nq;
+#pragma unroll
+        for (int a1 = 0; a1 < N; a1++)
+#pragma unroll
+            for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= wij[(a1 * N + a2) * N + a3];
+        sf3_bwd_partials<N>(cf, c3, y, s_red + grp * Np * N + a3);
+    }
+    __syncthreads();
+    if (act) {
+        sf3_bwd_reduce<N>(s_red + grp * Np * N, a3, out);
+#pragma unroll
+        for (int q = 0; q < T::LPT; q++) { const int l = a3 * T::LPT + q; if (l < Np) s_x[grp * Np + l] = out[q]; }
+    }
+    __syncthreads();
+    // w_q = V w
+    if (act) {
+        sf3_fwd<N>(cf, c3, s_x + grp * Np, y);
+#pragma unroll
+        for (int a1 = 0; a1 < N; a1++)
+#pragma unroll
+            for (int a2 = 0; a2 < N; a2++) s_q[grp * Nq + (a1 * N + a2) * N + a3] = y[a1][a2];
+    }
+    __syncthreads();
+    // u_q = u(w_q), u_f = u(R w_q)                           flux_differencing_form.jl:240-249
+    for (int it = tid; it < nel * (Nq + Nf); it += NT) {
+        const int el = it / (Nq + Nf), i = it - el * (Nq + Nf);
+        double wi[NC], ui[NC];
+        if (i < Nq) {
+#pragma unroll
+            for (int e = 0; e < NC; e++) wi[e] = s_q[(el * NC + e) * Nq + i];
+            entropy_to_cons<D, NC>(L, wi, ui);
+#pragma unroll
+            for (int e = 0; e < NC; e++) u_q[((size_t)(e0 + el) * NC + e) * Nq + i] = ui[e];
+        } else {
+            const int j = i - Nq;
+#pragma unroll
+            for (int e = 0; e < NC; e++) wi[e] = 0.0;
+            for (int q = t.R.ptr[j]; q < t.R.ptr[j + 1]; q++) {
+                const double rv = t.R.val[q];
+                const int c = t.R.idx[q];
+#pragma unroll
+                for (int e = 0; e < NC; e++) wi[e] = fma(rv, s_q[(el * NC + e) * Nq + c], wi[e]);
+            }
+            entropy_to_cons<D, NC>(L, wi, ui);
+#pragma unroll
+            for (int e = 0; e < NC; e++) u_f[(size_t)(e0 + el) * Nf + j + (size_t)g.NFT * e] = ui[e];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pass B-2 — dudt = M^-1 V' r_q     (r_q sits in the u_q scratch)
+template <int N>
+__global__ void __launch_bounds__(160, 2)
+k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, const double* __restrict__ r_q, double* __restrict__ dudt) {
+    constexpr int NC = 5;
+    using T = Tet<N>;
+    using S = ProjSmem<N, NC>;
+    constexpr int Nq = T::Nq, Np = T::Np, EPB = T::EPB;
+    extern __shared__ double sm[];
+    double* s_x = sm + S::x;
+    double* s_q = sm + S::big;
+    double* s_red = sm + S::big;
+    double* s_wij = sm + S::wij;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int gl = lane / N, a3 = lane - gl * N;
+    const int grp = warp * T::GPW + gl;
+    const long long e0 = first + (long long)blockIdx.x * EPB;
+    const long long rem = first + count - e0;
+    const int nel = (int)(rem < EPB ? rem : EPB);
+    const bool act = gl < T::GPW && (grp / NC) < nel;
+
+    double c3[Np];
+    if (gl < T::GPW) load_c3<N>(t, a3, c3);
+    for (int i = tid; i < nel * NC * Nq; i += NT) s_q[i] = r_q[(size_t)e0 * NC * Nq + i];
+    for (int it = tid; it < nel * Nq; it += NT) {
+        const int el = it / Nq, i = it - el * Nq;
+        s_wij[it] = t.W[i] / g.J_q[(size_t)(e0 + el) * Nq + i];
+    }
+    __syncthreads();
+    double y[N][N], out[T::LPT];
+    if (act) {
+#pragma unroll
+        for (int a1 = 0; a1 < N; a1++)
+#pragma unroll
+            for (int a2 = 0; a2 < N; a2++) y[a1][a2] = s_q[grp * Nq + (a1 * N + a2) * N + a3];
+    }
+    __syncthreads();
+    if (act) sf3_bwd_partials<N>(cf, c3, y, s_red + grp * Np * N + a3);
+    __syncthreads();
+    if (act) {
+        sf3_bwd_reduce<N>(s_red + grp * Np * N, a3, out);
+#pragma unroll
+        for (int q = 0; q < T::LPT; q++) { const int l = a3 * T::LPT + q; if (l < Np) s_x[grp * Np + l] = out[q]; }
+    }
+    __syncthreads();
+    if (act) {
+        sf3_fwd<N>(cf, c3, s_x + grp * Np, y);
+        const double* wij = s_wij + (grp / NC) * Nq;
+#pragma unroll
+        for (int a1 = 0; a1 < N; a1++)
+#pragma unroll
+            for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= wij[(a1 * N + a2) * N + a3];
+        sf3_bwd_partials<N>(cf, c3, y, s_red + grp * Np * N + a3);
+    }
+    __syncthreads();
+    if (act) {
+        sf3_bwd_reduce<N>(s_red + grp * Np * N, a3, out);
+#pragma unroll
+        for (int q = 0; q < T::LPT; q++) {
+            const int l = a3 * T::LPT + q;
+            if (l < Np) dudt[(size_t)e0 * NC * Np + grp * Np + l] = out[q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pass B-1 — one CTA per element, one thread per volume node (same schedule tables as k_fluxdiff_tensor)
+template <int N> struct FdSmem {
+    using T = Tet<N>;
+    static constexpr int NP = 6, NC = 5, D = 3;
+    static constexpr int prim = 0;                         // [NP][Nq]
+    static constexpr int lam = prim + NP * T::Nq;          // [D*D][Nq]
+    static constexpr int fprim = lam + D * D * T::Nq;      // [NP][Nf]
+    static constexpr int hnf = fprim + NP * T::Nf;         // [D][Nf]
+    static constexpr int ff = hnf + D * T::Nf;             // [NC][Nf]
+    static constexpr int stage = ff + NC * T::Nf;          // [2][NC][Nq]
+    static constexpr int total = stage + 2 * NC * T::Nq;
+};
+
+template <int N>
+__global__ void __launch_bounds__((Tet<N>::Nq + 31) / 32 * 32, 4)
+k_fluxdiff_ct(TensorDev t, CtDev ct, Geo g, Law L, const double* __restrict__ nref, const double* __restrict__ Bf,
+              long long first, double* __restrict__ u_q, const double* __restrict__ u_f) {
+    constexpr int NC = 5, D = 3, NP = 6;
+    using T = Tet<N>;
+    using S = FdSmem<N>;
+    constexpr int Nq = T::Nq, Nf = T::Nf;
+    extern __shared__ double sm[];
+    double* s_prim = sm + S::prim;
+    double* s_lam = sm + S::lam;
+    double* s_fprim = sm + S::fprim;
+    double* s_hnf = sm + S::hnf;
+    double* s_ff = sm + S::ff;
+    double* s_stage = sm + S::stage;
+    const int tid = threadIdx.x;
+    const long long k = first + blockIdx.x;
+    const bool node = tid < Nq;
+
+    double qi[NP], lam[D][D], r[NC];
+#pragma unroll
+    for (int e = 0; e < NC; e++) r[e] = 0.0;
+    if (node) {
+        double ui[NC];
+#pragma unroll
+        for (int e = 0; e < NC; e++) ui[e] = u_q[((size_t)k * NC + e) * Nq + tid];
+        to_prim<D, NC>(L, ui, qi);
+#pragma unroll
+        for (int c = 0; c < NP; c++) s_prim[c * Nq + tid] = qi[c];
+#pragma unroll
+        for (int n = 0; n < D; n++)
+#pragma unroll
+            for (int m = 0; m < D; m++) {
+                lam[m][n] = g.Lambda_q[((size_t)k * D * D + (m + D * n)) * Nq + tid];
+                s_lam[(m + D * n) * Nq + tid] = lam[m][n];
+            }
+    }
+    for (int j = tid; j < Nf; j += blockDim.x) {
+        double ui[NC], uo[NC], qa[NP], qb[NP], nf[D], phi[NC];
+        const size_t jo = (size_t)(g.mapP[(size_t)k * Nf + j] - 1);
+#pragma unroll
+        for (int e = 0; e < NC; e++) { ui[e] = u_f[(size_t)k * Nf + j + (size_t)g.NFT * e]; uo[e] = u_f[jo + (size_t)g.NFT * e]; }
+        const double jf = g.J_f[(size_t)k * Nf + j];
+        const double ijf = 1.0 / jf;
+#pragma unroll
+        for (int m = 0; m < D; m++) {
+            const double nj = g.nJf[m + D * ((size_t)k * Nf + j)];
+            nf[m] = nj * ijf;
+            s_hnf[m * Nf + j] = 0.5 * nj;
+        }
+        to_prim<D, NC>(L, ui, qa);
+        to_prim<D, NC>(L, uo, qb);
+#pragma unroll
+        for (int c = 0; c < NP; c++) s_fprim[c * Nf + j] = qa[c];
+        pair_flux<D, NC>(L, qa, qb, nf, phi);
+        if (L.inviscid == SSE_FLUX_LAX_FRIEDRICHS) {
+            double vni = 0.0, vno = 0.0;
+#pragma unroll
+            for (int m = 0; m < D; m++) { vni = fma(qa[1 + m], nf[m], vni); vno = fma(qb[1 + m], nf[m], vno); }
+            const double ci = sqrt(L.gamma * qa[D + 1] / qa[0]), co = sqrt(L.gamma * qb[D + 1] / qb[0]);
+            const double a = L.half_lambda * (fmax(fabs(vni), fabs(vno)) + fmax(ci, co));
+#pragma unroll
+            for (int e = 0; e < NC; e++) phi[e] = fma(a, ui[e] - uo[e], phi[e]);
+        }
+        const double bj = Bf[j] * jf;
+#pragma unroll
+        for (int e = 0; e < NC; e++) s_ff[e * Nf + j] = bj * phi[e];
+    }
+    __syncthreads();
+
+    int buf = 0;
+    for (int rd = 0; rd < t.n_vrounds; rd++, buf ^= 1) {
+        double* st = s_stage + buf * NC * Nq;
+        if (node) {
+            const int j = t.v_partner[rd * Nq + tid];
+            if (j >= 0) {
+                double gv[D], qj[NP], phi[NC];
+#pragma unroll
+                for (int n = 0; n < D; n++) gv[n] = 0.0;
+                const int mlo = t.v_mlo[rd];
+#pragma unroll
+                for (int m = 0; m < D; m++) {
+                    if (m >= mlo) {
+                        const double s = t.v_S[(rd * D + m) * Nq + tid];
+#pragma unroll
+                        for (int n = 0; n < D; n++) gv[n] = fma(s, lam[m][n] + s_lam[(m + D * n) * Nq + j], gv[n]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NP; c++) qj[c] = s_prim[c * Nq + j];
+                pair_flux<D, NC>(L, qi, qj, gv, phi);
+#pragma unroll
+                for (int e = 0; e < NC; e++) { r[e] -= phi[e]; st[e * Nq + j] = phi[e]; }
+            }
+        }
+        __syncthreads();
+        if (node && t.v_source[rd * Nq + tid] >= 0) {
+#pragma unroll
+            for (int e = 0; e < NC; e++) r[e] += st[e * Nq + tid];
+        }
+    }
+
+    int face_prev = -1;
+    double hq[D];
+#pragma unroll
+    for (int n = 0; n < D; n++) hq[n] = 0.0;
+    for (int fr = 0; fr < t.n_frounds; fr++, buf ^= 1) {
+        double* st = s_stage + buf * NC * Nq;
+        const int f = t.f_face[fr];
+        if (node) {
+            if (f != face_prev) {
+                if (g.nJq) {
+#pragma unroll
+                    for (int n = 0; n < D; n++) hq[n] = 0.5 * g.nJq[n + D * (f + (size_t)4 * (tid + (size_t)Nq * k))];
+                } else {
+#pragma unroll
+                    for (int n = 0; n < D; n++) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int l = 0; l < D; l++) s += lam[l][n] * nref[l + D * f];
+                        hq[n] = 0.5 * s;
+                    }
+                }
+            }
+            const int j = t.f_partner[fr * Nq + tid];
+            const double c = t.f_C[fr * Nq + tid];
+            double gv[D], qj[NP], phi[NC];
+#pragma unroll
+            for (int n = 0; n < D; n++) gv[n] = c * (s_hnf[n * Nf + j] + hq[n]);
+#pragma unroll
+            for (int cc = 0; cc < NP; cc++) qj[cc] = s_fprim[cc * Nf + j];
+            pair_flux<D, NC>(L, qi, qj, gv, phi);
+#pragma unroll
+            for (int e = 0; e < NC; e++) { r[e] -= phi[e]; st[e * Nq + tid] = phi[e]; }
+        }
+        face_prev = f;
+        __syncthreads();
+        const int nred = t.red_n[fr] * NC;
+        for (int q = tid; q < nred; q += blockDim.x) {
+            const int item = q / NC, e = q - item * NC;
+            const int base = fr * t.red_items_max + item;
+            const int* src = t.red_src + (size_t)base * t.red_max;
+            const int cnt = t.red_cnt[base];
+            double s = 0.0;
+            for (int c = 0; c < cnt; c++) s += st[e * Nq + src[c]];
+            s_ff[e * Nf + t.red_dst[base]] -= s;
+        }
+    }
+    __syncthreads();
+    // r_q -= R' f_f, handed to k_project_ct through the u_q scratch
+    if (node) {
+        for (int q = ct.Rt.ptr[tid]; q < ct.Rt.ptr[tid + 1]; q++) {
+            const double rv = ct.Rt.val[q];
+            const int j = ct.Rt.idx[q];
+#pragma unroll
+            for (int e = 0; e < NC; e++) r[e] = fma(-rv, s_ff[e * Nf + j], r[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < NC; e++) u_q[((size_t)k * NC + e) * Nq + tid] = r[e];
+    }
+}
+
+}  // namespace sse

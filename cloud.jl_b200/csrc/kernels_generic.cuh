@@ -592,12 +592,12 @@ __global__ void k_time_physical(Ops o, Geo g, Law L, long long first, int second
 }
 
 // ------------------------------------------------------------------ small streaming kernels
-__global__ void k_axpby(long long n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
+static __global__ void k_axpby(long long n, double a, const double* __restrict__ x, double b, double* __restrict__ y) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = (b == 0.0) ? a * x[i] : fma(a, x[i], b * y[i]);
 }
 // 2N-storage RK stage (Carpenter & Kennedy 1994): tmp = A tmp + dt dudt ; u += B tmp
-__global__ void k_lsrk_stage(long long n, double* __restrict__ u, double* __restrict__ tmp, const double* __restrict__ dudt,
+static __global__ void k_lsrk_stage(long long n, double* __restrict__ u, double* __restrict__ tmp, const double* __restrict__ dudt,
                              double A, double B, double dt) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         double t = fma(A, tmp[i], dt * dudt[i]);
@@ -606,14 +606,14 @@ __global__ void k_lsrk_stage(long long n, double* __restrict__ u, double* __rest
     }
 }
 // halo pack / unpack: buffers are variable-fastest [slot][var]
-__global__ void k_halo_pack(long long n_send, int nvar, long long NFT, const long long* __restrict__ send_idx,
+static __global__ void k_halo_pack(long long n_send, int nvar, long long NFT, const long long* __restrict__ send_idx,
                             const double* __restrict__ facet, double* __restrict__ buf) {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_send * nvar; t += (long long)gridDim.x * blockDim.x) {
         long long s = t / nvar; int e = (int)(t % nvar);
         buf[t] = facet[(send_idx[s] - 1) + NFT * e];
     }
 }
-__global__ void k_halo_unpack(long long n_ghost, int nvar, long long NFT, long long owned, const double* __restrict__ buf,
+static __global__ void k_halo_unpack(long long n_ghost, int nvar, long long NFT, long long owned, const double* __restrict__ buf,
                               double* __restrict__ facet) {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_ghost * nvar; t += (long long)gridDim.x * blockDim.x) {
         long long s = t / nvar; int e = (int)(t % nvar);
@@ -622,7 +622,7 @@ __global__ void k_halo_unpack(long long n_ghost, int nvar, long long NFT, long l
 }
 
 // register-resident DFMA peak (8 independent chains per thread)
-__global__ void k_fp64_peak(double* out, int iters) {
+static __global__ void k_fp64_peak(double* out, int iters) {
     double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
     const double b = 1.0000001, c = 1e-9;
     for (int i = 0; i < iters; i++) {

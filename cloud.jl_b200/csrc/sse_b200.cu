@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "kernels_generic.cuh"
 #include "kernels_tensor.cuh"
+#include "ct_api.h"
 
 using namespace sse;
 
@@ -47,6 +48,7 @@ struct sse_handle {
     Geo geo;
     Law law;
     TensorPlan tp;                  // tensor-line specialisation (kernels_tensor.cuh); tp.ok == 0 -> generic only
+    CtPlan ct;                      // compile-time-sized kernels (kernels_ct.cuh): Euler on p = 3, 4 ModalTensor tets
     int variant = 1;
     int project = 0;                // 0 none, 1 nodal, 2 general entropy projection
     int second_order = 0;
@@ -326,6 +328,17 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
              })))
             return fail(rc, "uploading the tensor-line tables failed");
     }
+    {
+        int N = 0;
+        if (ct_eligible(*cfg, *a, h->tp, &N)) {
+            h->ct.N = N;
+            h->ct.A.assign(a->A, a->A + N * N);
+            h->ct.B.assign(a->B, a->B + N * N * N);
+            h->ct.dev.C = o.C; h->ct.dev.W = o.W; h->ct.dev.R = o.R; h->ct.dev.Rt = o.Rt; h->ct.dev.Ne = Ne;
+            if (ct_set_attrs(N) != cudaSuccess) return fail(SSE_ERR_CUDA, "cudaFuncSetAttribute (compile-time kernels) failed");
+            h->ct.ok = 1;
+        }
+    }
     h->smem_nodal = smem_nodal_bytes(o);
     h->smem_time = smem_time_bytes(h);
     h->smem_aux = smem_aux_bytes(o);
@@ -386,7 +399,7 @@ extern "C" int32_t sse_set_kernel_variant(sse_handle* h, int32_t v) {
 }
 extern "C" int32_t sse_get_kernel_variant(const sse_handle* h, int32_t* v) {
     if (!h || !v) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
-    *v = (h->variant == 1 && h->tp.ok) ? 1 : 0;
+    *v = (h->variant == 1 && h->ct.ok) ? 2 : ((h->variant == 1 && h->tp.ok) ? 1 : 0);
     return SSE_OK;
 }
 
@@ -432,7 +445,9 @@ extern "C" int32_t sse_rhs_pass_a(sse_handle* h, const double* d_u) {
     if (!h || !d_u) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
     CU(cudaSetDevice(h->device));
     const unsigned Ne = (unsigned)h->cfg.N_e;
-    if (use_tensor(h) && h->tp.has_nodal) {
+    if (h->variant == 1 && h->ct.ok) {
+        ct_nodal(h->ct, h->geo, h->law, d_u, h->u_q, h->u_f, h->stream);
+    } else if (use_tensor(h) && h->tp.has_nodal) {
 #define LA(D_, NC_) tensor_launch_nodal<D_, NC_>(h->tp, h->ops, h->geo, h->law, h->project, d_u, h->u_q, h->u_f, h->cfg.N_e, h->sm_count, h->stream)
         DISPATCH_DNC(h, LA);
 #undef LA
@@ -465,7 +480,9 @@ extern "C" int32_t sse_rhs_pass_b(sse_handle* h, double* d_dudt, int64_t first, 
     CU(cudaSetDevice(h->device));
     const unsigned n = (unsigned)count;
     if (h->cfg.form == SSE_FORM_FLUX_DIFFERENCING) {
-        if (use_tensor(h) && h->tp.has_fluxdiff) {
+        if (h->variant == 1 && h->ct.ok) {
+            ct_fluxdiff(h->ct, h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream);
+        } else if (use_tensor(h) && h->tp.has_fluxdiff) {
 #define LA(D_, NC_) tensor_launch_fluxdiff<D_, NC_>(h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->sm_count, h->stream)
             DISPATCH_DNC(h, LA);
 #undef LA

@@ -1,0 +1,196 @@
+# SSEB200.jl — the reference-side binding of libsse_b200.so.
+#
+# Adds a third `AbstractParallelism` subtype (next to `Serial` / `Threaded`,
+# src/Solvers/Solvers.jl:72,79-80) whose `semi_discrete_residual!` method is one `ccall`.
+# Everything else of StableSpectralElements.jl (ConservationLaws, SpatialDiscretization,
+# semidiscretize, ODEProblem, Analysis, File) is used unchanged.
+#
+# NOTE: Julia is not installed in the build image, so this file is reviewed but not executed
+# there; the same entry points are exercised through the Python ctypes mirror
+# (cloud.jl_b200/sse_b200/_lib.py), which binds the identical C ABI.
+module SSEB200
+
+using StableSpectralElements
+using StableSpectralElements.Solvers: AbstractParallelism, Solver, FluxDifferencingOperators,
+    ReferenceOperators, PhysicalOperators, StandardForm, FluxDifferencingForm,
+    WeightAdjustedSolver, DiagonalSolver
+using StableSpectralElements.ConservationLaws
+using StableSpectralElements.MatrixFreeOperators: WarpedTensorProductMap2D, WarpedTensorProductMap3D
+using LinearMaps: UniformScalingMap
+
+const libsse = get(ENV, "SSE_B200_LIB", "libsse_b200.so")
+
+# --- mirror of include/sse_b200.h -----------------------------------------------------------
+struct SSEConfig
+    abi_version::Int32
+    d::Int32
+    N_c::Int32; N_p::Int32; N_q::Int32; N_f::Int32; N_fac::Int32
+    p::Int32
+    N_e::Int64
+    N_ghost::Int64
+    pde::Int32; form::Int32; inviscid_flux::Int32; viscous_flux::Int32
+    two_point_flux::Int32; mass_solver::Int32; v_kind::Int32
+    M1d::NTuple{3, Int32}
+    half_lambda::Float64
+    a::NTuple{3, Float64}
+    b::Float64
+    gamma::Float64
+end
+
+struct SSEArrays
+    V::Ptr{Float64}; A::Ptr{Float64}; B::Ptr{Float64}; C::Ptr{Float64}
+    sigma_i::Ptr{Int64}; sigma_o::Ptr{Int64}
+    R::Ptr{Float64}; W::Ptr{Float64}; Bf::Ptr{Float64}
+    D::NTuple{3, Ptr{Float64}}
+    S::NTuple{3, Ptr{Float64}}
+    Cfd::Ptr{Float64}
+    J_q::Ptr{Float64}; Lambda_q::Ptr{Float64}; J_f::Ptr{Float64}; nJf::Ptr{Float64}
+    nJq::Ptr{Float64}; nref::Ptr{Float64}
+    VOL::Ptr{Float64}; FAC::Ptr{Float64}
+    mapP::Ptr{Int64}
+end
+
+check(rc::Int32) = rc == 0 ? nothing :
+    error("libsse_b200 status $rc: ", unsafe_string(ccall((:sse_last_error_string, libsse), Cstring, ())))
+
+"""
+    CUDAB200(device = 0)
+
+Parallelism tag selecting the B200 residual.  Pass it as `parallelism = CUDAB200()` to
+`semidiscretize` (Solvers.jl:429-452).
+"""
+mutable struct CUDAB200 <: AbstractParallelism
+    device::Int32
+    handle::Ptr{Cvoid}
+    CUDAB200(device = 0) = new(Int32(device), C_NULL)
+end
+
+"Device-resident state: a thin `AbstractArray{Float64,3}` of size (N_p, N_c, N_e)."
+struct DeviceState <: AbstractArray{Float64, 3}
+    ptr::Ptr{Float64}
+    dims::NTuple{3, Int}
+    par::CUDAB200
+end
+Base.size(x::DeviceState) = x.dims
+Base.similar(x::DeviceState) = alloc_state(x.par, x.dims)
+Base.getindex(::DeviceState, I...) = error("DeviceState lives on the GPU: use Array(x)")
+
+function alloc_state(par::CUDAB200, dims)
+    p = Ref{Ptr{Float64}}()
+    check(ccall((:sse_state_alloc, libsse), Int32, (Ptr{Cvoid}, Ptr{Ptr{Float64}}), par.handle, p))
+    x = DeviceState(p[], dims, par)
+    return x
+end
+upload!(x::DeviceState, h::Array{Float64, 3}) =
+    check(ccall((:sse_state_upload, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), x.par.handle, x.ptr, h))
+function Base.Array(x::DeviceState)
+    h = Array{Float64}(undef, x.dims)
+    check(ccall((:sse_state_download, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), x.par.handle, h, x.ptr))
+    return h
+end
+# broadcast-free integrator updates (OrdinaryDiffEq low-storage methods call axpby-type kernels)
+axpby!(a, x::DeviceState, b, y::DeviceState) =
+    check(ccall((:sse_axpby, libsse), Int32, (Ptr{Cvoid}, Float64, Ptr{Float64}, Float64, Ptr{Float64}),
+        x.par.handle, a, x.ptr, b, y.ptr))
+
+pde_id(::LinearAdvectionEquation) = Int32(0)
+pde_id(::LinearAdvectionDiffusionEquation) = Int32(1)
+pde_id(::EulerEquations) = Int32(2)
+flux_id(::LaxFriedrichsNumericalFlux) = Int32(0)
+flux_id(::CentralNumericalFlux) = Int32(1)
+flux_id(::EntropyConservativeNumericalFlux) = Int32(2)
+halfλ(f::LaxFriedrichsNumericalFlux) = f.halfλ
+halfλ(_) = 0.0
+two_point_id(::ConservativeFlux) = Int32(0)
+two_point_id(::EntropyConservativeFlux) = Int32(1)
+mass_id(::WeightAdjustedSolver) = Int32(0)
+mass_id(::DiagonalSolver) = Int32(1)
+
+"""
+    attach!(solver::Solver{<:Any,<:Any,<:Any,<:Any,CUDAB200}, spatial_discretization)
+
+Uploads the Solver's operators and geometric factors (the arrays the reference constructors
+at Solvers.jl:287-376 / operators.jl:1-160 hold) and stores the opaque handle in the tag.
+"""
+function attach!(solver::Solver, sd::SpatialDiscretization{d}) where {d}
+    par = solver.parallelism::CUDAB200
+    law, ops, form = solver.conservation_law, solver.operators, solver.form
+    ra, gf = sd.reference_approximation, sd.geometric_factors
+    N_p, N_c, N_e = size(solver)
+    keep = Any[]                                    # GC roots for the duration of sse_create
+    ptr(x::Array) = (push!(keep, x); pointer(x))
+    dense(L) = ptr(Matrix(L))
+    nul = Ptr{Float64}(C_NULL)
+    V = ra.V
+    v_kind, pV, pA, pB, pC, pσi, pσo, M1d = if V isa UniformScalingMap
+        Int32(0), nul, nul, nul, nul, Ptr{Int64}(C_NULL), Ptr{Int64}(C_NULL), (Int32(0), Int32(0), Int32(0))
+    elseif V isa WarpedTensorProductMap3D
+        Int32(2), dense(V), ptr(Array(V.A)), ptr(Array(V.B)), ptr(Array(V.C)), ptr(Array{Int64}(V.σᵢ)),
+        ptr(Array{Int64}(V.σₒ)), Int32.((size(V.A, 1), size(V.B, 1), size(V.C, 1)))
+    elseif V isa WarpedTensorProductMap2D
+        Int32(2), dense(V), ptr(Array(V.A)), ptr(Array(V.B)), nul, ptr(Array{Int64}(V.σᵢ)),
+        ptr(Array{Int64}(V.σₒ)), Int32.((size(V.A, 1), size(V.B, 1), 0))
+    else
+        Int32(1), dense(V), nul, nul, nul, Ptr{Int64}(C_NULL), Ptr{Int64}(C_NULL), (Int32(0), Int32(0), Int32(0))
+    end
+    form_id, pD, pS, pC_fd, pΛ, pVOL, pFAC = if ops isa FluxDifferencingOperators
+        Int32(2), (nul, nul, nul), ntuple(m -> m <= d ? dense(ops.S[m]) : nul, 3),
+        isnothing(ops.C) ? nul : dense(ops.C), ptr(ops.Λ_q), nul, nul
+    elseif ops isa ReferenceOperators
+        Λη = apply_reference_mapping(gf, ra.reference_mapping).Λ_q
+        Int32(0), ntuple(m -> m <= d ? dense(ops.D[m]) : nul, 3), (nul, nul, nul), nul, ptr(Λη), nul, nul
+    else  # PhysicalOperators: VOL (N_p,N_q,d,N_e), FAC (N_p,N_f,N_e)
+        VOL = Array{Float64}(undef, N_p, ra.N_q, d, N_e)
+        FAC = Array{Float64}(undef, N_p, ra.N_f, N_e)
+        for k in 1:N_e
+            for m in 1:d
+                VOL[:, :, m, k] .= Matrix(ops.VOL[k][m])
+            end
+            FAC[:, :, k] .= Matrix(ops.FAC[k])
+        end
+        Int32(1), (nul, nul, nul), (nul, nul, nul), nul, ptr(gf.Λ_q), ptr(VOL), ptr(FAC)
+    end
+    nfac = length(ra.reference_element.fv)
+    npf = ra.N_f ÷ nfac
+    nref = [ra.reference_element.nrstJ[m][npf * (f - 1) + 1] for m in 1:d, f in 1:nfac]
+    tp = form isa FluxDifferencingForm ? two_point_id(form.two_point_flux) : Int32(0)
+    a = ntuple(m -> (hasproperty(law, :a) && m <= d) ? Float64(law.a[m]) : 0.0, 3)
+    cfg = SSEConfig(1, d, N_c, N_p, ra.N_q, ra.N_f, nfac, ra.approx_type.p, N_e, 0,
+        pde_id(law), form_id, flux_id(form.inviscid_numerical_flux),
+        law isa LinearAdvectionDiffusionEquation ? Int32(1) : Int32(0), tp, mass_id(solver.mass_solver), v_kind, M1d,
+        halfλ(form.inviscid_numerical_flux), a, hasproperty(law, :b) ? law.b : 0.0,
+        hasproperty(law, :γ) ? law.γ : 1.4)
+    arr = SSEArrays(pV, pA, pB, pC, pσi, pσo, dense(ra.R), ptr(Vector(ra.W.diag)), ptr(Vector(ra.B.diag)),
+        pD, pS, pC_fd, ptr(gf.J_q), pΛ, ptr(gf.J_f), ptr(gf.nJf), ptr(gf.nJq), ptr(nref), pVOL, pFAC,
+        ptr(Array{Int64}(solver.connectivity)))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:sse_create, libsse), Int32,
+        (Ref{SSEConfig}, Ref{SSEArrays}, Int32, Ptr{Ptr{Cvoid}}), cfg, arr, par.device, h))
+    par.handle = h[]
+    finalizer(p -> ccall((:sse_destroy, libsse), Int32, (Ptr{Cvoid},), p.handle), par)
+    return solver
+end
+
+# The drop-in: same signature as Solvers.jl:474-483, dispatched on the new parallelism tag.
+function StableSpectralElements.Solvers.semi_discrete_residual!(dudt::DeviceState, u::DeviceState,
+        solver::Solver{<:Any, <:Any, <:Any, <:Any, CUDAB200}, t::Float64 = 0.0)
+    check(ccall((:sse_rhs, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64),
+        solver.parallelism.handle, u.ptr, dudt.ptr, t))
+    return dudt
+end
+
+# Host arrays (e.g. the save callback's `similar(integrator.u)`, File/save.jl:58-61) are staged.
+function StableSpectralElements.Solvers.semi_discrete_residual!(dudt::Array{Float64, 3}, u::Array{Float64, 3},
+        solver::Solver{<:Any, <:Any, <:Any, <:Any, CUDAB200}, t::Float64 = 0.0)
+    par = solver.parallelism
+    du, uu = alloc_state(par, size(u)), alloc_state(par, size(u))
+    upload!(uu, u)
+    StableSpectralElements.Solvers.semi_discrete_residual!(du, uu, solver, t)
+    dudt .= Array(du)
+    for x in (du, uu)
+        ccall((:sse_state_free, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}), par.handle, x.ptr)
+    end
+    return dudt
+end
+
+end # module

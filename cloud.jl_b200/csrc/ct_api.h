@@ -11,15 +11,25 @@ struct CtDev {
     const double* W;        // volume quadrature weights
     SpMat R, Rt;
     long long Ne;
+    // flux-differencing schedule weights (partners are closed-form in the kernel)
+    const double* vS;       // [volume round][m][Nq]  skew-extended S_m[i, partner]
+    const double* fC;       // [facet sub-round][Nq]  C[i, partner]
+    const double* fR;       // [facet sub-round][Nq]  R[partner, i]
+    const double* Bf;       // [Nf]
+    double nref[12];        // d x N_fac reference normals
 };
 
 struct CtPlan {
     int ok = 0, N = 0;
     CtDev dev{};
     std::vector<double> A, B;       // host copies of the 1-D tensors handed to the kernels by value
+    std::vector<double> fR;         // host image of dev.fR
+    int minb = 4;                   // resident CTAs per SM requested for k_fluxdiff_ct (tuning knob)
 };
 
 bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& tp, int* Nout);
+// true when the generic tables of tp equal the closed-form schedule k_fluxdiff_ct hard-codes
+bool ct_schedule_matches(const TensorPlan& tp, int N);
 cudaError_t ct_set_attrs(int N);
 void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, const double* u, double* u_q, double* u_f, cudaStream_t s);
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,

@@ -23,6 +23,34 @@ bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& t
     return true;
 }
 
+bool ct_schedule_matches(const TensorPlan& tp, int N) {
+    const int NN = N * N, Nq = N * NN, NSH = N / 2;
+    if (tp.dev.n_vrounds != 3 * NSH || tp.dev.n_frounds != 3 + N) return false;
+    for (int i = 0; i < Nq; i++) {
+        const int c[3] = {i / NN, (i / N) % N, i % N};
+        const int stride[3] = {NN, N, 1};
+        for (int rd = 0; rd < 3 * NSH; rd++) {
+            const int l = rd / NSH, sh = rd % NSH + 1;
+            const bool half = 2 * sh == N;
+            const int cj = (c[l] + sh) % N, cs = (c[l] - sh + N) % N;
+            const int want_p = (half && c[l] >= sh) ? -1 : i + (cj - c[l]) * stride[l];
+            const int want_s = (half && cs >= sh) ? -1 : i + (cs - c[l]) * stride[l];
+            if (tp.v_partner[(size_t)rd * Nq + i] != want_p || tp.v_source[(size_t)rd * Nq + i] != want_s) return false;
+            if (tp.v_mlo[rd] < l) return false;              // the kernel skips m < l
+        }
+        for (int fr = 0; fr < 3 + N; fr++) {
+            int j;
+            if (fr == 0) j = c[0] * N + c[2];
+            else if (fr == 1) j = NN + c[1] * N + c[2];
+            else if (fr == 2) j = 2 * NN + c[1] * N + c[2];
+            else j = 3 * NN + c[0] * N + ((fr - 3 - c[2]) % N + N) % N;
+            if (tp.f_partner[(size_t)fr * Nq + i] != j) return false;
+            if (tp.f_face[fr] != (fr < 3 ? fr : 3)) return false;
+        }
+    }
+    return true;
+}
+
 template <int N> static SFCoef<N> make_coef(const CtPlan& p) {
     SFCoef<N> c;
     for (int i = 0; i < N * N; i++) c.A[i] = p.A[i];
@@ -34,7 +62,8 @@ template <int N> static cudaError_t set_attrs_n() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_nodal_ct<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
     if ((e = cudaFuncSetAttribute(k_project_ct<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
-    return cudaFuncSetAttribute(k_fluxdiff_ct<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total));
+    if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
+    return cudaFuncSetAttribute(k_fluxdiff_ct<N, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total));
 }
 cudaError_t ct_set_attrs(int N) { return N == 5 ? set_attrs_n<5>() : set_attrs_n<4>(); }
 
@@ -51,7 +80,9 @@ template <int N>
 static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
                        double* u_q, const double* u_f, double* dudt, cudaStream_t s) {
     constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
-    k_fluxdiff_ct<N><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(tp.dev, p.dev, g, L, o.nref, o.Bf, first, u_q, u_f);
+    (void)tp; (void)o;
+    if (p.minb >= 5) k_fluxdiff_ct<N, 5><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
+    else k_fluxdiff_ct<N, 4><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
     const unsigned grid = (unsigned)((count + Tet<N>::EPB - 1) / Tet<N>::EPB);
     k_project_ct<N><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
 }

@@ -333,14 +333,56 @@ template <int N> struct FdSmem {
     static constexpr int total = stage + 2 * NC * T::Nq;
 };
 
+// Ranocha's EC flux contracted with g, from primitives (rho, V, p, beta), log-means sharing reciprocals
+template <int D>
+__device__ __forceinline__ void ec_contract_fast(const double* a, const double* b, const double* g, double igm1, double* phi) {
+    double rho_hat, ilm;
+    logmean_pair(a[0], b[0], a[D + 2], b[D + 2], rho_hat, ilm);
+    double dot = 0.0, ga = 0.0, gb = 0.0;
+#pragma unroll
+    for (int m = 0; m < D; m++) { dot = fma(a[1 + m], b[1 + m], dot); ga = fma(g[m], a[1 + m], ga); gb = fma(g[m], b[1 + m], gb); }
+    const double Cc = fma(igm1, ilm, 0.5 * dot);
+    const double mf = rho_hat * (0.5 * (ga + gb));
+    const double p_avg = 0.5 * (a[D + 1] + b[D + 1]);
+    phi[0] = mf;
+#pragma unroll
+    for (int m = 0; m < D; m++) phi[1 + m] = fma(mf, 0.5 * (a[1 + m] + b[1 + m]), p_avg * g[m]);
+    phi[D + 1] = fma(mf, Cc, 0.5 * fma(a[D + 1], gb, b[D + 1] * ga));
+}
+
+// conservative -> (rho, V, p, rho/p); returns 1/rho
+template <int D>
+__device__ __forceinline__ double to_prim_fast(const Law& L, const double* u, double* q) {
+    const double ir = rcp_fast(u[0]);
+    double s = 0.0;
+    q[0] = u[0];
+#pragma unroll
+    for (int m = 0; m < D; m++) { q[1 + m] = u[1 + m] * ir; s = fma(q[1 + m], q[1 + m], s); }
+    q[D + 1] = L.gm1 * (u[D + 1] - 0.5 * u[0] * s);
+    q[D + 2] = u[0] * rcp_fast(q[D + 1]);
+    return ir;
+}
+
+// closed-form facet partner of volume node (a,b,c) in facet sub-round fr (the rotation schedule of
+// tensor_plan_build; ct_schedule_matches() verifies it against the generic tables on the host)
 template <int N>
-__global__ void __launch_bounds__((Tet<N>::Nq + 31) / 32 * 32, 4)
-k_fluxdiff_ct(TensorDev t, CtDev ct, Geo g, Law L, const double* __restrict__ nref, const double* __restrict__ Bf,
-              long long first, double* __restrict__ u_q, const double* __restrict__ u_f) {
+__device__ __forceinline__ int facet_partner(int fr, int ca, int cb, int cc) {
+    constexpr int NN = N * N;
+    if (fr == 0) return ca * N + cc;
+    if (fr == 1) return NN + cb * N + cc;
+    if (fr == 2) return 2 * NN + cb * N + cc;
+    int bp = (fr - 3) - cc;
+    if (bp < 0) bp += N;
+    return 3 * NN + ca * N + bp;
+}
+
+template <int N, int MINB>
+__global__ void __launch_bounds__((Tet<N>::Nq + 31) / 32 * 32, MINB)
+k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, const double* __restrict__ u_f) {
     constexpr int NC = 5, D = 3, NP = 6;
     using T = Tet<N>;
     using S = FdSmem<N>;
-    constexpr int Nq = T::Nq, Nf = T::Nf;
+    constexpr int Nq = T::Nq, Nf = T::Nf, NN = N * N, NSH = N / 2, NVR = D * NSH, NFR = 3 + N;
     extern __shared__ double sm[];
     double* s_prim = sm + S::prim;
     double* s_lam = sm + S::lam;
@@ -351,24 +393,30 @@ k_fluxdiff_ct(TensorDev t, CtDev ct, Geo g, Law L, const double* __restrict__ nr
     const int tid = threadIdx.x;
     const long long k = first + blockIdx.x;
     const bool node = tid < Nq;
+    const int ca = tid / NN, cb = (tid / N) % N, cc = tid % N;
 
-    double qi[NP], lam[D][D], r[NC];
+    double qi[NP], lam[D][D], r[NC], sw[D];
 #pragma unroll
     for (int e = 0; e < NC; e++) r[e] = 0.0;
+#pragma unroll
+    for (int m = 0; m < D; m++) sw[m] = 0.0;
     if (node) {
         double ui[NC];
 #pragma unroll
         for (int e = 0; e < NC; e++) ui[e] = u_q[((size_t)k * NC + e) * Nq + tid];
-        to_prim<D, NC>(L, ui, qi);
+#pragma unroll
+        for (int n = 0; n < D; n++)
+#pragma unroll
+            for (int m = 0; m < D; m++) lam[m][n] = g.Lambda_q[((size_t)k * D * D + (m + D * n)) * Nq + tid];
+#pragma unroll
+        for (int m = 0; m < D; m++) sw[m] = t.vS[(0 * D + m) * Nq + tid];        // weights of round 0
+        to_prim_fast<D>(L, ui, qi);
 #pragma unroll
         for (int c = 0; c < NP; c++) s_prim[c * Nq + tid] = qi[c];
 #pragma unroll
         for (int n = 0; n < D; n++)
 #pragma unroll
-            for (int m = 0; m < D; m++) {
-                lam[m][n] = g.Lambda_q[((size_t)k * D * D + (m + D * n)) * Nq + tid];
-                s_lam[(m + D * n) * Nq + tid] = lam[m][n];
-            }
+            for (int m = 0; m < D; m++) s_lam[(m + D * n) * Nq + tid] = lam[m][n];
     }
     for (int j = tid; j < Nf; j += blockDim.x) {
         double ui[NC], uo[NC], qa[NP], qb[NP], nf[D], phi[NC];
@@ -376,74 +424,88 @@ k_fluxdiff_ct(TensorDev t, CtDev ct, Geo g, Law L, const double* __restrict__ nr
 #pragma unroll
         for (int e = 0; e < NC; e++) { ui[e] = u_f[(size_t)k * Nf + j + (size_t)g.NFT * e]; uo[e] = u_f[jo + (size_t)g.NFT * e]; }
         const double jf = g.J_f[(size_t)k * Nf + j];
-        const double ijf = 1.0 / jf;
+        const double ijf = rcp_fast(jf);
 #pragma unroll
         for (int m = 0; m < D; m++) {
             const double nj = g.nJf[m + D * ((size_t)k * Nf + j)];
-            nf[m] = nj * ijf;
-            s_hnf[m * Nf + j] = 0.5 * nj;
+            nf[m] = nj * ijf;                      // n_f = nJf / J_f            operators.jl:59
+            s_hnf[m * Nf + j] = 0.5 * nj;          // halfnJf                    operators.jl:78
         }
-        to_prim<D, NC>(L, ui, qa);
-        to_prim<D, NC>(L, uo, qb);
+        const double ira = to_prim_fast<D>(L, ui, qa);
+        const double irb = to_prim_fast<D>(L, uo, qb);
 #pragma unroll
         for (int c = 0; c < NP; c++) s_fprim[c * Nf + j] = qa[c];
-        pair_flux<D, NC>(L, qa, qb, nf, phi);
+        ec_contract_fast<D>(qa, qb, nf, L.igm1, phi);          // F#(u-, u+) . n    ConservationLaws.jl:75-128
         if (L.inviscid == SSE_FLUX_LAX_FRIEDRICHS) {
             double vni = 0.0, vno = 0.0;
 #pragma unroll
             for (int m = 0; m < D; m++) { vni = fma(qa[1 + m], nf[m], vni); vno = fma(qb[1 + m], nf[m], vno); }
-            const double ci = sqrt(L.gamma * qa[D + 1] / qa[0]), co = sqrt(L.gamma * qb[D + 1] / qb[0]);
+            const double ci = sqrt(L.gamma * qa[D + 1] * ira), co = sqrt(L.gamma * qb[D + 1] * irb);
             const double a = L.half_lambda * (fmax(fabs(vni), fabs(vno)) + fmax(ci, co));
 #pragma unroll
             for (int e = 0; e < NC; e++) phi[e] = fma(a, ui[e] - uo[e], phi[e]);
         }
-        const double bj = Bf[j] * jf;
+        const double bj = t.Bf[j] * jf;                        // BJf               operators.jl:58
 #pragma unroll
         for (int e = 0; e < NC; e++) s_ff[e * Nf + j] = bj * phi[e];
     }
     __syncthreads();
 
+    // ---- volume term: NVR rounds along the tensor lines (flux_difference!, flux_differencing_form.jl:37-75)
     int buf = 0;
-    for (int rd = 0; rd < t.n_vrounds; rd++, buf ^= 1) {
+#pragma unroll 1
+    for (int rd = 0; rd < NVR; rd++, buf ^= 1) {
         double* st = s_stage + buf * NC * Nq;
-        if (node) {
-            const int j = t.v_partner[rd * Nq + tid];
-            if (j >= 0) {
-                double gv[D], qj[NP], phi[NC];
+        const int l = rd / NSH, sh = rd - l * NSH + 1;
+        const int cl = (l == 0) ? ca : ((l == 1) ? cb : cc);
+        const int stride = (l == 0) ? NN : ((l == 1) ? N : 1);
+        int cj = cl + sh; if (cj >= N) cj -= N;
+        int cs = cl - sh; if (cs < 0) cs += N;
+        const bool half = (2 * sh == N);
+        const bool active = node && !(half && cl >= sh);
+        const bool recv = node && !(half && cs >= sh);
+        const int j = tid + (cj - cl) * stride;
+        double swn[D];                                         // prefetch the next round's weights
 #pragma unroll
-                for (int n = 0; n < D; n++) gv[n] = 0.0;
-                const int mlo = t.v_mlo[rd];
+        for (int m = 0; m < D; m++) swn[m] = (node && rd + 1 < NVR) ? t.vS[((rd + 1) * D + m) * Nq + tid] : 0.0;
+        if (active) {
+            double gv[D], qj[NP], phi[NC];
 #pragma unroll
-                for (int m = 0; m < D; m++) {
-                    if (m >= mlo) {
-                        const double s = t.v_S[(rd * D + m) * Nq + tid];
+            for (int n = 0; n < D; n++) gv[n] = 0.0;
 #pragma unroll
-                        for (int n = 0; n < D; n++) gv[n] = fma(s, lam[m][n] + s_lam[(m + D * n) * Nq + j], gv[n]);
-                    }
+            for (int m = 0; m < D; m++) {
+                if (m >= l) {                                  // S_m couples eta_l-lines only for m >= l
+#pragma unroll
+                    for (int n = 0; n < D; n++) gv[n] = fma(sw[m], lam[m][n] + s_lam[(m + D * n) * Nq + j], gv[n]);
                 }
-#pragma unroll
-                for (int c = 0; c < NP; c++) qj[c] = s_prim[c * Nq + j];
-                pair_flux<D, NC>(L, qi, qj, gv, phi);
-#pragma unroll
-                for (int e = 0; e < NC; e++) { r[e] -= phi[e]; st[e * Nq + j] = phi[e]; }
             }
+#pragma unroll
+            for (int c = 0; c < NP; c++) qj[c] = s_prim[c * Nq + j];
+            ec_contract_fast<D>(qi, qj, gv, L.igm1, phi);
+#pragma unroll
+            for (int e = 0; e < NC; e++) { r[e] -= phi[e]; st[e * Nq + j] = phi[e]; }
         }
         __syncthreads();
-        if (node && t.v_source[rd * Nq + tid] >= 0) {
+        if (recv) {
 #pragma unroll
             for (int e = 0; e < NC; e++) r[e] += st[e * Nq + tid];
         }
+#pragma unroll
+        for (int m = 0; m < D; m++) sw[m] = swn[m];
     }
 
-    int face_prev = -1;
+    // ---- facet correction: NFR sub-rounds (facet_correction!, flux_differencing_form.jl:126-168)
+    double cw = node ? t.fC[tid] : 0.0;
     double hq[D];
 #pragma unroll
     for (int n = 0; n < D; n++) hq[n] = 0.0;
-    for (int fr = 0; fr < t.n_frounds; fr++, buf ^= 1) {
+#pragma unroll 1
+    for (int fr = 0; fr < NFR; fr++, buf ^= 1) {
         double* st = s_stage + buf * NC * Nq;
-        const int f = t.f_face[fr];
+        const int f = fr < 3 ? fr : 3;
+        const double cwn = (node && fr + 1 < NFR) ? t.fC[(fr + 1) * Nq + tid] : 0.0;
         if (node) {
-            if (f != face_prev) {
+            if (fr <= 3) {                         // halfnJq[:, f, i] = 0.5 sum_l Lambda[i,l,:] nref[l,f]   mesh.jl:262-269
                 if (g.nJq) {
 #pragma unroll
                     for (int n = 0; n < D; n++) hq[n] = 0.5 * g.nJq[n + D * (f + (size_t)4 * (tid + (size_t)Nq * k))];
@@ -452,43 +514,47 @@ k_fluxdiff_ct(TensorDev t, CtDev ct, Geo g, Law L, const double* __restrict__ nr
                     for (int n = 0; n < D; n++) {
                         double s = 0.0;
 #pragma unroll
-                        for (int l = 0; l < D; l++) s += lam[l][n] * nref[l + D * f];
+                        for (int l = 0; l < D; l++) s = fma(lam[l][n], t.nref[l + D * f], s);
                         hq[n] = 0.5 * s;
                     }
                 }
             }
-            const int j = t.f_partner[fr * Nq + tid];
-            const double c = t.f_C[fr * Nq + tid];
+            const int j = facet_partner<N>(fr, ca, cb, cc);
             double gv[D], qj[NP], phi[NC];
 #pragma unroll
-            for (int n = 0; n < D; n++) gv[n] = c * (s_hnf[n * Nf + j] + hq[n]);
+            for (int n = 0; n < D; n++) gv[n] = cw * (s_hnf[n * Nf + j] + hq[n]);
 #pragma unroll
-            for (int cc = 0; cc < NP; cc++) qj[cc] = s_fprim[cc * Nf + j];
-            pair_flux<D, NC>(L, qi, qj, gv, phi);
+            for (int c = 0; c < NP; c++) qj[c] = s_fprim[c * Nf + j];
+            ec_contract_fast<D>(qi, qj, gv, L.igm1, phi);
 #pragma unroll
             for (int e = 0; e < NC; e++) { r[e] -= phi[e]; st[e * Nq + tid] = phi[e]; }
         }
-        face_prev = f;
+        cw = cwn;
         __syncthreads();
-        const int nred = t.red_n[fr] * NC;
-        for (int q = tid; q < nred; q += blockDim.x) {
-            const int item = q / NC, e = q - item * NC;
-            const int base = fr * t.red_items_max + item;
-            const int* src = t.red_src + (size_t)base * t.red_max;
-            const int cnt = t.red_cnt[base];
+        // (facet node, variable) reducers: every facet node of the sub-round's face sums its N staged vectors
+        for (int q = tid; q < NN * NC; q += blockDim.x) {
+            const int e = q / NN, jj = q - e * NN, x = jj / N, y = jj - x * N;
+            int base, stride;
+            if (fr == 0) { base = x * NN + y; stride = N; }
+            else if (fr < 3) { base = jj; stride = NN; }
+            else { int c = (fr - 3) - y; if (c < 0) c += N; base = x * NN + c; stride = N; }
             double s = 0.0;
-            for (int c = 0; c < cnt; c++) s += st[e * Nq + src[c]];
-            s_ff[e * Nf + t.red_dst[base]] -= s;
+#pragma unroll
+            for (int i = 0; i < N; i++) s += st[e * Nq + base + i * stride];
+            s_ff[e * Nf + f * NN + jj] -= s;
         }
     }
     __syncthreads();
-    // r_q -= R' f_f, handed to k_project_ct through the u_q scratch
+    // ---- lift: r_q -= R' f_f (flux_differencing_form.jl:341-342); r_q goes to k_project_ct through the u_q scratch
     if (node) {
-        for (int q = ct.Rt.ptr[tid]; q < ct.Rt.ptr[tid + 1]; q++) {
-            const double rv = ct.Rt.val[q];
-            const int j = ct.Rt.idx[q];
+        double rw[NFR];
 #pragma unroll
-            for (int e = 0; e < NC; e++) r[e] = fma(-rv, s_ff[e * Nf + j], r[e]);
+        for (int fr = 0; fr < NFR; fr++) rw[fr] = t.fR[fr * Nq + tid];
+#pragma unroll
+        for (int fr = 0; fr < NFR; fr++) {
+            const int j = facet_partner<N>(fr, ca, cb, cc);
+#pragma unroll
+            for (int e = 0; e < NC; e++) r[e] = fma(-rw[fr], s_ff[e * Nf + j], r[e]);
         }
 #pragma unroll
         for (int e = 0; e < NC; e++) u_q[((size_t)k * NC + e) * Nq + tid] = r[e];

@@ -330,11 +330,18 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
     }
     {
         int N = 0;
-        if (ct_eligible(*cfg, *a, h->tp, &N)) {
+        if (ct_eligible(*cfg, *a, h->tp, &N) && ct_schedule_matches(h->tp, N)) {
             h->ct.N = N;
             h->ct.A.assign(a->A, a->A + N * N);
             h->ct.B.assign(a->B, a->B + N * N * N);
             h->ct.dev.C = o.C; h->ct.dev.W = o.W; h->ct.dev.R = o.R; h->ct.dev.Rt = o.Rt; h->ct.dev.Ne = Ne;
+            h->ct.dev.vS = h->tp.dev.v_S; h->ct.dev.fC = h->tp.dev.f_C; h->ct.dev.Bf = o.Bf;
+            for (int i = 0; i < 12; i++) h->ct.dev.nref[i] = (i < d * Nfac && a->nref) ? a->nref[i] : 0.0;
+            h->ct.fR.assign((size_t)h->tp.dev.n_frounds * Nq, 0.0);
+            for (int fr = 0; fr < h->tp.dev.n_frounds; fr++)
+                for (int i = 0; i < Nq; i++) h->ct.fR[(size_t)fr * Nq + i] = a->R[h->tp.f_partner[(size_t)fr * Nq + i] + (size_t)Nf * i];
+            if ((rc = upload(h, h->ct.fR, &h->ct.dev.fR))) return rc;
+            if (const char* mb = getenv("SSE_FD_MINB")) h->ct.minb = atoi(mb);
             if (ct_set_attrs(N) != cudaSuccess) return fail(SSE_ERR_CUDA, "cudaFuncSetAttribute (compile-time kernels) failed");
             h->ct.ok = 1;
         }

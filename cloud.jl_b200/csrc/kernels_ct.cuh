@@ -133,8 +133,8 @@ template <int N, int NC> struct ProjSmem {
 
 // ---------------------------------------------------------------------------------------------------------
 // pass A — nodal_values! with the general (modal) entropy projection
-template <int N>
-__global__ void __launch_bounds__(160, 2)
+template <int N, int MINB>
+__global__ void __launch_bounds__(160, MINB)
 k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, double* __restrict__ u_q, double* __restrict__ u_f) {
     constexpr int NC = 5, D = 3;
     using T = Tet<N>;
@@ -254,8 +254,8 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
 
 // ---------------------------------------------------------------------------------------------------------
 // pass B-2 — dudt = M^-1 V' r_q     (r_q sits in the u_q scratch)
-template <int N>
-__global__ void __launch_bounds__(160, 2)
+template <int N, int MINB>
+__global__ void __launch_bounds__(160, MINB)
 k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, const double* __restrict__ r_q, double* __restrict__ dudt) {
     constexpr int NC = 5;
     using T = Tet<N>;

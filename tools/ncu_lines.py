@@ -15,7 +15,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB = os.path.join(ROOT, "cloud.jl_b200", "lib", "libsse_b200.so")
+LIB = os.environ.get("SSE_LIB", os.path.join(ROOT, "cloud.jl_b200", "lib", "libsse_b200.so"))
 
 
 def sass_with_lines(kernel):

@@ -84,11 +84,8 @@ static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, cons
                        double* u_q, const double* u_f, double* dudt, cudaStream_t s) {
     constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
     (void)tp; (void)o;
-    if (p.minb >= 5) k_fluxdiff_ct<N, 5><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
-    else k_fluxdiff_ct<N, 4><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
-    const unsigned grid = (unsigned)((count + Tet<N>::EPB - 1) / Tet<N>::EPB);
-    if (p.proj_minb >= 3) k_project_ct<N, 3><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
-    else k_project_ct<N, 2><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
+    if (p.minb >= 5) k_fluxdiff_ct<N, 5><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(make_coef<N>(p), p.dev, g, L, first, u_q, u_f, dudt);
+    else k_fluxdiff_ct<N, 4><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(make_coef<N>(p), p.dev, g, L, first, u_q, u_f, dudt);
 }
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
                  double* u_q, const double* u_f, double* dudt, cudaStream_t s) {

@@ -44,8 +44,8 @@ template <int N> __host__ __device__ constexpr int tet_l(int b1, int b2, int b3)
 }
 
 // y[a1][a2] (fixed a3) = sum A[a1,b1] B[a2,b1,b2] C[a3,b1,b2,b3] x[l(b1,b2,b3)]      warped_product_3d.jl:47-84
-template <int N>
-__device__ __forceinline__ void sf3_fwd(const SFCoef<N>& cf, const double (&c3)[Tet<N>::Np], const double* __restrict__ xs, double (&y)[N][N]) {
+template <int N, int CS = 1>
+__device__ __forceinline__ void sf3_fwd(const SFCoef<N>& cf, const double* c3, const double* __restrict__ xs, double (&y)[N][N]) {
 #pragma unroll
     for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
@@ -59,7 +59,7 @@ __device__ __forceinline__ void sf3_fwd(const SFCoef<N>& cf, const double (&c3)[
         for (int b2 = 0; b2 < N - b1; b2++) {
             double z = 0.0;
 #pragma unroll
-            for (int b3 = 0; b3 < N - b1 - b2; b3++) { const int l = tet_l<N>(b1, b2, b3); z = fma(c3[l], xs[l], z); }
+            for (int b3 = 0; b3 < N - b1 - b2; b3++) { const int l = tet_l<N>(b1, b2, b3); z = fma(c3[l * CS], xs[l], z); }
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) w[a2] = fma(cf.B[a2 + N * (b1 + N * b2)], z, w[a2]);
         }
@@ -72,8 +72,8 @@ __device__ __forceinline__ void sf3_fwd(const SFCoef<N>& cf, const double (&c3)[
 
 // partial[l][a3] = C[a3,l] * sum_{a2} B[a2,b1,b2] sum_{a1} A[a1,b1] x[a1][a2]        warped_product_3d.jl:94-136
 // written to red[l * N] (the caller passes red already offset by group and a3)
-template <int N>
-__device__ __forceinline__ void sf3_bwd_partials(const SFCoef<N>& cf, const double (&c3)[Tet<N>::Np], const double (&x)[N][N], double* __restrict__ red) {
+template <int N, int CS = 1>
+__device__ __forceinline__ void sf3_bwd_partials(const SFCoef<N>& cf, const double* c3, const double (&x)[N][N], double* __restrict__ red) {
 #pragma unroll
     for (int b1 = 0; b1 < N; b1++) {
         double wt[N];
@@ -90,7 +90,7 @@ __device__ __forceinline__ void sf3_bwd_partials(const SFCoef<N>& cf, const doub
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) z = fma(cf.B[a2 + N * (b1 + N * b2)], wt[a2], z);
 #pragma unroll
-            for (int b3 = 0; b3 < N - b1 - b2; b3++) { const int l = tet_l<N>(b1, b2, b3); red[l * N] = c3[l] * z; }
+            for (int b3 = 0; b3 < N - b1 - b2; b3++) { const int l = tet_l<N>(b1, b2, b3); red[l * N] = c3[l * CS] * z; }
         }
     }
 }
@@ -330,7 +330,14 @@ template <int N> struct FdSmem {
     static constexpr int hnf = fprim + NP * T::Nf;         // [D][Nf]
     static constexpr int ff = hnf + D * T::Nf;             // [NC][Nf]
     static constexpr int stage = ff + NC * T::Nf;          // [2][NC][Nq]
-    static constexpr int total = stage + 2 * NC * T::Nq;
+    static constexpr int c3 = stage + 2 * NC * T::Nq;      // [Np][N]  C tensor, a3 fastest
+    static constexpr int wij = c3 + T::Np * N;             // [Nq]     W / J
+    static constexpr int total = wij + T::Nq;
+    // fused projection (after the pair phases everything in front of `stage` is dead)
+    static constexpr int p_r = stage;                      // [NC][Nq]   r_q
+    static constexpr int p_red = 0;                        // [NC][Np][N]
+    static constexpr int p_x = p_red + NC * T::Np * N;     // [NC][Np]
+    static_assert(p_x + NC * T::Np <= stage, "projection scratch must fit in front of the stage buffers");
 };
 
 // Ranocha's EC flux contracted with g, from primitives (rho, V, p, beta), log-means sharing reciprocals
@@ -378,7 +385,8 @@ __device__ __forceinline__ int facet_partner(int fr, int ca, int cb, int cc) {
 
 template <int N, int MINB>
 __global__ void __launch_bounds__((Tet<N>::Nq + 31) / 32 * 32, MINB)
-k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, const double* __restrict__ u_f) {
+k_fluxdiff_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, const double* __restrict__ u_q, const double* __restrict__ u_f,
+              double* __restrict__ dudt) {
     constexpr int NC = 5, D = 3, NP = 6;
     using T = Tet<N>;
     using S = FdSmem<N>;
@@ -400,6 +408,16 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
     for (int e = 0; e < NC; e++) r[e] = 0.0;
 #pragma unroll
     for (int m = 0; m < D; m++) sw[m] = 0.0;
+    // tables of the fused projection: C[l][a3] and W/J
+    for (int i = tid; i < T::Np * N; i += blockDim.x) {
+        const int l = i / N, a3 = i - l * N;
+        int b1 = 0, b2 = 0, b3 = 0, ll = l;               // invert the canonical modal ordering
+        while (ll >= (N - b1) * (N - b1 + 1) / 2) { ll -= (N - b1) * (N - b1 + 1) / 2; b1++; }
+        while (ll >= N - b1 - b2) { ll -= N - b1 - b2; b2++; }
+        b3 = ll;
+        sm[S::c3 + i] = t.C[a3 + N * (b1 + N * (b2 + N * b3))];
+    }
+    if (node) sm[S::wij + tid] = t.W[tid] * rcp_fast(g.J_q[(size_t)k * Nq + tid]);
     if (node) {
         double ui[NC];
 #pragma unroll
@@ -545,7 +563,8 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
         }
     }
     __syncthreads();
-    // ---- lift: r_q -= R' f_f (flux_differencing_form.jl:341-342); r_q goes to k_project_ct through the u_q scratch
+    // ---- lift: r_q -= R' f_f (flux_differencing_form.jl:341-342)
+    double* s_r = sm + S::p_r;
     if (node) {
         double rw[NFR];
 #pragma unroll
@@ -556,8 +575,51 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
 #pragma unroll
             for (int e = 0; e < NC; e++) r[e] = fma(-rw[fr], s_ff[e * Nf + j], r[e]);
         }
+    }
+    __syncthreads();                                   // all reads of s_ff / stage done; prim/lam/fprim are dead
+    if (node) {
 #pragma unroll
-        for (int e = 0; e < NC; e++) u_q[((size_t)k * NC + e) * Nq + tid] = r[e];
+        for (int e = 0; e < NC; e++) s_r[e * Nq + tid] = r[e];
+    }
+    __syncthreads();
+    // ---- dudt = M^-1 V' r_q (flux_differencing_form.jl:345-346, mass_matrix.jl:185-196): N*NC threads, thread = (e, a3)
+    const bool pj = tid < NC * N;
+    const int pe = tid / N, pa3 = tid - pe * N;
+    const double* c3s = sm + S::c3 + pa3;
+    double* s_red = sm + S::p_red;
+    double* s_x = sm + S::p_x;
+    double y[N][N], out[T::LPT];
+    if (pj) {
+#pragma unroll
+        for (int a1 = 0; a1 < N; a1++)
+#pragma unroll
+            for (int a2 = 0; a2 < N; a2++) y[a1][a2] = s_r[pe * Nq + (a1 * N + a2) * N + pa3];
+        sf3_bwd_partials<N, N>(cf, c3s, y, s_red + pe * T::Np * N + pa3);
+    }
+    __syncthreads();
+    if (pj) {
+        sf3_bwd_reduce<N>(s_red + pe * T::Np * N, pa3, out);
+#pragma unroll
+        for (int q = 0; q < T::LPT; q++) { const int l = pa3 * T::LPT + q; if (l < T::Np) s_x[pe * T::Np + l] = out[q]; }
+    }
+    __syncthreads();
+    if (pj) {
+        sf3_fwd<N, N>(cf, c3s, s_x + pe * T::Np, y);
+        const double* wij = sm + S::wij;
+#pragma unroll
+        for (int a1 = 0; a1 < N; a1++)
+#pragma unroll
+            for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= wij[(a1 * N + a2) * N + pa3];
+        sf3_bwd_partials<N, N>(cf, c3s, y, s_red + pe * T::Np * N + pa3);
+    }
+    __syncthreads();
+    if (pj) {
+        sf3_bwd_reduce<N>(s_red + pe * T::Np * N, pa3, out);
+#pragma unroll
+        for (int q = 0; q < T::LPT; q++) {
+            const int l = pa3 * T::LPT + q;
+            if (l < T::Np) dudt[((size_t)k * NC + pe) * T::Np + l] = out[q];
+        }
     }
 }
 

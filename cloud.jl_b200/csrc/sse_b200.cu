@@ -295,7 +295,7 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
     L.pde = cfg->pde; L.two_point = cfg->two_point_flux; L.inviscid = cfg->inviscid_flux;
     L.half_lambda = cfg->half_lambda; L.b = cfg->b;
     for (int m = 0; m < 3; m++) L.a[m] = cfg->a[m];
-    L.gamma = cfg->gamma; L.gm1 = cfg->gamma - 1.0; L.igm1 = 1.0 / (cfg->gamma - 1.0);
+    L.gamma = cfg->gamma; L.gm1 = cfg->gamma - 1.0; L.igm1 = 1.0 / (cfg->gamma - 1.0); L.log_gm1 = std::log(cfg->gamma - 1.0);
     h->second_order = (cfg->pde == SSE_PDE_ADVECTION_DIFFUSION);
     if (h->second_order && cfg->form != SSE_FORM_STANDARD_PHYSICAL)
         return fail(SSE_ERR_UNSUPPORTED, "second-order laws are only implemented with PhysicalOperators (Solvers.jl:357-376)");

@@ -64,6 +64,8 @@ template <int N> static cudaError_t set_attrs_n() {
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
     if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
+    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
+    if ((e = cudaFuncSetAttribute(k_project_ct<N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
     if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
     return cudaFuncSetAttribute(k_fluxdiff_ct<N, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total));
 }
@@ -72,7 +74,8 @@ cudaError_t ct_set_attrs(int N) { return N == 5 ? set_attrs_n<5>() : set_attrs_n
 template <int N>
 static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, const double* u, double* u_q, double* u_f, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.dev.Ne + Tet<N>::EPB - 1) / Tet<N>::EPB);
-    if (p.proj_minb >= 3) k_nodal_ct<N, 3><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
+    if (p.proj_minb >= 4) k_nodal_ct<N, 4><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
+    else if (p.proj_minb == 3) k_nodal_ct<N, 3><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
     else k_nodal_ct<N, 2><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
 }
 void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, const double* u, double* u_q, double* u_f, cudaStream_t s) {
@@ -84,8 +87,12 @@ static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, cons
                        double* u_q, const double* u_f, double* dudt, cudaStream_t s) {
     constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
     (void)tp; (void)o;
-    if (p.minb >= 5) k_fluxdiff_ct<N, 5><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(make_coef<N>(p), p.dev, g, L, first, u_q, u_f, dudt);
-    else k_fluxdiff_ct<N, 4><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(make_coef<N>(p), p.dev, g, L, first, u_q, u_f, dudt);
+    if (p.minb >= 5) k_fluxdiff_ct<N, 5><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
+    else k_fluxdiff_ct<N, 4><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
+    const unsigned grid = (unsigned)((count + Tet<N>::EPB - 1) / Tet<N>::EPB);
+    if (p.proj_minb >= 4) k_project_ct<N, 4><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
+    else if (p.proj_minb == 3) k_project_ct<N, 3><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
+    else k_project_ct<N, 2><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
 }
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
                  double* u_q, const double* u_f, double* dudt, cudaStream_t s) {

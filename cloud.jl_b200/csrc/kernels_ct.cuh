@@ -44,6 +44,7 @@ template <int N> __host__ __device__ constexpr int tet_l(int b1, int b2, int b3)
 }
 
 // y[a1][a2] (fixed a3) = sum A[a1,b1] B[a2,b1,b2] C[a3,b1,b2,b3] x[l(b1,b2,b3)]      warped_product_3d.jl:47-84
+// c3[l * CS]: CS = 1 for a register array, CS = N for the shared table [l][a3] (pointer offset by a3)
 template <int N, int CS = 1>
 __device__ __forceinline__ void sf3_fwd(const SFCoef<N>& cf, const double* c3, const double* __restrict__ xs, double (&y)[N][N]) {
 #pragma unroll
@@ -52,6 +53,7 @@ __device__ __forceinline__ void sf3_fwd(const SFCoef<N>& cf, const double* c3, c
         for (int a2 = 0; a2 < N; a2++) y[a1][a2] = 0.0;
 #pragma unroll
     for (int b1 = 0; b1 < N; b1++) {
+        asm volatile("" ::: "memory");             // keep the loads of each b1-slab next to their use (register pressure)
         double w[N];
 #pragma unroll
         for (int a2 = 0; a2 < N; a2++) w[a2] = 0.0;
@@ -76,6 +78,7 @@ template <int N, int CS = 1>
 __device__ __forceinline__ void sf3_bwd_partials(const SFCoef<N>& cf, const double* c3, const double (&x)[N][N], double* __restrict__ red) {
 #pragma unroll
     for (int b1 = 0; b1 < N; b1++) {
+        asm volatile("" ::: "memory");
         double wt[N];
 #pragma unroll
         for (int a2 = 0; a2 < N; a2++) {
@@ -110,6 +113,18 @@ __device__ __forceinline__ void sf3_bwd_reduce(const double* __restrict__ red, i
     }
 }
 
+// shared table s_c3[l * N + a3] = C[a3, b1, b2, b3] with l the canonical modal index
+template <int N>
+__device__ __forceinline__ void load_c3_shared(const CtDev& t, double* s_c3) {
+    for (int i = threadIdx.x; i < Tet<N>::Np * N; i += blockDim.x) {
+        const int l = i / N, a3 = i - l * N;
+        int b1 = 0, b2 = 0, ll = l;
+        while (ll >= (N - b1) * (N - b1 + 1) / 2) { ll -= (N - b1) * (N - b1 + 1) / 2; b1++; }
+        while (ll >= N - b1 - b2) { ll -= N - b1 - b2; b2++; }
+        s_c3[i] = t.C[a3 + N * (b1 + N * (b2 + N * ll))];
+    }
+}
+
 template <int N>
 __device__ __forceinline__ void load_c3(const CtDev& t, int a3, double (&c3)[Tet<N>::Np]) {
 #pragma unroll
@@ -128,7 +143,8 @@ template <int N, int NC> struct ProjSmem {
     static constexpr int big = x + NG * T::Np;                     // union: q [NG][Nq]  |  red [NG][Np][N]
     static constexpr int big_sz = (NG * T::Nq > NG * T::Np * N) ? NG * T::Nq : NG * T::Np * N;
     static constexpr int wij = big + big_sz;                       // [EPB][Nq]  W / J
-    static constexpr int total = wij + T::EPB * T::Nq;
+    static constexpr int c3 = wij + T::EPB * T::Nq;                // [Np][N]    C tensor, a3 fastest
+    static constexpr int total = c3 + T::Np * N;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -153,15 +169,15 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
     const int nel = (int)((t.Ne - e0 < EPB) ? (t.Ne - e0) : EPB);
     const bool act = gl < T::GPW && (grp / NC) < nel;
 
-    double c3[Np];
-    if (gl < T::GPW) load_c3<N>(t, a3, c3);
+    load_c3_shared<N>(t, sm + S::c3);
+    const double* c3 = sm + S::c3 + a3;
     for (int i = tid; i < nel * NC * Np; i += NT) s_x[i] = u[(size_t)e0 * NC * Np + i];
     __syncthreads();
 
     double y[N][N];
     // u_q = V u
     if (act) {
-        sf3_fwd<N>(cf, c3, s_x + grp * Np, y);
+        sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
 #pragma unroll
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
@@ -177,7 +193,7 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
         cons_to_entropy<D, NC>(L, ui, wi);
         const double J = g.J_q[(size_t)(e0 + el) * Nq + i], W = t.W[i];
         const double wj = W * J;
-        s_wij[el * Nq + i] = W / J;
+        s_wij[el * Nq + i] = W * rcp_fast(J);
 #pragma unroll
         for (int e = 0; e < NC; e++) s_q[(el * NC + e) * Nq + i] = wi[e] * wj;
     }
@@ -191,7 +207,7 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
     }
     __syncthreads();                                   // s_red aliases s_q
     double out[T::LPT];
-    if (act) sf3_bwd_partials<N>(cf, c3, y, s_red + grp * Np * N + a3);
+    if (act) sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * Np * N + a3);
     __syncthreads();
     if (act) {
         sf3_bwd_reduce<N>(s_red + grp * Np * N, a3, out);
@@ -201,13 +217,13 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
     __syncthreads();
     // w = M \ w : V, diag(W/J), V'                           mass_matrix.jl:185-196
     if (act) {
-        sf3_fwd<N>(cf, c3, s_x + grp * Np, y);
+        sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
         const double* wij = s_wij + (grp / NC) * Nq;
 #pragma unroll
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= wij[(a1 * N + a2) * N + a3];
-        sf3_bwd_partials<N>(cf, c3, y, s_red + grp * Np * N + a3);
+        sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * Np * N + a3);
     }
     __syncthreads();
     if (act) {
@@ -218,7 +234,7 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
     __syncthreads();
     // w_q = V w
     if (act) {
-        sf3_fwd<N>(cf, c3, s_x + grp * Np, y);
+        sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
 #pragma unroll
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
@@ -275,23 +291,23 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
     const int nel = (int)(rem < EPB ? rem : EPB);
     const bool act = gl < T::GPW && (grp / NC) < nel;
 
-    double c3[Np];
-    if (gl < T::GPW) load_c3<N>(t, a3, c3);
-    for (int i = tid; i < nel * NC * Nq; i += NT) s_q[i] = r_q[(size_t)e0 * NC * Nq + i];
-    for (int it = tid; it < nel * Nq; it += NT) {
-        const int el = it / Nq, i = it - el * Nq;
-        s_wij[it] = t.W[i] / g.J_q[(size_t)(e0 + el) * Nq + i];
-    }
-    __syncthreads();
     double y[N][N], out[T::LPT];
+    // r_q slab of this thread straight from global memory (25 independent loads in flight)
     if (act) {
+        const double* src = r_q + (size_t)e0 * NC * Nq + (size_t)grp * Nq + a3;
 #pragma unroll
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
-            for (int a2 = 0; a2 < N; a2++) y[a1][a2] = s_q[grp * Nq + (a1 * N + a2) * N + a3];
+            for (int a2 = 0; a2 < N; a2++) y[a1][a2] = src[(a1 * N + a2) * N];
+    }
+    load_c3_shared<N>(t, sm + S::c3);
+    const double* c3 = sm + S::c3 + a3;
+    for (int it = tid; it < nel * Nq; it += NT) {
+        const int el = it / Nq, i = it - el * Nq;
+        s_wij[it] = t.W[i] * rcp_fast(g.J_q[(size_t)(e0 + el) * Nq + i]);
     }
     __syncthreads();
-    if (act) sf3_bwd_partials<N>(cf, c3, y, s_red + grp * Np * N + a3);
+    if (act) sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * Np * N + a3);
     __syncthreads();
     if (act) {
         sf3_bwd_reduce<N>(s_red + grp * Np * N, a3, out);
@@ -300,13 +316,13 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
     }
     __syncthreads();
     if (act) {
-        sf3_fwd<N>(cf, c3, s_x + grp * Np, y);
+        sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
         const double* wij = s_wij + (grp / NC) * Nq;
 #pragma unroll
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= wij[(a1 * N + a2) * N + a3];
-        sf3_bwd_partials<N>(cf, c3, y, s_red + grp * Np * N + a3);
+        sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * Np * N + a3);
     }
     __syncthreads();
     if (act) {
@@ -330,14 +346,7 @@ template <int N> struct FdSmem {
     static constexpr int hnf = fprim + NP * T::Nf;         // [D][Nf]
     static constexpr int ff = hnf + D * T::Nf;             // [NC][Nf]
     static constexpr int stage = ff + NC * T::Nf;          // [2][NC][Nq]
-    static constexpr int c3 = stage + 2 * NC * T::Nq;      // [Np][N]  C tensor, a3 fastest
-    static constexpr int wij = c3 + T::Np * N;             // [Nq]     W / J
-    static constexpr int total = wij + T::Nq;
-    // fused projection (after the pair phases everything in front of `stage` is dead)
-    static constexpr int p_r = stage;                      // [NC][Nq]   r_q
-    static constexpr int p_red = 0;                        // [NC][Np][N]
-    static constexpr int p_x = p_red + NC * T::Np * N;     // [NC][Np]
-    static_assert(p_x + NC * T::Np <= stage, "projection scratch must fit in front of the stage buffers");
+    static constexpr int total = stage + 2 * NC * T::Nq;
 };
 
 // Ranocha's EC flux contracted with g, from primitives (rho, V, p, beta), log-means sharing reciprocals
@@ -385,8 +394,7 @@ __device__ __forceinline__ int facet_partner(int fr, int ca, int cb, int cc) {
 
 template <int N, int MINB>
 __global__ void __launch_bounds__((Tet<N>::Nq + 31) / 32 * 32, MINB)
-k_fluxdiff_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, const double* __restrict__ u_q, const double* __restrict__ u_f,
-              double* __restrict__ dudt) {
+k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, const double* __restrict__ u_f) {
     constexpr int NC = 5, D = 3, NP = 6;
     using T = Tet<N>;
     using S = FdSmem<N>;
@@ -408,16 +416,6 @@ k_fluxdiff_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, const double
     for (int e = 0; e < NC; e++) r[e] = 0.0;
 #pragma unroll
     for (int m = 0; m < D; m++) sw[m] = 0.0;
-    // tables of the fused projection: C[l][a3] and W/J
-    for (int i = tid; i < T::Np * N; i += blockDim.x) {
-        const int l = i / N, a3 = i - l * N;
-        int b1 = 0, b2 = 0, b3 = 0, ll = l;               // invert the canonical modal ordering
-        while (ll >= (N - b1) * (N - b1 + 1) / 2) { ll -= (N - b1) * (N - b1 + 1) / 2; b1++; }
-        while (ll >= N - b1 - b2) { ll -= N - b1 - b2; b2++; }
-        b3 = ll;
-        sm[S::c3 + i] = t.C[a3 + N * (b1 + N * (b2 + N * b3))];
-    }
-    if (node) sm[S::wij + tid] = t.W[tid] * rcp_fast(g.J_q[(size_t)k * Nq + tid]);
     if (node) {
         double ui[NC];
 #pragma unroll
@@ -563,8 +561,7 @@ k_fluxdiff_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, const double
         }
     }
     __syncthreads();
-    // ---- lift: r_q -= R' f_f (flux_differencing_form.jl:341-342)
-    double* s_r = sm + S::p_r;
+    // ---- lift: r_q -= R' f_f (flux_differencing_form.jl:341-342); r_q goes to k_project_ct through the u_q scratch
     if (node) {
         double rw[NFR];
 #pragma unroll
@@ -575,51 +572,8 @@ k_fluxdiff_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, const double
 #pragma unroll
             for (int e = 0; e < NC; e++) r[e] = fma(-rw[fr], s_ff[e * Nf + j], r[e]);
         }
-    }
-    __syncthreads();                                   // all reads of s_ff / stage done; prim/lam/fprim are dead
-    if (node) {
 #pragma unroll
-        for (int e = 0; e < NC; e++) s_r[e * Nq + tid] = r[e];
-    }
-    __syncthreads();
-    // ---- dudt = M^-1 V' r_q (flux_differencing_form.jl:345-346, mass_matrix.jl:185-196): N*NC threads, thread = (e, a3)
-    const bool pj = tid < NC * N;
-    const int pe = tid / N, pa3 = tid - pe * N;
-    const double* c3s = sm + S::c3 + pa3;
-    double* s_red = sm + S::p_red;
-    double* s_x = sm + S::p_x;
-    double y[N][N], out[T::LPT];
-    if (pj) {
-#pragma unroll
-        for (int a1 = 0; a1 < N; a1++)
-#pragma unroll
-            for (int a2 = 0; a2 < N; a2++) y[a1][a2] = s_r[pe * Nq + (a1 * N + a2) * N + pa3];
-        sf3_bwd_partials<N, N>(cf, c3s, y, s_red + pe * T::Np * N + pa3);
-    }
-    __syncthreads();
-    if (pj) {
-        sf3_bwd_reduce<N>(s_red + pe * T::Np * N, pa3, out);
-#pragma unroll
-        for (int q = 0; q < T::LPT; q++) { const int l = pa3 * T::LPT + q; if (l < T::Np) s_x[pe * T::Np + l] = out[q]; }
-    }
-    __syncthreads();
-    if (pj) {
-        sf3_fwd<N, N>(cf, c3s, s_x + pe * T::Np, y);
-        const double* wij = sm + S::wij;
-#pragma unroll
-        for (int a1 = 0; a1 < N; a1++)
-#pragma unroll
-            for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= wij[(a1 * N + a2) * N + pa3];
-        sf3_bwd_partials<N, N>(cf, c3s, y, s_red + pe * T::Np * N + pa3);
-    }
-    __syncthreads();
-    if (pj) {
-        sf3_bwd_reduce<N>(s_red + pe * T::Np * N, pa3, out);
-#pragma unroll
-        for (int q = 0; q < T::LPT; q++) {
-            const int l = pa3 * T::LPT + q;
-            if (l < T::Np) dudt[((size_t)k * NC + pe) * T::Np + l] = out[q];
-        }
+        for (int e = 0; e < NC; e++) u_q[((size_t)k * NC + e) * Nq + tid] = r[e];
     }
 }
 

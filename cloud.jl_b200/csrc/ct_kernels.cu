@@ -66,8 +66,12 @@ template <int N> static cudaError_t set_attrs_n() {
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
     if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
-    if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
-    return cudaFuncSetAttribute(k_fluxdiff_ct<N, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total));
+    if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
+    if constexpr (N == 5) {
+        if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N, true>::total)))) return e;
+        if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N, true>::total)))) return e;
+    }
+    return cudaFuncSetAttribute(k_fluxdiff_ct<N, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total));
 }
 cudaError_t ct_set_attrs(int N) { return N == 5 ? set_attrs_n<5>() : set_attrs_n<4>(); }
 
@@ -87,8 +91,13 @@ static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, cons
                        double* u_q, const double* u_f, double* dudt, cudaStream_t s) {
     constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
     (void)tp; (void)o;
-    if (p.minb >= 5) k_fluxdiff_ct<N, 5><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
-    else k_fluxdiff_ct<N, 4><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
+    if constexpr (N == 5) {
+        if (p.dual && p.minb <= 3) { k_fluxdiff_ct<N, 3, true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); goto projected; }
+        if (p.dual) { k_fluxdiff_ct<N, 4, true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); goto projected; }
+    }
+    if (p.minb >= 5) k_fluxdiff_ct<N, 5, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
+    else k_fluxdiff_ct<N, 4, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
+projected:
     const unsigned grid = (unsigned)((count + Tet<N>::EPB - 1) / Tet<N>::EPB);
     if (p.proj_minb >= 4) k_project_ct<N, 4><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
     else if (p.proj_minb == 3) k_project_ct<N, 3><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);

@@ -337,7 +337,7 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
 
 // ---------------------------------------------------------------------------------------------------------
 // pass B-1 — one CTA per element, one thread per volume node (same schedule tables as k_fluxdiff_tensor)
-template <int N> struct FdSmem {
+template <int N, bool DUAL = false> struct FdSmem {
     using T = Tet<N>;
     static constexpr int NP = 6, NC = 5, D = 3;
     static constexpr int prim = 0;                         // [NP][Nq]
@@ -346,7 +346,7 @@ template <int N> struct FdSmem {
     static constexpr int hnf = fprim + NP * T::Nf;         // [D][Nf]
     static constexpr int ff = hnf + D * T::Nf;             // [NC][Nf]
     static constexpr int stage = ff + NC * T::Nf;          // [2][NC][Nq]
-    static constexpr int total = stage + 2 * NC * T::Nq;
+    static constexpr int total = stage + (DUAL ? 4 : 2) * NC * T::Nq;
 };
 
 // Ranocha's EC flux contracted with g, from primitives (rho, V, p, beta), log-means sharing reciprocals
@@ -392,12 +392,13 @@ __device__ __forceinline__ int facet_partner(int fr, int ca, int cb, int cc) {
     return 3 * NN + ca * N + bp;
 }
 
-template <int N, int MINB>
+template <int N, int MINB, bool DUAL>
 __global__ void __launch_bounds__((Tet<N>::Nq + 31) / 32 * 32, MINB)
 k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, const double* __restrict__ u_f) {
     constexpr int NC = 5, D = 3, NP = 6;
     using T = Tet<N>;
-    using S = FdSmem<N>;
+    using S = FdSmem<N, DUAL>;
+    static_assert(!DUAL || (N % 2 == 1 && N / 2 == 2), "the two-pairs-per-round variant is written for N = 5");
     constexpr int Nq = T::Nq, Nf = T::Nf, NN = N * N, NSH = N / 2, NVR = D * NSH, NFR = 3 + N;
     extern __shared__ double sm[];
     double* s_prim = sm + S::prim;
@@ -467,6 +468,121 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
     }
     __syncthreads();
 
+    // ---- two pairs per thread and round: both shifts of a line direction / two facet sub-rounds are evaluated
+    //      back to back so their dependent FP64 chains interleave (ILP), with one barrier per two pairs
+    if constexpr (DUAL) {
+        int buf = 0;
+        double swb[D];
+#pragma unroll
+        for (int m = 0; m < D; m++) swb[m] = node ? t.vS[(1 * D + m) * Nq + tid] : 0.0;
+#pragma unroll 1
+        for (int l = 0; l < D; l++, buf ^= 1) {
+            double* stA = s_stage + (2 * buf) * NC * Nq;
+            double* stB = stA + NC * Nq;
+            const int cl = (l == 0) ? ca : ((l == 1) ? cb : cc);
+            const int stride = (l == 0) ? NN : ((l == 1) ? N : 1);
+            int c1 = cl + 1; if (c1 >= N) c1 -= N;
+            int c2 = cl + 2; if (c2 >= N) c2 -= N;
+            const int jA = tid + (c1 - cl) * stride, jB = tid + (c2 - cl) * stride;
+            double swnA[D], swnB[D];
+#pragma unroll
+            for (int m = 0; m < D; m++) {
+                swnA[m] = (node && l + 1 < D) ? t.vS[((2 * l + 2) * D + m) * Nq + tid] : 0.0;
+                swnB[m] = (node && l + 1 < D) ? t.vS[((2 * l + 3) * D + m) * Nq + tid] : 0.0;
+            }
+            if (node) {
+                double gA[D], gB[D], qA[NP], qB[NP], pA[NC], pB[NC];
+#pragma unroll
+                for (int n = 0; n < D; n++) { gA[n] = 0.0; gB[n] = 0.0; }
+#pragma unroll
+                for (int m = 0; m < D; m++) {
+                    if (m >= l) {
+#pragma unroll
+                        for (int n = 0; n < D; n++) {
+                            gA[n] = fma(sw[m], lam[m][n] + s_lam[(m + D * n) * Nq + jA], gA[n]);
+                            gB[n] = fma(swb[m], lam[m][n] + s_lam[(m + D * n) * Nq + jB], gB[n]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < NP; c++) { qA[c] = s_prim[c * Nq + jA]; qB[c] = s_prim[c * Nq + jB]; }
+                ec_contract_fast<D>(qi, qA, gA, L.igm1, pA);
+                ec_contract_fast<D>(qi, qB, gB, L.igm1, pB);
+#pragma unroll
+                for (int e = 0; e < NC; e++) { r[e] -= pA[e] + pB[e]; stA[e * Nq + jA] = pA[e]; stB[e * Nq + jB] = pB[e]; }
+            }
+            __syncthreads();
+            if (node) {
+#pragma unroll
+                for (int e = 0; e < NC; e++) r[e] += stA[e * Nq + tid] + stB[e * Nq + tid];
+            }
+#pragma unroll
+            for (int m = 0; m < D; m++) { sw[m] = swnA[m]; swb[m] = swnB[m]; }
+        }
+        double cwA = node ? t.fC[tid] : 0.0, cwB = node ? t.fC[Nq + tid] : 0.0;
+#pragma unroll 1
+        for (int fr = 0; fr < NFR; fr += 2, buf ^= 1) {
+            double* stA = s_stage + (2 * buf) * NC * Nq;
+            double* stB = stA + NC * Nq;
+            const int fA = fr < 3 ? fr : 3, fB = fr + 1 < 3 ? fr + 1 : 3;
+            const double cwnA = (node && fr + 2 < NFR) ? t.fC[(fr + 2) * Nq + tid] : 0.0;
+            const double cwnB = (node && fr + 3 < NFR) ? t.fC[(fr + 3) * Nq + tid] : 0.0;
+            if (node) {
+                double hA[D], hB[D];
+#pragma unroll
+                for (int n = 0; n < D; n++) {
+                    if (g.nJq) {
+                        hA[n] = 0.5 * g.nJq[n + D * (fA + (size_t)4 * (tid + (size_t)Nq * k))];
+                        hB[n] = 0.5 * g.nJq[n + D * (fB + (size_t)4 * (tid + (size_t)Nq * k))];
+                    } else {
+                        double sa = 0.0, sb = 0.0;
+#pragma unroll
+                        for (int l = 0; l < D; l++) { sa = fma(lam[l][n], t.nref[l + D * fA], sa); sb = fma(lam[l][n], t.nref[l + D * fB], sb); }
+                        hA[n] = 0.5 * sa; hB[n] = 0.5 * sb;
+                    }
+                }
+                const int jA = facet_partner<N>(fr, ca, cb, cc), jB = facet_partner<N>(fr + 1, ca, cb, cc);
+                double gA[D], gB[D], qA[NP], qB[NP], pA[NC], pB[NC];
+#pragma unroll
+                for (int n = 0; n < D; n++) { gA[n] = cwA * (s_hnf[n * Nf + jA] + hA[n]); gB[n] = cwB * (s_hnf[n * Nf + jB] + hB[n]); }
+#pragma unroll
+                for (int c = 0; c < NP; c++) { qA[c] = s_fprim[c * Nf + jA]; qB[c] = s_fprim[c * Nf + jB]; }
+                ec_contract_fast<D>(qi, qA, gA, L.igm1, pA);
+                ec_contract_fast<D>(qi, qB, gB, L.igm1, pB);
+#pragma unroll
+                for (int e = 0; e < NC; e++) { r[e] -= pA[e] + pB[e]; stA[e * Nq + tid] = pA[e]; stB[e * Nq + tid] = pB[e]; }
+            }
+            cwA = cwnA; cwB = cwnB;
+            __syncthreads();
+            if (fA != fB) {                 // two different faces: independent targets
+                for (int q = tid; q < 2 * NN * NC; q += blockDim.x) {
+                    const int which = q / (NN * NC), qq = q - which * NN * NC;
+                    const int frq = fr + which, f = which ? fB : fA;
+                    const double* st = which ? stB : stA;
+                    const int e = qq / NN, jj = qq - e * NN, x = jj / N, y = jj - x * N;
+                    int base, stride;
+                    if (frq == 0) { base = x * NN + y; stride = N; }
+                    else if (frq < 3) { base = jj; stride = NN; }
+                    else { int c = (frq - 3) - y; if (c < 0) c += N; base = x * NN + c; stride = N; }
+                    double s = 0.0;
+#pragma unroll
+                    for (int i = 0; i < N; i++) s += st[e * Nq + base + i * stride];
+                    s_ff[e * Nf + f * NN + jj] -= s;
+                }
+            } else {                        // both sub-rounds feed face 4: one reducer sums both stages
+                for (int q = tid; q < NN * NC; q += blockDim.x) {
+                    const int e = q / NN, jj = q - e * NN, x = jj / N, y = jj - x * N;
+                    int cA = (fr - 3) - y; if (cA < 0) cA += N;
+                    int cB = (fr - 2) - y; if (cB < 0) cB += N;
+                    double s = 0.0;
+#pragma unroll
+                    for (int i = 0; i < N; i++) s += stA[e * Nq + x * NN + cA + i * N] + stB[e * Nq + x * NN + cB + i * N];
+                    s_ff[e * Nf + 3 * NN + jj] -= s;
+                }
+            }
+            __syncthreads();      // two reducers of one iteration may hit the same facet node only across iterations
+        }
+    } else {
     // ---- volume term: NVR rounds along the tensor lines (flux_difference!, flux_differencing_form.jl:37-75)
     int buf = 0;
 #pragma unroll 1
@@ -559,6 +675,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
             for (int i = 0; i < N; i++) s += st[e * Nq + base + i * stride];
             s_ff[e * Nf + f * NN + jj] -= s;
         }
+    }
     }
     __syncthreads();
     // ---- lift: r_q -= R' f_f (flux_differencing_form.jl:341-342); r_q goes to k_project_ct through the u_q scratch

@@ -343,6 +343,7 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
             if ((rc = upload(h, h->ct.fR, &h->ct.dev.fR))) return rc;
             if (const char* mb = getenv("SSE_FD_MINB")) h->ct.minb = atoi(mb);
             if (const char* mb = getenv("SSE_PROJ_MINB")) h->ct.proj_minb = atoi(mb);
+            if (const char* mb = getenv("SSE_FD_DUAL")) h->ct.dual = atoi(mb);
             if (ct_set_attrs(N) != cudaSuccess) return fail(SSE_ERR_CUDA, "cudaFuncSetAttribute (compile-time kernels) failed");
             h->ct.ok = 1;
         }

@@ -25,7 +25,7 @@ struct CtPlan {
     std::vector<double> A, B;       // host copies of the 1-D tensors handed to the kernels by value
     std::vector<double> fR;         // host image of dev.fR
     int minb = 4;                   // resident CTAs per SM requested for k_fluxdiff_ct (tuning knob)
-    int dual = 0;                   // two pairs per thread and round in k_fluxdiff_ct (N = 5)
+    int dual = 1;                   // two pairs per thread and round in k_fluxdiff_ct (N = 5; SSE_FD_DUAL=0 disables)
     int proj_minb = 3;              // same for k_nodal_ct / k_project_ct
 };
 

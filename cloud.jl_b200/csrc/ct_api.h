@@ -21,6 +21,8 @@ struct CtDev {
 
 struct CtPlan {
     int ok = 0, N = 0;
+    int kind = 0;                   // 0: Euler flux differencing; 1: linear advection, StandardForm + ReferenceOperators
+    std::vector<double> D1;         // kind 1: the three 1-D derivative matrices, [m][t + N*s]
     CtDev dev{};
     std::vector<double> A, B;       // host copies of the 1-D tensors handed to the kernels by value
     std::vector<double> fR;         // host image of dev.fR
@@ -30,6 +32,10 @@ struct CtPlan {
 };
 
 bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& tp, int* Nout);
+// advection + StandardForm + ReferenceOperators on ModalTensor tets; fills D1 and fR (host images) on success
+bool ct_eligible_standard(const sse_config& cfg, const sse_arrays& a, int* Nout, std::vector<double>& D1, std::vector<double>& fR);
+void ct_standard(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
+                 double* dudt, cudaStream_t s);
 // true when the generic tables of tp equal the closed-form schedule k_fluxdiff_ct hard-codes
 bool ct_schedule_matches(const TensorPlan& tp, int N);
 cudaError_t ct_set_attrs(int N);

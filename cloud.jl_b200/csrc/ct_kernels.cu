@@ -60,27 +60,24 @@ template <int N> static SFCoef<N> make_coef(const CtPlan& p) {
 
 template <int N> static cudaError_t set_attrs_n() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
-    if ((e = cudaFuncSetAttribute(k_project_ct<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
-    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
-    if ((e = cudaFuncSetAttribute(k_project_ct<N, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
-    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
-    if ((e = cudaFuncSetAttribute(k_project_ct<N, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * ProjSmem<N, 5>::total)))) return e;
+    const int proj5 = (int)(sizeof(double) * ProjSmem<N, 5>::total), proj1 = (int)(sizeof(double) * ProjSmem<N, 1>::total);
+    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 5, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
+    if ((e = cudaFuncSetAttribute(k_project_ct<N, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
+    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 1, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
+    if ((e = cudaFuncSetAttribute(k_project_ct<N, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
     if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
     if constexpr (N == 5) {
-        if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N, true>::total)))) return e;
         if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N, true>::total)))) return e;
     }
-    return cudaFuncSetAttribute(k_fluxdiff_ct<N, 5, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total));
+    return cudaSuccess;
 }
 cudaError_t ct_set_attrs(int N) { return N == 5 ? set_attrs_n<5>() : set_attrs_n<4>(); }
 
 template <int N>
 static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, const double* u, double* u_q, double* u_f, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.dev.Ne + Tet<N>::EPB - 1) / Tet<N>::EPB);
-    if (p.proj_minb >= 4) k_nodal_ct<N, 4><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
-    else if (p.proj_minb == 3) k_nodal_ct<N, 3><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
-    else k_nodal_ct<N, 2><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
+    if (p.kind == 0) k_nodal_ct<N, 5, 3, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
+    else k_nodal_ct<N, 1, 8, false><<<grid, 32, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
 }
 void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, const double* u, double* u_q, double* u_f, cudaStream_t s) {
     if (p.N == 5) nodal_n<5>(p, g, L, u, u_q, u_f, s); else nodal_n<4>(p, g, L, u, u_q, u_f, s);
@@ -91,22 +88,83 @@ static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, cons
                        double* u_q, const double* u_f, double* dudt, cudaStream_t s) {
     constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
     (void)tp; (void)o;
+    bool done = false;
     if constexpr (N == 5) {
-        if (p.dual && p.minb <= 3) { k_fluxdiff_ct<N, 3, true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); goto projected; }
-        if (p.dual) { k_fluxdiff_ct<N, 4, true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); goto projected; }
+        if (p.dual) { k_fluxdiff_ct<N, 4, true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); done = true; }
     }
-    if (p.minb >= 5) k_fluxdiff_ct<N, 5, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
-    else k_fluxdiff_ct<N, 4, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
-projected:
+    if (!done) k_fluxdiff_ct<N, 4, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
     const unsigned grid = (unsigned)((count + Tet<N>::EPB - 1) / Tet<N>::EPB);
-    if (p.proj_minb >= 4) k_project_ct<N, 4><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
-    else if (p.proj_minb == 3) k_project_ct<N, 3><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
-    else k_project_ct<N, 2><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
+    k_project_ct<N, 5, 3><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
 }
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
                  double* u_q, const double* u_f, double* dudt, cudaStream_t s) {
     if (p.N == 5) fluxdiff_n<5>(p, tp, o, g, L, first, count, u_q, u_f, dudt, s);
     else fluxdiff_n<4>(p, tp, o, g, L, first, count, u_q, u_f, dudt, s);
+}
+
+
+bool ct_eligible_standard(const sse_config& cfg, const sse_arrays& a, int* Nout, std::vector<double>& D1, std::vector<double>& fR) {
+    if (cfg.d != 3 || cfg.N_c != 1 || cfg.pde != SSE_PDE_ADVECTION || cfg.form != SSE_FORM_STANDARD_REFERENCE) return false;
+    if (cfg.v_kind != SSE_V_WARPED || cfg.mass_solver != SSE_MASS_WEIGHT_ADJUSTED) return false;
+    const int N = cfg.p + 1;
+    if (N != 4 && N != 5) return false;
+    if (cfg.M1d[0] != N || cfg.M1d[1] != N || cfg.M1d[2] != N) return false;
+    const int NN = N * N, Nq = N * NN, Nf = 4 * NN;
+    if (cfg.N_q != Nq || cfg.N_p != N * (N + 1) * (N + 2) / 6 || cfg.N_f != Nf || cfg.N_fac != 4) return false;
+    for (int t = 0; t < Nq; t++) {
+        const int a1 = t % N, a2 = (t / N) % N, a3 = t / NN;
+        if (a.sigma_o[t] - 1 != (a1 * N + a2) * N + a3) return false;
+        const long long want = (a1 + a2 + a3 <= N - 1) ? (N == 4 ? tet_l<4>(a1, a2, a3) : tet_l<5>(a1, a2, a3)) + 1 : 0;
+        if (a.sigma_i[t] != want) return false;
+    }
+    // D[m] must be the Kronecker product I (x) D_1D (x) I along direction m
+    const int stride[3] = {NN, N, 1};
+    D1.assign(3 * NN, 0.0);
+    for (int m = 0; m < 3; m++) {
+        if (!a.D[m]) return false;
+        for (int t = 0; t < N; t++) for (int s = 0; s < N; s++) D1[m * NN + t + N * s] = a.D[m][t * stride[m] + (size_t)Nq * (s * stride[m])];
+        for (int i = 0; i < Nq; i++)
+            for (int j = 0; j < Nq; j++) {
+                const int ci[3] = {i / NN, (i / N) % N, i % N}, cj[3] = {j / NN, (j / N) % N, j % N};
+                bool line = true;
+                for (int q = 0; q < 3; q++) if (q != m && ci[q] != cj[q]) line = false;
+                const double want = line ? D1[m * NN + ci[m] + N * cj[m]] : 0.0;
+                if (a.D[m][i + (size_t)Nq * j] != want) return false;
+            }
+    }
+    // R must have exactly the closed-form facet partners of k_fluxdiff_ct
+    fR.assign((size_t)(3 + N) * Nq, 0.0);
+    std::vector<char> seen((size_t)Nf * Nq, 0);
+    for (int i = 0; i < Nq; i++) {
+        const int c[3] = {i / NN, (i / N) % N, i % N};
+        for (int fr = 0; fr < 3 + N; fr++) {
+            int j;
+            if (fr == 0) j = c[0] * N + c[2];
+            else if (fr == 1) j = NN + c[1] * N + c[2];
+            else if (fr == 2) j = 2 * NN + c[1] * N + c[2];
+            else j = 3 * NN + c[0] * N + ((fr - 3 - c[2]) % N + N) % N;
+            fR[(size_t)fr * Nq + i] = a.R[j + (size_t)Nf * i];
+            seen[j + (size_t)Nf * i] = 1;
+        }
+    }
+    for (size_t x = 0; x < seen.size(); x++) if (!seen[x] && a.R[x] != 0.0) return false;
+    *Nout = N;
+    return true;
+}
+
+template <int N>
+static void standard_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
+                       double* dudt, cudaStream_t s) {
+    constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
+    AdvTabs<N> tabs;
+    for (int m = 0; m < 3; m++) for (int i = 0; i < N * N; i++) tabs.D1[m][i] = p.D1[m * N * N + i];
+    k_standard_adv_ct<N, 8><<<(unsigned)count, NT, 0, s>>>(tabs, p.dev, g, L, first, u_q, u_f);
+    const unsigned grid = (unsigned)((count + Tet<N>::EPB - 1) / Tet<N>::EPB);
+    k_project_ct<N, 1, 8><<<grid, 32, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
+}
+void ct_standard(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
+                 double* dudt, cudaStream_t s) {
+    if (p.N == 5) standard_n<5>(p, g, L, first, count, u_q, u_f, dudt, s); else standard_n<4>(p, g, L, first, count, u_q, u_f, dudt, s);
 }
 
 }  // namespace sse

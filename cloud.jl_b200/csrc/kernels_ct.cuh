@@ -149,10 +149,10 @@ template <int N, int NC> struct ProjSmem {
 
 // ---------------------------------------------------------------------------------------------------------
 // pass A — nodal_values! with the general (modal) entropy projection
-template <int N, int MINB>
-__global__ void __launch_bounds__(160, MINB)
+template <int N, int NC, int MINB, bool PROJECT>
+__global__ void __launch_bounds__(NC * 32, MINB)
 k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, double* __restrict__ u_q, double* __restrict__ u_f) {
-    constexpr int NC = 5, D = 3;
+    constexpr int D = 3;
     using T = Tet<N>;
     using S = ProjSmem<N, NC>;
     constexpr int Nq = T::Nq, Np = T::Np, Nf = T::Nf, EPB = T::EPB, NG = S::NG;
@@ -184,6 +184,7 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
             for (int a2 = 0; a2 < N; a2++) s_q[grp * Nq + (a1 * N + a2) * N + a3] = y[a1][a2];
     }
     __syncthreads();
+    if constexpr (PROJECT) {
     // w_q = WJ * w(u_q)                                      flux_differencing_form.jl:230-235
     for (int it = tid; it < nel * Nq; it += NT) {
         const int el = it / Nq, i = it - el * Nq;
@@ -241,6 +242,7 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
             for (int a2 = 0; a2 < N; a2++) s_q[grp * Nq + (a1 * N + a2) * N + a3] = y[a1][a2];
     }
     __syncthreads();
+    }
     // u_q = u(w_q), u_f = u(R w_q)                           flux_differencing_form.jl:240-249
     for (int it = tid; it < nel * (Nq + Nf); it += NT) {
         const int el = it / (Nq + Nf), i = it - el * (Nq + Nf);
@@ -248,7 +250,11 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
         if (i < Nq) {
 #pragma unroll
             for (int e = 0; e < NC; e++) wi[e] = s_q[(el * NC + e) * Nq + i];
-            entropy_to_cons<D, NC>(L, wi, ui);
+            if constexpr (PROJECT) entropy_to_cons<D, NC>(L, wi, ui);
+            else {
+#pragma unroll
+                for (int e = 0; e < NC; e++) ui[e] = wi[e];
+            }
 #pragma unroll
             for (int e = 0; e < NC; e++) u_q[((size_t)(e0 + el) * NC + e) * Nq + i] = ui[e];
         } else {
@@ -261,7 +267,11 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
 #pragma unroll
                 for (int e = 0; e < NC; e++) wi[e] = fma(rv, s_q[(el * NC + e) * Nq + c], wi[e]);
             }
-            entropy_to_cons<D, NC>(L, wi, ui);
+            if constexpr (PROJECT) entropy_to_cons<D, NC>(L, wi, ui);
+            else {
+#pragma unroll
+                for (int e = 0; e < NC; e++) ui[e] = wi[e];
+            }
 #pragma unroll
             for (int e = 0; e < NC; e++) u_f[(size_t)(e0 + el) * Nf + j + (size_t)g.NFT * e] = ui[e];
         }
@@ -270,10 +280,9 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
 
 // ---------------------------------------------------------------------------------------------------------
 // pass B-2 — dudt = M^-1 V' r_q     (r_q sits in the u_q scratch)
-template <int N, int MINB>
-__global__ void __launch_bounds__(160, MINB)
+template <int N, int NC, int MINB>
+__global__ void __launch_bounds__(NC * 32, MINB)
 k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, const double* __restrict__ r_q, double* __restrict__ dudt) {
-    constexpr int NC = 5;
     using T = Tet<N>;
     using S = ProjSmem<N, NC>;
     constexpr int Nq = T::Nq, Np = T::Np, EPB = T::EPB;
@@ -691,6 +700,73 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
         }
 #pragma unroll
         for (int e = 0; e < NC; e++) u_q[((size_t)k * NC + e) * Nq + tid] = r[e];
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// pass B-1 for LinearAdvectionEquation + StandardForm + ReferenceOperators on collapsed tets
+// (standard_form_first_order.jl:16-63).  The flux is linear, f_n = a_n u, so the d^2 (D_m, D_m') pairs of the
+// reference collapse to d pairs acting on  g_m = (sum_n halfWLambda_mn a_n) u  and on u, and the facet
+// difference  sum_n halfN_n R f_n  is  0.5 (a.n) u_f  with the u_f = R u_q pass A already wrote.
+// HBM-bound: ~16 kB of metric/state traffic per element against ~30 kflop.
+template <int N> struct AdvTabs { double D1[3][N * N]; };     // D_1D[m][t + N*s]: row t, column s
+
+template <int N, int MINB>
+__global__ void __launch_bounds__((Tet<N>::Nq + 31) / 32 * 32, MINB)
+k_standard_adv_ct(AdvTabs<N> a, CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, const double* __restrict__ u_f) {
+    constexpr int D = 3;
+    using T = Tet<N>;
+    constexpr int Nq = T::Nq, Nf = T::Nf, NN = N * N, NFR = 3 + N;
+    __shared__ double s_u[Nq], s_g[D][Nq], s_ff[Nf], s_D[D][N * N];
+    const int tid = threadIdx.x;
+    const long long k = first + blockIdx.x;
+    const bool node = tid < Nq;
+    const int ca = tid / NN, cb = (tid / N) % N, cc = tid % N;
+    for (int i = tid; i < D * N * N; i += blockDim.x) s_D[i / (N * N)][i % (N * N)] = a.D1[i / (N * N)][i % (N * N)];
+    double c[D] = {0.0, 0.0, 0.0};
+    if (node) {
+        const double u = u_q[(size_t)k * Nq + tid];
+        const double hw = 0.5 * t.W[tid];
+#pragma unroll
+        for (int m = 0; m < D; m++) {
+            double s = 0.0;
+#pragma unroll
+            for (int n = 0; n < D; n++) s = fma(hw * g.Lambda_q[((size_t)k * D * D + (m + D * n)) * Nq + tid], L.a[n], s);   // halfWLambda_mn a_n
+            c[m] = s;
+            s_g[m][tid] = s * u;
+        }
+        s_u[tid] = u;
+    }
+    for (int j = tid; j < Nf; j += blockDim.x) {
+        const double ui = u_f[(size_t)k * Nf + j], uo = u_f[(size_t)(g.mapP[(size_t)k * Nf + j] - 1)];
+        const double jf = g.J_f[(size_t)k * Nf + j];
+        double an = 0.0;
+#pragma unroll
+        for (int m = 0; m < D; m++) an = fma(L.a[m], g.nJf[m + D * ((size_t)k * Nf + j)] / jf, an);
+        double fs = (0.5 * (ui + uo)) * an;                                   // F#.n        ConservationLaws.jl:75-128
+        if (L.inviscid == SSE_FLUX_LAX_FRIEDRICHS) fs = fma(L.half_lambda * fabs(an), ui - uo, fs);
+        s_ff[j] = (t.Bf[j] * jf) * (fs - 0.5 * an * ui);                      // BJf (f* - sum_n halfN_n R f_n)
+    }
+    __syncthreads();
+    if (node) {
+        double r = 0.0;
+#pragma unroll
+        for (int m = 0; m < D; m++) {
+            const int cm = (m == 0) ? ca : ((m == 1) ? cb : cc);
+            const int stride = (m == 0) ? NN : ((m == 1) ? N : 1);
+            const int base = tid - cm * stride;
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int q = 0; q < N; q++) {
+                s1 = fma(s_D[m][q + N * cm], s_g[m][base + q * stride], s1);     // D_m' (halfWLambda f)
+                s2 = fma(s_D[m][cm + N * q], s_u[base + q * stride], s2);       // D_m f
+            }
+            r += s1 - c[m] * s2;
+        }
+#pragma unroll
+        for (int fr = 0; fr < NFR; fr++) r = fma(-t.fR[fr * Nq + tid], s_ff[facet_partner<N>(fr, ca, cb, cc)], r);   // - R' f_f
+        u_q[(size_t)k * Nq + tid] = r;
     }
 }
 

@@ -348,6 +348,19 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
             h->ct.ok = 1;
         }
     }
+    {
+        int N = 0;
+        std::vector<double> D1;
+        if (!h->ct.ok && ct_eligible_standard(*cfg, *a, &N, D1, h->ct.fR)) {
+            h->ct.N = N; h->ct.kind = 1; h->ct.D1 = D1;
+            h->ct.A.assign(a->A, a->A + N * N);
+            h->ct.B.assign(a->B, a->B + N * N * N);
+            h->ct.dev.C = o.C; h->ct.dev.W = o.W; h->ct.dev.R = o.R; h->ct.dev.Rt = o.Rt; h->ct.dev.Ne = Ne; h->ct.dev.Bf = o.Bf;
+            if ((rc = upload(h, h->ct.fR, &h->ct.dev.fR))) return rc;
+            if (ct_set_attrs(N) != cudaSuccess) return fail(SSE_ERR_CUDA, "cudaFuncSetAttribute (compile-time kernels) failed");
+            h->ct.ok = 1;
+        }
+    }
     h->smem_nodal = smem_nodal_bytes(o);
     h->smem_time = smem_time_bytes(h);
     h->smem_aux = smem_aux_bytes(o);
@@ -500,6 +513,8 @@ extern "C" int32_t sse_rhs_pass_b(sse_handle* h, double* d_dudt, int64_t first, 
             DISPATCH_DNC(h, LA);
 #undef LA
         }
+    } else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE && h->variant == 1 && h->ct.ok && h->ct.kind == 1) {
+        ct_standard(h->ct, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream);
     } else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE) {
 #define LA(D_, NC_) k_time_standard_reference<D_, NC_><<<n, h->threads, h->smem_time, h->stream>>>(h->ops, h->geo, h->law, first, h->u_q, h->u_f, d_dudt)
         DISPATCH_DNC(h, LA);

@@ -429,11 +429,11 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
     if (node) {
         double ui[NC];
 #pragma unroll
-        for (int e = 0; e < NC; e++) ui[e] = u_q[((size_t)k * NC + e) * Nq + tid];
+        for (int e = 0; e < NC; e++) ui[e] = __ldcs(u_q + ((size_t)k * NC + e) * Nq + tid);
 #pragma unroll
         for (int n = 0; n < D; n++)
 #pragma unroll
-            for (int m = 0; m < D; m++) lam[m][n] = g.Lambda_q[((size_t)k * D * D + (m + D * n)) * Nq + tid];
+            for (int m = 0; m < D; m++) lam[m][n] = __ldcs(g.Lambda_q + ((size_t)k * D * D + (m + D * n)) * Nq + tid);
 #pragma unroll
         for (int m = 0; m < D; m++) sw[m] = t.vS[(0 * D + m) * Nq + tid];        // weights of round 0
         to_prim_fast<D>(L, ui, qi);
@@ -448,12 +448,12 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
         double ui[NC], uo[NC], qa[NP], qb[NP], nf[D], phi[NC];
         const size_t jo = (size_t)(g.mapP[(size_t)k * Nf + j] - 1);
 #pragma unroll
-        for (int e = 0; e < NC; e++) { ui[e] = u_f[(size_t)k * Nf + j + (size_t)g.NFT * e]; uo[e] = u_f[jo + (size_t)g.NFT * e]; }
-        const double jf = g.J_f[(size_t)k * Nf + j];
+        for (int e = 0; e < NC; e++) { ui[e] = __ldcs(u_f + (size_t)k * Nf + j + (size_t)g.NFT * e); uo[e] = __ldcs(u_f + jo + (size_t)g.NFT * e); }
+        const double jf = __ldcs(g.J_f + (size_t)k * Nf + j);
         const double ijf = rcp_fast(jf);
 #pragma unroll
         for (int m = 0; m < D; m++) {
-            const double nj = g.nJf[m + D * ((size_t)k * Nf + j)];
+            const double nj = __ldcs(g.nJf + m + D * ((size_t)k * Nf + j));
             nf[m] = nj * ijf;                      // n_f = nJf / J_f            operators.jl:59
             s_hnf[m * Nf + j] = 0.5 * nj;          // halfnJf                    operators.jl:78
         }

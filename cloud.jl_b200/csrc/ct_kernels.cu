@@ -63,8 +63,8 @@ template <int N> static cudaError_t set_attrs_n() {
     const int proj5 = (int)(sizeof(double) * ProjSmem<N, 5>::total), proj1 = (int)(sizeof(double) * ProjSmem<N, 1>::total);
     if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 5, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
-    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 1, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
-    if ((e = cudaFuncSetAttribute(k_project_ct<N, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
+    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 1, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
+    if ((e = cudaFuncSetAttribute(k_project_ct<N, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
     if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
     if constexpr (N == 5) {
         if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N, true>::total)))) return e;
@@ -75,9 +75,13 @@ cudaError_t ct_set_attrs(int N) { return N == 5 ? set_attrs_n<5>() : set_attrs_n
 
 template <int N>
 static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, const double* u, double* u_q, double* u_f, cudaStream_t s) {
-    const unsigned grid = (unsigned)((p.dev.Ne + Tet<N>::EPB - 1) / Tet<N>::EPB);
-    if (p.kind == 0) k_nodal_ct<N, 5, 3, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
-    else k_nodal_ct<N, 1, 8, false><<<grid, 32, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
+    if (p.kind == 0) {
+        const unsigned grid = (unsigned)((p.dev.Ne + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
+        k_nodal_ct<N, 5, 3, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
+    } else {
+        const unsigned grid = (unsigned)((p.dev.Ne + ProjSmem<N, 1>::EPB - 1) / ProjSmem<N, 1>::EPB);
+        k_nodal_ct<N, 1, 3, false><<<grid, 128, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
+    }
 }
 void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, const double* u, double* u_q, double* u_f, cudaStream_t s) {
     if (p.N == 5) nodal_n<5>(p, g, L, u, u_q, u_f, s); else nodal_n<4>(p, g, L, u, u_q, u_f, s);
@@ -93,7 +97,7 @@ static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, cons
         if (p.dual) { k_fluxdiff_ct<N, 4, true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); done = true; }
     }
     if (!done) k_fluxdiff_ct<N, 4, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
-    const unsigned grid = (unsigned)((count + Tet<N>::EPB - 1) / Tet<N>::EPB);
+    const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
     k_project_ct<N, 5, 3><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
 }
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
@@ -159,8 +163,8 @@ static void standard_n(const CtPlan& p, const Geo& g, const Law& L, long long fi
     AdvTabs<N> tabs;
     for (int m = 0; m < 3; m++) for (int i = 0; i < N * N; i++) tabs.D1[m][i] = p.D1[m * N * N + i];
     k_standard_adv_ct<N, 8><<<(unsigned)count, NT, 0, s>>>(tabs, p.dev, g, L, first, u_q, u_f);
-    const unsigned grid = (unsigned)((count + Tet<N>::EPB - 1) / Tet<N>::EPB);
-    k_project_ct<N, 1, 8><<<grid, 32, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
+    const unsigned grid = (unsigned)((count + ProjSmem<N, 1>::EPB - 1) / ProjSmem<N, 1>::EPB);
+    k_project_ct<N, 1, 3><<<grid, 128, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt);
 }
 void ct_standard(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
                  double* dudt, cudaStream_t s) {

@@ -138,24 +138,31 @@ __device__ __forceinline__ void load_c3(const CtDev& t, int a3, double (&c3)[Tet
 // shared-memory plan of the projection kernels (doubles)
 template <int N, int NC> struct ProjSmem {
     using T = Tet<N>;
-    static constexpr int NG = T::EPB * NC;                         // groups per CTA
+    static constexpr int WARPS = (NC == 1) ? 4 : NC;               // CTA = WARPS warps
+    static constexpr int NG = WARPS * T::GPW;                      // groups (element, variable) per CTA
+    static constexpr int EPB = NG / NC;                            // elements per CTA
+    static_assert(NG % NC == 0, "groups must split evenly into elements");
+    static constexpr int NNZ = 3 * N * N * N + N * N * N * N;      // non-zeros of R on the collapsed tet
     static constexpr int x = 0;                                    // [NG][Np]
     static constexpr int big = x + NG * T::Np;                     // union: q [NG][Nq]  |  red [NG][Np][N]
     static constexpr int big_sz = (NG * T::Nq > NG * T::Np * N) ? NG * T::Nq : NG * T::Np * N;
     static constexpr int wij = big + big_sz;                       // [EPB][Nq]  W / J
-    static constexpr int c3 = wij + T::EPB * T::Nq;                // [Np][N]    C tensor, a3 fastest
-    static constexpr int total = c3 + T::Np * N;
+    static constexpr int c3 = wij + EPB * T::Nq;                   // [Np][N]    C tensor, a3 fastest
+    static constexpr int rval = c3 + T::Np * N;                    // [NNZ]      R values (CSR by facet node)
+    static constexpr int ridx = rval + NNZ;                        // [NNZ] int  R column indices
+    static constexpr int rptr = ridx + (NNZ + 1) / 2;              // [Nf+1] int R row pointers
+    static constexpr int total = rptr + (T::Nf + 2) / 2;
 };
 
 // ---------------------------------------------------------------------------------------------------------
 // pass A — nodal_values! with the general (modal) entropy projection
 template <int N, int NC, int MINB, bool PROJECT>
-__global__ void __launch_bounds__(NC * 32, MINB)
+__global__ void __launch_bounds__(ProjSmem<N, NC>::WARPS * 32, MINB)
 k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, double* __restrict__ u_q, double* __restrict__ u_f) {
     constexpr int D = 3;
     using T = Tet<N>;
     using S = ProjSmem<N, NC>;
-    constexpr int Nq = T::Nq, Np = T::Np, Nf = T::Nf, EPB = T::EPB, NG = S::NG;
+    constexpr int Nq = T::Nq, Np = T::Np, Nf = T::Nf, EPB = S::EPB, NG = S::NG;
     extern __shared__ double sm[];
     double* s_x = sm + S::x;
     double* s_q = sm + S::big;
@@ -171,6 +178,11 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
 
     load_c3_shared<N>(t, sm + S::c3);
     const double* c3 = sm + S::c3 + a3;
+    double* s_rval = sm + S::rval;
+    int* s_ridx = reinterpret_cast<int*>(sm + S::ridx);
+    int* s_rptr = reinterpret_cast<int*>(sm + S::rptr);
+    for (int i = tid; i < S::NNZ; i += NT) { s_rval[i] = t.R.val[i]; s_ridx[i] = t.R.idx[i]; }
+    for (int i = tid; i <= Nf; i += NT) s_rptr[i] = t.R.ptr[i];
     for (int i = tid; i < nel * NC * Np; i += NT) s_x[i] = u[(size_t)e0 * NC * Np + i];
     __syncthreads();
 
@@ -261,9 +273,9 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
             const int j = i - Nq;
 #pragma unroll
             for (int e = 0; e < NC; e++) wi[e] = 0.0;
-            for (int q = t.R.ptr[j]; q < t.R.ptr[j + 1]; q++) {
-                const double rv = t.R.val[q];
-                const int c = t.R.idx[q];
+            for (int q = s_rptr[j]; q < s_rptr[j + 1]; q++) {
+                const double rv = s_rval[q];
+                const int c = s_ridx[q];
 #pragma unroll
                 for (int e = 0; e < NC; e++) wi[e] = fma(rv, s_q[(el * NC + e) * Nq + c], wi[e]);
             }
@@ -281,11 +293,11 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
 // ---------------------------------------------------------------------------------------------------------
 // pass B-2 — dudt = M^-1 V' r_q     (r_q sits in the u_q scratch)
 template <int N, int NC, int MINB>
-__global__ void __launch_bounds__(NC * 32, MINB)
+__global__ void __launch_bounds__(ProjSmem<N, NC>::WARPS * 32, MINB)
 k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, const double* __restrict__ r_q, double* __restrict__ dudt) {
     using T = Tet<N>;
     using S = ProjSmem<N, NC>;
-    constexpr int Nq = T::Nq, Np = T::Np, EPB = T::EPB;
+    constexpr int Nq = T::Nq, Np = T::Np, EPB = S::EPB;
     extern __shared__ double sm[];
     double* s_x = sm + S::x;
     double* s_q = sm + S::big;

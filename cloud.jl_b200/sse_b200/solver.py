@@ -59,7 +59,7 @@ class Solver:
         _lib.check(self._lib.sse_create(C.byref(image.cfg), C.byref(arr), device, C.byref(self._h)))
         self._pinned = {}
         self.launches = 0      # kernels launched through this handle (for bench accounting)
-        self._per_rhs = 3 if image.law.second_order else 2
+        self._refresh_launch_counts()
 
     # -- plumbing ------------------------------------------------------------------------
     def close(self):
@@ -90,8 +90,14 @@ class Solver:
         s = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self._lib.sse_set_stream(self._h, C.c_void_p(s)))
 
+    def _refresh_launch_counts(self):
+        # the compile-time path runs pass B as two kernels (pair kernel + projection)
+        self._pass_b = 2 if self.kernel_variant() == 2 else 1
+        self._per_rhs = 1 + self._pass_b + (1 if self.image.law.second_order else 0)
+
     def set_kernel_variant(self, v: int):
         _lib.check(self._lib.sse_set_kernel_variant(self._h, v))
+        self._refresh_launch_counts()
 
     def kernel_variant(self) -> int:
         v = C.c_int32(0)
@@ -122,7 +128,7 @@ class Solver:
 
     def pass_b(self, dudt, first, count):
         _lib.check(self._lib.sse_rhs_pass_b(self._h, self._check_state(dudt, "dudt"), first, count))
-        self.launches += 1 if count > 0 else 0
+        self.launches += self._pass_b if count > 0 else 0
 
     def rhs_host(self, dudt_host, u_host, t: float = 0.0):
         """Residual on HOST buffers: H2D copy of u, kernels, D2H copy of dudt.  torch CPU tensors

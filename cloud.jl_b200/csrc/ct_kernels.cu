@@ -74,17 +74,19 @@ template <int N> static cudaError_t set_attrs_n() {
 cudaError_t ct_set_attrs(int N) { return N == 5 ? set_attrs_n<5>() : set_attrs_n<4>(); }
 
 template <int N>
-static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, const double* u, double* u_q, double* u_f, cudaStream_t s) {
+static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q, double* u_f,
+                    cudaStream_t s) {
     if (p.kind == 0) {
-        const unsigned grid = (unsigned)((p.dev.Ne + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
-        k_nodal_ct<N, 5, 3, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
+        const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
+        k_nodal_ct<N, 5, 3, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
     } else {
-        const unsigned grid = (unsigned)((p.dev.Ne + ProjSmem<N, 1>::EPB - 1) / ProjSmem<N, 1>::EPB);
-        k_nodal_ct<N, 1, 3, false><<<grid, 128, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, L, u, u_q, u_f);
+        const unsigned grid = (unsigned)((count + ProjSmem<N, 1>::EPB - 1) / ProjSmem<N, 1>::EPB);
+        k_nodal_ct<N, 1, 3, false><<<grid, 128, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
     }
 }
-void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, const double* u, double* u_q, double* u_f, cudaStream_t s) {
-    if (p.N == 5) nodal_n<5>(p, g, L, u, u_q, u_f, s); else nodal_n<4>(p, g, L, u, u_q, u_f, s);
+void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q, double* u_f,
+              cudaStream_t s) {
+    if (p.N == 5) nodal_n<5>(p, g, L, first, count, u, u_q, u_f, s); else nodal_n<4>(p, g, L, first, count, u, u_q, u_f, s);
 }
 
 template <int N>

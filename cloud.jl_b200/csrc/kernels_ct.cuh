@@ -158,7 +158,8 @@ template <int N, int NC> struct ProjSmem {
 // pass A — nodal_values! with the general (modal) entropy projection
 template <int N, int NC, int MINB, bool PROJECT>
 __global__ void __launch_bounds__(ProjSmem<N, NC>::WARPS * 32, MINB)
-k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, double* __restrict__ u_q, double* __restrict__ u_f) {
+k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count, const double* __restrict__ u,
+           double* __restrict__ u_q, double* __restrict__ u_f) {
     constexpr int D = 3;
     using T = Tet<N>;
     using S = ProjSmem<N, NC>;
@@ -172,8 +173,8 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, const double* __restrict__ u, do
     const int warp = tid >> 5, lane = tid & 31;
     const int gl = lane / N, a3 = lane - gl * N;
     const int grp = warp * T::GPW + gl;                 // (element slot, variable) = (grp / NC, grp % NC)
-    const long long e0 = (long long)blockIdx.x * EPB;   // first element of this CTA
-    const int nel = (int)((t.Ne - e0 < EPB) ? (t.Ne - e0) : EPB);
+    const long long e0 = first + (long long)blockIdx.x * EPB;   // first element of this CTA
+    const int nel = (int)((first + count - e0 < EPB) ? (first + count - e0) : EPB);
     const bool act = gl < T::GPW && (grp / NC) < nel;
 
     load_c3_shared<N>(t, sm + S::c3);

@@ -146,10 +146,10 @@ __host__ __device__ inline int warp_w_size(const Ops& o, int NC) { return o.v_ki
 // project: 0 = none, 1 = nodal (w_f = R w(u_q)), 2 = general/modal entropy projection.
 // NV = number of "variables" moved per node = NC.
 template <int D, int NC>
-__global__ void k_nodal_generic(Ops o, Geo g, Law L, int project, const double* __restrict__ u,
+__global__ void k_nodal_generic(Ops o, Geo g, Law L, int project, long long first, const double* __restrict__ u,
                                 double* __restrict__ u_q, double* __restrict__ u_f) {
     extern __shared__ double sm[];
-    const long long k = blockIdx.x;
+    const long long k = first + blockIdx.x;
     const int Nq = o.Nq, Np = o.Np, Nf = o.Nf;
     double* s_u = sm;                       // Np x NC
     double* s_a = s_u + Np * NC;            // Nq x NC

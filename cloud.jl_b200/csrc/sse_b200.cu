@@ -463,23 +463,25 @@ extern "C" int32_t sse_synchronize(sse_handle* h) {
 // ------------------------------------------------------------------------------ the hot path
 static bool use_tensor(const sse_handle* h) { return h->variant == 1 && h->tp.ok; }
 
-extern "C" int32_t sse_rhs_pass_a(sse_handle* h, const double* d_u) {
+extern "C" int32_t sse_rhs_pass_a_range(sse_handle* h, const double* d_u, int64_t first, int64_t count) {
     if (!h || !d_u) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    if (count <= 0) return SSE_OK;
+    if (first < 0 || first + count > h->cfg.N_e) return fail(SSE_ERR_BAD_ARGUMENT, "element range out of bounds");
     CU(cudaSetDevice(h->device));
-    const unsigned Ne = (unsigned)h->cfg.N_e;
+    const unsigned n = (unsigned)count;
     if (h->variant == 1 && h->ct.ok) {
-        ct_nodal(h->ct, h->geo, h->law, d_u, h->u_q, h->u_f, h->stream);
-    } else if (use_tensor(h) && h->tp.has_nodal) {
-#define LA(D_, NC_) tensor_launch_nodal<D_, NC_>(h->tp, h->ops, h->geo, h->law, h->project, d_u, h->u_q, h->u_f, h->cfg.N_e, h->sm_count, h->stream)
-        DISPATCH_DNC(h, LA);
-#undef LA
+        ct_nodal(h->ct, h->geo, h->law, first, count, d_u, h->u_q, h->u_f, h->stream);
     } else {
-#define LA(D_, NC_) k_nodal_generic<D_, NC_><<<Ne, h->threads, h->smem_nodal, h->stream>>>(h->ops, h->geo, h->law, h->project, d_u, h->u_q, h->u_f)
+#define LA(D_, NC_) k_nodal_generic<D_, NC_><<<n, h->threads, h->smem_nodal, h->stream>>>(h->ops, h->geo, h->law, h->project, first, d_u, h->u_q, h->u_f)
         DISPATCH_DNC(h, LA);
 #undef LA
     }
     CU(cudaGetLastError());
     return SSE_OK;
+}
+extern "C" int32_t sse_rhs_pass_a(sse_handle* h, const double* d_u) {
+    if (!h) return fail(SSE_ERR_BAD_ARGUMENT, "null handle");
+    return sse_rhs_pass_a_range(h, d_u, 0, h->cfg.N_e);
 }
 
 extern "C" int32_t sse_rhs_pass_aux(sse_handle* h, double* d_dudt, int64_t first, int64_t count) {

@@ -29,6 +29,7 @@ SYMBOLS = {
     "sse_state_download": (C.c_int32, [_h, C.c_void_p, C.c_void_p]),
     "sse_rhs": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_double]),
     "sse_rhs_pass_a": (C.c_int32, [_h, C.c_void_p]),
+    "sse_rhs_pass_a_range": (C.c_int32, [_h, C.c_void_p, C.c_int64, C.c_int64]),
     "sse_rhs_pass_aux": (C.c_int32, [_h, C.c_void_p, C.c_int64, C.c_int64]),
     "sse_rhs_pass_b": (C.c_int32, [_h, C.c_void_p, C.c_int64, C.c_int64]),
     "sse_halo_configure": (C.c_int32, [_h, _pi64, C.c_int64]),

@@ -130,13 +130,20 @@ class Solver:
         _lib.check(self._lib.sse_rhs_pass_b(self._h, self._check_state(dudt, "dudt"), first, count))
         self.launches += self._pass_b if count > 0 else 0
 
-    def rhs_host(self, dudt_host, u_host, t: float = 0.0):
-        """Residual on HOST buffers: H2D copy of u, kernels, D2H copy of dudt.  torch CPU tensors
-        (ideally pinned) are copied directly; NumPy arrays are staged through pinned memory."""
+    def pass_a_range(self, u, first, count):
+        _lib.check(self._lib.sse_rhs_pass_a_range(self._h, self._check_state(u, "u"), first, count))
+        self.launches += 1 if count > 0 else 0
+
+    def rhs_host(self, dudt_host, u_host, t: float = 0.0, chunks: int = 8):
+        """Residual on HOST buffers (the reference-facing call with `Array` arguments): the H2D copy of u, the
+        kernels and the D2H copy of dudt are pipelined over `chunks` element ranges — pass A of a chunk starts as
+        soon as its slice of u has arrived, and the download of a chunk of dudt overlaps pass B of the next one.
+        torch CPU tensors (ideally pinned) are copied directly; NumPy arrays are staged through pinned memory."""
         torch = _torch()
         p = self._pinned
         if "d_u" not in p:
             p["d_u"], p["d_du"] = self.new_state(), self.new_state()
+            p["copy"] = torch.cuda.Stream(device=self.device)
         if isinstance(u_host, np.ndarray):
             if "u" not in p:
                 p["u"] = torch.empty(self.state_shape, dtype=torch.float64).pin_memory()
@@ -145,10 +152,35 @@ class Solver:
             src, dst = p["u"], p["du"]
         else:
             src, dst = u_host, dudt_host
-        p["d_u"].copy_(src, non_blocking=True)
-        self.rhs(p["d_du"], p["d_u"], t)
-        dst.copy_(p["d_du"], non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        ne = self.state_shape[0]
+        d_u, d_du, copy = p["d_u"], p["d_du"], p["copy"]
+        cur = torch.cuda.current_stream(self.device)
+        if self.image.law.second_order or int(self.cfg.N_ghost) or chunks <= 1 or ne < 4 * chunks:
+            d_u.copy_(src, non_blocking=True)
+            self.rhs(d_du, d_u, t)
+            dst.copy_(d_du, non_blocking=True)
+            cur.synchronize()
+        else:
+            bounds = [ne * c // chunks for c in range(chunks + 1)]
+            copy.wait_stream(cur)
+            for c in range(chunks):
+                a, b = bounds[c], bounds[c + 1]
+                with torch.cuda.stream(copy):
+                    d_u[a:b].copy_(src[a:b], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy)
+                cur.wait_event(ev)
+                self.pass_a_range(d_u, a, b - a)
+            for c in range(chunks):
+                a, b = bounds[c], bounds[c + 1]
+                self.pass_b(d_du, a, b - a)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                with torch.cuda.stream(copy):
+                    copy.wait_event(ev)
+                    dst[a:b].copy_(d_du[a:b], non_blocking=True)
+            cur.wait_stream(copy)
+            cur.synchronize()
         if isinstance(u_host, np.ndarray):
             dudt_host[...] = dst.numpy()
         return dudt_host

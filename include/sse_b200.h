@@ -150,6 +150,8 @@ int32_t sse_rhs(sse_handle* h, const double* d_u, double* d_dudt, double t);
    (NCCL) into sse_halo_recv_buffer; pass B (time_derivative!, Solvers.jl:509-511) runs on the
    element range [first, first+count).  Second-order laws have an extra aux pass + exchange. */
 int32_t sse_rhs_pass_a(sse_handle* h, const double* d_u);
+/* pass A on the element range [first, first+count): lets a host-buffer caller overlap the upload of u with pass A */
+int32_t sse_rhs_pass_a_range(sse_handle* h, const double* d_u, int64_t first, int64_t count);
 int32_t sse_rhs_pass_aux(sse_handle* h, double* d_dudt, int64_t first, int64_t count);
 int32_t sse_rhs_pass_b(sse_handle* h, double* d_dudt, int64_t first, int64_t count);
 /* halo plumbing: the send list holds 1-based linear indices into the owned (N_f, N_e) facet array */

@@ -19,6 +19,13 @@ struct CtDev {
     double nref[12];        // d x N_fac reference normals
 };
 
+// optional 2N-storage Runge-Kutta stage fused into the projection epilogue: tmp = A tmp + dt dudt; u += B tmp
+struct RkStage {
+    double* u = nullptr;
+    double* tmp = nullptr;
+    double A = 0.0, B = 0.0, dt = 0.0;
+};
+
 struct CtPlan {
     int ok = 0, N = 0;
     int kind = 0;                   // 0: Euler flux differencing; 1: linear advection, StandardForm + ReferenceOperators
@@ -35,13 +42,13 @@ bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& t
 // advection + StandardForm + ReferenceOperators on ModalTensor tets; fills D1 and fR (host images) on success
 bool ct_eligible_standard(const sse_config& cfg, const sse_arrays& a, int* Nout, std::vector<double>& D1, std::vector<double>& fR);
 void ct_standard(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
-                 double* dudt, cudaStream_t s);
+                 double* dudt, cudaStream_t s, RkStage rk = RkStage());
 // true when the generic tables of tp equal the closed-form schedule k_fluxdiff_ct hard-codes
 bool ct_schedule_matches(const TensorPlan& tp, int N);
 cudaError_t ct_set_attrs(int N);
 void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q, double* u_f,
               cudaStream_t s);
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
-                 double* u_q, const double* u_f, double* dudt, cudaStream_t s);
+                 double* u_q, const double* u_f, double* dudt, cudaStream_t s, RkStage rk = RkStage());
 
 }  // namespace sse

@@ -143,9 +143,13 @@ template <int N, int NC> struct ProjSmem {
     static constexpr int EPB = NG / NC;                            // elements per CTA
     static_assert(NG % NC == 0, "groups must split evenly into elements");
     static constexpr int NNZ = 3 * N * N * N + N * N * N * N;      // non-zeros of R on the collapsed tet
+    // group strides of the nodal tile and of the V' partials, padded to N (mod 16) doubles so that the N-lane groups of
+    // a warp fall on disjoint bank ranges (an un-padded 125 / 175 makes neighbouring groups overlap: 2-way conflicts)
+    static constexpr int QS = T::Nq + ((N - T::Nq % 16) % 16 + 16) % 16;
+    static constexpr int RS = T::Np * N + ((N - (T::Np * N) % 16) % 16 + 16) % 16;
     static constexpr int x = 0;                                    // [NG][Np]
     static constexpr int big = x + NG * T::Np;                     // union: q [NG][Nq]  |  red [NG][Np][N]
-    static constexpr int big_sz = (NG * T::Nq > NG * T::Np * N) ? NG * T::Nq : NG * T::Np * N;
+    static constexpr int big_sz = (NG * QS > NG * RS) ? NG * QS : NG * RS;
     static constexpr int wij = big + big_sz;                       // [EPB][Nq]  W / J
     static constexpr int c3 = wij + EPB * T::Nq;                   // [Np][N]    C tensor, a3 fastest
     static constexpr int rval = c3 + T::Np * N;                    // [NNZ]      R values (CSR by facet node)
@@ -194,7 +198,7 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
 #pragma unroll
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
-            for (int a2 = 0; a2 < N; a2++) s_q[grp * Nq + (a1 * N + a2) * N + a3] = y[a1][a2];
+            for (int a2 = 0; a2 < N; a2++) s_q[grp * S::QS + (a1 * N + a2) * N + a3] = y[a1][a2];
     }
     __syncthreads();
     if constexpr (PROJECT) {
@@ -203,13 +207,13 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
         const int el = it / Nq, i = it - el * Nq;
         double ui[NC], wi[NC];
 #pragma unroll
-        for (int e = 0; e < NC; e++) ui[e] = s_q[(el * NC + e) * Nq + i];
+        for (int e = 0; e < NC; e++) ui[e] = s_q[(el * NC + e) * S::QS + i];
         cons_to_entropy<D, NC>(L, ui, wi);
         const double J = g.J_q[(size_t)(e0 + el) * Nq + i], W = t.W[i];
         const double wj = W * J;
         s_wij[el * Nq + i] = W * rcp_fast(J);
 #pragma unroll
-        for (int e = 0; e < NC; e++) s_q[(el * NC + e) * Nq + i] = wi[e] * wj;
+        for (int e = 0; e < NC; e++) s_q[(el * NC + e) * S::QS + i] = wi[e] * wj;
     }
     __syncthreads();
     // w = V' w_q
@@ -217,14 +221,14 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
 #pragma unroll
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
-            for (int a2 = 0; a2 < N; a2++) y[a1][a2] = s_q[grp * Nq + (a1 * N + a2) * N + a3];
+            for (int a2 = 0; a2 < N; a2++) y[a1][a2] = s_q[grp * S::QS + (a1 * N + a2) * N + a3];
     }
     __syncthreads();                                   // s_red aliases s_q
     double out[T::LPT];
-    if (act) sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * Np * N + a3);
+    if (act) sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3);
     __syncthreads();
     if (act) {
-        sf3_bwd_reduce<N>(s_red + grp * Np * N, a3, out);
+        sf3_bwd_reduce<N>(s_red + grp * S::RS, a3, out);
 #pragma unroll
         for (int q = 0; q < T::LPT; q++) { const int l = a3 * T::LPT + q; if (l < Np) s_x[grp * Np + l] = out[q]; }
     }
@@ -237,11 +241,11 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= wij[(a1 * N + a2) * N + a3];
-        sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * Np * N + a3);
+        sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3);
     }
     __syncthreads();
     if (act) {
-        sf3_bwd_reduce<N>(s_red + grp * Np * N, a3, out);
+        sf3_bwd_reduce<N>(s_red + grp * S::RS, a3, out);
 #pragma unroll
         for (int q = 0; q < T::LPT; q++) { const int l = a3 * T::LPT + q; if (l < Np) s_x[grp * Np + l] = out[q]; }
     }
@@ -252,7 +256,7 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
 #pragma unroll
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
-            for (int a2 = 0; a2 < N; a2++) s_q[grp * Nq + (a1 * N + a2) * N + a3] = y[a1][a2];
+            for (int a2 = 0; a2 < N; a2++) s_q[grp * S::QS + (a1 * N + a2) * N + a3] = y[a1][a2];
     }
     __syncthreads();
     }
@@ -262,7 +266,7 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
         double wi[NC], ui[NC];
         if (i < Nq) {
 #pragma unroll
-            for (int e = 0; e < NC; e++) wi[e] = s_q[(el * NC + e) * Nq + i];
+            for (int e = 0; e < NC; e++) wi[e] = s_q[(el * NC + e) * S::QS + i];
             if constexpr (PROJECT) entropy_to_cons<D, NC>(L, wi, ui);
             else {
 #pragma unroll
@@ -278,7 +282,7 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
                 const double rv = s_rval[q];
                 const int c = s_ridx[q];
 #pragma unroll
-                for (int e = 0; e < NC; e++) wi[e] = fma(rv, s_q[(el * NC + e) * Nq + c], wi[e]);
+                for (int e = 0; e < NC; e++) wi[e] = fma(rv, s_q[(el * NC + e) * S::QS + c], wi[e]);
             }
             if constexpr (PROJECT) entropy_to_cons<D, NC>(L, wi, ui);
             else {
@@ -295,7 +299,8 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
 // pass B-2 — dudt = M^-1 V' r_q     (r_q sits in the u_q scratch)
 template <int N, int NC, int MINB>
 __global__ void __launch_bounds__(ProjSmem<N, NC>::WARPS * 32, MINB)
-k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, const double* __restrict__ r_q, double* __restrict__ dudt) {
+k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, const double* __restrict__ r_q, double* __restrict__ dudt,
+             RkStage rk) {
     using T = Tet<N>;
     using S = ProjSmem<N, NC>;
     constexpr int Nq = T::Nq, Np = T::Np, EPB = S::EPB;
@@ -329,10 +334,10 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
         s_wij[it] = t.W[i] * rcp_fast(g.J_q[(size_t)(e0 + el) * Nq + i]);
     }
     __syncthreads();
-    if (act) sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * Np * N + a3);
+    if (act) sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3);
     __syncthreads();
     if (act) {
-        sf3_bwd_reduce<N>(s_red + grp * Np * N, a3, out);
+        sf3_bwd_reduce<N>(s_red + grp * S::RS, a3, out);
 #pragma unroll
         for (int q = 0; q < T::LPT; q++) { const int l = a3 * T::LPT + q; if (l < Np) s_x[grp * Np + l] = out[q]; }
     }
@@ -344,15 +349,23 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= wij[(a1 * N + a2) * N + a3];
-        sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * Np * N + a3);
+        sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3);
     }
     __syncthreads();
     if (act) {
-        sf3_bwd_reduce<N>(s_red + grp * Np * N, a3, out);
+        sf3_bwd_reduce<N>(s_red + grp * S::RS, a3, out);
 #pragma unroll
         for (int q = 0; q < T::LPT; q++) {
             const int l = a3 * T::LPT + q;
-            if (l < Np) dudt[(size_t)e0 * NC * Np + grp * Np + l] = out[q];
+            if (l < Np) {
+                const size_t idx = (size_t)e0 * NC * Np + grp * Np + l;
+                dudt[idx] = out[q];
+                if (rk.u) {                        // fused 2N-storage RK stage (Carpenter & Kennedy 1994)
+                    const double tm = fma(rk.A, rk.tmp[idx], rk.dt * out[q]);
+                    rk.tmp[idx] = tm;
+                    rk.u[idx] = fma(rk.B, tm, rk.u[idx]);
+                }
+            }
         }
     }
 }

@@ -497,7 +497,12 @@ extern "C" int32_t sse_rhs_pass_aux(sse_handle* h, double* d_dudt, int64_t first
     return SSE_OK;
 }
 
+static int32_t pass_b_impl(sse_handle* h, double* d_dudt, int64_t first, int64_t count, RkStage rk);
 extern "C" int32_t sse_rhs_pass_b(sse_handle* h, double* d_dudt, int64_t first, int64_t count) {
+    return pass_b_impl(h, d_dudt, first, count, RkStage());
+}
+// rk.u != nullptr: the caller asks for the 2N-storage stage update to be fused; *fused reports whether it was
+static int32_t pass_b_impl(sse_handle* h, double* d_dudt, int64_t first, int64_t count, RkStage rk) {
     if (!h || !d_dudt) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
     if (count <= 0) return SSE_OK;
     if (first < 0 || first + count > h->cfg.N_e) return fail(SSE_ERR_BAD_ARGUMENT, "element range out of bounds");
@@ -505,7 +510,7 @@ extern "C" int32_t sse_rhs_pass_b(sse_handle* h, double* d_dudt, int64_t first, 
     const unsigned n = (unsigned)count;
     if (h->cfg.form == SSE_FORM_FLUX_DIFFERENCING) {
         if (h->variant == 1 && h->ct.ok) {
-            ct_fluxdiff(h->ct, h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream);
+            ct_fluxdiff(h->ct, h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream, rk);
         } else if (use_tensor(h) && h->tp.has_fluxdiff) {
 #define LA(D_, NC_) tensor_launch_fluxdiff<D_, NC_>(h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->sm_count, h->stream)
             DISPATCH_DNC(h, LA);
@@ -516,7 +521,7 @@ extern "C" int32_t sse_rhs_pass_b(sse_handle* h, double* d_dudt, int64_t first, 
 #undef LA
         }
     } else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE && h->variant == 1 && h->ct.ok && h->ct.kind == 1) {
-        ct_standard(h->ct, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream);
+        ct_standard(h->ct, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream, rk);
     } else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE) {
 #define LA(D_, NC_) k_time_standard_reference<D_, NC_><<<n, h->threads, h->smem_time, h->stream>>>(h->ops, h->geo, h->law, first, h->u_q, h->u_f, d_dudt)
         DISPATCH_DNC(h, LA);
@@ -614,12 +619,26 @@ static const double CK_B[5] = {1432997174477.0 / 9575080441755.0, 5161836677717.
                                2277821191437.0 / 14882151754819.0};
 static const double CK_C[5] = {0.0, 1432997174477.0 / 9575080441755.0, 2526269341429.0 / 6820363962896.0,
                                2006345519317.0 / 3224310063776.0, 2802321613138.0 / 2924317926251.0};
+// semi_discrete_residual! followed by one 2N-storage stage; on the compile-time path the stage update rides in the
+// epilogue of the projection kernel (no extra launch, dudt is not re-read)
+extern "C" int32_t sse_rhs_lsrk(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double A, double B, double dt, double t) {
+    (void)t;
+    if (!h || !d_u || !d_tmp || !d_dudt) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    if (h->cfg.N_ghost != 0) return fail(SSE_ERR_COMM, "handle has ghost facets: drive pass_a / halo exchange / pass_b explicitly");
+    int32_t rc;
+    if ((rc = sse_rhs_pass_a(h, d_u))) return rc;
+    if ((rc = sse_rhs_pass_aux(h, d_dudt, 0, h->cfg.N_e))) return rc;
+    const bool fused = h->variant == 1 && h->ct.ok;
+    RkStage rk;
+    if (fused) { rk.u = d_u; rk.tmp = d_tmp; rk.A = A; rk.B = B; rk.dt = dt; }
+    if ((rc = pass_b_impl(h, d_dudt, 0, h->cfg.N_e, rk))) return rc;
+    if (!fused) return sse_lsrk_stage(h, d_u, d_tmp, d_dudt, A, B, dt);
+    return SSE_OK;
+}
 extern "C" int32_t sse_step_ck54(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double t, double dt) {
     int32_t rc;
-    for (int s = 0; s < 5; s++) {
-        if ((rc = sse_rhs(h, d_u, d_dudt, t + CK_C[s] * dt))) return rc;
-        if ((rc = sse_lsrk_stage(h, d_u, d_tmp, d_dudt, CK_A[s], CK_B[s], dt))) return rc;
-    }
+    for (int s = 0; s < 5; s++)
+        if ((rc = sse_rhs_lsrk(h, d_u, d_tmp, d_dudt, CK_A[s], CK_B[s], dt, t + CK_C[s] * dt))) return rc;
     return SSE_OK;
 }
 

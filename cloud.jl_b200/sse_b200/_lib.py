@@ -39,6 +39,7 @@ SYMBOLS = {
     "sse_halo_unpack": (C.c_int32, [_h, C.c_int32]),
     "sse_axpby": (C.c_int32, [_h, C.c_double, C.c_void_p, C.c_double, C.c_void_p]),
     "sse_lsrk_stage": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double]),
+    "sse_rhs_lsrk": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]),
     "sse_step_ck54": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]),
     "sse_functionals": (C.c_int32, [_h, C.c_void_p, C.c_void_p, _pd]),
     "sse_synchronize": (C.c_int32, [_h]),

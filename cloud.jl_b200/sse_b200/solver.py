@@ -194,10 +194,16 @@ class Solver:
                                             self._check_state(dudt, "dudt"), A, B, dt))
         self.launches += 1
 
+    def rhs_lsrk(self, u, tmp, dudt, A, B, dt, t=0.0):
+        """Residual + one 2N-storage RK stage (fused on the compile-time kernel path)."""
+        _lib.check(self._lib.sse_rhs_lsrk(self._h, self._check_state(u, "u"), self._check_state(tmp, "tmp"),
+                                          self._check_state(dudt, "dudt"), A, B, dt, float(t)))
+        self.launches += self._per_rhs + (0 if self.kernel_variant() == 2 else 1)
+
     def step_ck54(self, u, tmp, dudt, t, dt):
         _lib.check(self._lib.sse_step_ck54(self._h, self._check_state(u, "u"), self._check_state(tmp, "tmp"),
                                            self._check_state(dudt, "dudt"), t, dt))
-        self.launches += 5 * (self._per_rhs + 1)
+        self.launches += 5 * (self._per_rhs + (0 if self.kernel_variant() == 2 else 1))
 
     def functionals(self, u, dudt) -> np.ndarray:
         out = np.zeros(int(self.cfg.N_c) + 2)

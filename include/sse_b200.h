@@ -167,6 +167,9 @@ int32_t sse_axpby(sse_handle* h, double a, const double* d_x, double b, double* 
 /* 2N low-storage RK stage: tmp = A*tmp + dt*dudt ; u += B*tmp   (CarpenterKennedy2N54 stage) */
 int32_t sse_lsrk_stage(sse_handle* h, double* d_u, double* d_tmp, const double* d_dudt,
                        double A, double B, double dt);
+/* semi_discrete_residual! + one 2N-storage stage in one call; on the compile-time kernel path the stage update is fused
+   into the epilogue of the projection kernel, so the state is updated where dudt is produced */
+int32_t sse_rhs_lsrk(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double A, double B, double dt, double t);
 /* one full CarpenterKennedy2N54 step on device (single GPU) */
 int32_t sse_step_ck54(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double t, double dt);
 /* conservation / energy / entropy residuals of Analysis/conservation.jl:145-189.

@@ -134,10 +134,6 @@ __device__ void mass_solve(const Ops& o, const Geo& g, long long k, double* rhs,
     apply_Vt<NC>(o, tq, rhs, zb, wb);
 }
 
-struct SmemPlan {       // offsets in doubles into the dynamic shared array
-    int u, a, b, f, f2, z, w, lam, nf, fq, total;
-};
-
 __host__ __device__ inline int warp_z_size(const Ops& o, int NC) { return o.v_kind == SSE_V_WARPED ? NC * o.P1 * o.P1 * o.M3 : 0; }
 __host__ __device__ inline int warp_w_size(const Ops& o, int NC) { return o.v_kind == SSE_V_WARPED ? NC * o.P1 * o.M2 * o.M3 : 0; }
 

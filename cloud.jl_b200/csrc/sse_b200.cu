@@ -728,6 +728,12 @@ extern "C" int32_t sse_plan_selfcheck(const sse_config* cfg, const sse_arrays* a
     for (int i = 0; i < 8; i++) info[i] = 0;
     *max_err = 0.0;
     info[0] = tp.ok;
+    {   // 2: compile-time flux-differencing kernels, 3: compile-time advection StandardForm kernels
+        int N = 0;
+        std::vector<double> D1, fR;
+        if (tp.ok && ct_eligible(*cfg, *arr, tp, &N) && ct_schedule_matches(tp, N)) info[0] = 2;
+        else if (ct_eligible_standard(*cfg, *arr, &N, D1, fR)) { info[0] = 3; info[1] = 128; return SSE_OK; }
+    }
     if (!tp.ok) return SSE_OK;
     info[1] = tp.threads; info[2] = tp.dev.n_vrounds; info[3] = tp.dev.n_frounds;
     info[4] = tp.dev.red_items_max; info[5] = tp.dev.red_max; info[6] = (int32_t)tp.smem_fluxdiff;

@@ -184,7 +184,8 @@ int32_t sse_abi_version(void);
 /* scratch views for testing/analysis: u_q (N_q,N_c,N_e) and u_f (N_f,N_e+ghost,N_c) device pointers */
 int32_t sse_debug_views(sse_handle* h, double** d_u_q, double** d_u_f);
 /* host-only diagnostic: build the tensor-line pair schedule for (cfg, arr) and replay it against S and C.
-   info[0..7] = {specialised?, threads per CTA, volume rounds, facet sub-rounds, reducer items max, reducer
+   info[0..7] = {kernel family (0 generic, 1 tensor-line, 2 compile-time flux differencing, 3 compile-time advection
+   StandardForm), threads per CTA, volume rounds, facet sub-rounds, reducer items max, reducer
    sources max, shared-memory bytes, two-point flux evaluations per element}; max_err = largest deviation of
    the replayed S_m / C from the operators passed in (0 when every pair is visited exactly once). */
 int32_t sse_plan_selfcheck(const sse_config* cfg, const sse_arrays* arr, int32_t* info, double* max_err);

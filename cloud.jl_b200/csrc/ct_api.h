@@ -12,8 +12,8 @@ struct CtDev {
     SpMat R, Rt;
     long long Ne;
     // flux-differencing schedule weights (partners are closed-form in the kernel)
-    const double* vS;       // [volume round][m][Nq]  skew-extended S_m[i, partner]
-    const double* fC;       // [facet sub-round][Nq]  C[i, partner]
+    const double* vS;       // [volume round][m][Nq]  skew-extended S_m[i, partner] / 4   (scaled pair flux, kernels_ct.cuh)
+    const double* fC;       // [facet sub-round][Nq]  C[i, partner] / 8
     const double* fR;       // [facet sub-round][Nq]  R[partner, i]
     const double* Bf;       // [Nf]
     double nref[12];        // d x N_fac reference normals

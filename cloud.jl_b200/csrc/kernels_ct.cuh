@@ -384,24 +384,52 @@ template <int N, bool DUAL = false> struct FdSmem {
     static constexpr int total = stage + (DUAL ? 4 : 2) * NC * T::Nq;
 };
 
-// Ranocha's EC flux contracted with g, from primitives (rho, V, p, beta), log-means sharing reciprocals
+// Ranocha's EC flux (euler_navierstokes.jl:171-195) contracted with g, in the scaled form of the compile-time kernels:
+// primitives are (rho, V, 2p, rho/p) and gq = g / 4, so that every factor 1/2 of the averages is a power-of-two scaling
+// folded into the tables (exact) instead of a multiplication:
+//   rho_hat (ga + gb)/2 = lm2 (gqa + gqb),  p_avg g = (2pa + 2pb) gq,  (pa gb + pb ga)/2 = 2pa gqb + 2pb gqa,
+//   mf C = (mf/2) (Va.Vb + cc2 ilm105).
 template <int D>
-__device__ __forceinline__ void ec_contract_fast(const double* a, const double* b, const double* g, double igm1, double* phi) {
-    double rho_hat, ilm;
-    logmean_pair(a[0], b[0], a[D + 2], b[D + 2], rho_hat, ilm);
+__device__ __forceinline__ void ec_finish_scaled(const Law& L, const double* a, const double* b, const double* gq, double lm2, double ilm105,
+                                                 double* phi) {
     double dot = 0.0, ga = 0.0, gb = 0.0;
 #pragma unroll
-    for (int m = 0; m < D; m++) { dot = fma(a[1 + m], b[1 + m], dot); ga = fma(g[m], a[1 + m], ga); gb = fma(g[m], b[1 + m], gb); }
-    const double Cc = fma(igm1, ilm, 0.5 * dot);
-    const double mf = rho_hat * (0.5 * (ga + gb));
-    const double p_avg = 0.5 * (a[D + 1] + b[D + 1]);
+    for (int m = 0; m < D; m++) { dot = fma(a[1 + m], b[1 + m], dot); ga = fma(gq[m], a[1 + m], ga); gb = fma(gq[m], b[1 + m], gb); }
+    const double C2 = fma(L.cc2, ilm105, dot);
+    const double mf = lm2 * (ga + gb);
+    const double mfh = 0.5 * mf;
+    const double ps = a[D + 1] + b[D + 1];
     phi[0] = mf;
 #pragma unroll
-    for (int m = 0; m < D; m++) phi[1 + m] = fma(mf, 0.5 * (a[1 + m] + b[1 + m]), p_avg * g[m]);
-    phi[D + 1] = fma(mf, Cc, 0.5 * fma(a[D + 1], gb, b[D + 1] * ga));
+    for (int m = 0; m < D; m++) phi[1 + m] = fma(mfh, a[1 + m] + b[1 + m], ps * gq[m]);
+    phi[D + 1] = fma(mfh, C2, fma(a[D + 1], gb, b[D + 1] * ga));
+}
+template <int D>
+__device__ __forceinline__ void ec_contract_scaled(const Law& L, const double* a, const double* b, const double* gq, double* phi) {
+    double lm2, ilm105;
+    if (logmean_pair_scaled(L, a[0], b[0], a[D + 2], b[D + 2], lm2, ilm105) >= 1.0e-4) {
+        const double2 v = logmean_pair_scaled_slow(a[0], b[0], a[D + 2], b[D + 2], lm2, ilm105);
+        lm2 = v.x; ilm105 = v.y;
+    }
+    ec_finish_scaled<D>(L, a, b, gq, lm2, ilm105, phi);
+}
+// two pairs sharing the left state, one (rare) out-of-line branch for both
+template <int D>
+__device__ __forceinline__ void ec_contract_scaled2(const Law& L, const double* a, const double* bA, const double* bB, const double* gA,
+                                                    const double* gB, double* pA, double* pB) {
+    double lmA, ilA, lmB, ilB;
+    const double fA = logmean_pair_scaled(L, a[0], bA[0], a[D + 2], bA[D + 2], lmA, ilA);
+    const double fB = logmean_pair_scaled(L, a[0], bB[0], a[D + 2], bB[D + 2], lmB, ilB);
+    if (fmax(fA, fB) >= 1.0e-4) {
+        const double2 vA = logmean_pair_scaled_slow(a[0], bA[0], a[D + 2], bA[D + 2], lmA, ilA);
+        const double2 vB = logmean_pair_scaled_slow(a[0], bB[0], a[D + 2], bB[D + 2], lmB, ilB);
+        lmA = vA.x; ilA = vA.y; lmB = vB.x; ilB = vB.y;
+    }
+    ec_finish_scaled<D>(L, a, bA, gA, lmA, ilA, pA);
+    ec_finish_scaled<D>(L, a, bB, gB, lmB, ilB, pB);
 }
 
-// conservative -> (rho, V, p, rho/p); returns 1/rho
+// conservative -> (rho, V, 2p, rho/p); returns 1/rho
 template <int D>
 __device__ __forceinline__ double to_prim_fast(const Law& L, const double* u, double* q) {
     const double ir = rcp_fast(u[0]);
@@ -409,8 +437,9 @@ __device__ __forceinline__ double to_prim_fast(const Law& L, const double* u, do
     q[0] = u[0];
 #pragma unroll
     for (int m = 0; m < D; m++) { q[1 + m] = u[1 + m] * ir; s = fma(q[1 + m], q[1 + m], s); }
-    q[D + 1] = L.gm1 * (u[D + 1] - 0.5 * u[0] * s);
-    q[D + 2] = u[0] * rcp_fast(q[D + 1]);
+    const double p = L.gm1 * (u[D + 1] - 0.5 * u[0] * s);
+    q[D + 1] = 2.0 * p;
+    q[D + 2] = u[0] * rcp_fast(p);
     return ir;
 }
 
@@ -481,18 +510,23 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
         for (int m = 0; m < D; m++) {
             const double nj = __ldcs(g.nJf + m + D * ((size_t)k * Nf + j));
             nf[m] = nj * ijf;                      // n_f = nJf / J_f            operators.jl:59
-            s_hnf[m * Nf + j] = 0.5 * nj;          // halfnJf                    operators.jl:78
+            s_hnf[m * Nf + j] = nj;                // 2 halfnJf (operators.jl:78); the 1/2 lives in the fC table
         }
         const double ira = to_prim_fast<D>(L, ui, qa);
         const double irb = to_prim_fast<D>(L, uo, qb);
 #pragma unroll
         for (int c = 0; c < NP; c++) s_fprim[c * Nf + j] = qa[c];
-        ec_contract_fast<D>(qa, qb, nf, L.igm1, phi);          // F#(u-, u+) . n    ConservationLaws.jl:75-128
+        {
+            double nfq[D];
+#pragma unroll
+            for (int m = 0; m < D; m++) nfq[m] = 0.25 * nf[m];
+            ec_contract_scaled<D>(L, qa, qb, nfq, phi);        // F#(u-, u+) . n    ConservationLaws.jl:75-128
+        }
         if (L.inviscid == SSE_FLUX_LAX_FRIEDRICHS) {
             double vni = 0.0, vno = 0.0;
 #pragma unroll
             for (int m = 0; m < D; m++) { vni = fma(qa[1 + m], nf[m], vni); vno = fma(qb[1 + m], nf[m], vno); }
-            const double ci = sqrt(L.gamma * qa[D + 1] * ira), co = sqrt(L.gamma * qb[D + 1] * irb);
+            const double ci = sqrt(L.gamma * (0.5 * qa[D + 1]) * ira), co = sqrt(L.gamma * (0.5 * qb[D + 1]) * irb);
             const double a = L.half_lambda * (fmax(fabs(vni), fabs(vno)) + fmax(ci, co));
 #pragma unroll
             for (int e = 0; e < NC; e++) phi[e] = fma(a, ui[e] - uo[e], phi[e]);
@@ -541,8 +575,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
                 }
 #pragma unroll
                 for (int c = 0; c < NP; c++) { qA[c] = s_prim[c * Nq + jA]; qB[c] = s_prim[c * Nq + jB]; }
-                ec_contract_fast<D>(qi, qA, gA, L.igm1, pA);
-                ec_contract_fast<D>(qi, qB, gB, L.igm1, pB);
+                ec_contract_scaled2<D>(L, qi, qA, qB, gA, gB, pA, pB);
 #pragma unroll
                 for (int e = 0; e < NC; e++) { r[e] -= pA[e] + pB[e]; stA[e * Nq + jA] = pA[e]; stB[e * Nq + jB] = pB[e]; }
             }
@@ -555,6 +588,9 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
             for (int m = 0; m < D; m++) { sw[m] = swnA[m]; swb[m] = swnB[m]; }
         }
         double cwA = node ? t.fC[tid] : 0.0, cwB = node ? t.fC[Nq + tid] : 0.0;
+        static_assert(NN * NC == Nq, "reducer items = volume nodes");
+        const int re = tid / NN, rjj = tid - re * NN, rx = rjj / N, ry = rjj - rx * N;
+        int rc3 = ry ? N - ry : 0;          // volume column (fr - 3 - y) mod N feeding facet node (x, y) of face 4, sub-round 3
 #pragma unroll 1
         for (int fr = 0; fr < NFR; fr += 2, buf ^= 1) {
             double* stA = s_stage + (2 * buf) * NC * Nq;
@@ -567,13 +603,13 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
 #pragma unroll
                 for (int n = 0; n < D; n++) {
                     if (g.nJq) {
-                        hA[n] = 0.5 * g.nJq[n + D * (fA + (size_t)4 * (tid + (size_t)Nq * k))];
-                        hB[n] = 0.5 * g.nJq[n + D * (fB + (size_t)4 * (tid + (size_t)Nq * k))];
+                        hA[n] = g.nJq[n + D * (fA + (size_t)4 * (tid + (size_t)Nq * k))];
+                        hB[n] = g.nJq[n + D * (fB + (size_t)4 * (tid + (size_t)Nq * k))];
                     } else {
                         double sa = 0.0, sb = 0.0;
 #pragma unroll
                         for (int l = 0; l < D; l++) { sa = fma(lam[l][n], t.nref[l + D * fA], sa); sb = fma(lam[l][n], t.nref[l + D * fB], sb); }
-                        hA[n] = 0.5 * sa; hB[n] = 0.5 * sb;
+                        hA[n] = sa; hB[n] = sb;
                     }
                 }
                 const int jA = facet_partner<N>(fr, ca, cb, cc), jB = facet_partner<N>(fr + 1, ca, cb, cc);
@@ -582,37 +618,30 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
                 for (int n = 0; n < D; n++) { gA[n] = cwA * (s_hnf[n * Nf + jA] + hA[n]); gB[n] = cwB * (s_hnf[n * Nf + jB] + hB[n]); }
 #pragma unroll
                 for (int c = 0; c < NP; c++) { qA[c] = s_fprim[c * Nf + jA]; qB[c] = s_fprim[c * Nf + jB]; }
-                ec_contract_fast<D>(qi, qA, gA, L.igm1, pA);
-                ec_contract_fast<D>(qi, qB, gB, L.igm1, pB);
+                ec_contract_scaled2<D>(L, qi, qA, qB, gA, gB, pA, pB);
 #pragma unroll
                 for (int e = 0; e < NC; e++) { r[e] -= pA[e] + pB[e]; stA[e * Nq + tid] = pA[e]; stB[e * Nq + tid] = pB[e]; }
             }
             cwA = cwnA; cwB = cwnB;
             __syncthreads();
-            if (fA != fB) {                 // two different faces: independent targets
-                for (int q = tid; q < 2 * NN * NC; q += blockDim.x) {
-                    const int which = q / (NN * NC), qq = q - which * NN * NC;
-                    const int frq = fr + which, f = which ? fB : fA;
-                    const double* st = which ? stB : stA;
-                    const int e = qq / NN, jj = qq - e * NN, x = jj / N, y = jj - x * N;
-                    int base, stride;
-                    if (frq == 0) { base = x * NN + y; stride = N; }
-                    else if (frq < 3) { base = jj; stride = NN; }
-                    else { int c = (frq - 3) - y; if (c < 0) c += N; base = x * NN + c; stride = N; }
-                    double s = 0.0;
+            // (facet node, variable) reducers: thread = (re, rjj) sums the N staged vectors of its facet node, for the
+            // face of either sub-round; with N = N_c = 5 there are exactly N^3 such items per face
+            if (node) {
+                double sA = 0.0, sB = 0.0;
+                if (fA != fB) {             // two different faces: independent targets
+                    int bA, dA, bB, dB;
+                    if (fr == 0) { bA = rx * NN + ry; dA = N; bB = rjj; dB = NN; }
+                    else { bA = rjj; dA = NN; bB = rx * NN + rc3; dB = N; rc3 = rc3 + 1 == N ? 0 : rc3 + 1; }
 #pragma unroll
-                    for (int i = 0; i < N; i++) s += st[e * Nq + base + i * stride];
-                    s_ff[e * Nf + f * NN + jj] -= s;
-                }
-            } else {                        // both sub-rounds feed face 4: one reducer sums both stages
-                for (int q = tid; q < NN * NC; q += blockDim.x) {
-                    const int e = q / NN, jj = q - e * NN, x = jj / N, y = jj - x * N;
-                    int cA = (fr - 3) - y; if (cA < 0) cA += N;
-                    int cB = (fr - 2) - y; if (cB < 0) cB += N;
-                    double s = 0.0;
+                    for (int i = 0; i < N; i++) { sA += stA[re * Nq + bA + i * dA]; sB += stB[re * Nq + bB + i * dB]; }
+                    s_ff[re * Nf + fA * NN + rjj] -= sA;
+                    s_ff[re * Nf + fB * NN + rjj] -= sB;
+                } else {                    // both sub-rounds feed face 4: one reducer sums both stages
+                    const int cA = rc3, cB = cA + 1 == N ? 0 : cA + 1;
+                    rc3 = cB + 1 == N ? 0 : cB + 1;
 #pragma unroll
-                    for (int i = 0; i < N; i++) s += stA[e * Nq + x * NN + cA + i * N] + stB[e * Nq + x * NN + cB + i * N];
-                    s_ff[e * Nf + 3 * NN + jj] -= s;
+                    for (int i = 0; i < N; i++) { sA += stA[re * Nq + rx * NN + cA + i * N]; sB += stB[re * Nq + rx * NN + cB + i * N]; }
+                    s_ff[re * Nf + 3 * NN + rjj] -= sA + sB;
                 }
             }
             __syncthreads();      // two reducers of one iteration may hit the same facet node only across iterations
@@ -648,7 +677,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
             }
 #pragma unroll
             for (int c = 0; c < NP; c++) qj[c] = s_prim[c * Nq + j];
-            ec_contract_fast<D>(qi, qj, gv, L.igm1, phi);
+            ec_contract_scaled<D>(L, qi, qj, gv, phi);
 #pragma unroll
             for (int e = 0; e < NC; e++) { r[e] -= phi[e]; st[e * Nq + j] = phi[e]; }
         }
@@ -672,17 +701,17 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
         const int f = fr < 3 ? fr : 3;
         const double cwn = (node && fr + 1 < NFR) ? t.fC[(fr + 1) * Nq + tid] : 0.0;
         if (node) {
-            if (fr <= 3) {                         // halfnJq[:, f, i] = 0.5 sum_l Lambda[i,l,:] nref[l,f]   mesh.jl:262-269
+            if (fr <= 3) {                         // 2 halfnJq[:, f, i] = sum_l Lambda[i,l,:] nref[l,f]   mesh.jl:262-269
                 if (g.nJq) {
 #pragma unroll
-                    for (int n = 0; n < D; n++) hq[n] = 0.5 * g.nJq[n + D * (f + (size_t)4 * (tid + (size_t)Nq * k))];
+                    for (int n = 0; n < D; n++) hq[n] = g.nJq[n + D * (f + (size_t)4 * (tid + (size_t)Nq * k))];
                 } else {
 #pragma unroll
                     for (int n = 0; n < D; n++) {
                         double s = 0.0;
 #pragma unroll
                         for (int l = 0; l < D; l++) s = fma(lam[l][n], t.nref[l + D * f], s);
-                        hq[n] = 0.5 * s;
+                        hq[n] = s;
                     }
                 }
             }
@@ -692,7 +721,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
             for (int n = 0; n < D; n++) gv[n] = cw * (s_hnf[n * Nf + j] + hq[n]);
 #pragma unroll
             for (int c = 0; c < NP; c++) qj[c] = s_fprim[c * Nf + j];
-            ec_contract_fast<D>(qi, qj, gv, L.igm1, phi);
+            ec_contract_scaled<D>(L, qi, qj, gv, phi);
 #pragma unroll
             for (int e = 0; e < NC; e++) { r[e] -= phi[e]; st[e * Nq + tid] = phi[e]; }
         }

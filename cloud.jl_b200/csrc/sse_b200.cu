@@ -296,6 +296,7 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
     L.half_lambda = cfg->half_lambda; L.b = cfg->b;
     for (int m = 0; m < 3; m++) L.a[m] = cfg->a[m];
     L.gamma = cfg->gamma; L.gm1 = cfg->gamma - 1.0; L.igm1 = 1.0 / (cfg->gamma - 1.0); L.log_gm1 = std::log(cfg->gamma - 1.0);
+    L.lmq[0] = -1.0 / 3.0; L.lmq[1] = -4.0 / 45.0; L.lmq[2] = -44.0 / 945.0; L.cc2 = 2.0 / (105.0 * (cfg->gamma - 1.0));
     h->second_order = (cfg->pde == SSE_PDE_ADVECTION_DIFFUSION);
     if (h->second_order && cfg->form != SSE_FORM_STANDARD_PHYSICAL)
         return fail(SSE_ERR_UNSUPPORTED, "second-order laws are only implemented with PhysicalOperators (Solvers.jl:357-376)");
@@ -335,7 +336,13 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
             h->ct.A.assign(a->A, a->A + N * N);
             h->ct.B.assign(a->B, a->B + N * N * N);
             h->ct.dev.C = o.C; h->ct.dev.W = o.W; h->ct.dev.R = o.R; h->ct.dev.Rt = o.Rt; h->ct.dev.Ne = Ne;
-            h->ct.dev.vS = h->tp.dev.v_S; h->ct.dev.fC = h->tp.dev.f_C; h->ct.dev.Bf = o.Bf;
+            h->ct.dev.Bf = o.Bf;
+            {   // power-of-two scalings of the pair weights (exact): see ec_finish_scaled in kernels_ct.cuh
+                std::vector<double> vS(h->tp.v_S), fC(h->tp.f_C);
+                for (double& x : vS) x *= 0.25;
+                for (double& x : fC) x *= 0.125;
+                if ((rc = upload(h, vS, &h->ct.dev.vS)) || (rc = upload(h, fC, &h->ct.dev.fC))) return rc;
+            }
             for (int i = 0; i < 12; i++) h->ct.dev.nref[i] = (i < d * Nfac && a->nref) ? a->nref[i] : 0.0;
             h->ct.fR.assign((size_t)h->tp.dev.n_frounds * Nq, 0.0);
             for (int fr = 0; fr < h->tp.dev.n_frounds; fr++)

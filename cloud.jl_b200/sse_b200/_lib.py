@@ -10,7 +10,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsse_b200.so")
+LIB_PATH = os.environ.get("SSE_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libsse_b200.so")
 
 # every symbol include/sse_b200.h declares: name -> (restype, argtypes)
 _pd = C.POINTER(C.c_double)

@@ -406,27 +406,27 @@ __device__ __forceinline__ void ec_finish_scaled(const Law& L, const double* a, 
 }
 template <int D>
 __device__ __forceinline__ void ec_contract_scaled(const Law& L, const double* a, const double* b, const double* gq, double* phi) {
-    double lm2, ilm105;
-    if (logmean_pair_scaled(L, a[0], b[0], a[D + 2], b[D + 2], lm2, ilm105) >= 1.0e-4) {
-        const double2 v = logmean_pair_scaled_slow(a[0], b[0], a[D + 2], b[D + 2], lm2, ilm105);
-        lm2 = v.x; ilm105 = v.y;
+    LmPair o;
+    if (logmean_pair_scaled(L, a[0], b[0], a[D + 2], b[D + 2], o) >= 1.0e-4) {
+        const double2 v = logmean_pair_scaled_rare(a[0], b[0], a[D + 2], b[D + 2], o.s1, o.is2, o.f1, o.f2);
+        o.lm2 = v.x; o.ilm105 = v.y;
     }
-    ec_finish_scaled<D>(L, a, b, gq, lm2, ilm105, phi);
+    ec_finish_scaled<D>(L, a, b, gq, o.lm2, o.ilm105, phi);
 }
-// two pairs sharing the left state, one (rare) out-of-line branch for both
+// two pairs sharing the left state, one (rare) branch for both
 template <int D>
 __device__ __forceinline__ void ec_contract_scaled2(const Law& L, const double* a, const double* bA, const double* bB, const double* gA,
                                                     const double* gB, double* pA, double* pB) {
-    double lmA, ilA, lmB, ilB;
-    const double fA = logmean_pair_scaled(L, a[0], bA[0], a[D + 2], bA[D + 2], lmA, ilA);
-    const double fB = logmean_pair_scaled(L, a[0], bB[0], a[D + 2], bB[D + 2], lmB, ilB);
+    LmPair oA, oB;
+    const double fA = logmean_pair_scaled(L, a[0], bA[0], a[D + 2], bA[D + 2], oA);
+    const double fB = logmean_pair_scaled(L, a[0], bB[0], a[D + 2], bB[D + 2], oB);
     if (fmax(fA, fB) >= 1.0e-4) {
-        const double2 vA = logmean_pair_scaled_slow(a[0], bA[0], a[D + 2], bA[D + 2], lmA, ilA);
-        const double2 vB = logmean_pair_scaled_slow(a[0], bB[0], a[D + 2], bB[D + 2], lmB, ilB);
-        lmA = vA.x; ilA = vA.y; lmB = vB.x; ilB = vB.y;
+        const double2 vA = logmean_pair_scaled_rare(a[0], bA[0], a[D + 2], bA[D + 2], oA.s1, oA.is2, oA.f1, oA.f2);
+        const double2 vB = logmean_pair_scaled_rare(a[0], bB[0], a[D + 2], bB[D + 2], oB.s1, oB.is2, oB.f1, oB.f2);
+        oA.lm2 = vA.x; oA.ilm105 = vA.y; oB.lm2 = vB.x; oB.ilm105 = vB.y;
     }
-    ec_finish_scaled<D>(L, a, bA, gA, lmA, ilA, pA);
-    ec_finish_scaled<D>(L, a, bB, gB, lmB, ilB, pB);
+    ec_finish_scaled<D>(L, a, bA, gA, oA.lm2, oA.ilm105, pA);
+    ec_finish_scaled<D>(L, a, bB, gB, oB.lm2, oB.ilm105, pB);
 }
 
 // conservative -> (rho, V, 2p, rho/p); returns 1/rho

@@ -13,7 +13,7 @@ import numpy as np
 
 from .assembly import (FluxDifferencingForm, PHYSICAL_OPERATOR, REFERENCE_OPERATOR, SpatialDiscretization,
                        StandardForm, assemble)
-from .laws import (CentralNumericalFlux, EntropyConservativeNumericalFlux, EulerEquations,
+from .laws import (CentralNumericalFlux, EntropyConservativeNumericalFlux, EulerEquations, euler_periodic_test,
                    LaxFriedrichsNumericalFlux, LinearAdvectionDiffusionEquation, LinearAdvectionEquation,
                    initial_data_cosine, initial_data_sine, isentropic_vortex, project_function,
                    taylor_green_vortex)
@@ -110,6 +110,29 @@ def euler_tgv_3d(M=2, p=4, flux="lf", kind="modal", part=None) -> Case:
                 taylor_green_vortex(1.4, 0.1))
 
 
+def euler_periodic_3d_hex(M=2, p=4, flux="ec") -> Case:
+    """test/euler_3d.jl (runtests.jl:131-144): 3-D Euler density wave on warped hexahedra, NodalTensor Lobatto
+    collocation (diagonal-E), flux differencing, conservative-curl metrics."""
+    L = 2.0
+    ra = reference_approximation(NodalTensor(p), "Hex", mapping_degree=p)
+    mesh = uniform_periodic_mesh(ra, ((0.0, L),) * 3, (M,) * 3, ChanWarping(1.0 / 16.0, (L,) * 3))
+    sd = SpatialDiscretization.build(mesh, ra, "curl")
+    return Case("euler_periodic_3d_hex", EulerEquations(3, 1.4), sd,
+                FluxDifferencingForm(inviscid_numerical_flux=_flux(flux)), REFERENCE_OPERATOR,
+                euler_periodic_test(3, 1.4, 0.2, L))
+
+
+def advection_2d_quad(M=2, p=4, flux="lf", warp=0.1) -> Case:
+    """runtests.jl:62-80: 2-D advection, flux-differencing form on warped quadrilaterals (NodalTensor Lobatto)."""
+    ra = reference_approximation(NodalTensor(p), "Quad", mapping_degree=p)
+    mesh = uniform_periodic_mesh(ra, ((0.0, 1.0),) * 2, (M, M), DelReyWarping(warp, (1.0, 1.0)))
+    sd = SpatialDiscretization.build(mesh, ra, "exact", True)
+    return Case("advection_2d_quad", LinearAdvectionEquation((1.0, 1.0)), sd,
+                FluxDifferencingForm(inviscid_numerical_flux=_flux(flux)), REFERENCE_OPERATOR,
+                initial_data_sine(1.0, (2 * np.pi, 2 * np.pi)))
+
+
 BUILDERS = {"advection_2d": advection_2d, "euler_vortex_2d": euler_vortex_2d,
             "advection_diffusion_2d": advection_diffusion_2d, "advection_3d": advection_3d,
-            "euler_tgv_3d": euler_tgv_3d}
+            "euler_tgv_3d": euler_tgv_3d,
+            "euler_periodic_3d_hex": euler_periodic_3d_hex, "advection_2d_quad": advection_2d_quad}

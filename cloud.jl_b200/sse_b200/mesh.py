@@ -141,6 +141,14 @@ def _cartesian_simplex_cells(d: int, M: Tuple[int, ...], cells: np.ndarray):
             return c[:, 0] + n1[0] * c[:, 1]
         return c[:, 0] + n1[0] * (c[:, 1] + n1[1] * c[:, 2])
 
+    if d == 2:
+        # StartUpDG's uniform_mesh(Tri(), Kx, Ky), identified through the reference's triangle goldens (runtests.jl:38-60,
+        # 111-121 are reproduced to round-off with exactly this split): every square is cut along the lower-left /
+        # upper-right diagonal into (ll, lr, ur) and (ur, ul, ll); the reference keeps this order for triangles.
+        ll, lr = vid(base), vid(base + [1, 0])
+        ur, ul = vid(base + [1, 1]), vid(base + [0, 1])
+        EtoV = np.stack([np.stack([ll, lr, ur], axis=1), np.stack([ur, ul, ll], axis=1)], axis=1).reshape(-1, 3)
+        return EtoV, n1
     tets = []
     for perm in permutations(range(d)):
         c = base.copy()
@@ -167,6 +175,8 @@ def _vertex_coords(d, n1, limits, ids):
 
 
 def _orient(d, EtoV, n1, limits):
+    if d == 2:
+        return EtoV                                        # triangles keep the generator's vertex order
     E = -np.sort(-EtoV, axis=1)                            # descending global ids
     X = [_vertex_coords(d, n1, limits, E[:, v]) for v in range(d + 1)]
     A = np.stack([np.stack([X[v][m] - X[0][m] for m in range(d)], axis=1)
@@ -240,6 +250,10 @@ def uniform_periodic_mesh(ra: ReferenceApproximation, limits, M, warp=None,
     M = tuple(int(m) for m in M)
     limits = tuple(tuple(l) for l in limits)
     ncell = int(np.prod(M))
+    if ra.element in ("Quad", "Hex"):
+        if part is not None and part != (0, 1):
+            raise NotImplementedError("partitioned Quad / Hex meshes")
+        return _box_mesh(ra, limits, M, warp)
     nsimp = 2 if d == 2 else 6
     if structured is None:
         structured = min(M) >= 4
@@ -259,6 +273,23 @@ def uniform_periodic_mesh(ra: ReferenceApproximation, limits, M, warp=None,
                     [x @ geom.Vf.T for x in xyz], mapP, limits,
                     elem_gid=np.arange(EtoV.shape[0]))
     return _partitioned_mesh(ra, limits, M, warp, part)
+
+
+def _box_mesh(ra: ReferenceApproximation, limits, M, warp) -> Mesh:
+    """Periodic Cartesian mesh of Quad / Hex elements (one element per cell, first axis fastest), optionally warped."""
+    d, geom = ra.d, ra.geom
+    ncell = int(np.prod(M))
+    c = np.arange(ncell)
+    comps = [c % M[0], (c // M[0]) % M[1]] + ([c // (M[0] * M[1])] if d == 3 else [])
+    xyz = []
+    for m in range(d):
+        lo, hi = limits[m]
+        h = (hi - lo) / M[m]
+        xyz.append(lo + h * (comps[m][:, None] + 0.5 * (1.0 + geom.rst[m][None, :])))
+    mapP = _match_faces([x @ geom.Vf.T for x in xyz], ra.N_fac, limits)
+    xyz = apply_warp(xyz, warp)
+    return Mesh(d, ncell, xyz, [x @ geom.Vq.T for x in xyz], [x @ geom.Vf.T for x in xyz], mapP, limits,
+                elem_gid=np.arange(ncell))
 
 
 def _template_connectivity(ra: ReferenceApproximation):
@@ -485,9 +516,35 @@ def _gf_curl_2d(ra, xyz, need_nJq=True):
 _CURL_CACHE = {}
 
 
+def _gf_curl_hex(ra, xyz, need_nJq=True):
+    """Conservative-curl metrics on hexahedra (mesh.jl:341-408): StartUpDG's geometric_factors(x, y, z, Dr, Ds, Dt) at
+    the degree-N tensor Lobatto mapping nodes (products collocated there), then interpolated by Vq / Vf."""
+    g = ra.geom
+    x, y, z = xyz
+    Dr, Ds, Dt = (np.ascontiguousarray(a.T) for a in g.Drst)
+    xr, xs, xt = x @ Dr, x @ Ds, x @ Dt
+    yr, ys, yt = y @ Dr, y @ Ds, y @ Dt
+    zr, zs, zt = z @ Dr, z @ Ds, z @ Dt
+    J = xr * (ys * zt - zs * yt) - yr * (xs * zt - zs * xt) + zr * (xs * yt - ys * xt)
+
+    def curl(a, b):
+        Fr, Fs, Ft = (a @ Dr) * b, (a @ Ds) * b, (a @ Dt) * b
+        return Fs @ Dt - Ft @ Ds, Ft @ Dr - Fr @ Dt, Fr @ Ds - Fs @ Dr
+
+    acc = _Acc(ra, x.shape[0], need_nJq)
+    VqT, VfT = np.ascontiguousarray(g.Vq.T), np.ascontiguousarray(g.Vf.T)
+    for m, (a, b, sgn) in enumerate(((y, z, 1.0), (x, z, -1.0), (y, x, -1.0))):
+        for l, comp in enumerate(curl(a, b)):
+            comp = sgn * comp
+            acc.add(l, m, comp @ VqT, comp @ VfT)
+    return acc.finish(J @ VqT)
+
+
 def _gf_curl_3d(ra, xyz, need_nJq=True):
     """Conservative-curl metrics on tets (mesh.jl:410-506; Chan & Wilcox 2019): the
     curl argument is a degree N+1 polynomial, the metric itself degree N."""
+    if ra.element == "Hex":
+        return _gf_curl_hex(ra, xyz, need_nJq)
     g = ra.geom
     N = g.N
     key = (id(ra), N)

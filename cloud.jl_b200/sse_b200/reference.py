@@ -241,12 +241,60 @@ def _lattice_nodes(d: int, N: int):
     return [pts[:, m].copy() for m in range(d)]
 
 
-def _poly_basis(d: int, N: int, rst, grad: bool = False):
-    """Total-degree-N basis prod_m P_{a_m}(x_m), sum a_m <= N, and its gradients."""
+def _warp_blend_nodes_tri(N: int):
+    """Interpolation nodes of the triangle mapping element: equispaced lattice warped so that every edge carries the
+    Gauss-Lobatto nodes, blended into the interior without the alpha-optimisation of Hesthaven & Warburton (alpha = 0).
+    This is the node set that reproduces the reference's triangle goldens (runtests.jl:38-60, 111-121) to round-off,
+    i.e. what the un-vendored NodesAndModes `nodes(Tri(), N)` returns; the curved geometry is the interpolant of the
+    warping function at these nodes, so the set matters whenever the mapping is not polynomial."""
+    if N == 1:
+        return [np.array([-1.0, 1.0, -1.0]), np.array([-1.0, -1.0, 1.0])]
+    gll, _ = quadrature_line(GaussLobattoQuadrature(N))
+    req = np.linspace(-1.0, 1.0, N + 1)
+    Veq = vandermonde_1d(N, req)
+
+    def warpfactor(rout):
+        warp = np.linalg.solve(Veq.T, vandermonde_1d(N, rout).T).T @ (gll - req)
+        inside = (np.abs(rout) < 1.0 - 1e-10).astype(float)
+        return warp / (1.0 - (inside * rout) ** 2) + warp * (inside - 1.0)
+
+    L1, L3 = [], []
+    for n in range(N + 1):
+        for m in range(N + 1 - n):
+            L1.append(n / N)
+            L3.append(m / N)
+    L1, L3 = np.array(L1), np.array(L3)
+    L2 = 1.0 - L1 - L3
+    x, y = -L2 + L3, (-L2 - L3 + 2.0 * L1) / np.sqrt(3.0)
+    w1 = 4.0 * L2 * L3 * warpfactor(L3 - L2)
+    w2 = 4.0 * L1 * L3 * warpfactor(L1 - L3)
+    w3 = 4.0 * L1 * L2 * warpfactor(L2 - L1)
+    x = x + w1 + np.cos(2 * np.pi / 3) * w2 + np.cos(4 * np.pi / 3) * w3
+    y = y + np.sin(2 * np.pi / 3) * w2 + np.sin(4 * np.pi / 3) * w3
+    L1 = (np.sqrt(3.0) * y + 1.0) / 3.0
+    L2 = (-3.0 * x - np.sqrt(3.0) * y + 2.0) / 6.0
+    L3 = (3.0 * x - np.sqrt(3.0) * y + 2.0) / 6.0
+    return [-L2 + L3 - L1, -L2 - L3 + L1]
+
+
+def _tensor_nodes(d: int, N: int):
+    """Tensor-product Gauss-Lobatto interpolation nodes of the Quad / Hex mapping element (NodesAndModes' nodes(Quad/Hex, N)
+    are the tensor product of the 1-D Lobatto nodes), first coordinate slowest."""
+    x, _ = quadrature_line(GaussLobattoQuadrature(N))
+    g = np.meshgrid(*([x] * d), indexing="ij")
+    return [a.reshape(-1).copy() for a in g]
+
+
+def _poly_basis(d: int, N: int, rst, grad: bool = False, tensor: bool = False):
+    """Total-degree-N basis prod_m P_{a_m}(x_m), sum a_m <= N (simplices), or the full tensor basis a_m <= N
+    (tensor=True: Quad / Hex), and its gradients."""
     from numpy.polynomial import legendre as L
     n = rst[0].size
     idx = []
-    if d == 1:
+    if tensor:
+        from itertools import product
+        idx = list(product(range(N + 1), repeat=d))
+    elif d == 1:
         idx = [(a,) for a in range(N + 1)]
     elif d == 2:
         idx = [(a, b) for a in range(N + 1) for b in range(N + 1 - a)]
@@ -286,16 +334,17 @@ class GeometryElement:
     Drst: List[np.ndarray]
     Vq: np.ndarray
     Vf: np.ndarray
+    tensor: bool = False
 
     def interp(self, pts) -> np.ndarray:
-        return np.linalg.solve(self.VDM.T, _poly_basis(self.d, self.N, pts).T).T
+        return np.linalg.solve(self.VDM.T, _poly_basis(self.d, self.N, pts, tensor=self.tensor).T).T
 
 
-def geometry_element(d: int, N: int, rstq, rstf) -> GeometryElement:
-    rst = _lattice_nodes(d, N)
-    VDM, G = _poly_basis(d, N, rst, grad=True)
+def geometry_element(d: int, N: int, rstq, rstf, tensor: bool = False) -> GeometryElement:
+    rst = _tensor_nodes(d, N) if tensor else (_warp_blend_nodes_tri(N) if d == 2 else _lattice_nodes(d, N))
+    VDM, G = _poly_basis(d, N, rst, grad=True, tensor=tensor)
     Drst = [np.linalg.solve(VDM.T, g.T).T for g in G]
-    ge = GeometryElement(d, N, rst, VDM, Drst, None, None)
+    ge = GeometryElement(d, N, rst, VDM, Drst, None, None, tensor)
     ge.Vq = ge.interp(rstq)
     ge.Vf = ge.interp(rstf)
     return ge
@@ -403,6 +452,8 @@ def reference_approximation(approx_type, element: str, mapping_degree: int = 1,
                         facet_quadrature_rule)
     if element == "Line":
         return _ref_line(approx_type, p, mapping_degree, volume_quadrature_rule)
+    if element in ("Quad", "Hex"):
+        return _ref_box(approx_type, element, p, mapping_degree, volume_quadrature_rule, facet_quadrature_rule)
     raise ValueError(f"unsupported element {element}")
 
 
@@ -507,3 +558,53 @@ def _ref_line(approx_type, p, mapping_degree, vq):
                                       VDM, None, False, Vf @ P, wq, wf, None, None, [rq], [rf],
                                       [nrJ], geom, [rq], [], False, False)
     raise ValueError(approx_type)
+
+
+# tensor_cartesian.jl:34-131 — NodalTensor on Quad / Hex
+def _ref_box(approx_type, element, p, mapping_degree, vq, fq):
+    """Collocated tensor-product element: V = I, D_m = I (x) D_1D (x) I, W = w (x) w [(x) w]; with Lobatto rules R is a
+    selection of the boundary nodes (diagonal-E), otherwise the Kronecker product of 1-D extrapolations.  Node index =
+    (i_1 * n + i_2) [* n + i_3]; faces are ordered (xi_1 = -1, xi_1 = +1, xi_2 = -1, ...) and their nodes run over the
+    remaining coordinates in the same order (any consistent convention gives the same scheme)."""
+    if not isinstance(approx_type, NodalTensor):
+        raise ValueError("Quad / Hex elements carry NodalTensor approximations (tensor_cartesian.jl)")
+    d = 2 if element == "Quad" else 3
+    vq = vq or LGLQuadrature(p)
+    fq = fq or vq
+    if fq != vq:
+        raise NotImplementedError("distinct facet quadrature on Quad / Hex")
+    x1, w1 = quadrature_line(vq)
+    q = len(x1) - 1
+    n = q + 1
+    V1 = vandermonde_1d(q, x1)
+    D1 = np.linalg.solve(V1.T, grad_vandermonde_1d(q, x1).T).T
+    sel = isinstance(vq, GaussLobattoQuadrature)
+    RL = np.linalg.solve(V1.T, vandermonde_1d(q, [-1.0]).T).T
+    RR = np.linalg.solve(V1.T, vandermonde_1d(q, [1.0]).T).T
+    if sel:
+        RL, RR = np.round(RL), np.round(RR)
+    I1 = np.eye(n)
+    D = [_kron(*[D1 if mm == m else I1 for mm in range(d)]) for m in range(d)]
+    R = np.vstack([_kron(*[(RL if side == 0 else RR) if mm == m else I1 for mm in range(d)])
+                   for m in range(d) for side in (0, 1)])
+    grid = np.meshgrid(*([x1] * d), indexing="ij")
+    rstq = [a.reshape(-1).copy() for a in grid]
+    wq = _kron(*([w1[:, None]] * d)).reshape(-1)
+    fgrid = np.meshgrid(*([x1] * (d - 1)), indexing="ij")
+    fpts = [a.reshape(-1) for a in fgrid]
+    wface = _kron(*([w1[:, None]] * (d - 1))).reshape(-1)
+    npf = wface.size
+    rstf = [[] for _ in range(d)]
+    nrstJ = [[] for _ in range(d)]
+    for m in range(d):
+        for side in (-1.0, 1.0):
+            others = iter(fpts)
+            for mm in range(d):
+                rstf[mm].append(np.full(npf, side) if mm == m else next(others))
+                nrstJ[mm].append(np.full(npf, side) if mm == m else np.zeros(npf))
+    rstf = [np.concatenate(a) for a in rstf]
+    nrstJ = [np.concatenate(a) for a in nrstJ]
+    wf = np.tile(wface, 2 * d)
+    geom = geometry_element(d, mapping_degree, rstq, rstf, tensor=True)
+    return ReferenceApproximation(NodalTensor(q), element, d, q, n ** d, n ** d, R.shape[0], 2 * d, D, np.eye(n ** d), None,
+                                  True, R, wq, wf, None, None, rstq, rstf, nrstJ, geom, [x1] * d, [D1] * d, True, sel)

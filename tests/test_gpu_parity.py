@@ -86,6 +86,35 @@ def test_logmean_branches_are_both_exercised():
         assert relerr(gpu_rhs(img, u, v)[0], ref) <= RTOL
 
 
+def _strong_gradient_state(c, amp):
+    """L2 projection of a smooth state whose density and pressure vary by a factor (1 + amp) / (1 - amp) over the box."""
+    from sse_b200.laws import project_function
+    sd = c.sd
+
+    def f(xyz):
+        x, y, z = xyz[0], xyz[1], xyz[2]
+        rho = 1.0 + amp * np.sin(x) * np.cos(y + 0.3) * np.cos(z)
+        p = 10.0 * (1.0 + amp * np.cos(x - 0.2) * np.sin(y) * np.sin(z + 0.5))
+        v = np.stack([np.sin(x) * np.cos(y), -np.cos(x) * np.sin(y), 0.3 * np.sin(z)], axis=-1)
+        e = p / (c.law.gamma - 1.0) + 0.5 * rho * (v ** 2).sum(-1)
+        return np.concatenate([rho[..., None], rho[..., None] * v, e[..., None]], axis=-1)
+
+    return np.ascontiguousarray(project_function(f, sd.reference_approximation, sd.geometric_factors.J_q, sd.mesh.xyzq))
+
+
+@pytest.mark.parametrize("amp,p", [(0.3, 4), (0.6, 4), (0.5, 3)])
+def test_logmean_tiers_on_compile_time_path(amp, p):
+    """Under-resolved 3-D Euler states drive the pair kernel's log-mean through all three tiers (degree-3 series,
+    degree-10 series, log formula: physics.cuh logmean_pair_scaled*); the oracle takes the reference's two branches."""
+    c = cases.euler_tgv_3d(M=2, p=p, flux="lf")
+    img, u = c.image(), _strong_gradient_state(c, amp)
+    ref = oracle.rhs(img, u)
+    assert np.all(np.isfinite(ref))
+    out, extra = gpu_rhs(img, u, 1, check_scratch=True)
+    assert extra[2] == 2                       # compile-time kernels
+    assert relerr(out, ref) <= RTOL
+
+
 def test_golden_fixture():
     """tests/golden/euler_tgv_3d_M2.npz (made by tests/golden/make_golden.py from the pinned oracle)."""
     import os

@@ -1,12 +1,17 @@
 """Pins the oracle against the reference's own golden vectors (test/runtests.jl).
 
-Only the 1-D testsets can be reproduced without the un-vendored StartUpDG mesh/node data; they
-exercise the same residual code (flux_differencing_form.jl, standard_form_second_order.jl,
-ConservationLaws) with d = 1.  Time integration is CarpenterKennedy2N54 with the reference's dt."""
+Reproduced to round-off: the 1-D testsets (runtests.jl:14-36, 89-96), the 2-D triangle testsets of the collapsed
+ModalTensor operators (advection :38-60; Euler vortex with flux differencing, entropy projection, facet correction and
+the weight-adjusted mass solve :111-121), the quadrilateral flux-differencing testset (:62-80) and the 3-D Euler
+hexahedral testset (:131-144).  The triangle mesh split and mapping nodes of the un-vendored StartUpDG / NodesAndModes
+were identified through these goldens (sse_b200/mesh.py, sse_b200/reference.py).  Not reproducible here: the tetrahedral
+advection golden (:123-129, StartUpDG's tet split and 3-D warp-and-blend nodes) and the NodalMultiDiagE golden (:98-109,
+tabulated SBP nodes).  Time integration is CarpenterKennedy2N54 with the reference's dt, except for the Hex testset,
+whose DP8 tableau (OrdinaryDiffEq, un-vendored) is replaced by CK54 at a time step where the ODE is solved to 2e-11."""
 import numpy as np
 
 import oracle
-from sse_b200 import analysis
+from sse_b200 import analysis, cases
 from sse_b200.assembly import (FluxDifferencingForm, PHYSICAL_OPERATOR, SpatialDiscretization, StandardForm,
                                assemble)
 from sse_b200.laws import (EntropyConservativeNumericalFlux, EulerEquations, LaxFriedrichsNumericalFlux,
@@ -74,3 +79,68 @@ def test_advection_diffusion_1d_br1_golden():
     l2 = np.sqrt(np.einsum("kei,ki,kei->e", ue - uq, ra.W[None, :] * sd.geometric_factors.J_q, ue - uq))
     assert abs(l2[0] - 6.988216111882884e-6) < TOL                          # runtests.jl:34
     assert np.abs(analysis.conservation_residual(img, oracle.rhs(img, u))).max() < TOL
+
+
+def _l2_error(c, u):
+    """ErrorAnalysis with the scheme's own quadrature (Analysis/error.jl:14-24, 60-80)."""
+    sd = c.sd
+    ra = sd.reference_approximation
+    uq = np.einsum("qa,kea->keq", ra.V, u)
+    ue = np.transpose(c.ic(sd.mesh.xyzq), (0, 2, 1))
+    return np.sqrt(np.einsum("kei,ki,kei->e", ue - uq, ra.W[None, :] * sd.geometric_factors.J_q, ue - uq))
+
+
+ADVECTION_2D_TRI_GOLDEN = 0.2660013939427627                                   # runtests.jl:57
+ADVECTION_2D_QUAD_GOLDEN = 0.04790536605026519                                 # runtests.jl:78
+EULER_VORTEX_2D_MODAL_GOLDEN = [0.015568197027072704, 0.040539693811761104,
+                                0.04060141777050208, 0.043960971468832745]     # runtests.jl:114-119
+EULER_3D_HEX_GOLDEN = [0.18342164491797003, 0.1834216449179776, 0.18342164491796725,
+                       0.18342164491796784, 0.2751324673769553]                # runtests.jl:134-140
+
+
+def test_advection_2d_modal_tri_golden():
+    """runtests.jl:38-60: StandardForm, skew-symmetric mapping, LF(0) = central flux, ModalTensor(4) on 2 x 2 x 2 warped
+    triangles, one period with dt = 1/100."""
+    c = cases.advection_2d(M=2, p=4, flux="lf0", warp=0.1)
+    img = c.image()
+    u = ck54(img, c.u0(), 1.0 / 100, 100)
+    assert abs(_l2_error(c, u)[0] - ADVECTION_2D_TRI_GOLDEN) < TOL
+    du = oracle.rhs(img, u)
+    assert np.abs(analysis.conservation_residual(img, du)).max() < TOL        # runtests.jl:58
+    assert abs(analysis.energy_residual(img, u, du)) < TOL                     # runtests.jl:59
+
+
+def test_advection_2d_quad_fluxdiff_golden():
+    """runtests.jl:62-80: FluxDifferencingForm() on NodalTensor(4) Lobatto quadrilaterals (diagonal-E, no correction)."""
+    c = cases.advection_2d_quad(M=2, p=4, flux="lf", warp=0.1)
+    img = c.image()
+    u = ck54(img, c.u0(), 1.0 / 100, 100)
+    assert abs(_l2_error(c, u)[0] - ADVECTION_2D_QUAD_GOLDEN) < TOL
+    assert np.abs(analysis.conservation_residual(img, oracle.rhs(img, u))).max() < TOL   # runtests.jl:79
+
+
+def test_euler_vortex_2d_modal_tri_golden():
+    """test/euler_vortex_2d_modal.jl, runtests.jl:111-121: the 2-D instance of the headline path — ModalTensor(3)
+    collapsed triangles, flux differencing with the Ranocha flux, entropy projection, facet correction, weight-adjusted
+    mass solve, Lax-Friedrichs interface flux, ChanWilcox metrics on a ChanWarping(1/16) mesh; 1000 CK54 steps."""
+    c = cases.euler_vortex_2d(M=4, p=3, flux="lf")
+    img = c.image()
+    T = 1.0 / 0.4
+    u = ck54(img, c.u0(), T / 1000, 1000)
+    assert np.allclose(_l2_error(c, u), EULER_VORTEX_2D_MODAL_GOLDEN, rtol=0, atol=TOL)
+    assert np.abs(analysis.conservation_residual(img, oracle.rhs(img, u))).max() < TOL   # runtests.jl:120
+
+
+def test_euler_3d_hex_golden():
+    """test/euler_3d.jl, runtests.jl:131-144: 3-D Euler, EC two-point and interface flux, NodalTensor(4) Lobatto
+    hexahedra, conservative-curl metrics on a ChanWarping(1/16) mesh, one period T = 2.  The reference integrates with
+    DP8 (250 steps); CK54 with 2500 steps solves the same ODE to 2e-11 (the error falls 16x per halving of dt:
+    1.4e-8, 5.5e-11, 3.4e-12 at 500, 2000, 4000 steps)."""
+    c = cases.euler_periodic_3d_hex(M=2, p=4, flux="ec")
+    img = c.image()
+    u0 = c.u0()
+    du0 = oracle.rhs(img, u0)
+    assert np.abs(analysis.conservation_residual(img, du0)).max() < TOL       # runtests.jl:141
+    assert abs(analysis.entropy_residual(img, u0, du0)) < TOL                 # runtests.jl:142
+    u = ck54(img, u0, 2.0 / 2500, 2500)
+    assert np.allclose(_l2_error(c, u), EULER_3D_HEX_GOLDEN, rtol=0, atol=TOL)

@@ -139,6 +139,30 @@ def test_euler_1d_reference_golden_on_gpu():
     s.close()
 
 
+GOLDEN_RUNS = {
+    # name: (case builder, end time, CK54 steps, golden attribute in test_oracle_goldens, expected kernel variant)
+    "advection_2d_tri": (lambda: cases.advection_2d(M=2, p=4, flux="lf0", warp=0.1), 1.0, 100, "ADVECTION_2D_TRI_GOLDEN", 0),
+    "advection_2d_quad": (lambda: cases.advection_2d_quad(M=2, p=4, flux="lf", warp=0.1), 1.0, 100, "ADVECTION_2D_QUAD_GOLDEN", None),
+    "euler_vortex_2d_modal_tri": (lambda: cases.euler_vortex_2d(M=4, p=3, flux="lf"), 2.5, 1000,
+                                  "EULER_VORTEX_2D_MODAL_GOLDEN", 1),
+    "euler_3d_hex": (lambda: cases.euler_periodic_3d_hex(M=2, p=4, flux="ec"), 2.0, 2500, "EULER_3D_HEX_GOLDEN", None),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_RUNS))
+def test_reference_goldens_2d_3d_on_gpu(name):
+    """The reference's own 2-D / 3-D golden L2 errors (runtests.jl:38-80, 111-144; see test_oracle_goldens.py) reproduced
+    by the CUDA path alone: device-resident fused CarpenterKennedy2N54 steps through the C ABI, no oracle involved."""
+    import test_oracle_goldens as og
+    build, T, n, gold, variant = GOLDEN_RUNS[name]
+    c = build()
+    s = Solver(c.image(), 0)
+    assert variant is None or s.kernel_variant() == variant
+    u = solve_ck54(ODEProblem(semi_discrete_residual, c.u0(), (0.0, T), s), T / n, n)
+    assert np.allclose(og._l2_error(c, u), getattr(og, gold), rtol=0, atol=1e-10)
+    s.close()
+
+
 def test_invariants_at_scale_and_functionals():
     """Size-independent properties on a mesh the oracle is not run on: conservation and entropy
     conservation (EC interface flux) to roundoff, via the device functionals."""

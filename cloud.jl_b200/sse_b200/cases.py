@@ -14,6 +14,7 @@ import numpy as np
 from .assembly import (FluxDifferencingForm, PHYSICAL_OPERATOR, REFERENCE_OPERATOR, SpatialDiscretization,
                        StandardForm, assemble)
 from .laws import (CentralNumericalFlux, EntropyConservativeNumericalFlux, EulerEquations, euler_periodic_test,
+                   InviscidBurgersEquation, initial_data_gassner,
                    LaxFriedrichsNumericalFlux, LinearAdvectionDiffusionEquation, LinearAdvectionEquation,
                    initial_data_cosine, initial_data_sine, isentropic_vortex, project_function,
                    taylor_green_vortex)
@@ -122,6 +123,16 @@ def euler_periodic_3d_hex(M=2, p=4, flux="ec") -> Case:
                 euler_periodic_test(3, 1.4, 0.2, L))
 
 
+def burgers_1d(M=20, p=7, flux="ec") -> Case:
+    """test/burgers_fluxdiff_1d.jl (runtests.jl:82-87): inviscid Burgers, flux differencing on Lobatto NodalTensor lines."""
+    ra = reference_approximation(NodalTensor(p), "Line")
+    mesh = uniform_periodic_mesh(ra, (0.0, 2.0), M)
+    sd = SpatialDiscretization.build(mesh, ra, "exact", True)
+    return Case("burgers_1d", InviscidBurgersEquation(), sd,
+                FluxDifferencingForm(inviscid_numerical_flux=_flux(flux)), REFERENCE_OPERATOR,
+                initial_data_gassner(np.pi, 0.01))
+
+
 def advection_2d_quad(M=2, p=4, flux="lf", warp=0.1) -> Case:
     """runtests.jl:62-80: 2-D advection, flux-differencing form on warped quadrilaterals (NodalTensor Lobatto)."""
     ra = reference_approximation(NodalTensor(p), "Quad", mapping_degree=p)
@@ -135,4 +146,4 @@ def advection_2d_quad(M=2, p=4, flux="lf", warp=0.1) -> Case:
 BUILDERS = {"advection_2d": advection_2d, "euler_vortex_2d": euler_vortex_2d,
             "advection_diffusion_2d": advection_diffusion_2d, "advection_3d": advection_3d,
             "euler_tgv_3d": euler_tgv_3d,
-            "euler_periodic_3d_hex": euler_periodic_3d_hex, "advection_2d_quad": advection_2d_quad}
+            "euler_periodic_3d_hex": euler_periodic_3d_hex, "burgers_1d": burgers_1d, "advection_2d_quad": advection_2d_quad}

@@ -14,7 +14,7 @@ from typing import Tuple
 import numpy as np
 
 # ids shared with include/sse_b200.h
-PDE_ADVECTION, PDE_ADVECTION_DIFFUSION, PDE_EULER = 0, 1, 2
+PDE_ADVECTION, PDE_ADVECTION_DIFFUSION, PDE_EULER, PDE_BURGERS = 0, 1, 2, 3
 FLUX_LAX_FRIEDRICHS, FLUX_CENTRAL, FLUX_ENTROPY_CONSERVATIVE = 0, 1, 2
 TWO_POINT_CONSERVATIVE, TWO_POINT_ENTROPY_CONSERVATIVE = 0, 1
 
@@ -23,6 +23,20 @@ TWO_POINT_CONSERVATIVE, TWO_POINT_ENTROPY_CONSERVATIVE = 0, 1
 class LinearAdvectionEquation:
     a: Tuple[float, ...]
     pde_id: int = PDE_ADVECTION
+
+    @property
+    def d(self):
+        return len(self.a)
+
+    N_c = 1
+    second_order = False
+
+
+@dataclass(frozen=True)
+class InviscidBurgersEquation:
+    """burgers.jl:1-21, 46: flux a u^2 / 2; `InviscidBurgersEquation()` is the 1-D law with a = (1,)."""
+    a: Tuple[float, ...] = (1.0,)
+    pde_id: int = PDE_BURGERS
 
     @property
     def d(self):
@@ -102,6 +116,11 @@ class EntropyConservativeFlux:
 def initial_data_sine(A, k):
     k = np.atleast_1d(k)
     return lambda x: (A * np.prod([np.sin(k[m] * x[m]) for m in range(len(x))], axis=0))[..., None]
+
+
+def initial_data_gassner(k, eps):
+    """InitialDataGassner (GridFunctions.jl:60-68, 144-146)."""
+    return lambda x: (np.sin(k * x[0]) + eps)[..., None]
 
 
 def initial_data_cosine(A, k):

@@ -13,11 +13,16 @@
  * Nothing under cloud.jl_b200/ may import, link or call it.
  *
  * Pinning (see oracle/README.md): the reference cannot run in this image (no
- * Julia).  The oracle is pinned against the reference's own golden vectors that do
- * not depend on un-vendored StartUpDG mesh/node data — the 1-D testsets of
- * test/runtests.jl (:14-36 advection-diffusion BR1, :89-96 Euler Gauss collocation)
- * — and against the reference's invariant assertions (conservation / energy /
- * entropy, runtests.jl:35-142) on 2-D/3-D curved meshes; see tests/test_oracle_*.py.
+ * Julia).  The oracle reproduces the reference's own golden vectors of
+ * test/runtests.jl to round-off: 1-D (:14-36 advection-diffusion BR1, :89-96 Euler
+ * Gauss collocation), 2-D (:38-60 ModalTensor Tri advection, :62-80 NodalTensor
+ * Quad flux differencing, :111-121 ModalTensor Tri Euler vortex: flux differencing,
+ * entropy projection, facet correction, weight-adjusted mass solve) and 3-D
+ * (:131-144 NodalTensor Hex Euler), plus the reference's invariant assertions
+ * (conservation / energy / entropy, runtests.jl:35-142); see tests/test_oracle_*.py.
+ * Not reproducible here: :98-109 (tabulated SBP nodes) and :123-129 (tetrahedral
+ * mesh split, 3-D warp-and-blend nodes and Jaskowiec-Sukumar error quadrature of the
+ * un-vendored StartUpDG/NodesAndModes): for the tetrahedral golden parity is unpinned.
  *
  * Third-party arithmetic restated here: LinearMaps.jl "3" (Kronecker/Block/
  * Transpose mul!, column-by-column application) and Octavian.jl "0.3"
@@ -273,6 +278,9 @@ static void two_point_flux(const sse_config *c, int tp, const double *uL, const 
     const int d = c->d;
     if (c->pde != SSE_PDE_EULER) {
         double f1 = 0.5 * (uL[0] + uR[0]);
+        if (c->pde == SSE_PDE_BURGERS)                 /* burgers.jl:111-143 */
+            f1 = (tp == SSE_TWO_POINT_ENTROPY_CONSERVATIVE) ? (uL[0] * uL[0] + uL[0] * uR[0] + uR[0] * uR[0]) / 6
+                                                            : (uL[0] * uL[0] + uR[0] * uR[0]) * 0.25;
         for (int m = 0; m < d; m++) F[0][m] = c->a[m] * f1;
         return;
     }
@@ -304,6 +312,7 @@ static double wave_speed(const sse_config *c, const double *ui, const double *uo
     const int d = c->d;
     if (c->pde != SSE_PDE_EULER) {
         double s = 0; for (int m = 0; m < d; m++) s += c->a[m] * n[m];
+        if (c->pde == SSE_PDE_BURGERS) return fmax(fabs(s * ui[0]), fabs(s * uo[0]));    /* burgers.jl:103-109 */
         return fabs(s);
     }
     double si = 0, so = 0, vni = 0, vno = 0;
@@ -496,6 +505,7 @@ static void physical_flux(const ora_t *o, const double *u_q, const double *q_q, 
     for (int m = 0; m < d; m++)
         for (int i = 0; i < Nq; i++) {
             double f = c->a[m] * u_q[i];
+            if (c->pde == SSE_PDE_BURGERS) f = 0.5 * c->a[m] * u_q[i] * u_q[i];           /* burgers.jl:52-58 */
             if (c->pde == SSE_PDE_ADVECTION_DIFFUSION) f = c->a[m] * u_q[i] - c->b * q_q[i + (size_t)Nq * Nc * m];
             f_q[i + (size_t)Nq * Nc * m] = f;
         }

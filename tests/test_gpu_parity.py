@@ -49,6 +49,11 @@ CASES = {
     "euler_tgv_3d_p3": lambda: cases.euler_tgv_3d(M=2, p=3, flux="lf"),
     "euler_tgv_3d_nodal": lambda: cases.euler_tgv_3d(M=2, p=3, flux="ec", kind="nodal"),
     "euler_tgv_3d_M4": lambda: cases.euler_tgv_3d(M=4, flux="lf"),
+    "burgers_1d_ec": lambda: cases.burgers_1d(M=8, p=7, flux="ec"),
+    "burgers_1d_lf": lambda: cases.burgers_1d(M=8, p=5, flux="lf"),
+    "advection_2d_quad": lambda: cases.advection_2d_quad(M=3, p=4, flux="lf"),
+    "euler_3d_hex_ec": lambda: cases.euler_periodic_3d_hex(M=2, p=3, flux="ec"),
+    "euler_3d_hex_lf": lambda: cases.euler_periodic_3d_hex(M=2, p=4, flux="lf"),
 }
 
 

@@ -61,3 +61,24 @@ def test_pointwise_physics():
         assert abs(L.sse_oracle_logmean(x, y) - ref) <= 2e-13 * ref
         assert abs(L.sse_oracle_inv_logmean(x, y) - 1 / ref) <= 2e-13 / ref
     assert L.sse_oracle_logmean(1.5, 1.5) == 1.5
+
+
+def test_burgers_1d_fluxdiff_reference_testset():
+    """test/burgers_fluxdiff_1d.jl, runtests.jl:82-87: inviscid Burgers with the EC two-point and interface flux on
+    NodalTensor(7) Lobatto lines conserves the primary variable and the energy u^2/2 to round-off along the whole run
+    (T = 0.3, CFL 0.1, CarpenterKennedy2N54)."""
+    from sse_b200.solver import CK54_A, CK54_B
+    c = cases.burgers_1d(M=20, p=7, flux="ec")
+    img, u = c.image(), c.u0()
+    ra = c.sd.reference_approximation
+    dt = 0.1 * (2.0 / (ra.N_p * c.sd.N_e))
+    tmp = np.zeros_like(u)
+    for it in range(int(round(0.3 / dt))):
+        for s in range(5):
+            tmp = CK54_A[s] * tmp + dt * oracle.rhs(img, u)
+            u = u + CK54_B[s] * tmp
+        if it % 24 == 0:
+            du = oracle.rhs(img, u)
+            assert np.abs(analysis.conservation_residual(img, du)).max() < 1e-10      # runtests.jl:85
+            assert abs(analysis.energy_residual(img, u, du)) < 1e-10                  # runtests.jl:86
+    assert np.all(np.isfinite(u))

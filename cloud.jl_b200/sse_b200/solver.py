@@ -134,16 +134,39 @@ class Solver:
         _lib.check(self._lib.sse_rhs_pass_a_range(self._h, self._check_state(u, "u"), first, count))
         self.launches += 1 if count > 0 else 0
 
-    def rhs_host(self, dudt_host, u_host, t: float = 0.0, chunks: int = 8):
+    def _chunk_plan(self, chunks: int):
+        """Schedule of the pipelined host-buffer residual: element ranges, their upload order, and for every upload
+        position the ranges whose pass B becomes runnable there — a range is runnable once pass A has covered all the
+        ranges holding one of its face neighbours (read from mapP).  On a periodic slab ordering the last range is
+        uploaded first so that only two ranges are left when the uploads end."""
+        key = ("plan", chunks)
+        if key not in self._pinned:
+            ne, nf = self.state_shape[0], int(self.cfg.N_f)
+            bounds = [ne * c // chunks for c in range(chunks + 1)]
+            nb = (np.asarray(self.image.arrays["mapP"]).reshape(ne, nf) - 1) // nf
+            owner = np.searchsorted(np.asarray(bounds[1:]), np.arange(ne), side="right")
+            deps = [set(np.unique(owner[nb[bounds[c]:bounds[c + 1]]]).tolist()) | {c} for c in range(chunks)]
+            up = list(range(chunks))
+            if chunks - 1 in deps[0]:
+                up = [chunks - 1] + up[:-1]
+            pos = {c: i for i, c in enumerate(up)}
+            ready = [max(pos[d] for d in deps[c]) for c in range(chunks)]
+            after = [[c for c in sorted(range(chunks), key=lambda c: pos[c]) if ready[c] == i] for i in range(chunks)]
+            self._pinned[key] = (bounds, up, after)
+        return self._pinned[key]
+
+    def rhs_host(self, dudt_host, u_host, t: float = 0.0, chunks: int = 16):
         """Residual on HOST buffers (the reference-facing call with `Array` arguments): the H2D copy of u, the
-        kernels and the D2H copy of dudt are pipelined over `chunks` element ranges — pass A of a chunk starts as
-        soon as its slice of u has arrived, and the download of a chunk of dudt overlaps pass B of the next one.
-        torch CPU tensors (ideally pinned) are copied directly; NumPy arrays are staged through pinned memory."""
+        kernels and the D2H copy of dudt are pipelined over `chunks` element ranges on three streams — pass A of a
+        range starts as soon as its slice of u has arrived, pass B of a range as soon as pass A has covered its face
+        neighbours (read from mapP), and the download of its dudt overlaps the uploads still in flight (full-duplex
+        PCIe).  torch CPU tensors (ideally pinned) are copied directly; NumPy arrays are staged through pinned memory."""
         torch = _torch()
         p = self._pinned
         if "d_u" not in p:
             p["d_u"], p["d_du"] = self.new_state(), self.new_state()
             p["copy"] = torch.cuda.Stream(device=self.device)
+            p["copy_out"] = torch.cuda.Stream(device=self.device)
         if isinstance(u_host, np.ndarray):
             if "u" not in p:
                 p["u"] = torch.empty(self.state_shape, dtype=torch.float64).pin_memory()
@@ -153,7 +176,7 @@ class Solver:
         else:
             src, dst = u_host, dudt_host
         ne = self.state_shape[0]
-        d_u, d_du, copy = p["d_u"], p["d_du"], p["copy"]
+        d_u, d_du, copy, copy_out = p["d_u"], p["d_du"], p["copy"], p["copy_out"]
         cur = torch.cuda.current_stream(self.device)
         if self.image.law.second_order or int(self.cfg.N_ghost) or chunks <= 1 or ne < 4 * chunks:
             d_u.copy_(src, non_blocking=True)
@@ -161,9 +184,10 @@ class Solver:
             dst.copy_(d_du, non_blocking=True)
             cur.synchronize()
         else:
-            bounds = [ne * c // chunks for c in range(chunks + 1)]
+            bounds, up, after = self._chunk_plan(chunks)
             copy.wait_stream(cur)
-            for c in range(chunks):
+            copy_out.wait_stream(cur)
+            for i, c in enumerate(up):
                 a, b = bounds[c], bounds[c + 1]
                 with torch.cuda.stream(copy):
                     d_u[a:b].copy_(src[a:b], non_blocking=True)
@@ -171,14 +195,15 @@ class Solver:
                     ev.record(copy)
                 cur.wait_event(ev)
                 self.pass_a_range(d_u, a, b - a)
-            for c in range(chunks):
-                a, b = bounds[c], bounds[c + 1]
-                self.pass_b(d_du, a, b - a)
-                ev = torch.cuda.Event()
-                ev.record(cur)
-                with torch.cuda.stream(copy):
-                    copy.wait_event(ev)
-                    dst[a:b].copy_(d_du[a:b], non_blocking=True)
+                for k in after[i]:
+                    ka, kb = bounds[k], bounds[k + 1]
+                    self.pass_b(d_du, ka, kb - ka)
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    with torch.cuda.stream(copy_out):
+                        copy_out.wait_event(ev)
+                        dst[ka:kb].copy_(d_du[ka:kb], non_blocking=True)
+            cur.wait_stream(copy_out)
             cur.wait_stream(copy)
             cur.synchronize()
         if isinstance(u_host, np.ndarray):

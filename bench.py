@@ -39,7 +39,7 @@ def parse():
                     help="cubes per direction (6 tets each); 56 -> 1 053 696 elements")
     ap.add_argument("--flux", default="lf", choices=["lf", "ec"])
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-cells", type=int, default=8, help="mesh of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-cells", type=int, default=16, help="cubes per direction of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=1)
     return ap.parse_args()
@@ -103,17 +103,20 @@ def build_case(cells, flux, part):
     return c, u0
 
 
-def cpu_baseline(cells, flux, reps=2):
+def cpu_baseline(cells, flux, budget_s=12.0):
     """The reference algorithm (oracle port, OpenMP over elements like Threads.@threads) on a bounded
-    sample of the same workload, on this box's host cores."""
+    sample of the same workload, on this box's host cores: about `budget_s` seconds of CPU work."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
     c, u0 = build_case(cells, flux, None)
     img = c.image()
+    t1, used, _ = oracle.time_rhs(img, u0, 0, 1)                       # warm-up and cost estimate
+    reps = int(min(max(budget_s / max(t1, 1e-6), 3), 60))
     t, used, _ = oracle.time_rhs(img, u0, 0, reps)
     return {"value": c.dof / t, "unit": "DOF/s", "cores": used, "kind": "port",
             "sample": f"same workload on {cells}^3 cubes ({c.sd.N_e} elements, {c.dof} DOF), best of {reps} RHS, "
-                      f"{t:.3f} s each; C/OpenMP restatement of the reference algorithm (Julia cannot run here)"}
+                      f"{t:.3f} s each ({reps * t:.1f} s of CPU work); C/OpenMP restatement of the reference "
+                      "algorithm (Julia cannot run here)"}
 
 
 def run_reference(a):

@@ -476,22 +476,35 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
     const bool node = tid < Nq;
     const int ca = tid / NN, cb = (tid / N) % N, cc = tid % N;
 
+    // ---- prologue: every global load of the element is issued before any arithmetic.  Idle lanes load a clamped
+    //      (valid) address so that the loads need no branch: node data, own facet data and the mapP-dependent
+    //      neighbour gather are all in flight together instead of one dependent round trip after another.
+    static_assert(Nf <= (Nq + 31) / 32 * 32, "one facet node per thread");
+    const bool fac = tid < Nf;
+    const int tn = node ? tid : Nq - 1, tj = fac ? tid : Nf - 1;
     double qi[NP], lam[D][D], r[NC], sw[D];
+    const size_t jo = (size_t)(g.mapP[(size_t)k * Nf + tj] - 1);
+    double un[NC], ui[NC], uo[NC], njf[D];
+#pragma unroll
+    for (int e = 0; e < NC; e++) un[e] = __ldcs(u_q + ((size_t)k * NC + e) * Nq + tn);
+#pragma unroll
+    for (int e = 0; e < NC; e++) ui[e] = __ldcs(u_f + (size_t)k * Nf + tj + (size_t)g.NFT * e);
+    const double jf = __ldcs(g.J_f + (size_t)k * Nf + tj);
+#pragma unroll
+    for (int m = 0; m < D; m++) njf[m] = __ldcs(g.nJf + m + D * ((size_t)k * Nf + tj));
+#pragma unroll
+    for (int n = 0; n < D; n++)
+#pragma unroll
+        for (int m = 0; m < D; m++) lam[m][n] = __ldcs(g.Lambda_q + ((size_t)k * D * D + (m + D * n)) * Nq + tn);
+#pragma unroll
+    for (int e = 0; e < NC; e++) uo[e] = __ldcs(u_f + jo + (size_t)g.NFT * e);
+#pragma unroll
+    for (int m = 0; m < D; m++) sw[m] = t.vS[(0 * D + m) * Nq + tn];            // weights of round 0
+    const double bf = t.Bf[tj];
 #pragma unroll
     for (int e = 0; e < NC; e++) r[e] = 0.0;
-#pragma unroll
-    for (int m = 0; m < D; m++) sw[m] = 0.0;
+    to_prim_fast<D>(L, un, qi);
     if (node) {
-        double ui[NC];
-#pragma unroll
-        for (int e = 0; e < NC; e++) ui[e] = __ldcs(u_q + ((size_t)k * NC + e) * Nq + tid);
-#pragma unroll
-        for (int n = 0; n < D; n++)
-#pragma unroll
-            for (int m = 0; m < D; m++) lam[m][n] = __ldcs(g.Lambda_q + ((size_t)k * D * D + (m + D * n)) * Nq + tid);
-#pragma unroll
-        for (int m = 0; m < D; m++) sw[m] = t.vS[(0 * D + m) * Nq + tid];        // weights of round 0
-        to_prim_fast<D>(L, ui, qi);
 #pragma unroll
         for (int c = 0; c < NP; c++) s_prim[c * Nq + tid] = qi[c];
 #pragma unroll
@@ -499,29 +512,14 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
 #pragma unroll
             for (int m = 0; m < D; m++) s_lam[(m + D * n) * Nq + tid] = lam[m][n];
     }
-    for (int j = tid; j < Nf; j += blockDim.x) {
-        double ui[NC], uo[NC], qa[NP], qb[NP], nf[D], phi[NC];
-        const size_t jo = (size_t)(g.mapP[(size_t)k * Nf + j] - 1);
-#pragma unroll
-        for (int e = 0; e < NC; e++) { ui[e] = __ldcs(u_f + (size_t)k * Nf + j + (size_t)g.NFT * e); uo[e] = __ldcs(u_f + jo + (size_t)g.NFT * e); }
-        const double jf = __ldcs(g.J_f + (size_t)k * Nf + j);
+    {
+        double qa[NP], qb[NP], nf[D], nfq[D], phi[NC];
         const double ijf = rcp_fast(jf);
 #pragma unroll
-        for (int m = 0; m < D; m++) {
-            const double nj = __ldcs(g.nJf + m + D * ((size_t)k * Nf + j));
-            nf[m] = nj * ijf;                      // n_f = nJf / J_f            operators.jl:59
-            s_hnf[m * Nf + j] = nj;                // 2 halfnJf (operators.jl:78); the 1/2 lives in the fC table
-        }
+        for (int m = 0; m < D; m++) { nf[m] = njf[m] * ijf; nfq[m] = 0.25 * nf[m]; }     // n_f = nJf / J_f   operators.jl:59
         const double ira = to_prim_fast<D>(L, ui, qa);
         const double irb = to_prim_fast<D>(L, uo, qb);
-#pragma unroll
-        for (int c = 0; c < NP; c++) s_fprim[c * Nf + j] = qa[c];
-        {
-            double nfq[D];
-#pragma unroll
-            for (int m = 0; m < D; m++) nfq[m] = 0.25 * nf[m];
-            ec_contract_scaled<D>(L, qa, qb, nfq, phi);        // F#(u-, u+) . n    ConservationLaws.jl:75-128
-        }
+        ec_contract_scaled<D>(L, qa, qb, nfq, phi);            // F#(u-, u+) . n    ConservationLaws.jl:75-128
         if (L.inviscid == SSE_FLUX_LAX_FRIEDRICHS) {
             double vni = 0.0, vno = 0.0;
 #pragma unroll
@@ -531,9 +529,15 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
 #pragma unroll
             for (int e = 0; e < NC; e++) phi[e] = fma(a, ui[e] - uo[e], phi[e]);
         }
-        const double bj = t.Bf[j] * jf;                        // BJf               operators.jl:58
+        const double bj = bf * jf;                             // BJf               operators.jl:58
+        if (fac) {
 #pragma unroll
-        for (int e = 0; e < NC; e++) s_ff[e * Nf + j] = bj * phi[e];
+            for (int m = 0; m < D; m++) s_hnf[m * Nf + tid] = njf[m];       // 2 halfnJf (operators.jl:78); the 1/2 lives in fC
+#pragma unroll
+            for (int c = 0; c < NP; c++) s_fprim[c * Nf + tid] = qa[c];
+#pragma unroll
+            for (int e = 0; e < NC; e++) s_ff[e * Nf + tid] = bj * phi[e];
+        }
     }
     __syncthreads();
 
@@ -543,7 +547,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
         int buf = 0;
         double swb[D];
 #pragma unroll
-        for (int m = 0; m < D; m++) swb[m] = node ? t.vS[(1 * D + m) * Nq + tid] : 0.0;
+        for (int m = 0; m < D; m++) swb[m] = t.vS[(1 * D + m) * Nq + tn];
 #pragma unroll 1
         for (int l = 0; l < D; l++, buf ^= 1) {
             double* stA = s_stage + (2 * buf) * NC * Nq;
@@ -556,8 +560,8 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
             double swnA[D], swnB[D];
 #pragma unroll
             for (int m = 0; m < D; m++) {
-                swnA[m] = (node && l + 1 < D) ? t.vS[((2 * l + 2) * D + m) * Nq + tid] : 0.0;
-                swnB[m] = (node && l + 1 < D) ? t.vS[((2 * l + 3) * D + m) * Nq + tid] : 0.0;
+                swnA[m] = (l + 1 < D) ? t.vS[((2 * l + 2) * D + m) * Nq + tn] : 0.0;
+                swnB[m] = (l + 1 < D) ? t.vS[((2 * l + 3) * D + m) * Nq + tn] : 0.0;
             }
             if (node) {
                 double gA[D], gB[D], qA[NP], qB[NP], pA[NC], pB[NC];
@@ -587,7 +591,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
 #pragma unroll
             for (int m = 0; m < D; m++) { sw[m] = swnA[m]; swb[m] = swnB[m]; }
         }
-        double cwA = node ? t.fC[tid] : 0.0, cwB = node ? t.fC[Nq + tid] : 0.0;
+        double cwA = t.fC[tn], cwB = t.fC[Nq + tn];
         static_assert(NN * NC == Nq, "reducer items = volume nodes");
         const int re = tid / NN, rjj = tid - re * NN, rx = rjj / N, ry = rjj - rx * N;
         int rc3 = ry ? N - ry : 0;          // volume column (fr - 3 - y) mod N feeding facet node (x, y) of face 4, sub-round 3
@@ -596,8 +600,8 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
             double* stA = s_stage + (2 * buf) * NC * Nq;
             double* stB = stA + NC * Nq;
             const int fA = fr < 3 ? fr : 3, fB = fr + 1 < 3 ? fr + 1 : 3;
-            const double cwnA = (node && fr + 2 < NFR) ? t.fC[(fr + 2) * Nq + tid] : 0.0;
-            const double cwnB = (node && fr + 3 < NFR) ? t.fC[(fr + 3) * Nq + tid] : 0.0;
+            const double cwnA = (fr + 2 < NFR) ? t.fC[(fr + 2) * Nq + tn] : 0.0;
+            const double cwnB = (fr + 3 < NFR) ? t.fC[(fr + 3) * Nq + tn] : 0.0;
             if (node) {
                 double hA[D], hB[D];
 #pragma unroll
@@ -663,7 +667,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
         const int j = tid + (cj - cl) * stride;
         double swn[D];                                         // prefetch the next round's weights
 #pragma unroll
-        for (int m = 0; m < D; m++) swn[m] = (node && rd + 1 < NVR) ? t.vS[((rd + 1) * D + m) * Nq + tid] : 0.0;
+        for (int m = 0; m < D; m++) swn[m] = (rd + 1 < NVR) ? t.vS[((rd + 1) * D + m) * Nq + tn] : 0.0;
         if (active) {
             double gv[D], qj[NP], phi[NC];
 #pragma unroll
@@ -691,7 +695,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
     }
 
     // ---- facet correction: NFR sub-rounds (facet_correction!, flux_differencing_form.jl:126-168)
-    double cw = node ? t.fC[tid] : 0.0;
+    double cw = t.fC[tn];
     double hq[D];
 #pragma unroll
     for (int n = 0; n < D; n++) hq[n] = 0.0;
@@ -699,7 +703,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
     for (int fr = 0; fr < NFR; fr++, buf ^= 1) {
         double* st = s_stage + buf * NC * Nq;
         const int f = fr < 3 ? fr : 3;
-        const double cwn = (node && fr + 1 < NFR) ? t.fC[(fr + 1) * Nq + tid] : 0.0;
+        const double cwn = (fr + 1 < NFR) ? t.fC[(fr + 1) * Nq + tn] : 0.0;
         if (node) {
             if (fr <= 3) {                         // 2 halfnJq[:, f, i] = sum_l Lambda[i,l,:] nref[l,f]   mesh.jl:262-269
                 if (g.nJq) {

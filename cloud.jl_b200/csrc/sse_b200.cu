@@ -649,18 +649,28 @@ extern "C" int32_t sse_step_ck54(sse_handle* h, double* d_u, double* d_tmp, doub
     return SSE_OK;
 }
 
-// conservation / entropy residual reductions (Analysis/conservation.jl:145-189)
+// conservation / energy / entropy residual reductions (Analysis/conservation.jl:145-189)
+//   out[e < NC] = sum_k 1' WJ_k V dudt_k[:, e]                      (:145-152)
+//   out[NC]     = sum_k sum_e u_k[:, e]' M_k dudt_k[:, e]           (:154-167), M_k = mass_matrix(mass_solver, k):
+//                 diag(W J_k) for the DiagonalSolver; for the WeightAdjustedSolver M_k = (V' diag(W / J_k) V)^-1
+//                 (mass_matrix.jl:140-153), applied by conjugate gradients on the SPD operator the residual itself
+//                 applies (its condition number is max J / min J over the element, so a few iterations suffice)
+//   out[NC + 1] = sum_k (V' WJ_k w(V u_k))' dudt_k                   (:169-189, M_k symmetric)
 template <int D, int NC>
 __global__ void k_functionals(Ops o, Geo g, Law L, const double* __restrict__ u, const double* __restrict__ dudt, double* __restrict__ out) {
     extern __shared__ double sm[];
     const int Nq = o.Nq, Np = o.Np;
     double* s_u = sm;                 // Np x NC
-    double* s_d = s_u + Np * NC;      // Np x NC
-    double* s_uq = s_d + Np * NC;     // Nq x NC
+    double* s_d = s_u + Np * NC;      // Np x NC   dudt, then the CG residual
+    double* s_y = s_d + Np * NC;      // Np x NC   CG iterate
+    double* s_p = s_y + Np * NC;      // Np x NC   CG direction
+    double* s_ap = s_p + Np * NC;     // Np x NC
+    double* s_uq = s_ap + Np * NC;    // Nq x NC
     double* s_dq = s_uq + Nq * NC;    // Nq x NC
     double* s_z = s_dq + Nq * NC;
     double* s_w = s_z + warp_z_size(o, NC);
-    __shared__ double acc[NC + 2];
+    __shared__ double acc[NC + 2], rr[NC], pap[NC], rr0[NC];
+    __shared__ int go;
     if (threadIdx.x < NC + 2) acc[threadIdx.x] = 0.0;
     for (long long k = blockIdx.x; k < g.Ne; k += gridDim.x) {
         __syncthreads();
@@ -674,6 +684,10 @@ __global__ void k_functionals(Ops o, Geo g, Law L, const double* __restrict__ u,
             double ui[NC], wi[NC];
 #pragma unroll
             for (int e = 0; e < NC; e++) { ui[e] = s_uq[i + Nq * e]; atomicAdd(&acc[e], wj * s_dq[i + Nq * e]); }
+            if (g.mass_solver == SSE_MASS_DIAGONAL) {
+#pragma unroll
+                for (int e = 0; e < NC; e++) atomicAdd(&acc[NC], wj * ui[e] * s_dq[i + Nq * e]);
+            }
             if (L.pde == SSE_PDE_EULER) {
                 cons_to_entropy<D, NC>(L, ui, wi);
                 double s = 0.0;
@@ -681,6 +695,48 @@ __global__ void k_functionals(Ops o, Geo g, Law L, const double* __restrict__ u,
                 for (int e = 0; e < NC; e++) s += wi[e] * s_dq[i + Nq * e];
                 atomicAdd(&acc[NC + 1], wj * s);
             }
+        }
+        if (g.mass_solver != SSE_MASS_DIAGONAL) {
+            __syncthreads();
+            if (threadIdx.x < NC) rr[threadIdx.x] = 0.0;
+            SSE_FOR(t, Np * NC) { s_y[t] = 0.0; s_p[t] = s_d[t]; }
+            __syncthreads();
+            SSE_FOR(t, Np * NC) atomicAdd(&rr[t / Np], s_d[t] * s_d[t]);
+            __syncthreads();
+            if (threadIdx.x < NC) rr0[threadIdx.x] = rr[threadIdx.x];
+            for (int it = 0; it < 60; it++) {
+                SSE_FOR(t, Np * NC) s_ap[t] = s_p[t];
+                if (threadIdx.x < NC) pap[threadIdx.x] = 0.0;
+                if (threadIdx.x == 0) go = 0;
+                __syncthreads();
+                mass_solve<NC>(o, g, k, s_ap, s_dq, s_z, s_w);                   // A p = V' diag(W/J) V p
+                __syncthreads();
+                SSE_FOR(t, Np * NC) atomicAdd(&pap[t / Np], s_p[t] * s_ap[t]);
+                __syncthreads();
+                SSE_FOR(t, Np * NC) {
+                    const int e = t / Np;
+                    const double al = pap[e] > 0.0 ? rr[e] / pap[e] : 0.0;
+                    s_y[t] = fma(al, s_p[t], s_y[t]);
+                    s_d[t] = fma(-al, s_ap[t], s_d[t]);
+                }
+                __syncthreads();
+                if (threadIdx.x < NC) pap[threadIdx.x] = 0.0;                    // reused for the new <r, r>
+                __syncthreads();
+                SSE_FOR(t, Np * NC) atomicAdd(&pap[t / Np], s_d[t] * s_d[t]);
+                __syncthreads();
+                SSE_FOR(t, Np * NC) {
+                    const int e = t / Np;
+                    const double be = rr[e] > 0.0 ? pap[e] / rr[e] : 0.0;
+                    s_p[t] = fma(be, s_p[t], s_d[t]);
+                }
+                if (threadIdx.x < NC && pap[threadIdx.x] > 1e-30 * rr0[threadIdx.x]) go = 1;
+                __syncthreads();
+                if (threadIdx.x < NC) rr[threadIdx.x] = pap[threadIdx.x];
+                const int cont = go;
+                __syncthreads();
+                if (!cont) break;
+            }
+            SSE_FOR(t, Np * NC) atomicAdd(&acc[NC], s_u[t] * s_y[t]);
         }
     }
     __syncthreads();
@@ -695,7 +751,7 @@ extern "C" int32_t sse_functionals(sse_handle* h, const double* d_u, const doubl
     CU(cudaMalloc((void**)&d_out, sizeof(double) * (NC + 2)));
     CU(cudaMemsetAsync(d_out, 0, sizeof(double) * (NC + 2), h->stream));
     const Ops& o = h->ops;
-    size_t smem = sizeof(double) * (size_t)(2 * o.Np * NC + 2 * o.Nq * NC + warp_z_size(o, NC) + warp_w_size(o, NC));
+    size_t smem = sizeof(double) * (size_t)(5 * o.Np * NC + 2 * o.Nq * NC + warp_z_size(o, NC) + warp_w_size(o, NC));
     unsigned grid = (unsigned)std::min<long long>(h->cfg.N_e, 4LL * h->sm_count);
 #define LA(D_, NC_)                                                                                                  \
     do {                                                                                                             \
@@ -708,8 +764,6 @@ extern "C" int32_t sse_functionals(sse_handle* h, const double* d_u, const doubl
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(d_out);
     if (e != cudaSuccess) return fail(SSE_ERR_CUDA, "functionals failed: %s", cudaGetErrorString(e));
-    // energy residual u' M dudt needs the per-element mass matrix; provided for the diagonal solver only
-    out[NC] = NAN;
     return SSE_OK;
 }
 

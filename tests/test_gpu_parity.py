@@ -187,6 +187,29 @@ def test_invariants_at_scale_and_functionals():
     s.close()
 
 
+@pytest.mark.parametrize("name", ["advection_2d_lf", "advection_2d_central", "advection_3d_lf", "euler_tgv_3d_lf",
+                                  "burgers_1d_ec", "euler_3d_hex_lf"])
+def test_energy_functional_matches_host_analysis(name):
+    """out[N_c] of sse_functionals = sum_e u' M dudt (Analysis/conservation.jl:154-167) with the mass matrix of the
+    solver: diag(W J) for collocated schemes, the inverse of the weight-adjusted inverse for modal ones (solved by
+    conjugate gradients on the device)."""
+    c = CASES[name]()
+    img, u = c.image(), c.u0(seed=9)
+    s = Solver(img, 0)
+    du = s.new_state()
+    ud = torch.from_numpy(u).cuda()
+    s.rhs(du, ud)
+    f = s.functionals(ud, du)
+    d = du.cpu().numpy()
+    ref = analysis.energy_residual(img, u, d)
+    scale = np.abs(np.einsum("kea,kea->", np.abs(u), np.abs(d))) + 1e-300
+    assert np.isfinite(f[img.cfg.N_c])
+    assert abs(f[img.cfg.N_c] - ref.sum()) < 1e-11 * max(scale, abs(ref.sum()))
+    if name == "advection_2d_central":
+        assert abs(f[1]) < 1e-10                  # energy conservation with the central flux (runtests.jl:59)
+    s.close()
+
+
 def test_host_buffer_api_and_linearity():
     c = cases.advection_3d(M=2, flux="lf")
     img = c.image()

@@ -135,24 +135,9 @@ class Solver:
         self.launches += 1 if count > 0 else 0
 
     def _chunk_plan(self, chunks: int):
-        """Schedule of the pipelined host-buffer residual: element ranges, their upload order, and for every upload
-        position the ranges whose pass B becomes runnable there — a range is runnable once pass A has covered all the
-        ranges holding one of its face neighbours (read from mapP).  On a periodic slab ordering the last range is
-        uploaded first so that only two ranges are left when the uploads end."""
         key = ("plan", chunks)
         if key not in self._pinned:
-            ne, nf = self.state_shape[0], int(self.cfg.N_f)
-            bounds = [ne * c // chunks for c in range(chunks + 1)]
-            nb = (np.asarray(self.image.arrays["mapP"]).reshape(ne, nf) - 1) // nf
-            owner = np.searchsorted(np.asarray(bounds[1:]), np.arange(ne), side="right")
-            deps = [set(np.unique(owner[nb[bounds[c]:bounds[c + 1]]]).tolist()) | {c} for c in range(chunks)]
-            up = list(range(chunks))
-            if chunks - 1 in deps[0]:
-                up = [chunks - 1] + up[:-1]
-            pos = {c: i for i, c in enumerate(up)}
-            ready = [max(pos[d] for d in deps[c]) for c in range(chunks)]
-            after = [[c for c in sorted(range(chunks), key=lambda c: pos[c]) if ready[c] == i] for i in range(chunks)]
-            self._pinned[key] = (bounds, up, after)
+            self._pinned[key] = chunk_plan(self.image.arrays["mapP"], self.state_shape[0], int(self.cfg.N_f), chunks)
         return self._pinned[key]
 
     def rhs_host(self, dudt_host, u_host, t: float = 0.0, chunks: int = 16):
@@ -275,6 +260,22 @@ class Solver:
     def halo_unpack(self, which: int = 0):
         _lib.check(self._lib.sse_halo_unpack(self._h, which))
         self.launches += 1
+
+
+def chunk_plan(mapP_1based, ne: int, nf: int, chunks: int):
+    """Schedule of the pipelined host-buffer residual (Solver.rhs_host): element ranges `bounds`, their upload order
+    `up`, and for every upload position the ranges whose pass B becomes runnable there (`after`) — a range is runnable
+    once pass A has covered all the ranges holding one of its face neighbours (read from mapP).  On a slab-ordered
+    periodic mesh every range waits for its two neighbours, so three ranges are left when the uploads end."""
+    bounds = [ne * c // chunks for c in range(chunks + 1)]
+    nb = (np.asarray(mapP_1based).reshape(ne, nf) - 1) // nf
+    owner = np.searchsorted(np.asarray(bounds[1:]), np.arange(ne), side="right")
+    deps = [set(np.unique(owner[nb[bounds[c]:bounds[c + 1]]]).tolist()) | {c} for c in range(chunks)]
+    up = list(range(chunks))
+    pos = {c: i for i, c in enumerate(up)}
+    ready = [max(pos[d] for d in deps[c]) for c in range(chunks)]
+    after = [[c for c in sorted(range(chunks), key=lambda c: pos[c]) if ready[c] == i] for i in range(chunks)]
+    return bounds, up, after
 
 
 def fp64_peak(device: int = 0) -> float:

@@ -46,3 +46,28 @@ def test_kernel_family_selection():
     assert selfcheck(cases.advection_3d(M=2, p=2).image())[0][0] == 0       # generic
     assert selfcheck(cases.advection_2d(M=2).image())[0][0] == 0
     assert selfcheck(cases.advection_diffusion_2d(M=2).image())[0][0] == 0
+
+
+def test_host_pipeline_chunk_plan():
+    """Schedule of Solver.rhs_host: every range is uploaded once, its pass B is released exactly when pass A has covered
+    all ranges holding one of its face neighbours, and on the slab-ordered periodic mesh only three ranges wait for the
+    last upload."""
+    from sse_b200.solver import chunk_plan
+    c = cases.euler_tgv_3d(M=8, p=2)
+    img = c.image()
+    ne, nf = int(img.cfg.N_e), int(img.cfg.N_f)
+    mapP = np.asarray(img.arrays["mapP"])
+    nb = (mapP.reshape(ne, nf) - 1) // nf
+    for chunks in (3, 8, 16):
+        bounds, up, after = chunk_plan(mapP, ne, nf, chunks)
+        assert sorted(up) == list(range(chunks)) and bounds[0] == 0 and bounds[-1] == ne
+        released = [k for a in after for k in a]
+        assert sorted(released) == list(range(chunks))
+        done = set()
+        for i, cth in enumerate(up):
+            done |= set(range(bounds[cth], bounds[cth + 1]))
+            for k in after[i]:
+                need = set(nb[bounds[k]:bounds[k + 1]].reshape(-1).tolist()) | set(range(bounds[k], bounds[k + 1]))
+                assert need <= done, "pass B released before pass A covered its neighbours"
+        if chunks == 8:                      # one cube layer per range: a range depends on its two neighbours
+            assert len(after[-1]) == 3 and all(len(a) <= 1 for a in after[:-1])

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "kernels_generic.cuh"
 #include "kernels_tensor.cuh"
+#include "kernels_geometry.cuh"
 #include "ct_api.h"
 
 using namespace sse;
@@ -764,6 +765,82 @@ extern "C" int32_t sse_functionals(sse_handle* h, const double* d_u, const doubl
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(d_out);
     if (e != cudaSuccess) return fail(SSE_ERR_CUDA, "functionals failed: %s", cudaGetErrorString(e));
+    return SSE_OK;
+}
+
+// GeometricFactors for a whole mesh (mesh.jl:229-506): host in, host out, element chunks staged through the device
+extern "C" int32_t sse_geometric_factors(const sse_geom_config* c, const sse_geom_ops* op, int32_t device, const double* const xyz[3],
+                                         double* J_q, double* Lambda_q, double* J_f, double* nJf) {
+    if (!c || !op || !xyz || !J_q || !Lambda_q || !J_f || !nJf) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    const int d = c->d, Nm = c->N_map, N1 = c->N1, Nq = c->N_q, Nf = c->N_f;
+    if (d < 1 || d > 3 || Nm < 2 || Nq < 1 || Nf < 1 || c->N_e < 0) return fail(SSE_ERR_BAD_ARGUMENT, "bad geometry sizes");
+    const bool curl3 = c->metric == SSE_METRIC_CURL && d == 3;
+    if (!op->Vq || !op->Vf || !op->nrstJ) return fail(SSE_ERR_BAD_ARGUMENT, "Vq, Vf and nrstJ are required");
+    for (int m = 0; m < d; m++) if (!op->Drst[m] || !xyz[m]) return fail(SSE_ERR_BAD_ARGUMENT, "Drst / xyz missing");
+    if (curl3) {
+        if (!op->Vq1 || !op->Vf1 || !op->D1[0] || !op->D1[1] || !op->D1[2]) return fail(SSE_ERR_BAD_ARGUMENT, "3-D curl metrics need D1, Vq1, Vf1");
+        if ((N1 != Nm) != (op->up != nullptr)) return fail(SSE_ERR_BAD_ARGUMENT, "up must be given exactly when N1 != N_map");
+    } else if (N1 != Nm) return fail(SSE_ERR_BAD_ARGUMENT, "N1 != N_map only for the 3-D curl metrics");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(SSE_ERR_CUDA, "no usable CUDA device %d (libsse_b200 has no CPU fallback)", device);
+    std::vector<void*> owned;
+    auto cleanup = [&]() { for (void* p : owned) cudaFree(p); };
+    auto up_ = [&](const double* src, size_t n, const double** out) -> bool {
+        void* p = nullptr;
+        if (cudaMalloc(&p, sizeof(double) * std::max<size_t>(n, 1)) != cudaSuccess) return false;
+        owned.push_back(p);
+        if (n && cudaMemcpy(p, src, sizeof(double) * n, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+        *out = (const double*)p;
+        return true;
+    };
+    GeomDev g;
+    memset(&g, 0, sizeof(g));
+    g.d = d; g.Nmap = Nm; g.N1 = N1; g.Nq = Nq; g.Nf = Nf; g.metric = c->metric;
+    bool ok = up_(op->Vq, (size_t)Nq * Nm, &g.Vq) && up_(op->Vf, (size_t)Nf * Nm, &g.Vf) && up_(op->nrstJ, (size_t)Nf * d, &g.nrstJ);
+    for (int m = 0; m < d && ok; m++) ok = up_(op->Drst[m], (size_t)Nm * Nm, &g.Drst[m]);
+    if (ok && curl3) {
+        ok = up_(op->Vq1, (size_t)Nq * N1, &g.Vq1) && up_(op->Vf1, (size_t)Nf * N1, &g.Vf1);
+        for (int m = 0; m < 3 && ok; m++) ok = up_(op->D1[m], (size_t)N1 * N1, &g.D1[m]);
+        if (ok && op->up) ok = up_(op->up, (size_t)N1 * Nm, &g.up);
+    }
+    const long long CH = 65536;
+    const long long nch = std::min<long long>(CH, std::max<long long>(c->N_e, 1));
+    double *dx[3] = {nullptr, nullptr, nullptr}, *dJq = nullptr, *dL = nullptr, *dJf = nullptr, *dn = nullptr;
+    auto dal = [&](size_t n, double** out) -> bool {
+        void* p = nullptr;
+        if (cudaMalloc(&p, sizeof(double) * std::max<size_t>(n, 1)) != cudaSuccess) return false;
+        owned.push_back(p);
+        *out = (double*)p;
+        return true;
+    };
+    for (int m = 0; m < d && ok; m++) ok = dal((size_t)Nm * nch, &dx[m]);
+    ok = ok && dal((size_t)Nq * nch, &dJq) && dal((size_t)Nq * d * d * nch, &dL) && dal((size_t)Nf * nch, &dJf) && dal((size_t)Nf * d * nch, &dn);
+    if (!ok) { cleanup(); return fail(SSE_ERR_CUDA, "device allocation / upload failed in sse_geometric_factors"); }
+    const int NM = std::max(N1, Nm);
+    const size_t smem = sizeof(double) * (size_t)(d * NM + d * d * NM + 3 * NM + Nm);
+    if (smem > 227 * 1024) { cleanup(); return fail(SSE_ERR_UNSUPPORTED, "mapping element too large for the geometry kernel"); }
+    cudaFuncSetAttribute(k_geometry<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_geometry<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_geometry<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaSuccess;
+    for (long long k0 = 0; k0 < c->N_e && e == cudaSuccess; k0 += nch) {
+        const long long n = std::min<long long>(nch, c->N_e - k0);
+        for (int m = 0; m < d && e == cudaSuccess; m++) {
+            e = cudaMemcpy(dx[m], xyz[m] + (size_t)Nm * k0, sizeof(double) * (size_t)Nm * n, cudaMemcpyHostToDevice);
+            g.xyz[m] = dx[m];
+        }
+        if (e != cudaSuccess) break;
+        g.Ne = n; g.J_q = dJq; g.Lambda_q = dL; g.J_f = dJf; g.nJf = dn;
+        if (d == 1) k_geometry<1><<<(unsigned)n, 128, smem>>>(g);
+        else if (d == 2) k_geometry<2><<<(unsigned)n, 128, smem>>>(g);
+        else k_geometry<3><<<(unsigned)n, 128, smem>>>(g);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if ((e = cudaMemcpy(J_q + (size_t)Nq * k0, dJq, sizeof(double) * (size_t)Nq * n, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(Lambda_q + (size_t)Nq * d * d * k0, dL, sizeof(double) * (size_t)Nq * d * d * n, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(J_f + (size_t)Nf * k0, dJf, sizeof(double) * (size_t)Nf * n, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        e = cudaMemcpy(nJf + (size_t)Nf * d * k0, dn, sizeof(double) * (size_t)Nf * d * n, cudaMemcpyDeviceToHost);
+    }
+    cleanup();
+    if (e != cudaSuccess) return fail(SSE_ERR_CUDA, "sse_geometric_factors failed: %s", cudaGetErrorString(e));
     return SSE_OK;
 }
 

@@ -42,6 +42,19 @@ class sse_arrays(C.Structure):
     ]
 
 
+SSE_METRIC_EXACT, SSE_METRIC_CURL = 0, 1
+
+
+class sse_geom_config(C.Structure):
+    _fields_ = [("d", C.c_int32), ("N_map", C.c_int32), ("N1", C.c_int32), ("N_q", C.c_int32), ("N_f", C.c_int32),
+                ("metric", C.c_int32), ("N_e", C.c_int64)]
+
+
+class sse_geom_ops(C.Structure):
+    _fields_ = [("Drst", _pd * 3), ("Vq", _pd), ("Vf", _pd), ("nrstJ", _pd), ("up", _pd), ("D1", _pd * 3),
+                ("Vq1", _pd), ("Vf1", _pd)]
+
+
 def _ptr(a, ty):
     if a is None:
         return C.cast(None, ty)

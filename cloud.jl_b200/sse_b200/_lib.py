@@ -48,6 +48,8 @@ SYMBOLS = {
     "sse_debug_views": (C.c_int32, [_h, _ppd, _ppd]),
     "sse_plan_selfcheck": (C.c_int32, [C.POINTER(_abi.sse_config), C.POINTER(_abi.sse_arrays), C.POINTER(C.c_int32), _pd]),
     "sse_fp64_peak": (C.c_int32, [C.c_int32, _pd]),
+    "sse_geometric_factors": (C.c_int32, [C.POINTER(_abi.sse_geom_config), C.POINTER(_abi.sse_geom_ops), C.c_int32,
+                                          C.POINTER(_pd), _pd, _pd, _pd, _pd]),
 }
 
 _LIB = None

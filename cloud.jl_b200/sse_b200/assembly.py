@@ -49,8 +49,8 @@ class SpatialDiscretization:
 
     @staticmethod
     def build(mesh: Mesh, ra: ReferenceApproximation, metric_type: str = "exact",
-              project_jacobian_flag: bool = True, need_nJq: bool = True) -> "SpatialDiscretization":
-        gf = geometric_factors(mesh, ra, metric_type, need_nJq=need_nJq)
+              project_jacobian_flag: bool = True, need_nJq: bool = True, device=None) -> "SpatialDiscretization":
+        gf = geometric_factors(mesh, ra, metric_type, need_nJq=need_nJq, device=device)
         if metric_type == "exact" and project_jacobian_flag:
             gf.J_q = np.ascontiguousarray(project_jacobian(gf.J_q, ra))
         return SpatialDiscretization(mesh, ra, gf, mesh.N_e)

@@ -461,9 +461,12 @@ class _Acc:
 
 
 def geometric_factors(mesh: Mesh, ra: ReferenceApproximation, metric_type: str = "exact",
-                      chunk: int = 32768, need_nJq: bool = True) -> GeometricFactors:
-    """metric_type: 'exact' (mesh.jl:229-282) or 'curl' (ConservativeCurl/ChanWilcox)."""
+                      chunk: int = 32768, need_nJq: bool = True, device: Optional[int] = None) -> GeometricFactors:
+    """metric_type: 'exact' (mesh.jl:229-282) or 'curl' (ConservativeCurl/ChanWilcox).  With `device` the metrics are
+    computed by the CUDA library (sse_geometric_factors) instead of NumPy."""
     d, g = ra.d, ra.geom
+    if device is not None:
+        return _gf_device(mesh, ra, metric_type, need_nJq, device)
     outs = []
     for s in range(0, mesh.N_e, chunk):
         xyz = [x[s:s + chunk] for x in mesh.xyz]
@@ -478,6 +481,60 @@ def geometric_factors(mesh: Mesh, ra: ReferenceApproximation, metric_type: str =
     return GeometricFactors(*[None if getattr(outs[0], f) is None else
                               np.concatenate([getattr(o, f) for o in outs], axis=0)
                               for f in ("J_q", "Lambda_q", "J_f", "nJf", "nJq")])
+
+
+def _curl_lift(ra):
+    """Operators of the degree N+1 element on which the curl argument of the tetrahedral metrics lives
+    (mesh.jl:417-433): (g1, N -> N+1 interpolation, (Vq N+1->N)^T, (Vf N+1->N)^T)."""
+    g = ra.geom
+    key = (id(ra), g.N)
+    if key not in _CURL_CACHE:
+        g1 = geometry_element(3, g.N + 1, g.rst, g.rst)        # Vq of g1 = interp (N+1 nodes -> N nodes)
+        up = g.interp(g1.rst)                                  # N nodes -> N+1 nodes
+        down = g1.Vq                                           # N+1 nodes -> N nodes
+        _CURL_CACHE[key] = (g1, up, np.ascontiguousarray((g.Vq @ down).T), np.ascontiguousarray((g.Vf @ down).T))
+    return _CURL_CACHE[key]
+
+
+def _gf_device(mesh, ra, metric_type, need_nJq, device):
+    """GeometricFactors through sse_geometric_factors (csrc/kernels_geometry.cuh); arrays come back in the ABI layouts."""
+    import ctypes as C
+    from . import _abi, _lib
+    d, g = ra.d, ra.geom
+    ne = mesh.N_e
+    col = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64).T).reshape(-1)       # column-major image
+    cfg = _abi.sse_geom_config()
+    cfg.d, cfg.N_map, cfg.N_q, cfg.N_f, cfg.N_e = d, g.rst[0].size, ra.N_q, ra.N_f, ne
+    cfg.metric = _abi.SSE_METRIC_CURL if (metric_type == "curl" and d > 1) else _abi.SSE_METRIC_EXACT
+    cfg.N1 = cfg.N_map
+    keep = {"Drst": [col(D) for D in g.Drst], "Vq": col(g.Vq), "Vf": col(g.Vf), "nrstJ": col(np.stack(ra.nrstJ, axis=1))}
+    if cfg.metric == _abi.SSE_METRIC_CURL and d == 3:
+        if ra.element == "Hex":
+            keep.update(D1=keep["Drst"], Vq1=keep["Vq"], Vf1=keep["Vf"])
+        else:
+            g1, up, VqT, VfT = _curl_lift(ra)
+            cfg.N1 = g1.rst[0].size
+            keep.update(D1=[col(D) for D in g1.Drst], Vq1=col(VqT.T), Vf1=col(VfT.T), up=col(up))
+    ops = _abi.sse_geom_ops()
+    pd = C.POINTER(C.c_double)
+    ptr = lambda a: a.ctypes.data_as(pd) if a is not None else C.cast(None, pd)
+    ops.Drst = (pd * 3)(*[ptr(keep["Drst"][m]) if m < d else ptr(None) for m in range(3)])
+    ops.D1 = (pd * 3)(*[ptr(keep["D1"][m]) if "D1" in keep else ptr(None) for m in range(3)])
+    ops.Vq, ops.Vf, ops.nrstJ = ptr(keep["Vq"]), ptr(keep["Vf"]), ptr(keep["nrstJ"])
+    ops.up, ops.Vq1, ops.Vf1 = ptr(keep.get("up")), ptr(keep.get("Vq1")), ptr(keep.get("Vf1"))
+    xs = [np.ascontiguousarray(x, dtype=np.float64) for x in mesh.xyz]
+    xyz = (pd * 3)(*[ptr(xs[m]) if m < d else ptr(None) for m in range(3)])
+    J_q = np.empty((ne, ra.N_q))
+    Lam = np.empty((ne, d, d, ra.N_q))
+    J_f = np.empty((ne, ra.N_f))
+    nJf = np.empty((ne, ra.N_f, d))
+    _lib.check(_lib.load().sse_geometric_factors(C.byref(cfg), C.byref(ops), int(device), xyz, ptr(J_q), ptr(Lam), ptr(J_f), ptr(nJf)))
+    nJq = None
+    if need_nJq:
+        npf = ra.nodes_per_face
+        nrf = np.array([[ra.nrstJ[l][npf * f] for l in range(d)] for f in range(ra.N_fac)])
+        nJq = np.ascontiguousarray(np.einsum("knli,fl->kifn", Lam, nrf))
+    return GeometricFactors(J_q, Lam, J_f, nJf, nJq)
 
 
 def _gf_exact(ra, xyz, need_nJq=True):
@@ -546,14 +603,7 @@ def _gf_curl_3d(ra, xyz, need_nJq=True):
     if ra.element == "Hex":
         return _gf_curl_hex(ra, xyz, need_nJq)
     g = ra.geom
-    N = g.N
-    key = (id(ra), N)
-    if key not in _CURL_CACHE:
-        g1 = geometry_element(3, N + 1, g.rst, g.rst)          # Vq of g1 = interp (N+1 nodes -> N nodes)
-        up = g.interp(g1.rst)                                  # N nodes -> N+1 nodes
-        down = g1.Vq                                           # N+1 nodes -> N nodes
-        _CURL_CACHE[key] = (g1, up, np.ascontiguousarray((g.Vq @ down).T), np.ascontiguousarray((g.Vf @ down).T))
-    g1, up, VqT, VfT = _CURL_CACHE[key]
+    g1, up, VqT, VfT = _curl_lift(ra)
     x, y, z = xyz
     Dr, Ds, Dt = g.Drst
     xr, xs, xt = x @ Dr.T, x @ Ds.T, x @ Dt.T

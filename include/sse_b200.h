@@ -193,6 +193,34 @@ int32_t sse_plan_selfcheck(const sse_config* cfg, const sse_arrays* arr, int32_t
 /* register-resident DFMA microbenchmark: achieved FP64 FLOP/s on the handle's device (FMA = 2) */
 int32_t sse_fp64_peak(int32_t device, double* flops_per_s);
 
+/* -- device-side geometry --------------------------------------------------------
+   GeometricFactors(mesh, reference_element, metric_type) (mesh.jl:229-506) for a whole mesh: from the mapping-node
+   coordinates xyz[m] (N_map, N_e) to J_q (N_q,N_e), Λ_q (N_q,d,d,N_e), J_f (N_f,N_e), nJf (d,N_f,N_e) — exactly the arrays
+   sse_arrays takes.  All matrices are column-major as Julia stores them; all pointers are HOST pointers (the library
+   stages element chunks through the device).  Operators of the reference element (StartUpDG RefElemData fields):
+   Drst = (Dr, Ds, Dt) (N_map,N_map), Vq (N_q,N_map), Vf (N_f,N_map), nrstJ[m] concatenated as (N_f, d).
+   SSE_METRIC_EXACT: mesh.jl:229-282.  SSE_METRIC_CURL: 2-D mesh.jl:284-339; 3-D conservative curl form evaluated on N1
+   nodes with derivative matrices D1 (N1,N1) and interpolations Vq1 (N_q,N1), Vf1 (N_f,N1): for Hex N1 = N_map and
+   up = NULL (mesh.jl:341-408); for Tet the degree N+1 nodes with up = N_to_Nplus1 (N1,N_map), Vq1 = Vq*Nplus1_to_N
+   (mesh.jl:410-506). */
+enum { SSE_METRIC_EXACT = 0, SSE_METRIC_CURL = 1 };
+typedef struct {
+    int32_t d, N_map, N1, N_q, N_f, metric;
+    int64_t N_e;
+} sse_geom_config;
+typedef struct {
+    const double* Drst[3];
+    const double* Vq;
+    const double* Vf;
+    const double* nrstJ;
+    const double* up;        /* NULL when N1 == N_map */
+    const double* D1[3];     /* 3-D curl only */
+    const double* Vq1;
+    const double* Vf1;
+} sse_geom_ops;
+int32_t sse_geometric_factors(const sse_geom_config* cfg, const sse_geom_ops* ops, int32_t device, const double* const xyz[3],
+                              double* J_q, double* Lambda_q, double* J_f, double* nJf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,7 +85,7 @@ def workload_name(cells, n_e, dof, flux):
             f"{'Lax-Friedrichs' if flux == 'lf' else 'EC'} interface), ChanWarping 1/16, conservative-curl metrics")
 
 
-def build_case(cells, flux, part):
+def build_case(cells, flux, part, device=None):
     from sse_b200 import cases
     from sse_b200.assembly import FluxDifferencingForm, REFERENCE_OPERATOR, SpatialDiscretization
     from sse_b200.laws import EulerEquations, project_function_reference, taylor_green_vortex
@@ -94,7 +94,7 @@ def build_case(cells, flux, part):
     L = 2 * np.pi
     ra = reference_approximation(ModalTensor(4), "Tet", mapping_degree=4)
     mesh = uniform_periodic_mesh(ra, ((0.0, L),) * 3, (cells,) * 3, ChanWarping(1.0 / 16.0, (L,) * 3), part)
-    sd = SpatialDiscretization.build(mesh, ra, "curl", need_nJq=False)
+    sd = SpatialDiscretization.build(mesh, ra, "curl", need_nJq=False, device=device)   # metrics on the GPU when given
     ic = taylor_green_vortex(1.4, 0.1)
     c = cases.Case("euler_tgv_3d", EulerEquations(3, 1.4), sd,
                    FluxDifferencingForm(inviscid_numerical_flux=cases._flux(flux)), REFERENCE_OPERATOR, ic)
@@ -170,7 +170,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 
     t_setup = time.time()
-    case, u0 = build_case(a.cells, a.flux, (rank, world) if world > 1 else None)
+    case, u0 = build_case(a.cells, a.flux, (rank, world) if world > 1 else None, device=local)
     img = case.image()
     solver = Solver(img, local)
     solver.set_kernel_variant(a.variant)

@@ -167,7 +167,7 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
     constexpr int D = 3;
     using T = Tet<N>;
     using S = ProjSmem<N, NC>;
-    constexpr int Nq = T::Nq, Np = T::Np, Nf = T::Nf, EPB = S::EPB, NG = S::NG;
+    constexpr int Nq = T::Nq, Np = T::Np, Nf = T::Nf, EPB = S::EPB;
     extern __shared__ double sm[];
     double* s_x = sm + S::x;
     double* s_q = sm + S::big;

@@ -79,14 +79,12 @@ __host__ __device__ inline FdLayout fd_layout(const Ops& o, int D, int NC, int N
     // scratch may run over ff/hnf (dead by then) but must stay clear of stage buffer 0
     l.total = fd_total;
     if (post_end > l.stage) {      // not enough dead space in front of the stage: append
-        int shift = post_end - l.stage;
         l.post_r = l.stage;        // keep r where it is and move the scratch behind the stage buffers
         l.post_m = fd_total;
         l.post_tq = l.post_m + o.Np * NC;
         l.post_z = l.post_tq + o.Nq * NC;
         l.post_w = l.post_z + warp_z_size(o, NC);
         l.total = l.post_w + warp_w_size(o, NC);
-        (void)shift;
     }
     return l;
 }

@@ -255,6 +255,21 @@ def main():
         e2e_ms = float(t.item())
     state_bytes = int(u0.size) * 8
 
+    # size-independent properties of the residual at the full size (outside every timed region): the discrete
+    # conservation functionals 1' M dudt vanish for the periodic mesh, and the host-buffer call returns the device result
+    checks = {}
+    try:
+        ds.rhs(du, u) if ds is not None else solver.rhs(du, u)
+        f = torch.tensor(solver.functionals(u, du)[:5], dtype=torch.float64, device="cuda")
+        sc = torch.tensor([float(du.abs().max())], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(f)
+            dist.all_reduce(sc, op=dist.ReduceOp.MAX)
+        checks["conservation_residual_rel"] = float(f.abs().max() / (sc[0] * (2 * np.pi) ** 3))
+        if world == 1:
+            checks["host_buffer_result_equals_device"] = bool(torch.equal(hdu, du.cpu()))
+    except Exception as e:
+        checks["error"] = str(e)
     if rank == 0:
         peaks = {}
         try:
@@ -297,6 +312,7 @@ def main():
                                                           "algorithmic_bytes_per_element": ALG_BYTES_RHS}}
             except Exception as e:
                 out["roofline_fp64"] = {"error": str(e)}
+        out["checks"] = checks
         if not a.no_cpu_baseline and world == 1:
             try:
                 out["cpu_baseline"] = cpu_baseline(a.cpu_cells, a.flux)

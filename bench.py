@@ -234,6 +234,8 @@ def main():
     hdu = torch.empty_like(hu).pin_memory()
     if ds is None:
         semi_discrete_residual(hdu, hu, solver)
+    else:
+        ds.rhs_host(hdu, hu)
     sync_all()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
@@ -242,10 +244,7 @@ def main():
         if ds is None:
             semi_discrete_residual(hdu, hu, solver)
         else:
-            u.copy_(hu, non_blocking=True)
-            ds.rhs(du, u)
-            hdu.copy_(du, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            ds.rhs_host(hdu, hu)
     t1.record()
     sync_all()
     e2e_ms = t0.elapsed_time(t1) / a.e2e_steps
@@ -266,8 +265,11 @@ def main():
             dist.all_reduce(f)
             dist.all_reduce(sc, op=dist.ReduceOp.MAX)
         checks["conservation_residual_rel"] = float(f.abs().max() / (sc[0] * (2 * np.pi) ** 3))
-        if world == 1:
-            checks["host_buffer_result_equals_device"] = bool(torch.equal(hdu, du.cpu()))
+        checks["host_buffer_result_equals_device"] = bool(torch.equal(hdu, du.cpu()))
+        if world > 1:
+            okt = torch.tensor([1.0 if checks["host_buffer_result_equals_device"] else 0.0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            checks["host_buffer_result_equals_device"] = bool(okt.item() == 1.0)
     except Exception as e:
         checks["error"] = str(e)
     if rank == 0:

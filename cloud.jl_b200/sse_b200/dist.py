@@ -108,3 +108,63 @@ class DistributedSolver:
             s.halo_unpack(0)
             s.pass_b(dudt, self.n_int, self.mesh.n_boundary)
         return dudt
+
+    def rhs_host(self, dudt_host, u_host, t: float = 0.0, chunks: int = 8):
+        """Residual on this rank's HOST buffers (pinned torch CPU tensors): the boundary elements are uploaded and put
+        through pass A first so that the facet halos travel while the interior ranges are uploaded; pass B of an
+        interior range starts as soon as pass A has covered its face neighbours (mapP) and its dudt is downloaded while
+        later ranges are still arriving; the boundary elements finish after the halo has been unpacked."""
+        import torch
+        from .solver import range_plan
+        s, ne, nb, n_int = self.s, self.mesh.N_e, self.mesh.n_boundary, self.n_int
+        if self.second or nb == 0 or n_int < 4 * chunks:
+            d_u, d_du = self._host_state()
+            d_u.copy_(u_host, non_blocking=True)
+            self.rhs(d_du, d_u, t)
+            dudt_host.copy_(d_du, non_blocking=True)
+            torch.cuda.current_stream(s.device).synchronize()
+            return dudt_host
+        d_u, d_du = self._host_state()
+        if getattr(self, "_plan", None) is None or self._plan[0] != chunks:
+            ranges = [(n_int, ne)] + [(n_int * c // chunks, n_int * (c + 1) // chunks) for c in range(chunks)]
+            self._plan = (chunks, ranges, range_plan(s.image.arrays["mapP"], ne, int(s.cfg.N_f), ranges))
+            self._copy_in, self._copy_out = torch.cuda.Stream(device=s.device), torch.cuda.Stream(device=s.device)
+        _, ranges, after = self._plan
+        cur = torch.cuda.current_stream(s.device)
+        cin, cout = self._copy_in, self._copy_out
+        cin.wait_stream(cur)
+        cout.wait_stream(cur)
+
+        def pass_b_and_download(a, b):
+            s.pass_b(d_du, a, b - a)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            with torch.cuda.stream(cout):
+                cout.wait_event(ev)
+                dudt_host[a:b].copy_(d_du[a:b], non_blocking=True)
+
+        done = None
+        for i, (a, b) in enumerate(ranges):
+            with torch.cuda.stream(cin):
+                d_u[a:b].copy_(u_host[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cin)
+            cur.wait_event(ev)
+            s.pass_a_range(d_u, a, b - a)
+            if i == 0:
+                done = self._exchange(0)                 # boundary facets are complete: halos travel from here on
+            for k in after[i]:
+                if k:
+                    pass_b_and_download(*ranges[k])
+        cur.wait_event(done)
+        s.halo_unpack(0)
+        pass_b_and_download(*ranges[0])
+        cur.wait_stream(cout)
+        cur.wait_stream(cin)
+        cur.synchronize()
+        return dudt_host
+
+    def _host_state(self):
+        if getattr(self, "_hs", None) is None:
+            self._hs = (self.s.new_state(), self.s.new_state())
+        return self._hs

@@ -262,20 +262,29 @@ class Solver:
         self.launches += 1
 
 
+def range_plan(mapP_1based, ne: int, nf: int, ranges):
+    """For element ranges (a, b) listed in upload order: after[i] = the ranges whose pass B may run once pass A has
+    covered ranges[0..i], i.e. once every range holding one of their face neighbours (read from mapP) is through.
+    Neighbours beyond the local elements (ghost facet slots of a partitioned mesh) are not range dependencies."""
+    nb = (np.asarray(mapP_1based).reshape(-1, nf)[:ne] - 1) // nf
+    owner = np.full(ne, -1, dtype=np.int64)
+    for i, (a, b) in enumerate(ranges):
+        owner[a:b] = i
+    ready = []
+    for i, (a, b) in enumerate(ranges):
+        nbr = nb[a:b].reshape(-1)
+        dep = owner[nbr[nbr < ne]]
+        ready.append(max(i, int(dep.max()) if dep.size else i))
+    return [[k for k in range(len(ranges)) if ready[k] == i] for i in range(len(ranges))]
+
+
 def chunk_plan(mapP_1based, ne: int, nf: int, chunks: int):
     """Schedule of the pipelined host-buffer residual (Solver.rhs_host): element ranges `bounds`, their upload order
-    `up`, and for every upload position the ranges whose pass B becomes runnable there (`after`) — a range is runnable
-    once pass A has covered all the ranges holding one of its face neighbours (read from mapP).  On a slab-ordered
+    `up`, and for every upload position the ranges whose pass B becomes runnable there (`after`).  On a slab-ordered
     periodic mesh every range waits for its two neighbours, so three ranges are left when the uploads end."""
     bounds = [ne * c // chunks for c in range(chunks + 1)]
-    nb = (np.asarray(mapP_1based).reshape(ne, nf) - 1) // nf
-    owner = np.searchsorted(np.asarray(bounds[1:]), np.arange(ne), side="right")
-    deps = [set(np.unique(owner[nb[bounds[c]:bounds[c + 1]]]).tolist()) | {c} for c in range(chunks)]
-    up = list(range(chunks))
-    pos = {c: i for i, c in enumerate(up)}
-    ready = [max(pos[d] for d in deps[c]) for c in range(chunks)]
-    after = [[c for c in sorted(range(chunks), key=lambda c: pos[c]) if ready[c] == i] for i in range(chunks)]
-    return bounds, up, after
+    after = range_plan(mapP_1based, ne, nf, [(bounds[c], bounds[c + 1]) for c in range(chunks)])
+    return bounds, list(range(chunks)), after
 
 
 def fp64_peak(device: int = 0) -> float:

@@ -35,6 +35,13 @@ def main():
         for _ in range(2):
             ds.rhs(du, u)
         torch.cuda.synchronize()
+        # the pipelined host-buffer call of every rank returns the device residual bit for bit
+        hu = u.cpu().pin_memory()
+        hdu = torch.empty_like(hu).pin_memory()
+        for chunks in (2, 5):
+            hdu.zero_()
+            ds.rhs_host(hdu, hu, chunks=chunks)
+            assert torch.equal(hdu, du.cpu()), (name, rank, chunks)
         got = [None] * world
         dist.all_gather_object(got, (gid, du.cpu().numpy()))
         if rank == 0:

@@ -63,7 +63,7 @@ template <int N> static cudaError_t set_attrs_n() {
     const int proj5 = (int)(sizeof(double) * ProjSmem<N, 5>::total), proj1 = (int)(sizeof(double) * ProjSmem<N, 1>::total);
     if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 5, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
-    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 1, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
+    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 1, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
     if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
     if constexpr (N == 5) {
@@ -81,7 +81,7 @@ static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first
         k_nodal_ct<N, 5, 3, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
     } else {
         const unsigned grid = (unsigned)((count + ProjSmem<N, 1>::EPB - 1) / ProjSmem<N, 1>::EPB);
-        k_nodal_ct<N, 1, 3, false><<<grid, 128, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
+        k_nodal_ct<N, 1, 4, false><<<grid, 128, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
     }
 }
 void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q, double* u_f,

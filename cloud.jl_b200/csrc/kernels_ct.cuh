@@ -150,8 +150,9 @@ template <int N, int NC> struct ProjSmem {
     static constexpr int x = 0;                                    // [NG][Np]
     static constexpr int big = x + NG * T::Np;                     // union: q [NG][Nq]  |  red [NG][Np][N]
     static constexpr int big_sz = (NG * QS > NG * RS) ? NG * QS : NG * RS;
-    static constexpr int wij = big + big_sz;                       // [EPB][Nq]  W / J
-    static constexpr int c3 = wij + EPB * T::Nq;                   // [Np][N]    C tensor, a3 fastest
+    static constexpr int wij = big + big_sz;                       // [EPB][Nq]  W / J (systems only: the scalar kernels, 24
+                                                                   //            elements per CTA, read W and J_q directly)
+    static constexpr int c3 = wij + (NC == 1 ? 0 : EPB * T::Nq);   // [Np][N]    C tensor, a3 fastest
     static constexpr int rval = c3 + T::Np * N;                    // [NNZ]      R values (CSR by facet node)
     static constexpr int ridx = rval + NNZ;                        // [NNZ] int  R column indices
     static constexpr int rptr = ridx + (NNZ + 1) / 2;              // [Nf+1] int R row pointers
@@ -329,9 +330,11 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
     }
     load_c3_shared<N>(t, sm + S::c3);
     const double* c3 = sm + S::c3 + a3;
-    for (int it = tid; it < nel * Nq; it += NT) {
-        const int el = it / Nq, i = it - el * Nq;
-        s_wij[it] = t.W[i] * rcp_fast(g.J_q[(size_t)(e0 + el) * Nq + i]);
+    if constexpr (NC > 1) {
+        for (int it = tid; it < nel * Nq; it += NT) {
+            const int el = it / Nq, i = it - el * Nq;
+            s_wij[it] = t.W[i] * rcp_fast(g.J_q[(size_t)(e0 + el) * Nq + i]);
+        }
     }
     __syncthreads();
     if (act) sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3);
@@ -344,11 +347,19 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
     __syncthreads();
     if (act) {
         sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
-        const double* wij = s_wij + (grp / NC) * Nq;
+        if constexpr (NC > 1) {
+            const double* wij = s_wij + (grp / NC) * Nq;
 #pragma unroll
-        for (int a1 = 0; a1 < N; a1++)
+            for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
-            for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= wij[(a1 * N + a2) * N + a3];
+                for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= wij[(a1 * N + a2) * N + a3];
+        } else {
+            const double* Jq = g.J_q + (size_t)(e0 + grp) * Nq + a3;
+#pragma unroll
+            for (int a1 = 0; a1 < N; a1++)
+#pragma unroll
+                for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= t.W[(a1 * N + a2) * N + a3] * rcp_fast(Jq[(a1 * N + a2) * N]);
+        }
         sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3);
     }
     __syncthreads();

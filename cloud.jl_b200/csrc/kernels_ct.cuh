@@ -794,29 +794,44 @@ k_standard_adv_ct(AdvTabs<N> a, CtDev t, Geo g, Law L, long long first, double* 
     const bool node = tid < Nq;
     const int ca = tid / NN, cb = (tid / N) % N, cc = tid % N;
     for (int i = tid; i < D * N * N; i += blockDim.x) s_D[i / (N * N)][i % (N * N)] = a.D1[i / (N * N)][i % (N * N)];
-    double c[D] = {0.0, 0.0, 0.0};
-    if (node) {
-        const double u = u_q[(size_t)k * Nq + tid];
-        const double hw = 0.5 * t.W[tid];
+    // every global load of the element is issued before any arithmetic (idle lanes load a clamped, valid address): the
+    // kernel is a few hundred instructions long, so its time is the latency of these loads unless they overlap
+    static_assert(Nf <= (Nq + 31) / 32 * 32, "one facet node per thread");
+    const bool fac = tid < Nf;
+    const int tn = node ? tid : Nq - 1, tj = fac ? tid : Nf - 1;
+    const size_t jo = (size_t)(g.mapP[(size_t)k * Nf + tj] - 1);
+    const double u = __ldcs(u_q + (size_t)k * Nq + tn);
+    double lam[D][D], njf[D], rw[NFR];
 #pragma unroll
-        for (int m = 0; m < D; m++) {
-            double s = 0.0;
+    for (int m = 0; m < D; m++)
 #pragma unroll
-            for (int n = 0; n < D; n++) s = fma(hw * g.Lambda_q[((size_t)k * D * D + (m + D * n)) * Nq + tid], L.a[n], s);   // halfWLambda_mn a_n
-            c[m] = s;
-            s_g[m][tid] = s * u;
-        }
-        s_u[tid] = u;
+        for (int n = 0; n < D; n++) lam[m][n] = __ldcs(g.Lambda_q + ((size_t)k * D * D + (m + D * n)) * Nq + tn);
+    const double ui = __ldcs(u_f + (size_t)k * Nf + tj);
+    const double jf = __ldcs(g.J_f + (size_t)k * Nf + tj);
+#pragma unroll
+    for (int m = 0; m < D; m++) njf[m] = __ldcs(g.nJf + m + D * ((size_t)k * Nf + tj));
+    const double uo = __ldcs(u_f + jo);
+#pragma unroll
+    for (int fr = 0; fr < NFR; fr++) rw[fr] = t.fR[fr * Nq + tn];
+    const double hw = 0.5 * t.W[tn], bf = t.Bf[tj];
+    double c[D];
+#pragma unroll
+    for (int m = 0; m < D; m++) {
+        double s = 0.0;
+#pragma unroll
+        for (int n = 0; n < D; n++) s = fma(hw * lam[m][n], L.a[n], s);      // halfWLambda_mn a_n
+        c[m] = s;
+        if (node) s_g[m][tid] = s * u;
     }
-    for (int j = tid; j < Nf; j += blockDim.x) {
-        const double ui = u_f[(size_t)k * Nf + j], uo = u_f[(size_t)(g.mapP[(size_t)k * Nf + j] - 1)];
-        const double jf = g.J_f[(size_t)k * Nf + j];
+    if (node) s_u[tid] = u;
+    {
+        const double ijf = rcp_fast(jf);
         double an = 0.0;
 #pragma unroll
-        for (int m = 0; m < D; m++) an = fma(L.a[m], g.nJf[m + D * ((size_t)k * Nf + j)] / jf, an);
+        for (int m = 0; m < D; m++) an = fma(L.a[m], njf[m] * ijf, an);
         double fs = (0.5 * (ui + uo)) * an;                                   // F#.n        ConservationLaws.jl:75-128
         if (L.inviscid == SSE_FLUX_LAX_FRIEDRICHS) fs = fma(L.half_lambda * fabs(an), ui - uo, fs);
-        s_ff[j] = (t.Bf[j] * jf) * (fs - 0.5 * an * ui);                      // BJf (f* - sum_n halfN_n R f_n)
+        if (fac) s_ff[tid] = (bf * jf) * (fs - 0.5 * an * ui);                // BJf (f* - sum_n halfN_n R f_n)
     }
     __syncthreads();
     if (node) {
@@ -835,7 +850,7 @@ k_standard_adv_ct(AdvTabs<N> a, CtDev t, Geo g, Law L, long long first, double* 
             r += s1 - c[m] * s2;
         }
 #pragma unroll
-        for (int fr = 0; fr < NFR; fr++) r = fma(-t.fR[fr * Nq + tid], s_ff[facet_partner<N>(fr, ca, cb, cc)], r);   // - R' f_f
+        for (int fr = 0; fr < NFR; fr++) r = fma(-rw[fr], s_ff[facet_partner<N>(fr, ca, cb, cc)], r);   // - R' f_f
         u_q[(size_t)k * Nq + tid] = r;
     }
 }

@@ -18,6 +18,14 @@
 #include "kernels_tensor.cuh"
 #include "ct_api.h"
 
+// independent entropy-variable transforms per thread and trip in k_nodal_ct: volume-node loops / facet-node loop
+#ifndef SSE_NODAL_ILP_Q
+#define SSE_NODAL_ILP_Q 3
+#endif
+#ifndef SSE_NODAL_ILP_F
+#define SSE_NODAL_ILP_F 3
+#endif
+
 namespace sse {
 
 template <int N> struct SFCoef {       // A[a1 + N*b1], B[a2 + N*(b1 + N*b2)]  (reference column-major)
@@ -166,6 +174,7 @@ __global__ void __launch_bounds__(ProjSmem<N, NC>::WARPS * 32, MINB)
 k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count, const double* __restrict__ u,
            double* __restrict__ u_q, double* __restrict__ u_f) {
     constexpr int D = 3;
+    static_assert(!PROJECT || NC == D + 2, "the entropy projection of this kernel is written for the Euler equations");
     using T = Tet<N>;
     using S = ProjSmem<N, NC>;
     constexpr int Nq = T::Nq, Np = T::Np, Nf = T::Nf, EPB = S::EPB;
@@ -204,17 +213,40 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
     __syncthreads();
     if constexpr (PROJECT) {
     // w_q = WJ * w(u_q)                                      flux_differencing_form.jl:230-235
-    for (int it = tid; it < nel * Nq; it += NT) {
-        const int el = it / Nq, i = it - el * Nq;
-        double ui[NC], wi[NC];
+    // UT independent nodes per thread and trip: the branch-free maps of physics.cuh make the trip one basic block, so
+    // the ~75-deep dependent FP64 chains of the nodes interleave (the kernel runs 15 warps per SM)
+    if constexpr (NC == D + 2) {
+        constexpr int UT = SSE_NODAL_ILP_Q;
+        const int total = nel * Nq;
+        for (int it0 = tid; it0 < total; it0 += UT * NT) {
+            double ui[UT][NC], wi[UT][NC], J[UT], W[UT];
+            int sq[UT], sw[UT];
+            bool ok[UT];
 #pragma unroll
-        for (int e = 0; e < NC; e++) ui[e] = s_q[(el * NC + e) * S::QS + i];
-        cons_to_entropy<D, NC>(L, ui, wi);
-        const double J = g.J_q[(size_t)(e0 + el) * Nq + i], W = t.W[i];
-        const double wj = W * J;
-        s_wij[el * Nq + i] = W * rcp_fast(J);
+            for (int k = 0; k < UT; k++) {
+                int it = it0 + k * NT;
+                ok[k] = it < total;
+                if (!ok[k]) it = it0;                          // idle slot: recompute a valid node, store nothing
+                const int el = it / Nq, i = it - el * Nq;
+                sq[k] = el * NC * S::QS + i;
+                sw[k] = it;
+                J[k] = g.J_q[(size_t)(e0 + el) * Nq + i];
+                W[k] = t.W[i];
 #pragma unroll
-        for (int e = 0; e < NC; e++) s_q[(el * NC + e) * S::QS + i] = wi[e] * wj;
+                for (int e = 0; e < NC; e++) ui[k][e] = s_q[sq[k] + e * S::QS];
+            }
+#pragma unroll
+            for (int k = 0; k < UT; k++) euler_cons_to_entropy_nb<D>(L.gamma, L.gm1, L.igm1, ui[k], wi[k]);
+#pragma unroll
+            for (int k = 0; k < UT; k++) {
+                if (ok[k]) {
+                    const double wj = W[k] * J[k];
+                    s_wij[sw[k]] = W[k] * rcp_fast(J[k]);
+#pragma unroll
+                    for (int e = 0; e < NC; e++) s_q[sq[k] + e * S::QS] = wi[k][e] * wj;
+                }
+            }
+        }
     }
     __syncthreads();
     // w = V' w_q
@@ -262,19 +294,77 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
     __syncthreads();
     }
     // u_q = u(w_q), u_f = u(R w_q)                           flux_differencing_form.jl:240-249
-    for (int it = tid; it < nel * (Nq + Nf); it += NT) {
-        const int el = it / (Nq + Nf), i = it - el * (Nq + Nf);
-        double wi[NC], ui[NC];
-        if (i < Nq) {
+    if constexpr (PROJECT && NC == D + 2) {
+        constexpr int UT = SSE_NODAL_ILP_Q, UF = SSE_NODAL_ILP_F;
+        // volume nodes
+        const int totq = nel * Nq;
+        for (int it0 = tid; it0 < totq; it0 += UT * NT) {
+            double wi[UT][NC], ui[UT][NC];
+            size_t dst[UT];
+            bool ok[UT];
 #pragma unroll
-            for (int e = 0; e < NC; e++) wi[e] = s_q[(el * NC + e) * S::QS + i];
-            if constexpr (PROJECT) entropy_to_cons<D, NC>(L, wi, ui);
-            else {
+            for (int k = 0; k < UT; k++) {
+                int it = it0 + k * NT;
+                ok[k] = it < totq;
+                if (!ok[k]) it = it0;
+                const int el = it / Nq, i = it - el * Nq;
+                dst[k] = (size_t)(e0 + el) * NC * Nq + i;
 #pragma unroll
-                for (int e = 0; e < NC; e++) ui[e] = wi[e];
+                for (int e = 0; e < NC; e++) wi[k][e] = s_q[(el * NC + e) * S::QS + i];
             }
 #pragma unroll
-            for (int e = 0; e < NC; e++) u_q[((size_t)(e0 + el) * NC + e) * Nq + i] = ui[e];
+            for (int k = 0; k < UT; k++) euler_entropy_to_cons_nb<D>(L.gamma, L.gm1, L.igm1, L.log_gm1, wi[k], ui[k]);
+#pragma unroll
+            for (int k = 0; k < UT; k++) {
+                if (ok[k]) {
+#pragma unroll
+                    for (int e = 0; e < NC; e++) u_q[dst[k] + (size_t)e * Nq] = ui[k][e];
+                }
+            }
+        }
+        // facet nodes, face-major over the CTA's elements so that the rows of one warp have the same length in R
+        // (five entries on the faces eta_2 = -1, eta_1 = +-1, N^2 on the face eta_3 = -1)
+        constexpr int npf = T::npf;
+        const int totf = nel * Nf, perface = nel * npf;
+        for (int it0 = tid; it0 < totf; it0 += UF * NT) {
+            double wi[UF][NC], ui[UF][NC];
+            size_t dst[UF];
+            bool ok[UF];
+#pragma unroll
+            for (int k = 0; k < UF; k++) {
+                int it = it0 + k * NT;
+                ok[k] = it < totf;
+                if (!ok[k]) it = it0;
+                const int f = it / perface, rem = it - f * perface;
+                const int el = rem / npf, j = f * npf + (rem - el * npf);
+                dst[k] = (size_t)(e0 + el) * Nf + j;
+#pragma unroll
+                for (int e = 0; e < NC; e++) wi[k][e] = 0.0;
+                const double* q0 = s_q + el * NC * S::QS;
+                for (int q = s_rptr[j]; q < s_rptr[j + 1]; q++) {
+                    const double rv = s_rval[q];
+                    const int c = s_ridx[q];
+#pragma unroll
+                    for (int e = 0; e < NC; e++) wi[k][e] = fma(rv, q0[e * S::QS + c], wi[k][e]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < UF; k++) euler_entropy_to_cons_nb<D>(L.gamma, L.gm1, L.igm1, L.log_gm1, wi[k], ui[k]);
+#pragma unroll
+            for (int k = 0; k < UF; k++) {
+                if (ok[k]) {
+#pragma unroll
+                    for (int e = 0; e < NC; e++) u_f[dst[k] + (size_t)g.NFT * e] = ui[k][e];
+                }
+            }
+        }
+    } else {
+    for (int it = tid; it < nel * (Nq + Nf); it += NT) {
+        const int el = it / (Nq + Nf), i = it - el * (Nq + Nf);
+        double wi[NC];
+        if (i < Nq) {
+#pragma unroll
+            for (int e = 0; e < NC; e++) u_q[((size_t)(e0 + el) * NC + e) * Nq + i] = s_q[(el * NC + e) * S::QS + i];
         } else {
             const int j = i - Nq;
 #pragma unroll
@@ -285,14 +375,10 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
 #pragma unroll
                 for (int e = 0; e < NC; e++) wi[e] = fma(rv, s_q[(el * NC + e) * S::QS + c], wi[e]);
             }
-            if constexpr (PROJECT) entropy_to_cons<D, NC>(L, wi, ui);
-            else {
 #pragma unroll
-                for (int e = 0; e < NC; e++) ui[e] = wi[e];
-            }
-#pragma unroll
-            for (int e = 0; e < NC; e++) u_f[(size_t)(e0 + el) * Nf + j + (size_t)g.NFT * e] = ui[e];
+            for (int e = 0; e < NC; e++) u_f[(size_t)(e0 + el) * Nf + j + (size_t)g.NFT * e] = wi[e];
         }
+    }
     }
 }
 

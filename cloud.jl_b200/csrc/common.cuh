@@ -47,6 +47,7 @@ struct Geo {
     long long Ne;
     long long NFT;           // Nf*Ne + N_ghost: stride between variables of u_f / q_f
     int mass_solver;
+    const double* chol;      // CholeskySolver: upper factors U_k, Np x Np column-major per element (mass_matrix.jl:30-39)
 };
 
 #define SSE_FOR(t, n) for (int t = threadIdx.x; t < (n); t += blockDim.x)

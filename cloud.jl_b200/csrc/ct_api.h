@@ -33,6 +33,7 @@ struct CtPlan {
     CtDev dev{};
     std::vector<double> A, B;       // host copies of the 1-D tensors handed to the kernels by value
     std::vector<double> fR;         // host image of dev.fR
+    std::vector<double> facetR;     // 1-D factors of R: r0, r1, r2, r3 (N each), I3 (N x N)   (FacetR in kernels_ct.cuh)
     int minb = 4;                   // resident CTAs per SM requested for k_fluxdiff_ct (tuning knob)
     int dual = 1;                   // two pairs per thread and round in k_fluxdiff_ct (N = 5; SSE_FD_DUAL=0 disables)
     int proj_minb = 3;              // same for k_nodal_ct / k_project_ct
@@ -43,6 +44,7 @@ bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& t
 bool ct_eligible_standard(const sse_config& cfg, const sse_arrays& a, int* Nout, std::vector<double>& D1, std::vector<double>& fR);
 void ct_standard(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
                  double* dudt, cudaStream_t s, RkStage rk = RkStage());
+bool ct_facet_factors(const sse_config& cfg, const sse_arrays& a, int N, std::vector<double>& out);
 // true when the generic tables of tp equal the closed-form schedule k_fluxdiff_ct hard-codes
 bool ct_schedule_matches(const TensorPlan& tp, int N);
 cudaError_t ct_set_attrs(int N);

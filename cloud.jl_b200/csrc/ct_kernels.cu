@@ -51,6 +51,45 @@ bool ct_schedule_matches(const TensorPlan& tp, int N) {
     return true;
 }
 
+// 1-D factors of R (FacetR in kernels_ct.cuh) from the dense Matrix(R) (N_f x N_q, column-major); false unless every
+// entry of R equals its structured value to 1e-14 (zeros exactly)
+bool ct_facet_factors(const sse_config& cfg, const sse_arrays& a, int N, std::vector<double>& out) {
+    const int NN = N * N, Nq = N * NN, Nf = 4 * NN;
+    if (!a.R || cfg.N_q != Nq || cfg.N_f != Nf) return false;
+    auto R = [&](int j, int a1, int a2, int a3) { return a.R[j + (size_t)Nf * ((a1 * N + a2) * N + a3)]; };
+    out.assign(4 * N + NN, 0.0);
+    double *r0 = out.data(), *r1 = r0 + N, *r2 = r1 + N, *r3 = r2 + N, *I3 = r3 + N;
+    for (int c = 0; c < N; c++) { r0[c] = R(0, 0, c, 0); r1[c] = R(NN, c, 0, 0); r2[c] = R(2 * NN, c, 0, 0); }
+    // face 3: R[(a1, b), (a1, a2, a3)] = I3[b, a2] r3[a3], normalised to I3[0, 0] = 1; split at the largest entry of the
+    // (b, a2) = (0, 0) fibre
+    int cm = 0;
+    for (int c = 0; c < N; c++) { r3[c] = R(3 * NN, 0, 0, c); if (std::fabs(r3[c]) > std::fabs(r3[cm])) cm = c; }
+    if (r3[cm] == 0.0) return false;
+    for (int b = 0; b < N; b++) for (int a2 = 0; a2 < N; a2++) I3[b + N * a2] = R(3 * NN + b, 0, a2, cm) / r3[cm];
+    double scale = 0.0;
+    for (size_t i = 0; i < (size_t)Nf * Nq; i++) scale = std::max(scale, std::fabs(a.R[i]));
+    for (int a1 = 0; a1 < N; a1++) for (int a2 = 0; a2 < N; a2++) for (int a3 = 0; a3 < N; a3++)
+        for (int j = 0; j < Nf; j++) {
+            const int f = j / NN, x = (j % NN) / N, y = j % N;
+            double want = 0.0;
+            if (f == 0) want = (x == a1 && y == a3) ? r0[a2] : 0.0;
+            else if (f == 1) want = (x == a2 && y == a3) ? r1[a1] : 0.0;
+            else if (f == 2) want = (x == a2 && y == a3) ? r2[a1] : 0.0;
+            else want = (x == a1) ? I3[y + N * a2] * r3[a3] : 0.0;
+            const double got = R(j, a1, a2, a3);
+            if (want == 0.0 ? got != 0.0 : std::fabs(got - want) > 1e-14 * scale) return false;
+        }
+    return true;
+}
+
+template <int N> static FacetR<N> make_facet(const CtPlan& p) {
+    FacetR<N> f;
+    const double* s = p.facetR.data();
+    for (int i = 0; i < N; i++) { f.r0[i] = s[i]; f.r1[i] = s[N + i]; f.r2[i] = s[2 * N + i]; f.r3[i] = s[3 * N + i]; }
+    for (int i = 0; i < N * N; i++) f.I3[i] = s[4 * N + i];
+    return f;
+}
+
 template <int N> static SFCoef<N> make_coef(const CtPlan& p) {
     SFCoef<N> c;
     for (int i = 0; i < N * N; i++) c.A[i] = p.A[i];
@@ -61,9 +100,10 @@ template <int N> static SFCoef<N> make_coef(const CtPlan& p) {
 template <int N> static cudaError_t set_attrs_n() {
     cudaError_t e;
     const int proj5 = (int)(sizeof(double) * ProjSmem<N, 5>::total), proj1 = (int)(sizeof(double) * ProjSmem<N, 1>::total);
-    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 5, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
+    const int nod5 = (int)(sizeof(double) * ProjSmem<N, 5, true>::total), nod1 = (int)(sizeof(double) * ProjSmem<N, 1, true>::total);
+    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 5, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod5))) return e;
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
-    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 1, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
+    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 1, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod1))) return e;
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
     if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
     if constexpr (N == 5) {
@@ -78,10 +118,10 @@ static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first
                     cudaStream_t s) {
     if (p.kind == 0) {
         const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
-        k_nodal_ct<N, 5, 3, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
+        k_nodal_ct<N, 5, 3, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5, true>::total, s>>>(make_coef<N>(p), make_facet<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
     } else {
         const unsigned grid = (unsigned)((count + ProjSmem<N, 1>::EPB - 1) / ProjSmem<N, 1>::EPB);
-        k_nodal_ct<N, 1, 4, false><<<grid, 128, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
+        k_nodal_ct<N, 1, 4, false><<<grid, 128, sizeof(double) * ProjSmem<N, 1, true>::total, s>>>(make_coef<N>(p), make_facet<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
     }
 }
 void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q, double* u_f,

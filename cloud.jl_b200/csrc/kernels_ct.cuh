@@ -41,6 +41,11 @@ template <int N> struct Tet {
     static constexpr int GPW = 32 / N;          // groups (of N lanes) per warp
     static constexpr int EPB = GPW;             // elements per CTA in the projection kernels
     static constexpr int LPT = (Np + N - 1) / N;  // modal outputs per lane in the a3-reduction
+    // V' partials of one (element, variable): partial (l, a3) sits at l * RED_SL + a3 * RED_SA.  For N = 5 the pair (5, 3)
+    // with a group stride of 15 (mod 16) makes both the stores (lanes = (group, a3), fixed l) and the reducer loads
+    // (lane a3 sums its LPT consecutive l) free of bank conflicts; the plain (N, 1) layout costs the loads a 2-way conflict
+    static constexpr int RED_SL = N, RED_SA = (N == 5) ? 3 : 1;
+    static constexpr int RED_SPAN = (Np - 1) * RED_SL + (N - 1) * RED_SA + 1;
 };
 
 // canonical modal ordering of warped_product (tensor_simplex.jl:113-131): i slowest, k fastest, i+j+k <= p
@@ -81,7 +86,7 @@ __device__ __forceinline__ void sf3_fwd(const SFCoef<N>& cf, const double* c3, c
 }
 
 // partial[l][a3] = C[a3,l] * sum_{a2} B[a2,b1,b2] sum_{a1} A[a1,b1] x[a1][a2]        warped_product_3d.jl:94-136
-// written to red[l * N] (the caller passes red already offset by group and a3)
+// written to red[l * RED_SL] (the caller passes red already offset by group and a3 * RED_SA)
 template <int N, int CS = 1>
 __device__ __forceinline__ void sf3_bwd_partials(const SFCoef<N>& cf, const double* c3, const double (&x)[N][N], double* __restrict__ red) {
 #pragma unroll
@@ -101,7 +106,7 @@ __device__ __forceinline__ void sf3_bwd_partials(const SFCoef<N>& cf, const doub
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) z = fma(cf.B[a2 + N * (b1 + N * b2)], wt[a2], z);
 #pragma unroll
-            for (int b3 = 0; b3 < N - b1 - b2; b3++) { const int l = tet_l<N>(b1, b2, b3); red[l * N] = c3[l * CS] * z; }
+            for (int b3 = 0; b3 < N - b1 - b2; b3++) { const int l = tet_l<N>(b1, b2, b3); red[l * Tet<N>::RED_SL] = c3[l * CS] * z; }
         }
     }
 }
@@ -115,7 +120,7 @@ __device__ __forceinline__ void sf3_bwd_reduce(const double* __restrict__ red, i
         double s = 0.0;
         if (l < Tet<N>::Np) {
 #pragma unroll
-            for (int a = 0; a < N; a++) s += red[l * N + a];
+            for (int a = 0; a < N; a++) s += red[l * Tet<N>::RED_SL + a * Tet<N>::RED_SA];
         }
         out[q] = s;
     }
@@ -143,46 +148,95 @@ __device__ __forceinline__ void load_c3(const CtDev& t, int a3, double (&c3)[Tet
             for (int b3 = 0; b3 < N - b1 - b2; b3++) c3[tet_l<N>(b1, b2, b3)] = t.C[a3 + N * (b1 + N * (b2 + N * b3))];
 }
 
-// shared-memory plan of the projection kernels (doubles)
-template <int N, int NC> struct ProjSmem {
+// 1-D factors of the facet extrapolation R on the collapsed tet (tensor_simplex.jl:265-268), extracted from Matrix(R)
+// and verified entry by entry on the host (ct_facet_factors):
+//   face 0 (eta_2 = -1), node (a1, a3): sum_a2 r0[a2] q[a1,a2,a3]      face 1 / 2 (eta_1 = +1 / -1), node (a2, a3): sum_a1 r1|r2[a1] q
+//   face 3 (eta_3 = -1), node (a1, b):  sum_a2 I3[b + N a2] sum_a3 r3[a3] q[a1,a2,a3]
+template <int N> struct FacetR { double r0[N], r1[N], r2[N], r3[N], I3[N * N]; };
+
+// faces 0..2 from the slab y[a1][a2] of one eta_3 index: no shared-memory reads.  wf is the facet tile of (element, variable)
+template <int N>
+__device__ __forceinline__ void facet_rows_slab(const FacetR<N>& fr, const double (&y)[N][N], int a3, double* __restrict__ wf) {
+    constexpr int NN = N * N;
+#pragma unroll
+    for (int a1 = 0; a1 < N; a1++) {
+        double s = 0.0;
+#pragma unroll
+        for (int a2 = 0; a2 < N; a2++) s = fma(fr.r0[a2], y[a1][a2], s);
+        wf[a1 * N + a3] = s;
+    }
+#pragma unroll
+    for (int a2 = 0; a2 < N; a2++) {
+        double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+        for (int a1 = 0; a1 < N; a1++) { s1 = fma(fr.r1[a1], y[a1][a2], s1); s2 = fma(fr.r2[a1], y[a1][a2], s2); }
+        wf[NN + a2 * N + a3] = s1;
+        wf[2 * NN + a2 * N + a3] = s2;
+    }
+}
+// face 3, the N nodes (a1, .) of one a1, from the nodal tile q of (element, variable)
+template <int N>
+__device__ __forceinline__ void facet_rows_face3(const FacetR<N>& fr, const double* __restrict__ q, int a1, double* __restrict__ wf) {
+    double tt[N];
+#pragma unroll
+    for (int a2 = 0; a2 < N; a2++) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < N; c++) s = fma(fr.r3[c], q[(a1 * N + a2) * N + c], s);
+        tt[a2] = s;
+    }
+#pragma unroll
+    for (int b = 0; b < N; b++) {
+        double s = 0.0;
+#pragma unroll
+        for (int a2 = 0; a2 < N; a2++) s = fma(fr.I3[b + N * a2], tt[a2], s);
+        wf[3 * N * N + a1 * N + b] = s;
+    }
+}
+
+// shared-memory plan of the projection kernels (doubles).  FACETS: room for the facet tile wf of pass A, which aliases
+// x and wij (both dead once the last V has been applied)
+template <int N, int NC, bool FACETS = false> struct ProjSmem {
     using T = Tet<N>;
     static constexpr int WARPS = (NC == 1) ? 4 : NC;               // CTA = WARPS warps
     static constexpr int NG = WARPS * T::GPW;                      // groups (element, variable) per CTA
     static constexpr int EPB = NG / NC;                            // elements per CTA
     static_assert(NG % NC == 0, "groups must split evenly into elements");
-    static constexpr int NNZ = 3 * N * N * N + N * N * N * N;      // non-zeros of R on the collapsed tet
     // group strides of the nodal tile and of the V' partials, padded to N (mod 16) doubles so that the N-lane groups of
     // a warp fall on disjoint bank ranges (an un-padded 125 / 175 makes neighbouring groups overlap: 2-way conflicts)
     static constexpr int QS = T::Nq + ((N - T::Nq % 16) % 16 + 16) % 16;
-    static constexpr int RS = T::Np * N + ((N - (T::Np * N) % 16) % 16 + 16) % 16;
+    static constexpr int RSM = (N == 5) ? 15 : N;                  // group stride of the partials modulo 16 (see Tet::RED_SA)
+    static constexpr int RS = T::RED_SPAN + ((RSM - T::RED_SPAN % 16) % 16 + 16) % 16;
+    static constexpr int WS = T::Nf + ((N - T::Nf % 16) % 16 + 16) % 16;   // group stride of the facet tile
     static constexpr int x = 0;                                    // [NG][Np]
-    static constexpr int big = x + NG * T::Np;                     // union: q [NG][Nq]  |  red [NG][Np][N]
-    static constexpr int big_sz = (NG * QS > NG * RS) ? NG * QS : NG * RS;
-    static constexpr int wij = big + big_sz;                       // [EPB][Nq]  W / J (systems only: the scalar kernels, 24
+    static constexpr int wij = x + NG * T::Np;                     // [EPB][QS]  W / J (systems only: the scalar kernels, 24
                                                                    //            elements per CTA, read W and J_q directly)
-    static constexpr int c3 = wij + (NC == 1 ? 0 : EPB * T::Nq);   // [Np][N]    C tensor, a3 fastest
-    static constexpr int rval = c3 + T::Np * N;                    // [NNZ]      R values (CSR by facet node)
-    static constexpr int ridx = rval + NNZ;                        // [NNZ] int  R column indices
-    static constexpr int rptr = ridx + (NNZ + 1) / 2;              // [Nf+1] int R row pointers
-    static constexpr int total = rptr + (T::Nf + 2) / 2;
+    static constexpr int wf = 0;                                   // [NG][WS]   facet tile (pass A), over x | wij
+    static constexpr int lo_a = wij + (NC == 1 ? 0 : EPB * QS);
+    static constexpr int lo_b = FACETS ? NG * WS : 0;
+    static constexpr int big = lo_a > lo_b ? lo_a : lo_b;          // union: q [NG][Nq]  |  red [NG][Np][N]
+    static constexpr int big_sz = (NG * QS > NG * RS) ? NG * QS : NG * RS;
+    static constexpr int c3 = big + big_sz;                        // [Np][N]    C tensor, a3 fastest
+    static constexpr int total = c3 + T::Np * N;
 };
 
 // ---------------------------------------------------------------------------------------------------------
 // pass A — nodal_values! with the general (modal) entropy projection
 template <int N, int NC, int MINB, bool PROJECT>
 __global__ void __launch_bounds__(ProjSmem<N, NC>::WARPS * 32, MINB)
-k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count, const double* __restrict__ u,
+k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, long long count, const double* __restrict__ u,
            double* __restrict__ u_q, double* __restrict__ u_f) {
     constexpr int D = 3;
     static_assert(!PROJECT || NC == D + 2, "the entropy projection of this kernel is written for the Euler equations");
     using T = Tet<N>;
-    using S = ProjSmem<N, NC>;
+    using S = ProjSmem<N, NC, true>;
     constexpr int Nq = T::Nq, Np = T::Np, Nf = T::Nf, EPB = S::EPB;
     extern __shared__ double sm[];
     double* s_x = sm + S::x;
     double* s_q = sm + S::big;
     double* s_red = sm + S::big;
     double* s_wij = sm + S::wij;
+    double* s_wf = sm + S::wf;
     const int tid = threadIdx.x, NT = blockDim.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int gl = lane / N, a3 = lane - gl * N;
@@ -193,29 +247,24 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
 
     load_c3_shared<N>(t, sm + S::c3);
     const double* c3 = sm + S::c3 + a3;
-    double* s_rval = sm + S::rval;
-    int* s_ridx = reinterpret_cast<int*>(sm + S::ridx);
-    int* s_rptr = reinterpret_cast<int*>(sm + S::rptr);
-    for (int i = tid; i < S::NNZ; i += NT) { s_rval[i] = t.R.val[i]; s_ridx[i] = t.R.idx[i]; }
-    for (int i = tid; i <= Nf; i += NT) s_rptr[i] = t.R.ptr[i];
     for (int i = tid; i < nel * NC * Np; i += NT) s_x[i] = u[(size_t)e0 * NC * Np + i];
     __syncthreads();
 
     double y[N][N];
     // u_q = V u
+    if (act) sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
+    if constexpr (PROJECT) {
     if (act) {
-        sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
 #pragma unroll
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) s_q[grp * S::QS + (a1 * N + a2) * N + a3] = y[a1][a2];
     }
     __syncthreads();
-    if constexpr (PROJECT) {
     // w_q = WJ * w(u_q)                                      flux_differencing_form.jl:230-235
     // UT independent nodes per thread and trip: the branch-free maps of physics.cuh make the trip one basic block, so
     // the ~75-deep dependent FP64 chains of the nodes interleave (the kernel runs 15 warps per SM)
-    if constexpr (NC == D + 2) {
+    {
         constexpr int UT = SSE_NODAL_ILP_Q;
         const int total = nel * Nq;
         for (int it0 = tid; it0 < total; it0 += UT * NT) {
@@ -229,7 +278,7 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
                 if (!ok[k]) it = it0;                          // idle slot: recompute a valid node, store nothing
                 const int el = it / Nq, i = it - el * Nq;
                 sq[k] = el * NC * S::QS + i;
-                sw[k] = it;
+                sw[k] = el * S::QS + i;
                 J[k] = g.J_q[(size_t)(e0 + el) * Nq + i];
                 W[k] = t.W[i];
 #pragma unroll
@@ -249,6 +298,8 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
         }
     }
     __syncthreads();
+    // From here to the last V every tile a thread touches (its group's partials, modal coefficients and nodal slab)
+    // belongs to the N lanes of its own group, which sit in one warp: __syncwarp orders them, not a CTA barrier.
     // w = V' w_q
     if (act) {
 #pragma unroll
@@ -256,43 +307,50 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) y[a1][a2] = s_q[grp * S::QS + (a1 * N + a2) * N + a3];
     }
-    __syncthreads();                                   // s_red aliases s_q
+    __syncthreads();                                   // the partials of a group lie over the nodal tiles of other groups
     double out[T::LPT];
-    if (act) sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3);
-    __syncthreads();
+    if (act) sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
+    __syncwarp();
     if (act) {
         sf3_bwd_reduce<N>(s_red + grp * S::RS, a3, out);
 #pragma unroll
         for (int q = 0; q < T::LPT; q++) { const int l = a3 * T::LPT + q; if (l < Np) s_x[grp * Np + l] = out[q]; }
     }
-    __syncthreads();
+    __syncwarp();
     // w = M \ w : V, diag(W/J), V'                           mass_matrix.jl:185-196
     if (act) {
         sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
-        const double* wij = s_wij + (grp / NC) * Nq;
+        const double* wij = s_wij + (grp / NC) * S::QS;
 #pragma unroll
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= wij[(a1 * N + a2) * N + a3];
-        sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3);
+        sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
     }
-    __syncthreads();
+    __syncwarp();
     if (act) {
         sf3_bwd_reduce<N>(s_red + grp * S::RS, a3, out);
 #pragma unroll
         for (int q = 0; q < T::LPT; q++) { const int l = a3 * T::LPT + q; if (l < Np) s_x[grp * Np + l] = out[q]; }
     }
-    __syncthreads();
+    __syncwarp();
     // w_q = V w
+    if (act) sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
+    }
+    // Every warp is past its partials, modal coefficients and W / J: the nodal tile (over the partials of other groups) and
+    // the facet tile (over x | wij) may be written.  Facet values R w_q (R u_q for scalar laws) come from the 1-D factors
+    // of R: faces 0..2 from the slab still in registers, face 3 from the group's own nodal tile.
+    __syncthreads();
     if (act) {
-        sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
 #pragma unroll
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) s_q[grp * S::QS + (a1 * N + a2) * N + a3] = y[a1][a2];
+        facet_rows_slab<N>(fr, y, a3, s_wf + grp * S::WS);
     }
+    __syncwarp();
+    if (act) facet_rows_face3<N>(fr, s_q + grp * S::QS, a3, s_wf + grp * S::WS);
     __syncthreads();
-    }
     // u_q = u(w_q), u_f = u(R w_q)                           flux_differencing_form.jl:240-249
     if constexpr (PROJECT && NC == D + 2) {
         constexpr int UT = SSE_NODAL_ILP_Q, UF = SSE_NODAL_ILP_F;
@@ -322,10 +380,8 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
                 }
             }
         }
-        // facet nodes, face-major over the CTA's elements so that the rows of one warp have the same length in R
-        // (five entries on the faces eta_2 = -1, eta_1 = +-1, N^2 on the face eta_3 = -1)
-        constexpr int npf = T::npf;
-        const int totf = nel * Nf, perface = nel * npf;
+        // facet nodes
+        const int totf = nel * Nf;
         for (int it0 = tid; it0 < totf; it0 += UF * NT) {
             double wi[UF][NC], ui[UF][NC];
             size_t dst[UF];
@@ -335,18 +391,10 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
                 int it = it0 + k * NT;
                 ok[k] = it < totf;
                 if (!ok[k]) it = it0;
-                const int f = it / perface, rem = it - f * perface;
-                const int el = rem / npf, j = f * npf + (rem - el * npf);
+                const int el = it / Nf, j = it - el * Nf;
                 dst[k] = (size_t)(e0 + el) * Nf + j;
 #pragma unroll
-                for (int e = 0; e < NC; e++) wi[k][e] = 0.0;
-                const double* q0 = s_q + el * NC * S::QS;
-                for (int q = s_rptr[j]; q < s_rptr[j + 1]; q++) {
-                    const double rv = s_rval[q];
-                    const int c = s_ridx[q];
-#pragma unroll
-                    for (int e = 0; e < NC; e++) wi[k][e] = fma(rv, q0[e * S::QS + c], wi[k][e]);
-                }
+                for (int e = 0; e < NC; e++) wi[k][e] = s_wf[(el * NC + e) * S::WS + j];
             }
 #pragma unroll
             for (int k = 0; k < UF; k++) euler_entropy_to_cons_nb<D>(L.gamma, L.gm1, L.igm1, L.log_gm1, wi[k], ui[k]);
@@ -359,26 +407,17 @@ k_nodal_ct(SFCoef<N> cf, CtDev t, Geo g, Law L, long long first, long long count
             }
         }
     } else {
-    for (int it = tid; it < nel * (Nq + Nf); it += NT) {
-        const int el = it / (Nq + Nf), i = it - el * (Nq + Nf);
-        double wi[NC];
-        if (i < Nq) {
+        for (int it = tid; it < nel * (Nq + Nf); it += NT) {
+            const int el = it / (Nq + Nf), i = it - el * (Nq + Nf);
+            if (i < Nq) {
 #pragma unroll
-            for (int e = 0; e < NC; e++) u_q[((size_t)(e0 + el) * NC + e) * Nq + i] = s_q[(el * NC + e) * S::QS + i];
-        } else {
-            const int j = i - Nq;
+                for (int e = 0; e < NC; e++) u_q[((size_t)(e0 + el) * NC + e) * Nq + i] = s_q[(el * NC + e) * S::QS + i];
+            } else {
+                const int j = i - Nq;
 #pragma unroll
-            for (int e = 0; e < NC; e++) wi[e] = 0.0;
-            for (int q = s_rptr[j]; q < s_rptr[j + 1]; q++) {
-                const double rv = s_rval[q];
-                const int c = s_ridx[q];
-#pragma unroll
-                for (int e = 0; e < NC; e++) wi[e] = fma(rv, s_q[(el * NC + e) * S::QS + c], wi[e]);
+                for (int e = 0; e < NC; e++) u_f[(size_t)(e0 + el) * Nf + j + (size_t)g.NFT * e] = s_wf[(el * NC + e) * S::WS + j];
             }
-#pragma unroll
-            for (int e = 0; e < NC; e++) u_f[(size_t)(e0 + el) * Nf + j + (size_t)g.NFT * e] = wi[e];
         }
-    }
     }
 }
 
@@ -419,22 +458,23 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
     if constexpr (NC > 1) {
         for (int it = tid; it < nel * Nq; it += NT) {
             const int el = it / Nq, i = it - el * Nq;
-            s_wij[it] = t.W[i] * rcp_fast(g.J_q[(size_t)(e0 + el) * Nq + i]);
+            s_wij[el * S::QS + i] = t.W[i] * rcp_fast(g.J_q[(size_t)(e0 + el) * Nq + i]);
         }
     }
     __syncthreads();
-    if (act) sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3);
-    __syncthreads();
+    // the partials and modal coefficients of a group are touched by its own N lanes only (one warp): __syncwarp suffices
+    if (act) sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
+    __syncwarp();
     if (act) {
         sf3_bwd_reduce<N>(s_red + grp * S::RS, a3, out);
 #pragma unroll
         for (int q = 0; q < T::LPT; q++) { const int l = a3 * T::LPT + q; if (l < Np) s_x[grp * Np + l] = out[q]; }
     }
-    __syncthreads();
+    __syncwarp();
     if (act) {
         sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
         if constexpr (NC > 1) {
-            const double* wij = s_wij + (grp / NC) * Nq;
+            const double* wij = s_wij + (grp / NC) * S::QS;
 #pragma unroll
             for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
@@ -446,9 +486,9 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
 #pragma unroll
                 for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= t.W[(a1 * N + a2) * N + a3] * rcp_fast(Jq[(a1 * N + a2) * N]);
         }
-        sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3);
+        sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
     }
-    __syncthreads();
+    __syncwarp();
     if (act) {
         sf3_bwd_reduce<N>(s_red + grp * S::RS, a3, out);
 #pragma unroll

@@ -119,6 +119,9 @@ __device__ void apply_sp(const SpMat& A, int nrow, const double* x, int ldx, dou
     __syncthreads();
 }
 
+__host__ __device__ inline int warp_z_size(const Ops& o, int NC) { return o.v_kind == SSE_V_WARPED ? NC * o.P1 * o.P1 * o.M3 : 0; }
+__host__ __device__ inline int warp_w_size(const Ops& o, int NC) { return o.v_kind == SSE_V_WARPED ? NC * o.P1 * o.M2 * o.M3 : 0; }
+
 // mass_matrix_solve! (mass_matrix.jl:169-196) on a shared Np x NC tile; tq: Nq x NC scratch
 template <int NC>
 __device__ void mass_solve(const Ops& o, const Geo& g, long long k, double* rhs, double* tq, double* zb, double* wb) {
@@ -128,14 +131,75 @@ __device__ void mass_solve(const Ops& o, const Geo& g, long long k, double* rhs,
         __syncthreads();
         return;
     }
+    if (g.mass_solver == SSE_MASS_CHOLESKY) {
+        // ldiv!(cholesky(Symmetric(V' WJ_k V)), rhs) (mass_matrix.jl:169-175): U' y = rhs, then U x = y, column sweeps
+        // over the shared tile; the (i, variable) updates of one column run in parallel
+        const int Np = o.Np;
+        const double* U = g.chol + (size_t)Np * Np * k;
+        for (int j = 0; j < Np; j++) {
+            if (threadIdx.x < NC) rhs[j + Np * threadIdx.x] /= U[j + (size_t)Np * j];
+            __syncthreads();
+            SSE_FOR(t, (Np - 1 - j) * NC) {
+                const int i = j + 1 + t % (Np - 1 - j), e = t / (Np - 1 - j);
+                rhs[i + Np * e] = fma(-U[j + (size_t)Np * i], rhs[j + Np * e], rhs[i + Np * e]);
+            }
+            __syncthreads();
+        }
+        for (int j = Np - 1; j >= 0; j--) {
+            if (threadIdx.x < NC) rhs[j + Np * threadIdx.x] /= U[j + (size_t)Np * j];
+            __syncthreads();
+            SSE_FOR(t, j * NC) {
+                const int i = t % j, e = t / j;
+                rhs[i + Np * e] = fma(-U[i + (size_t)Np * j], rhs[j + Np * e], rhs[i + Np * e]);
+            }
+            __syncthreads();
+        }
+        return;
+    }
     apply_V<NC>(o, rhs, tq, zb, wb);
     SSE_FOR(t, o.Nq * NC) { int i = t % o.Nq; tq[t] *= o.W[i] / J[i]; }
     __syncthreads();
     apply_Vt<NC>(o, tq, rhs, zb, wb);
 }
 
-__host__ __device__ inline int warp_z_size(const Ops& o, int NC) { return o.v_kind == SSE_V_WARPED ? NC * o.P1 * o.P1 * o.M3 : 0; }
-__host__ __device__ inline int warp_w_size(const Ops& o, int NC) { return o.v_kind == SSE_V_WARPED ? NC * o.P1 * o.M2 * o.M3 : 0; }
+// CholeskySolver constructor (mass_matrix.jl:30-39) on the device: M_k = V' diag(W J_k) V column by column through the
+// matrix-free V, then its upper Cholesky factor in place (right-looking); one CTA per element.
+// shared: M (Np x Np) | e (Np) | q (Nq) | z | w
+static __global__ void k_cholesky_factor(Ops o, Geo g, double* __restrict__ chol, int* __restrict__ bad) {
+    extern __shared__ double sm[];
+    const int Np = o.Np, Nq = o.Nq;
+    const long long k = blockIdx.x;
+    double* s_M = sm;
+    double* s_e = s_M + Np * Np;
+    double* s_q = s_e + Np;
+    double* s_z = s_q + Nq;
+    double* s_w = s_z + warp_z_size(o, 1);
+    const double* J = g.J_q + (size_t)Nq * k;
+    for (int c = 0; c < Np; c++) {
+        SSE_FOR(t, Np) s_e[t] = (t == c) ? 1.0 : 0.0;
+        __syncthreads();
+        apply_V<1>(o, s_e, s_q, s_z, s_w);
+        SSE_FOR(i, Nq) s_q[i] *= o.W[i] * J[i];
+        __syncthreads();
+        apply_Vt<1>(o, s_q, s_M + Np * c, s_z, s_w);
+    }
+    for (int j = 0; j < Np; j++) {
+        const double piv = s_M[j + Np * j];
+        __syncthreads();
+        if (!(piv > 0.0)) { if (threadIdx.x == 0) *bad = 1; return; }      // PosDefException in the reference (Solvers.jl:411-412)
+        const double ujj = sqrt(piv);
+        SSE_FOR(i, Np - j) s_M[j + Np * (j + i)] = (i == 0) ? ujj : s_M[j + Np * (j + i)] / ujj;
+        __syncthreads();
+        const int n = Np - 1 - j;
+        SSE_FOR(t, n * n) {
+            const int i = j + 1 + t % n, l = j + 1 + t / n;
+            if (i <= l) s_M[i + Np * l] = fma(-s_M[j + Np * i], s_M[j + Np * l], s_M[i + Np * l]);
+        }
+        __syncthreads();
+    }
+    SSE_FOR(t, Np * Np) chol[(size_t)Np * Np * k + t] = (t % Np <= t / Np) ? s_M[t] : 0.0;
+}
+
 
 // ------------------------------------------------------------------ pass A: nodal_values!
 // standard_form_first_order.jl:1-14; flux_differencing_form.jl:171-292.

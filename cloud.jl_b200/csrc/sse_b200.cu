@@ -235,6 +235,10 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
     Geo& g = h->geo;
     memset(&g, 0, sizeof(g));
     g.Ne = Ne; g.NFT = (long long)Nf * Ne + cfg->N_ghost; g.mass_solver = cfg->mass_solver;
+    if (cfg->mass_solver != SSE_MASS_WEIGHT_ADJUSTED && cfg->mass_solver != SSE_MASS_DIAGONAL && cfg->mass_solver != SSE_MASS_CHOLESKY)
+        return fail(SSE_ERR_BAD_ARGUMENT, "unknown mass_solver %d", cfg->mass_solver);
+    // CholeskySolver with V = I is the DiagonalSolver (mass_matrix.jl:26-28)
+    if (cfg->mass_solver == SSE_MASS_CHOLESKY && cfg->v_kind == SSE_V_IDENTITY) g.mass_solver = SSE_MASS_DIAGONAL;
     if (cfg->form == SSE_FORM_STANDARD_REFERENCE) {
         if (!a->Lambda_q) return fail(SSE_ERR_BAD_ARGUMENT, "Lambda_q required");
         for (int m = 0; m < d; m++) {
@@ -291,6 +295,24 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
         if ((rc = upload_raw(h, (const long long*)a->mapP, (size_t)Nf * Ne, &mp))) return rc;
         g.mapP = mp;
     }
+    if (g.mass_solver == SSE_MASS_CHOLESKY) {
+        // CholeskySolver(J_q, V, W) (mass_matrix.jl:30-39): one factorisation per element, on the device
+        double* chol = nullptr;
+        if ((rc = dalloc(h, (size_t)Np * Np * Ne, &chol))) return rc;
+        int* bad = nullptr;
+        CU(cudaMalloc((void**)&bad, sizeof(int)));
+        h->owned.push_back(bad);
+        CU(cudaMemset(bad, 0, sizeof(int)));
+        const size_t smem = sizeof(double) * (size_t)(Np * Np + Np + Nq + warp_z_size(o, 1) + warp_w_size(o, 1));
+        if (smem > 227 * 1024) return fail(SSE_ERR_UNSUPPORTED, "element mass matrix exceeds 227 KB of shared memory");
+        CU(cudaFuncSetAttribute(k_cholesky_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_cholesky_factor<<<(unsigned)Ne, 128, smem, h->stream>>>(o, g, chol, bad);
+        int hbad = 0;
+        CU(cudaMemcpy(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost));
+        CU(cudaGetLastError());
+        if (hbad) return fail(SSE_ERR_BAD_ARGUMENT, "mass matrix V' WJ V is not positive definite (PosDefException, Solvers.jl:411-412)");
+        g.chol = chol;
+    }
     // ---- law
     Law& L = h->law;
     L.pde = cfg->pde; L.two_point = cfg->two_point_flux; L.inviscid = cfg->inviscid_flux;
@@ -332,7 +354,7 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
     }
     {
         int N = 0;
-        if (ct_eligible(*cfg, *a, h->tp, &N) && ct_schedule_matches(h->tp, N)) {
+        if (ct_eligible(*cfg, *a, h->tp, &N) && ct_schedule_matches(h->tp, N) && ct_facet_factors(*cfg, *a, N, h->ct.facetR)) {
             h->ct.N = N;
             h->ct.A.assign(a->A, a->A + N * N);
             h->ct.B.assign(a->B, a->B + N * N * N);
@@ -359,7 +381,7 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
     {
         int N = 0;
         std::vector<double> D1;
-        if (!h->ct.ok && ct_eligible_standard(*cfg, *a, &N, D1, h->ct.fR)) {
+        if (!h->ct.ok && ct_eligible_standard(*cfg, *a, &N, D1, h->ct.fR) && ct_facet_factors(*cfg, *a, N, h->ct.facetR)) {
             h->ct.N = N; h->ct.kind = 1; h->ct.D1 = D1;
             h->ct.A.assign(a->A, a->A + N * N);
             h->ct.B.assign(a->B, a->B + N * N * N);
@@ -653,7 +675,7 @@ extern "C" int32_t sse_step_ck54(sse_handle* h, double* d_u, double* d_tmp, doub
 // conservation / energy / entropy residual reductions (Analysis/conservation.jl:145-189)
 //   out[e < NC] = sum_k 1' WJ_k V dudt_k[:, e]                      (:145-152)
 //   out[NC]     = sum_k sum_e u_k[:, e]' M_k dudt_k[:, e]           (:154-167), M_k = mass_matrix(mass_solver, k):
-//                 diag(W J_k) for the DiagonalSolver; for the WeightAdjustedSolver M_k = (V' diag(W / J_k) V)^-1
+//                 diag(W J_k) for the DiagonalSolver, V' diag(W J_k) V for the CholeskySolver; for the WeightAdjustedSolver M_k = (V' diag(W / J_k) V)^-1
 //                 (mass_matrix.jl:140-153), applied by conjugate gradients on the SPD operator the residual itself
 //                 applies (its condition number is max J / min J over the element, so a few iterations suffice)
 //   out[NC + 1] = sum_k (V' WJ_k w(V u_k))' dudt_k                   (:169-189, M_k symmetric)
@@ -685,7 +707,7 @@ __global__ void k_functionals(Ops o, Geo g, Law L, const double* __restrict__ u,
             double ui[NC], wi[NC];
 #pragma unroll
             for (int e = 0; e < NC; e++) { ui[e] = s_uq[i + Nq * e]; atomicAdd(&acc[e], wj * s_dq[i + Nq * e]); }
-            if (g.mass_solver == SSE_MASS_DIAGONAL) {
+            if (g.mass_solver != SSE_MASS_WEIGHT_ADJUSTED) {      // M = V' WJ V (V = I for the DiagonalSolver)
 #pragma unroll
                 for (int e = 0; e < NC; e++) atomicAdd(&acc[NC], wj * ui[e] * s_dq[i + Nq * e]);
             }
@@ -697,7 +719,7 @@ __global__ void k_functionals(Ops o, Geo g, Law L, const double* __restrict__ u,
                 atomicAdd(&acc[NC + 1], wj * s);
             }
         }
-        if (g.mass_solver != SSE_MASS_DIAGONAL) {
+        if (g.mass_solver == SSE_MASS_WEIGHT_ADJUSTED) {
             __syncthreads();
             if (threadIdx.x < NC) rr[threadIdx.x] = 0.0;
             SSE_FOR(t, Np * NC) { s_y[t] = 0.0; s_p[t] = s_d[t]; }
@@ -868,9 +890,9 @@ extern "C" int32_t sse_plan_selfcheck(const sse_config* cfg, const sse_arrays* a
     info[0] = tp.ok;
     {   // 2: compile-time flux-differencing kernels, 3: compile-time advection StandardForm kernels
         int N = 0;
-        std::vector<double> D1, fR;
-        if (tp.ok && ct_eligible(*cfg, *arr, tp, &N) && ct_schedule_matches(tp, N)) info[0] = 2;
-        else if (ct_eligible_standard(*cfg, *arr, &N, D1, fR)) { info[0] = 3; info[1] = 128; return SSE_OK; }
+        std::vector<double> D1, fR, fac;
+        if (tp.ok && ct_eligible(*cfg, *arr, tp, &N) && ct_schedule_matches(tp, N) && ct_facet_factors(*cfg, *arr, N, fac)) info[0] = 2;
+        else if (ct_eligible_standard(*cfg, *arr, &N, D1, fR) && ct_facet_factors(*cfg, *arr, N, fac)) { info[0] = 3; info[1] = 128; return SSE_OK; }
     }
     if (!tp.ok) return SSE_OK;
     info[1] = tp.threads; info[2] = tp.dev.n_vrounds; info[3] = tp.dev.n_frounds;

@@ -13,7 +13,7 @@ SSE_FORM_STANDARD_REFERENCE, SSE_FORM_STANDARD_PHYSICAL, SSE_FORM_FLUX_DIFFERENC
 SSE_FLUX_LAX_FRIEDRICHS, SSE_FLUX_CENTRAL, SSE_FLUX_ENTROPY_CONSERVATIVE = 0, 1, 2
 SSE_VISCOUS_NONE, SSE_VISCOUS_BR1 = 0, 1
 SSE_TWO_POINT_CONSERVATIVE, SSE_TWO_POINT_ENTROPY_CONSERVATIVE = 0, 1
-SSE_MASS_WEIGHT_ADJUSTED, SSE_MASS_DIAGONAL = 0, 1
+SSE_MASS_WEIGHT_ADJUSTED, SSE_MASS_DIAGONAL, SSE_MASS_CHOLESKY = 0, 1, 2
 SSE_V_IDENTITY, SSE_V_DENSE, SSE_V_WARPED = 0, 1, 2
 
 _pd = C.POINTER(C.c_double)

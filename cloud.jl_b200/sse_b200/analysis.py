@@ -14,6 +14,8 @@ def _mass_matrix(ra, gf, mass_solver):
     if mass_solver == _abi.SSE_MASS_DIAGONAL:
         return np.einsum("ki,ij->kij", ra.W[None, :] * gf.J_q, np.eye(ra.N_p))
     V = ra.V
+    if mass_solver == _abi.SSE_MASS_CHOLESKY:                  # V' WJ V   mass_matrix.jl:140-143
+        return np.einsum("qa,kq,qb->kab", V, ra.W[None, :] * gf.J_q, V)
     Minv = np.einsum("qa,kq,qb->kab", V, ra.W[None, :] / gf.J_q, V)
     return np.linalg.inv(Minv)
 

@@ -75,6 +75,8 @@ def mass_matrix_inverse(ra, gf, mass_solver: int) -> np.ndarray:
         inv = 1.0 / (ra.W[None, :] * gf.J_q)
         return np.einsum("ki,ij->kij", inv, np.eye(ra.N_p))
     V = ra.V
+    if mass_solver == _abi.SSE_MASS_CHOLESKY:                  # inv(V' WJ V)   mass_matrix.jl:155-158
+        return np.linalg.inv(np.einsum("qa,kq,qb->kab", V, ra.W[None, :] * gf.J_q, V))
     return np.einsum("qa,kq,qb->kab", V, ra.W[None, :] / gf.J_q, V)
 
 
@@ -142,6 +144,8 @@ def assemble(law, sd: SpatialDiscretization, form, strategy: str = REFERENCE_OPE
         raise ValueError("dimension mismatch between conservation law and discretization")
     if mass_solver is None:
         mass_solver = default_mass_solver(ra)
+    if mass_solver == _abi.SSE_MASS_CHOLESKY and ra.V_is_identity:      # CholeskySolver(J_q, V::UniformScalingMap, W)
+        mass_solver = _abi.SSE_MASS_DIAGONAL                             # is the DiagonalSolver (mass_matrix.jl:26-28)
     cfg = _abi.sse_config()
     cfg.abi_version = _abi.SSE_ABI_VERSION
     cfg.d, cfg.N_c, cfg.N_p, cfg.N_q, cfg.N_f, cfg.N_fac = d, law.N_c, ra.N_p, ra.N_q, ra.N_f, ra.N_fac

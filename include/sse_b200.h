@@ -68,7 +68,9 @@ enum { SSE_VISCOUS_NONE = 0, SSE_VISCOUS_BR1 = 1 };
 enum { SSE_TWO_POINT_CONSERVATIVE = 0, SSE_TWO_POINT_ENTROPY_CONSERVATIVE = 1 };
 /* AbstractMassMatrixSolver (mass_matrix.jl:1-17) */
 enum { SSE_MASS_WEIGHT_ADJUSTED = 0,     /* M^-1 = I assumed (assume_orthonormal=true default, mass_matrix.jl:59-75) */
-       SSE_MASS_DIAGONAL = 1 };
+       SSE_MASS_DIAGONAL = 1,
+       SSE_MASS_CHOLESKY = 2 };          /* CholeskySolver: ldiv!(cholesky(Symmetric(V' WJ_k V)), rhs)  mass_matrix.jl:26-39, 169-175;
+                                            the factors are computed on the device at sse_create (N_p^2 doubles per element) */
 /* type of the generalized Vandermonde V (MatrixFreeOperators) */
 enum { SSE_V_IDENTITY = 0,               /* LinearMaps.UniformScalingMap (nodal schemes)               */
        SSE_V_DENSE = 1,                  /* OctavianMap / WrappedMap                                   */

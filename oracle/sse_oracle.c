@@ -115,6 +115,7 @@ typedef struct {
     int has_C;
     int64_t *sig_i, *sig_o; /* 0-based copies */
     int N2[8], N3[8][8];
+    double *chol;           /* CholeskySolver: upper factors U_k (N_p x N_p column-major per element), mass_matrix.jl:30-39 */
 } ora_t;
 
 /* ---------------------------------------------------------------- V, V' */
@@ -238,6 +239,23 @@ static void mass_solve(const ora_t *o, int64_t k, double *rhs, double *temp, int
     if (o->c.mass_solver == SSE_MASS_DIAGONAL) { /* :177-183, WJ^-1 = inv(Diagonal(W .* J)) */
         for (int e = 0; e < nc; e++)
             for (int i = 0; i < Np; i++) rhs[i + (size_t)Np * e] *= 1.0 / (W[i] * J[i]);
+        return;
+    }
+    if (o->c.mass_solver == SSE_MASS_CHOLESKY) { /* :169-175, ldiv!(cholesky(Symmetric(V' WJ V)), rhs): U' \ then U \ */
+        const double *U = o->chol + (size_t)Np * Np * k;
+        for (int e = 0; e < nc; e++) {
+            double *b = rhs + (size_t)Np * e;
+            for (int i = 0; i < Np; i++) {
+                double t = b[i];
+                for (int j = 0; j < i; j++) t -= U[j + (size_t)Np * i] * b[j];
+                b[i] = t / U[i + (size_t)Np * i];
+            }
+            for (int i = Np - 1; i >= 0; i--) {
+                double t = b[i];
+                for (int j = i + 1; j < Np; j++) t -= U[i + (size_t)Np * j] * b[j];
+                b[i] = t / U[i + (size_t)Np * i];
+            }
+        }
         return;
     }
     /* WeightAdjusted, M^-1 = I (:185-196; ctor :59-75) */
@@ -751,12 +769,39 @@ static int ora_init(ora_t *o, const sse_config *cfg, const sse_arrays *arr) {
                 }
         }
     }
+    if (cfg->mass_solver == SSE_MASS_CHOLESKY) {
+        /* CholeskySolver (mass_matrix.jl:26-39): with V = I it is the DiagonalSolver; otherwise
+           M_k = V' diag(W J_k) V column by column and its upper Cholesky factor (LAPACK potrf 'U' order) */
+        if (cfg->v_kind == SSE_V_IDENTITY) { o->c.mass_solver = SSE_MASS_DIAGONAL; return SSE_OK; }
+        o->chol = malloc(sizeof(double) * (size_t)Np * Np * cfg->N_e);
+        double *e_c = calloc(Np, sizeof(double)), *vq = malloc(sizeof(double) * Nq);
+        for (int64_t k = 0; k < cfg->N_e; k++) {
+            double *M = o->chol + (size_t)Np * Np * k;
+            const double *J = arr->J_q + (size_t)Nq * k;
+            for (int c = 0; c < Np; c++) {
+                e_c[c] = 1.0;
+                V_mul(o, e_c, vq, 1);
+                for (int i = 0; i < Nq; i++) vq[i] *= arr->W[i] * J[i];
+                Vt_mul(o, vq, M + (size_t)Np * c, 1);
+                e_c[c] = 0.0;
+            }
+            for (int j = 0; j < Np; j++) {          /* U'U = M, column by column, upper triangle in place */
+                for (int i = 0; i <= j; i++) {
+                    double t = M[i + (size_t)Np * j];
+                    for (int l = 0; l < i; l++) t -= M[l + (size_t)Np * i] * M[l + (size_t)Np * j];
+                    if (i < j) M[i + (size_t)Np * j] = t / M[i + (size_t)Np * i];
+                    else { if (t <= 0.0) { free(e_c); free(vq); return SSE_ERR_BAD_ARGUMENT; } M[i + (size_t)Np * j] = sqrt(t); }
+                }
+            }
+        }
+        free(e_c); free(vq);
+    }
     return SSE_OK;
 }
 static void ora_free(ora_t *o) {
     sp_free(&o->Vcsr); sp_free(&o->Rcsr); sp_free(&o->Ccsc);
     for (int m = 0; m < MAXD; m++) { sp_free(&o->Dcsr[m]); sp_free(&o->Scsc[m]); }
-    free(o->sig_i); free(o->sig_o);
+    free(o->sig_i); free(o->sig_o); free(o->chol);
 }
 
 /* semi_discrete_residual! (Solvers.jl:474-564), Threaded variant.  Scratch u_q (N_q,N_c,N_e) and

@@ -20,10 +20,10 @@
 
 // independent entropy-variable transforms per thread and trip in k_nodal_ct: volume-node loops / facet-node loop
 #ifndef SSE_NODAL_ILP_Q
-#define SSE_NODAL_ILP_Q 3
+#define SSE_NODAL_ILP_Q 2
 #endif
 #ifndef SSE_NODAL_ILP_F
-#define SSE_NODAL_ILP_F 3
+#define SSE_NODAL_ILP_F 2
 #endif
 
 namespace sse {
@@ -593,6 +593,14 @@ __device__ __forceinline__ int facet_partner(int fr, int ca, int cb, int cc) {
     return 3 * NN + ca * N + bp;
 }
 
+// schedule-weight tables (vS, fC, fR: 34 x Nq doubles, the same for every element): kept in L1 against the streaming
+// element data with an evict-last hint (pass B 1.976 -> 1.935 ms at 82 944 elements)
+__device__ __forceinline__ double ld_tab(const double* p) {
+    double v;
+    asm("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 template <int N, int MINB, bool DUAL>
 __global__ void __launch_bounds__((Tet<N>::Nq + 31) / 32 * 32, MINB)
 k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, const double* __restrict__ u_f) {
@@ -636,7 +644,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
 #pragma unroll
     for (int e = 0; e < NC; e++) uo[e] = __ldcs(u_f + jo + (size_t)g.NFT * e);
 #pragma unroll
-    for (int m = 0; m < D; m++) sw[m] = t.vS[(0 * D + m) * Nq + tn];            // weights of round 0
+    for (int m = 0; m < D; m++) sw[m] = ld_tab(t.vS + ((0 * D + m) * Nq + tn));            // weights of round 0
     const double bf = t.Bf[tj];
 #pragma unroll
     for (int e = 0; e < NC; e++) r[e] = 0.0;
@@ -684,8 +692,9 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
         int buf = 0;
         double swb[D];
 #pragma unroll
-        for (int m = 0; m < D; m++) swb[m] = t.vS[(1 * D + m) * Nq + tn];
-#pragma unroll 1
+        for (int m = 0; m < D; m++) swb[m] = ld_tab(t.vS + ((1 * D + m) * Nq + tn));
+#pragma unroll               // the three line directions as straight-line code: static strides and m >= l tests, no weight
+                             // hand-over moves (pass B 1.936 -> 1.820 ms at 82 944 elements; unrolling the facet loop as well loses)
         for (int l = 0; l < D; l++, buf ^= 1) {
             double* stA = s_stage + (2 * buf) * NC * Nq;
             double* stB = stA + NC * Nq;
@@ -697,8 +706,8 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
             double swnA[D], swnB[D];
 #pragma unroll
             for (int m = 0; m < D; m++) {
-                swnA[m] = (l + 1 < D) ? t.vS[((2 * l + 2) * D + m) * Nq + tn] : 0.0;
-                swnB[m] = (l + 1 < D) ? t.vS[((2 * l + 3) * D + m) * Nq + tn] : 0.0;
+                swnA[m] = (l + 1 < D) ? ld_tab(t.vS + (((2 * l + 2) * D + m) * Nq + tn)) : 0.0;
+                swnB[m] = (l + 1 < D) ? ld_tab(t.vS + (((2 * l + 3) * D + m) * Nq + tn)) : 0.0;
             }
             if (node) {
                 double gA[D], gB[D], qA[NP], qB[NP], pA[NC], pB[NC];
@@ -728,17 +737,21 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
 #pragma unroll
             for (int m = 0; m < D; m++) { sw[m] = swnA[m]; swb[m] = swnB[m]; }
         }
-        double cwA = t.fC[tn], cwB = t.fC[Nq + tn];
+        double cwA = ld_tab(t.fC + (tn)), cwB = ld_tab(t.fC + (Nq + tn));
         static_assert(NN * NC == Nq, "reducer items = volume nodes");
         const int re = tid / NN, rjj = tid - re * NN, rx = rjj / N, ry = rjj - rx * N;
         int rc3 = ry ? N - ry : 0;          // volume column (fr - 3 - y) mod N feeding facet node (x, y) of face 4, sub-round 3
-#pragma unroll 1
+#ifndef SSE_FD_UNROLL_F
+#define SSE_FD_UNROLL_F 2
+#endif
+        constexpr int FUN = SSE_FD_UNROLL_F;
+#pragma unroll FUN
         for (int fr = 0; fr < NFR; fr += 2, buf ^= 1) {
             double* stA = s_stage + (2 * buf) * NC * Nq;
             double* stB = stA + NC * Nq;
             const int fA = fr < 3 ? fr : 3, fB = fr + 1 < 3 ? fr + 1 : 3;
-            const double cwnA = (fr + 2 < NFR) ? t.fC[(fr + 2) * Nq + tn] : 0.0;
-            const double cwnB = (fr + 3 < NFR) ? t.fC[(fr + 3) * Nq + tn] : 0.0;
+            const double cwnA = (fr + 2 < NFR) ? ld_tab(t.fC + ((fr + 2) * Nq + tn)) : 0.0;
+            const double cwnB = (fr + 3 < NFR) ? ld_tab(t.fC + ((fr + 3) * Nq + tn)) : 0.0;
             if (node) {
                 double hA[D], hB[D];
 #pragma unroll
@@ -804,7 +817,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
         const int j = tid + (cj - cl) * stride;
         double swn[D];                                         // prefetch the next round's weights
 #pragma unroll
-        for (int m = 0; m < D; m++) swn[m] = (rd + 1 < NVR) ? t.vS[((rd + 1) * D + m) * Nq + tn] : 0.0;
+        for (int m = 0; m < D; m++) swn[m] = (rd + 1 < NVR) ? ld_tab(t.vS + (((rd + 1) * D + m) * Nq + tn)) : 0.0;
         if (active) {
             double gv[D], qj[NP], phi[NC];
 #pragma unroll
@@ -832,7 +845,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
     }
 
     // ---- facet correction: NFR sub-rounds (facet_correction!, flux_differencing_form.jl:126-168)
-    double cw = t.fC[tn];
+    double cw = ld_tab(t.fC + (tn));
     double hq[D];
 #pragma unroll
     for (int n = 0; n < D; n++) hq[n] = 0.0;
@@ -840,7 +853,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
     for (int fr = 0; fr < NFR; fr++, buf ^= 1) {
         double* st = s_stage + buf * NC * Nq;
         const int f = fr < 3 ? fr : 3;
-        const double cwn = (fr + 1 < NFR) ? t.fC[(fr + 1) * Nq + tn] : 0.0;
+        const double cwn = (fr + 1 < NFR) ? ld_tab(t.fC + ((fr + 1) * Nq + tn)) : 0.0;
         if (node) {
             if (fr <= 3) {                         // 2 halfnJq[:, f, i] = sum_l Lambda[i,l,:] nref[l,f]   mesh.jl:262-269
                 if (g.nJq) {
@@ -887,7 +900,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
     if (node) {
         double rw[NFR];
 #pragma unroll
-        for (int fr = 0; fr < NFR; fr++) rw[fr] = t.fR[fr * Nq + tid];
+        for (int fr = 0; fr < NFR; fr++) rw[fr] = ld_tab(t.fR + (fr * Nq + tid));
 #pragma unroll
         for (int fr = 0; fr < NFR; fr++) {
             const int j = facet_partner<N>(fr, ca, cb, cc);

@@ -3,6 +3,14 @@
 
 namespace sse {
 
+// C[a3, i, j, k] depends on (i + j, k) only (kernels_ct.cuh: c3_sym)
+static bool c_tensor_symmetric(const sse_arrays& a, int N) {
+    if (!a.C) return false;
+    for (int b1 = 0; b1 < N; b1++) for (int b2 = 0; b1 + b2 < N; b2++) for (int b3 = 0; b1 + b2 + b3 < N; b3++) for (int a3 = 0; a3 < N; a3++)
+        if (a.C[a3 + N * (b1 + N * (b2 + N * b3))] != a.C[a3 + N * (0 + N * ((b1 + b2) + N * b3))]) return false;
+    return true;
+}
+
 // the compile-time path needs: d = 3, Euler + EC two-point flux, flux differencing, warped V with
 // M1 = M2 = M3 = p + 1 in the canonical orderings, weight-adjusted mass solver, and a tensor plan
 bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& tp, int* Nout) {
@@ -19,6 +27,7 @@ bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& t
         const long long want = (a1 + a2 + a3 <= N - 1) ? (N == 4 ? tet_l<4>(a1, a2, a3) : tet_l<5>(a1, a2, a3)) + 1 : 0;
         if (a.sigma_i[t] != want) return false;
     }
+    if (!c_tensor_symmetric(a, N)) return false;
     *Nout = N;
     return true;
 }
@@ -194,6 +203,7 @@ bool ct_eligible_standard(const sse_config& cfg, const sse_arrays& a, int* Nout,
         }
     }
     for (size_t x = 0; x < seen.size(); x++) if (!seen[x] && a.R[x] != 0.0) return false;
+    if (!c_tensor_symmetric(a, N)) return false;
     *Nout = N;
     return true;
 }

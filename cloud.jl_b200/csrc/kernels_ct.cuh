@@ -58,8 +58,23 @@ template <int N> __host__ __device__ constexpr int tet_l(int b1, int b2, int b3)
 
 // y[a1][a2] (fixed a3) = sum A[a1,b1] B[a2,b1,b2] C[a3,b1,b2,b3] x[l(b1,b2,b3)]      warped_product_3d.jl:47-84
 // c3[l * CS]: CS = 1 for a register array, CS = N for the shared table [l][a3] (pointer offset by a3)
-template <int N, int CS = 1>
+// The collapsed-tet C tensor, 2 (1 - eta_3)^(i+j) P_k^(2i+2j+2,0)(eta_3) (tensor_simplex.jl:123-130), depends on (i + j, k) only
+// (ct_eligible verifies C[a3,i,j,k] == C[a3,0,i+j,k] bit for bit), so a thread needs N (N + 1) / 2 values of it per
+// application instead of N_p: they are read once into registers (c3_sym) ahead of the b1 slabs.
+// SYM selects it per call site: it pays in k_project_ct (pass B 1.796 -> 1.782 ms at 82 944 elements) and loses in k_nodal_ct,
+// whose transforms leave no registers for the N (N + 1) / 2 values (pass A 0.646 -> 0.707 ms with spills).
+template <int N> __host__ __device__ constexpr int c3_sym_idx(int s, int k) { return s * N - s * (s - 1) / 2 + k; }   // k <= N - 1 - s
+template <int N, int CS>
+__device__ __forceinline__ void load_c3_sym(const double* c3, double (&cs)[N * (N + 1) / 2]) {
+#pragma unroll
+    for (int sidx = 0; sidx < N; sidx++)
+#pragma unroll
+        for (int k = 0; k < N - sidx; k++) cs[c3_sym_idx<N>(sidx, k)] = c3[tet_l<N>(0, sidx, k) * CS];
+}
+template <int N, int CS = 1, bool SYM = false>
 __device__ __forceinline__ void sf3_fwd(const SFCoef<N>& cf, const double* c3, const double* __restrict__ xs, double (&y)[N][N]) {
+    double cs[SYM ? N * (N + 1) / 2 : 1];
+    if constexpr (SYM) load_c3_sym<N, CS>(c3, cs);
 #pragma unroll
     for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
@@ -74,7 +89,11 @@ __device__ __forceinline__ void sf3_fwd(const SFCoef<N>& cf, const double* c3, c
         for (int b2 = 0; b2 < N - b1; b2++) {
             double z = 0.0;
 #pragma unroll
-            for (int b3 = 0; b3 < N - b1 - b2; b3++) { const int l = tet_l<N>(b1, b2, b3); z = fma(c3[l * CS], xs[l], z); }
+            for (int b3 = 0; b3 < N - b1 - b2; b3++) {
+                const int l = tet_l<N>(b1, b2, b3);
+                if constexpr (SYM) z = fma(cs[c3_sym_idx<N>(b1 + b2, b3)], xs[l], z);
+                else z = fma(c3[l * CS], xs[l], z);
+            }
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) w[a2] = fma(cf.B[a2 + N * (b1 + N * b2)], z, w[a2]);
         }
@@ -87,8 +106,10 @@ __device__ __forceinline__ void sf3_fwd(const SFCoef<N>& cf, const double* c3, c
 
 // partial[l][a3] = C[a3,l] * sum_{a2} B[a2,b1,b2] sum_{a1} A[a1,b1] x[a1][a2]        warped_product_3d.jl:94-136
 // written to red[l * RED_SL] (the caller passes red already offset by group and a3 * RED_SA)
-template <int N, int CS = 1>
+template <int N, int CS = 1, bool SYM = false>
 __device__ __forceinline__ void sf3_bwd_partials(const SFCoef<N>& cf, const double* c3, const double (&x)[N][N], double* __restrict__ red) {
+    double cs[SYM ? N * (N + 1) / 2 : 1];
+    if constexpr (SYM) load_c3_sym<N, CS>(c3, cs);
 #pragma unroll
     for (int b1 = 0; b1 < N; b1++) {
         asm volatile("" ::: "memory");
@@ -106,7 +127,11 @@ __device__ __forceinline__ void sf3_bwd_partials(const SFCoef<N>& cf, const doub
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) z = fma(cf.B[a2 + N * (b1 + N * b2)], wt[a2], z);
 #pragma unroll
-            for (int b3 = 0; b3 < N - b1 - b2; b3++) { const int l = tet_l<N>(b1, b2, b3); red[l * Tet<N>::RED_SL] = c3[l * CS] * z; }
+            for (int b3 = 0; b3 < N - b1 - b2; b3++) {
+                const int l = tet_l<N>(b1, b2, b3);
+                if constexpr (SYM) red[l * Tet<N>::RED_SL] = cs[c3_sym_idx<N>(b1 + b2, b3)] * z;
+                else red[l * Tet<N>::RED_SL] = c3[l * CS] * z;
+            }
         }
     }
 }
@@ -463,7 +488,7 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
     }
     __syncthreads();
     // the partials and modal coefficients of a group are touched by its own N lanes only (one warp): __syncwarp suffices
-    if (act) sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
+    if (act) sf3_bwd_partials<N, N, true>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
     __syncwarp();
     if (act) {
         sf3_bwd_reduce<N>(s_red + grp * S::RS, a3, out);
@@ -472,7 +497,7 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
     }
     __syncwarp();
     if (act) {
-        sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
+        sf3_fwd<N, N, true>(cf, c3, s_x + grp * Np, y);
         if constexpr (NC > 1) {
             const double* wij = s_wij + (grp / NC) * S::QS;
 #pragma unroll
@@ -486,7 +511,7 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
 #pragma unroll
                 for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= t.W[(a1 * N + a2) * N + a3] * rcp_fast(Jq[(a1 * N + a2) * N]);
         }
-        sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
+        sf3_bwd_partials<N, N, true>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
     }
     __syncwarp();
     if (act) {

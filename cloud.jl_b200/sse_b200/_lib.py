@@ -28,6 +28,9 @@ SYMBOLS = {
     "sse_state_upload": (C.c_int32, [_h, C.c_void_p, C.c_void_p]),
     "sse_state_download": (C.c_int32, [_h, C.c_void_p, C.c_void_p]),
     "sse_rhs": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_double]),
+    "sse_rhs_host": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_double, C.c_int32]),
+    "sse_host_pin": (C.c_int32, [C.c_void_p, C.c_int64]),
+    "sse_host_unpin": (C.c_int32, [C.c_void_p]),
     "sse_rhs_pass_a": (C.c_int32, [_h, C.c_void_p]),
     "sse_rhs_pass_a_range": (C.c_int32, [_h, C.c_void_p, C.c_int64, C.c_int64]),
     "sse_rhs_pass_aux": (C.c_int32, [_h, C.c_void_p, C.c_int64, C.c_int64]),

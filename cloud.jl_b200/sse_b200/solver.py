@@ -140,18 +140,15 @@ class Solver:
             self._pinned[key] = chunk_plan(self.image.arrays["mapP"], self.state_shape[0], int(self.cfg.N_f), chunks)
         return self._pinned[key]
 
-    def rhs_host(self, dudt_host, u_host, t: float = 0.0, chunks: int = 16):
-        """Residual on HOST buffers (the reference-facing call with `Array` arguments): the H2D copy of u, the
-        kernels and the D2H copy of dudt are pipelined over `chunks` element ranges on three streams — pass A of a
-        range starts as soon as its slice of u has arrived, pass B of a range as soon as pass A has covered its face
-        neighbours (read from mapP), and the download of its dudt overlaps the uploads still in flight (full-duplex
-        PCIe).  torch CPU tensors (ideally pinned) are copied directly; NumPy arrays are staged through pinned memory."""
+    def rhs_host(self, dudt_host, u_host, t: float = 0.0, chunks: int = 0):
+        """Residual on HOST buffers (the reference-facing call with `Array` arguments) = one `sse_rhs_host`: the H2D copy
+        of u, the kernels and the D2H copy of dudt are pipelined inside the library over `chunks` element ranges (0: the
+        library default) on three streams — pass A of a range starts as soon as its slice of u has arrived, pass B of a
+        range as soon as pass A has covered its face neighbours (read from mapP), and the download of its dudt overlaps
+        the uploads still in flight (full-duplex PCIe).  torch CPU tensors (ideally pinned) are passed directly; NumPy
+        arrays are staged through pinned memory."""
         torch = _torch()
         p = self._pinned
-        if "d_u" not in p:
-            p["d_u"], p["d_du"] = self.new_state(), self.new_state()
-            p["copy"] = torch.cuda.Stream(device=self.device)
-            p["copy_out"] = torch.cuda.Stream(device=self.device)
         if isinstance(u_host, np.ndarray):
             if "u" not in p:
                 p["u"] = torch.empty(self.state_shape, dtype=torch.float64).pin_memory()
@@ -160,37 +157,16 @@ class Solver:
             src, dst = p["u"], p["du"]
         else:
             src, dst = u_host, dudt_host
+        for x, name in ((src, "u"), (dst, "dudt")):
+            if x.is_cuda or x.dtype != torch.float64 or tuple(x.shape) != tuple(self.state_shape) or not x.is_contiguous():
+                raise ValueError(f"{name}: expected a contiguous float64 CPU tensor of shape {self.state_shape}")
+        _lib.check(self._lib.sse_rhs_host(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), float(t), int(chunks)))
         ne = self.state_shape[0]
-        d_u, d_du, copy, copy_out = p["d_u"], p["d_du"], p["copy"], p["copy_out"]
-        cur = torch.cuda.current_stream(self.device)
-        if self.image.law.second_order or int(self.cfg.N_ghost) or chunks <= 1 or ne < 4 * chunks:
-            d_u.copy_(src, non_blocking=True)
-            self.rhs(d_du, d_u, t)
-            dst.copy_(d_du, non_blocking=True)
-            cur.synchronize()
+        used = int(chunks) if chunks > 0 else 48
+        if self.image.law.second_order or int(self.cfg.N_ghost) or used == 1 or ne < 4 * used:
+            self.launches += self._per_rhs
         else:
-            bounds, up, after = self._chunk_plan(chunks)
-            copy.wait_stream(cur)
-            copy_out.wait_stream(cur)
-            for i, c in enumerate(up):
-                a, b = bounds[c], bounds[c + 1]
-                with torch.cuda.stream(copy):
-                    d_u[a:b].copy_(src[a:b], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy)
-                cur.wait_event(ev)
-                self.pass_a_range(d_u, a, b - a)
-                for k in after[i]:
-                    ka, kb = bounds[k], bounds[k + 1]
-                    self.pass_b(d_du, ka, kb - ka)
-                    ev = torch.cuda.Event()
-                    ev.record(cur)
-                    with torch.cuda.stream(copy_out):
-                        copy_out.wait_event(ev)
-                        dst[ka:kb].copy_(d_du[ka:kb], non_blocking=True)
-            cur.wait_stream(copy_out)
-            cur.wait_stream(copy)
-            cur.synchronize()
+            self.launches += used * (1 + self._pass_b)
         if isinstance(u_host, np.ndarray):
             dudt_host[...] = dst.numpy()
         return dudt_host

@@ -148,6 +148,13 @@ int32_t sse_state_download(sse_handle* h, double* h_dst, const double* d_src);
 /* -- the hot path ------------------------------------------------------------------------------ */
 /* semi_discrete_residual!(dudt, u, solver, t)  (Solvers.jl:474-564).  Single GPU: all passes. */
 int32_t sse_rhs(sse_handle* h, const double* d_u, double* d_dudt, double t);
+
+/* The same call on HOST arrays (`Array{Float64,3}` arguments, as OrdinaryDiffEq passes CPU state to
+ * semi_discrete_residual!, Solvers.jl:474-483): upload, both passes and download are pipelined over `chunks` element
+ * ranges (<= 0: default) on three streams.  Synchronous; page-lock the arrays with sse_host_pin for full overlap. */
+int32_t sse_rhs_host(sse_handle* h, const double* h_u, double* h_dudt, double t, int32_t chunks);
+int32_t sse_host_pin(void* p, int64_t bytes);
+int32_t sse_host_unpin(void* p);
 /* Split form used by the multi-GPU driver.  Pass A (nodal_values!, Solvers.jl:505-507)
    fills u_q and the owned part of u_f and packs the halo send buffer; the caller exchanges halos
    (NCCL) into sse_halo_recv_buffer; pass B (time_derivative!, Solvers.jl:509-511) runs on the

@@ -273,6 +273,14 @@ k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, l
     load_c3_shared<N>(t, sm + S::c3);
     const double* c3 = sm + S::c3 + a3;
     for (int i = tid; i < nel * NC * Np; i += NT) s_x[i] = u[(size_t)e0 * NC * Np + i];
+    if constexpr (PROJECT) {
+        // J_q rides along with u: one exposed memory round trip at the start of the CTA instead of a second one in the
+        // entropy-variable phase, which turns the tile into W / J
+        for (int it = tid; it < nel * Nq; it += NT) {
+            const int el = it / Nq, i = it - el * Nq;
+            s_wij[el * S::QS + i] = g.J_q[(size_t)(e0 + el) * Nq + i];
+        }
+    }
     __syncthreads();
 
     double y[N][N];
@@ -304,7 +312,7 @@ k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, l
                 const int el = it / Nq, i = it - el * Nq;
                 sq[k] = el * NC * S::QS + i;
                 sw[k] = el * S::QS + i;
-                J[k] = g.J_q[(size_t)(e0 + el) * Nq + i];
+                J[k] = s_wij[sw[k]];
                 W[k] = t.W[i];
 #pragma unroll
                 for (int e = 0; e < NC; e++) ui[k][e] = s_q[sq[k] + e * S::QS];
@@ -543,7 +551,14 @@ template <int N, bool DUAL = false> struct FdSmem {
     static constexpr int hnf = fprim + NP * T::Nf;         // [D][Nf]
     static constexpr int ff = hnf + D * T::Nf;             // [NC][Nf]
     static constexpr int stage = ff + NC * T::Nf;          // [2][NC][Nq]
-    static constexpr int total = stage + (DUAL ? 4 : 2) * NC * T::Nq;
+    // DUAL: in the facet sub-rounds a staged vector of volume node (a, b, c) sits at a * PS + b * N + c with the planes
+    // padded to PS = N (mod 16) and the variables FS = N * PS apart, which puts the (facet node, variable) reducer of
+    // thread t on bank t (mod 16) for every face: no conflicts on its N loads (they cost 3.5 - 4 wavefronts each unpadded)
+    static constexpr int PS = N * N + ((N - (N * N) % 16) % 16 + 16) % 16;
+    static constexpr int FS = N * PS;
+    static constexpr int buf = NC * T::Nq;                 // doubles per stage buffer of the volume rounds
+    static constexpr int total = stage + (DUAL ? 4 : 2) * buf;
+    static_assert(!DUAL || 2 * NC * FS <= 4 * buf, "the two padded facet stages reuse the four volume stages");
 };
 
 // Ranocha's EC flux (euler_navierstokes.jl:171-195) contracted with g, in the scaled form of the compile-time kernels:
@@ -721,8 +736,8 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
 #pragma unroll               // the three line directions as straight-line code: static strides and m >= l tests, no weight
                              // hand-over moves (pass B 1.936 -> 1.820 ms at 82 944 elements; unrolling the facet loop as well loses)
         for (int l = 0; l < D; l++, buf ^= 1) {
-            double* stA = s_stage + (2 * buf) * NC * Nq;
-            double* stB = stA + NC * Nq;
+            double* stA = s_stage + (2 * buf) * S::buf;
+            double* stB = stA + S::buf;
             const int cl = (l == 0) ? ca : ((l == 1) ? cb : cc);
             const int stride = (l == 0) ? NN : ((l == 1) ? N : 1);
             int c1 = cl + 1; if (c1 >= N) c1 -= N;
@@ -764,6 +779,13 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
         }
         double cwA = ld_tab(t.fC + (tn)), cwB = ld_tab(t.fC + (Nq + tn));
         static_assert(NN * NC == Nq, "reducer items = volume nodes");
+        constexpr int PS = S::PS, FS = S::FS;
+        const int fslot = tid + (PS - NN) * ca;               // padded slot of this thread's volume node (FdSmem)
+        // one pair of padded stages for all facet sub-rounds (the barrier that closes a sub-round already separates its
+        // reducer loads from the next stores); they lie over the volume stages, hence the barrier here
+        double* stA = s_stage;
+        double* stB = s_stage + NC * FS;
+        __syncthreads();
         const int re = tid / NN, rjj = tid - re * NN, rx = rjj / N, ry = rjj - rx * N;
         int rc3 = ry ? N - ry : 0;          // volume column (fr - 3 - y) mod N feeding facet node (x, y) of face 4, sub-round 3
 #ifndef SSE_FD_UNROLL_F
@@ -771,9 +793,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
 #endif
         constexpr int FUN = SSE_FD_UNROLL_F;
 #pragma unroll FUN
-        for (int fr = 0; fr < NFR; fr += 2, buf ^= 1) {
-            double* stA = s_stage + (2 * buf) * NC * Nq;
-            double* stB = stA + NC * Nq;
+        for (int fr = 0; fr < NFR; fr += 2) {
             const int fA = fr < 3 ? fr : 3, fB = fr + 1 < 3 ? fr + 1 : 3;
             const double cwnA = (fr + 2 < NFR) ? ld_tab(t.fC + ((fr + 2) * Nq + tn)) : 0.0;
             const double cwnB = (fr + 3 < NFR) ? ld_tab(t.fC + ((fr + 3) * Nq + tn)) : 0.0;
@@ -799,7 +819,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
                 for (int c = 0; c < NP; c++) { qA[c] = s_fprim[c * Nf + jA]; qB[c] = s_fprim[c * Nf + jB]; }
                 ec_contract_scaled2<D>(L, qi, qA, qB, gA, gB, pA, pB);
 #pragma unroll
-                for (int e = 0; e < NC; e++) { r[e] -= pA[e] + pB[e]; stA[e * Nq + tid] = pA[e]; stB[e * Nq + tid] = pB[e]; }
+                for (int e = 0; e < NC; e++) { r[e] -= pA[e] + pB[e]; stA[e * FS + fslot] = pA[e]; stB[e * FS + fslot] = pB[e]; }
             }
             cwA = cwnA; cwB = cwnB;
             __syncthreads();
@@ -809,17 +829,17 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
                 double sA = 0.0, sB = 0.0;
                 if (fA != fB) {             // two different faces: independent targets
                     int bA, dA, bB, dB;
-                    if (fr == 0) { bA = rx * NN + ry; dA = N; bB = rjj; dB = NN; }
-                    else { bA = rjj; dA = NN; bB = rx * NN + rc3; dB = N; rc3 = rc3 + 1 == N ? 0 : rc3 + 1; }
+                    if (fr == 0) { bA = rx * PS + ry; dA = N; bB = rjj; dB = PS; }
+                    else { bA = rjj; dA = PS; bB = rx * PS + rc3; dB = N; rc3 = rc3 + 1 == N ? 0 : rc3 + 1; }
 #pragma unroll
-                    for (int i = 0; i < N; i++) { sA += stA[re * Nq + bA + i * dA]; sB += stB[re * Nq + bB + i * dB]; }
+                    for (int i = 0; i < N; i++) { sA += stA[re * FS + bA + i * dA]; sB += stB[re * FS + bB + i * dB]; }
                     s_ff[re * Nf + fA * NN + rjj] -= sA;
                     s_ff[re * Nf + fB * NN + rjj] -= sB;
                 } else {                    // both sub-rounds feed face 4: one reducer sums both stages
                     const int cA = rc3, cB = cA + 1 == N ? 0 : cA + 1;
                     rc3 = cB + 1 == N ? 0 : cB + 1;
 #pragma unroll
-                    for (int i = 0; i < N; i++) { sA += stA[re * Nq + rx * NN + cA + i * N]; sB += stB[re * Nq + rx * NN + cB + i * N]; }
+                    for (int i = 0; i < N; i++) { sA += stA[re * FS + rx * PS + cA + i * N]; sB += stB[re * FS + rx * PS + cB + i * N]; }
                     s_ff[re * Nf + 3 * NN + rjj] -= sA + sB;
                 }
             }

@@ -463,7 +463,7 @@ __device__ void physical_flux_tile(const Ops& o, const Law& L, const double* s_u
             for (int m = 0; m < D; m++) {
                 double f = L.a[m] * s_uq[i];
                 if (L.pde == SSE_PDE_BURGERS) f = 0.5 * L.a[m] * s_uq[i] * s_uq[i];        // burgers.jl:52-58
-                if (L.pde == SSE_PDE_ADVECTION_DIFFUSION) f = L.a[m] * s_uq[i] - L.b * s_qq[i + Nq * NC * m];
+                if (L.viscous) f -= L.b * s_qq[i + Nq * NC * m];     // linear_advection_diffusion.jl:64-71, burgers.jl:60-70
                 s_fq[i + Nq * NC * m] = f;
             }
         }

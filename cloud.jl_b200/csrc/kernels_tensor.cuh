@@ -324,7 +324,7 @@ inline void tensor_plan_build(TensorPlan& tp, const sse_config& cfg, const sse_a
     const int d = cfg.d, Nq = cfg.N_q, Nf = cfg.N_f, Nfac = cfg.N_fac;
     if (cfg.form != SSE_FORM_FLUX_DIFFERENCING || d < 2) return;
     if (cfg.pde == SSE_PDE_EULER && cfg.two_point_flux != SSE_TWO_POINT_ENTROPY_CONSERVATIVE) return;
-    if (cfg.pde == SSE_PDE_ADVECTION_DIFFUSION || cfg.pde == SSE_PDE_BURGERS) return;     // scalar path is linear advection
+    if (cfg.pde == SSE_PDE_ADVECTION_DIFFUSION || cfg.pde == SSE_PDE_BURGERS || cfg.pde == SSE_PDE_VISCOUS_BURGERS) return;     // scalar path is linear advection
     int N1 = (int)std::lround(std::pow((double)Nq, 1.0 / d));
     int chk = 1;
     for (int m = 0; m < d; m++) chk *= N1;

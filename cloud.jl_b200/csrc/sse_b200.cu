@@ -330,12 +330,14 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
     }
     // ---- law
     Law& L = h->law;
-    L.pde = cfg->pde; L.two_point = cfg->two_point_flux; L.inviscid = cfg->inviscid_flux;
+    // the kernels see the viscous Burgers law as Burgers (two-point flux, wave speed: burgers.jl:45, 103-143) + the BR1 terms
+    L.pde = cfg->pde == SSE_PDE_VISCOUS_BURGERS ? SSE_PDE_BURGERS : cfg->pde; L.two_point = cfg->two_point_flux; L.inviscid = cfg->inviscid_flux;
     L.half_lambda = cfg->half_lambda; L.b = cfg->b;
+    L.viscous = (cfg->pde == SSE_PDE_ADVECTION_DIFFUSION || cfg->pde == SSE_PDE_VISCOUS_BURGERS);
     for (int m = 0; m < 3; m++) L.a[m] = cfg->a[m];
     L.gamma = cfg->gamma; L.gm1 = cfg->gamma - 1.0; L.igm1 = 1.0 / (cfg->gamma - 1.0); L.log_gm1 = std::log(cfg->gamma - 1.0);
     L.lmq[0] = -1.0 / 3.0; L.lmq[1] = -4.0 / 45.0; L.lmq[2] = -44.0 / 945.0; L.cc2 = 2.0 / (105.0 * (cfg->gamma - 1.0));
-    h->second_order = (cfg->pde == SSE_PDE_ADVECTION_DIFFUSION);
+    h->second_order = (cfg->pde == SSE_PDE_ADVECTION_DIFFUSION || cfg->pde == SSE_PDE_VISCOUS_BURGERS);
     if (h->second_order && cfg->form != SSE_FORM_STANDARD_PHYSICAL)
         return fail(SSE_ERR_UNSUPPORTED, "second-order laws are only implemented with PhysicalOperators (Solvers.jl:357-376)");
     if (cfg->pde == SSE_PDE_EULER && NC != d + 2) return fail(SSE_ERR_BAD_ARGUMENT, "Euler needs N_c = d + 2");

@@ -13,7 +13,7 @@ module SSEB200
 using StableSpectralElements
 using StableSpectralElements.Solvers: AbstractParallelism, Solver, FluxDifferencingOperators,
     ReferenceOperators, PhysicalOperators, StandardForm, FluxDifferencingForm,
-    WeightAdjustedSolver, DiagonalSolver
+    WeightAdjustedSolver, DiagonalSolver, CholeskySolver
 using StableSpectralElements.ConservationLaws
 using StableSpectralElements.MatrixFreeOperators: WarpedTensorProductMap2D, WarpedTensorProductMap3D
 using LinearMaps: UniformScalingMap
@@ -96,6 +96,8 @@ axpby!(a, x::DeviceState, b, y::DeviceState) =
 pde_id(::LinearAdvectionEquation) = Int32(0)
 pde_id(::LinearAdvectionDiffusionEquation) = Int32(1)
 pde_id(::EulerEquations) = Int32(2)
+pde_id(::InviscidBurgersEquation) = Int32(3)
+pde_id(::ViscousBurgersEquation) = Int32(4)
 flux_id(::LaxFriedrichsNumericalFlux) = Int32(0)
 flux_id(::CentralNumericalFlux) = Int32(1)
 flux_id(::EntropyConservativeNumericalFlux) = Int32(2)
@@ -105,6 +107,7 @@ two_point_id(::ConservativeFlux) = Int32(0)
 two_point_id(::EntropyConservativeFlux) = Int32(1)
 mass_id(::WeightAdjustedSolver) = Int32(0)
 mass_id(::DiagonalSolver) = Int32(1)
+mass_id(::CholeskySolver) = Int32(2)          # the library factorises V' WJ_k V itself (mass_matrix.jl:30-39)
 
 """
     attach!(solver::Solver{<:Any,<:Any,<:Any,<:Any,CUDAB200}, spatial_discretization)
@@ -157,7 +160,7 @@ function attach!(solver::Solver, sd::SpatialDiscretization{d}) where {d}
     a = ntuple(m -> (hasproperty(law, :a) && m <= d) ? Float64(law.a[m]) : 0.0, 3)
     cfg = SSEConfig(1, d, N_c, N_p, ra.N_q, ra.N_f, nfac, ra.approx_type.p, N_e, 0,
         pde_id(law), form_id, flux_id(form.inviscid_numerical_flux),
-        law isa LinearAdvectionDiffusionEquation ? Int32(1) : Int32(0), tp, mass_id(solver.mass_solver), v_kind, M1d,
+        (law isa LinearAdvectionDiffusionEquation || law isa ViscousBurgersEquation) ? Int32(1) : Int32(0), tp, mass_id(solver.mass_solver), v_kind, M1d,
         halfλ(form.inviscid_numerical_flux), a, hasproperty(law, :b) ? law.b : 0.0,
         hasproperty(law, :γ) ? law.γ : 1.4)
     arr = SSEArrays(pV, pA, pB, pC, pσi, pσo, dense(ra.R), ptr(Vector(ra.W.diag)), ptr(Vector(ra.B.diag)),
@@ -179,17 +182,16 @@ function StableSpectralElements.Solvers.semi_discrete_residual!(dudt::DeviceStat
     return dudt
 end
 
-# Host arrays (e.g. the save callback's `similar(integrator.u)`, File/save.jl:58-61) are staged.
+# Host arrays (OrdinaryDiffEq with CPU state, the save callback's `similar(integrator.u)`, File/save.jl:58-61): one
+# ccall of sse_rhs_host, which pipelines upload, both passes and download over element ranges inside the library.
+# Page-lock long-lived arrays once with `pin!` (cudaHostRegister) so the copies overlap in both PCIe directions.
+pin!(x::Array{Float64}) = (check(ccall((:sse_host_pin, libsse), Int32, (Ptr{Cvoid}, Int64), x, sizeof(x))); x)
+unpin!(x::Array{Float64}) = (check(ccall((:sse_host_unpin, libsse), Int32, (Ptr{Cvoid},), x)); x)
+
 function StableSpectralElements.Solvers.semi_discrete_residual!(dudt::Array{Float64, 3}, u::Array{Float64, 3},
         solver::Solver{<:Any, <:Any, <:Any, <:Any, CUDAB200}, t::Float64 = 0.0)
-    par = solver.parallelism
-    du, uu = alloc_state(par, size(u)), alloc_state(par, size(u))
-    upload!(uu, u)
-    StableSpectralElements.Solvers.semi_discrete_residual!(du, uu, solver, t)
-    dudt .= Array(du)
-    for x in (du, uu)
-        ccall((:sse_state_free, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}), par.handle, x.ptr)
-    end
+    GC.@preserve dudt u check(ccall((:sse_rhs_host, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Int32),
+        solver.parallelism.handle, u, dudt, t, 0))
     return dudt
 end
 

@@ -8,7 +8,7 @@ import numpy as np
 SSE_ABI_VERSION = 1
 
 SSE_OK, SSE_ERR_BAD_ARGUMENT, SSE_ERR_UNSUPPORTED, SSE_ERR_CUDA, SSE_ERR_NONFINITE, SSE_ERR_COMM = range(6)
-SSE_PDE_ADVECTION, SSE_PDE_ADVECTION_DIFFUSION, SSE_PDE_EULER, SSE_PDE_BURGERS = 0, 1, 2, 3
+SSE_PDE_ADVECTION, SSE_PDE_ADVECTION_DIFFUSION, SSE_PDE_EULER, SSE_PDE_BURGERS, SSE_PDE_VISCOUS_BURGERS = 0, 1, 2, 3, 4
 SSE_FORM_STANDARD_REFERENCE, SSE_FORM_STANDARD_PHYSICAL, SSE_FORM_FLUX_DIFFERENCING = 0, 1, 2
 SSE_FLUX_LAX_FRIEDRICHS, SSE_FLUX_CENTRAL, SSE_FLUX_ENTROPY_CONSERVATIVE = 0, 1, 2
 SSE_VISCOUS_NONE, SSE_VISCOUS_BR1 = 0, 1

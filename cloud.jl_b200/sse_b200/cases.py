@@ -14,7 +14,7 @@ import numpy as np
 from .assembly import (FluxDifferencingForm, PHYSICAL_OPERATOR, REFERENCE_OPERATOR, SpatialDiscretization,
                        StandardForm, assemble)
 from .laws import (CentralNumericalFlux, EntropyConservativeNumericalFlux, EulerEquations, euler_periodic_test,
-                   InviscidBurgersEquation, initial_data_gassner,
+                   InviscidBurgersEquation, ViscousBurgersEquation, initial_data_gassner,
                    LaxFriedrichsNumericalFlux, LinearAdvectionDiffusionEquation, LinearAdvectionEquation,
                    initial_data_cosine, initial_data_sine, isentropic_vortex, project_function,
                    taylor_green_vortex)
@@ -131,6 +131,25 @@ def burgers_1d(M=20, p=7, flux="ec") -> Case:
     return Case("burgers_1d", InviscidBurgersEquation(), sd,
                 FluxDifferencingForm(inviscid_numerical_flux=_flux(flux)), REFERENCE_OPERATOR,
                 initial_data_gassner(np.pi, 0.01))
+
+
+def viscous_burgers_1d(M=8, p=5, b=5e-2, flux="lf") -> Case:
+    """ViscousBurgersEquation(b) (burgers.jl:23-49) with BR1 on Lobatto NodalTensor lines, PhysicalOperators."""
+    ra = reference_approximation(NodalTensor(p), "Line")
+    mesh = uniform_periodic_mesh(ra, (0.0, 2.0), M)
+    sd = SpatialDiscretization.build(mesh, ra, "exact", True)
+    return Case("viscous_burgers_1d", ViscousBurgersEquation((1.0,), b), sd,
+                StandardForm(inviscid_numerical_flux=_flux(flux)), PHYSICAL_OPERATOR, initial_data_gassner(np.pi, 0.01))
+
+
+def viscous_burgers_2d(M=3, p=4, b=5e-2, kind="modal") -> Case:
+    """ViscousBurgersEquation((1, 1), b) with BR1 on curved triangles, PhysicalOperators."""
+    ra = reference_approximation(_approx(kind, p), "Tri", mapping_degree=p)
+    mesh = uniform_periodic_mesh(ra, ((0.0, 1.0),) * 2, (M, M), DelReyWarping(0.1, (1.0, 1.0)))
+    sd = SpatialDiscretization.build(mesh, ra, "exact", True)
+    return Case("viscous_burgers_2d", ViscousBurgersEquation((1.0, 1.0), b), sd,
+                StandardForm(inviscid_numerical_flux=_flux("lf")), PHYSICAL_OPERATOR,
+                initial_data_sine(1.0, (2 * np.pi, 2 * np.pi)))
 
 
 def advection_2d_quad(M=2, p=4, flux="lf", warp=0.1) -> Case:

@@ -14,7 +14,7 @@ from typing import Tuple
 import numpy as np
 
 # ids shared with include/sse_b200.h
-PDE_ADVECTION, PDE_ADVECTION_DIFFUSION, PDE_EULER, PDE_BURGERS = 0, 1, 2, 3
+PDE_ADVECTION, PDE_ADVECTION_DIFFUSION, PDE_EULER, PDE_BURGERS, PDE_VISCOUS_BURGERS = 0, 1, 2, 3, 4
 FLUX_LAX_FRIEDRICHS, FLUX_CENTRAL, FLUX_ENTROPY_CONSERVATIVE = 0, 1, 2
 TWO_POINT_CONSERVATIVE, TWO_POINT_ENTROPY_CONSERVATIVE = 0, 1
 
@@ -44,6 +44,21 @@ class InviscidBurgersEquation:
 
     N_c = 1
     second_order = False
+
+
+@dataclass(frozen=True)
+class ViscousBurgersEquation:
+    """burgers.jl:23-49: flux a u^2 / 2 - b q (BR1); `ViscousBurgersEquation(b)` is the 1-D law with a = (1,)."""
+    a: Tuple[float, ...] = (1.0,)
+    b: float = 0.0
+    pde_id: int = PDE_VISCOUS_BURGERS
+
+    @property
+    def d(self):
+        return len(self.a)
+
+    N_c = 1
+    second_order = True
 
 
 @dataclass(frozen=True)

@@ -52,7 +52,8 @@ enum {
 enum { SSE_PDE_ADVECTION = 0,            /* LinearAdvectionEquation{d}           linear_advection_diffusion.jl:10-20 */
        SSE_PDE_ADVECTION_DIFFUSION = 1,  /* LinearAdvectionDiffusionEquation{d}  linear_advection_diffusion.jl:30-42 */
        SSE_PDE_EULER = 2,                /* EulerEquations{d}                    euler_navierstokes.jl:23-38        */
-       SSE_PDE_BURGERS = 3 };            /* InviscidBurgersEquation{d} (a in sse_config.a)  burgers.jl:1-21          */
+       SSE_PDE_BURGERS = 3,              /* InviscidBurgersEquation{d} (a in sse_config.a)  burgers.jl:1-21          */
+       SSE_PDE_VISCOUS_BURGERS = 4 };    /* ViscousBurgersEquation{d} (a, b): F = a u^2/2 - b q, BR1   burgers.jl:23-49, 59-99 */
 
 /* residual form x operator strategy (Solvers.jl:75-115, constructors :287-376) */
 enum { SSE_FORM_STANDARD_REFERENCE = 0,  /* StandardForm + ReferenceOperator  standard_form_first_order.jl:16-63 */

@@ -296,7 +296,7 @@ static void two_point_flux(const sse_config *c, int tp, const double *uL, const 
     const int d = c->d;
     if (c->pde != SSE_PDE_EULER) {
         double f1 = 0.5 * (uL[0] + uR[0]);
-        if (c->pde == SSE_PDE_BURGERS)                 /* burgers.jl:111-143 */
+        if (c->pde == SSE_PDE_BURGERS || c->pde == SSE_PDE_VISCOUS_BURGERS)   /* BurgersType, burgers.jl:45, 111-143 */
             f1 = (tp == SSE_TWO_POINT_ENTROPY_CONSERVATIVE) ? (uL[0] * uL[0] + uL[0] * uR[0] + uR[0] * uR[0]) / 6
                                                             : (uL[0] * uL[0] + uR[0] * uR[0]) * 0.25;
         for (int m = 0; m < d; m++) F[0][m] = c->a[m] * f1;
@@ -330,7 +330,7 @@ static double wave_speed(const sse_config *c, const double *ui, const double *uo
     const int d = c->d;
     if (c->pde != SSE_PDE_EULER) {
         double s = 0; for (int m = 0; m < d; m++) s += c->a[m] * n[m];
-        if (c->pde == SSE_PDE_BURGERS) return fmax(fabs(s * ui[0]), fabs(s * uo[0]));    /* burgers.jl:103-109 */
+        if (c->pde == SSE_PDE_BURGERS || c->pde == SSE_PDE_VISCOUS_BURGERS) return fmax(fabs(s * ui[0]), fabs(s * uo[0]));    /* burgers.jl:103-109 */
         return fabs(s);
     }
     double si = 0, so = 0, vni = 0, vno = 0;
@@ -525,6 +525,7 @@ static void physical_flux(const ora_t *o, const double *u_q, const double *q_q, 
             double f = c->a[m] * u_q[i];
             if (c->pde == SSE_PDE_BURGERS) f = 0.5 * c->a[m] * u_q[i] * u_q[i];           /* burgers.jl:52-58 */
             if (c->pde == SSE_PDE_ADVECTION_DIFFUSION) f = c->a[m] * u_q[i] - c->b * q_q[i + (size_t)Nq * Nc * m];
+            if (c->pde == SSE_PDE_VISCOUS_BURGERS) f = 0.5 * c->a[m] * u_q[i] * u_q[i] - c->b * q_q[i + (size_t)Nq * Nc * m];   /* burgers.jl:60-70 */
             f_q[i + (size_t)Nq * Nc * m] = f;
         }
 }
@@ -814,7 +815,7 @@ int32_t sse_oracle_rhs(const sse_config *cfg, const sse_arrays *arr, const doubl
     const sse_config *c = &o.c;
     const int64_t Ne = c->N_e;
     const size_t Nq = c->N_q, Nf = c->N_f, Nc = c->N_c, d = c->d;
-    const int second = (c->pde == SSE_PDE_ADVECTION_DIFFUSION);
+    const int second = (c->pde == SSE_PDE_ADVECTION_DIFFUSION || c->pde == SSE_PDE_VISCOUS_BURGERS);
     double *u_q = malloc(sizeof(double) * Nq * Nc * Ne);
     double *u_f = malloc(sizeof(double) * Nf * Nc * Ne);
     double *q_q = second ? malloc(sizeof(double) * Nq * Nc * d * Ne) : NULL;
@@ -861,7 +862,7 @@ double sse_oracle_time_rhs(const sse_config *cfg, const sse_arrays *arr, const d
     const sse_config *c = &o.c;
     const int64_t Ne = c->N_e;
     const size_t Nq = c->N_q, Nf = c->N_f, Nc = c->N_c, d = c->d;
-    const int second = (c->pde == SSE_PDE_ADVECTION_DIFFUSION);
+    const int second = (c->pde == SSE_PDE_ADVECTION_DIFFUSION || c->pde == SSE_PDE_VISCOUS_BURGERS);
     double *u_q = malloc(sizeof(double) * Nq * Nc * Ne);
     double *u_f = malloc(sizeof(double) * Nf * Nc * Ne);
     double *q_q = second ? malloc(sizeof(double) * Nq * Nc * d * Ne) : NULL;

@@ -102,3 +102,43 @@ def test_gpu_cholesky_parity(name):
         want_e = analysis.energy_residual(img, u, ref).sum()
         assert abs(f[nc] - want_e) <= 1e-9 * max(1.0, abs(want_e), np.abs(ref).max())
     s.close()
+
+
+# ---- ViscousBurgersEquation (burgers.jl:23-49, 59-99): Burgers flux + the BR1 terms of the advection-diffusion law
+def test_viscous_burgers_oracle_terms():
+    """F(u, q) = a u^2/2 - b q (burgers.jl:60-70): with b -> 0 the residual is the inviscid Burgers StandardForm residual,
+    and the viscous part is linear in b; the BR1 law dissipates the energy u^2/2 (conservation.jl:154-167)."""
+    from sse_b200.laws import InviscidBurgersEquation, ViscousBurgersEquation
+    c = cases.viscous_burgers_2d(M=3, p=3, b=5e-2)
+    u = c.u0(seed=0)
+
+    def rhs(law, strategy=PHYSICAL_OPERATOR):
+        return oracle.rhs(assemble(law, c.sd, c.form, strategy), u)
+    r0 = rhs(ViscousBurgersEquation((1.0, 1.0), 0.0))
+    ri = rhs(InviscidBurgersEquation((1.0, 1.0)))
+    assert np.abs(r0 - ri).max() <= 1e-12 * np.abs(ri).max()
+    r1, r2 = rhs(ViscousBurgersEquation((1.0, 1.0), 5e-2)), rhs(ViscousBurgersEquation((1.0, 1.0), 1e-1))
+    assert np.abs((r2 - r0) - 2 * (r1 - r0)).max() <= 1e-11 * np.abs(r2).max()
+    assert np.abs(r1 - r0).max() > 1e-3 * np.abs(r0).max()
+    img = c.image()
+    du = oracle.rhs(img, u)
+    assert np.abs(analysis.conservation_residual(img, du)).max() < 1e-11 * max(1.0, np.abs(du).max())
+    # the viscous terms alone dissipate: u' M (r(b) - r(0)) < 0
+    assert analysis.energy_residual(img, u, r1 - r0)[0] < 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [lambda: cases.viscous_burgers_1d(M=8, p=5), lambda: cases.viscous_burgers_2d(M=3, p=4),
+                                  lambda: cases.viscous_burgers_2d(M=3, p=3, kind="nodal")])
+def test_gpu_viscous_burgers_parity(case):
+    import torch
+    from sse_b200.solver import Solver
+    c = case()
+    img, u = c.image(), c.u0(seed=0)
+    ref = oracle.rhs(img, u)
+    s = Solver(img, 0)
+    du = s.new_state()
+    s.rhs(du, torch.from_numpy(u).cuda())
+    s.synchronize()
+    assert np.abs(du.cpu().numpy() - ref).max() <= 1e-12 * np.abs(ref).max()
+    s.close()

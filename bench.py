@@ -26,7 +26,7 @@ METRIC = "FP64 RHS DOF/s (3D Euler p=4 tets, flux-diff)"
 ALG_BYTES_RHS = 23200.0          # compulsory HBM traffic of one RHS
 ALG_BYTES_PASS_B = 26800.0       # time_derivative kernel alone: u_q 5000 + own/nbr u_f 8000 + Λ 9000 + J_q 1000 + nJf 2400 + dudt 1400
 ALG_FLOPS_RHS = 476000.0         # FMA = 2
-NCU_DRAM_BYTES_PASS_B = 32500.0  # measured DRAM bytes / element of pass B (ncu, profiles/r1_ncu_final_kernels.csv): 25.7 kB pair kernel + 6.8 kB projection
+NCU_DRAM_BYTES_PASS_B = 32750.0  # measured DRAM bytes / element of pass B (ncu, profiles/r1_ncu_final2_kernels.csv): 25.7 kB pair kernel + 7.0 kB projection
 
 
 def parse():
@@ -300,7 +300,7 @@ def main():
                                "traffic": NCU_DRAM_BYTES_PASS_B * n_e_local, "peak_source": hbm_src, "kernel_ms": pass_b_ms,
                                "algorithmic_bytes_per_element": ALG_BYTES_PASS_B,
                                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per element from the ncu --set full "
-                                                 "capture profiles/r1_ncu_final_kernels.csv (24 576 "
+                                                 "capture profiles/r1_ncu_final2_kernels.csv (24 576 "
                                                  "elements), scaled to this launch",
                                "note": "this path is bound by the FP64 vector pipe, see roofline_fp64"}
             try:

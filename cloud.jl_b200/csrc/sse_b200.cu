@@ -65,6 +65,9 @@ struct sse_handle {
     // host-buffer residual (sse_rhs_host): highest local face neighbour of every element (from mapP), device staging
     // states, copy streams and events, all created on first use
     std::vector<long long> nbr_hi;
+    std::vector<long long> nbr;     // up to N_fac distinct local face neighbours per element (-1: none); empty if some element has more
+    int plan_chunks = 0;            // cached schedule of sse_rhs_host for this many ranges
+    std::vector<int> plan_order, plan_ready;
     double *h2d_u = nullptr, *d2h_du = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> events;
@@ -298,14 +301,23 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
         for (size_t t = 0; t < (size_t)Nf * Ne; t++)
             if (a->mapP[t] < 1 || a->mapP[t] > lim) return fail(SSE_ERR_BAD_ARGUMENT, "mapP[%zu] = %lld out of range (BoundsError)", t, (long long)a->mapP[t]);
         h->nbr_hi.assign((size_t)Ne, 0);
+        h->nbr.assign((size_t)Ne * Nfac, -1);
+        bool few = true;
         for (long long k = 0; k < Ne; k++) {
             long long hi = k;
+            int cnt = 0;
             for (int j = 0; j < Nf; j++) {
                 const long long nb = (a->mapP[(size_t)k * Nf + j] - 1) / Nf;        // ghost slots lie beyond the local elements
-                if (nb < Ne && nb > hi) hi = nb;
+                if (nb >= Ne) continue;
+                if (nb > hi) hi = nb;
+                if (!few || nb == k) continue;
+                bool seen = false;
+                for (int q = 0; q < cnt; q++) seen = seen || h->nbr[(size_t)k * Nfac + q] == nb;
+                if (!seen) { if (cnt < Nfac) h->nbr[(size_t)k * Nfac + cnt++] = nb; else few = false; }
             }
             h->nbr_hi[(size_t)k] = hi;
         }
+        if (!few) h->nbr.clear();
         const long long* mp = nullptr;
         if ((rc = upload_raw(h, (const long long*)a->mapP, (size_t)Nf * Ne, &mp))) return rc;
         g.mapP = mp;
@@ -628,19 +640,42 @@ extern "C" int32_t sse_rhs_host(sse_handle* h, const double* h_u, double* h_dudt
     }
     std::vector<long long> bounds((size_t)chunks + 1);
     for (int c = 0; c <= chunks; c++) bounds[(size_t)c] = ne * c / chunks;
-    auto owner = [&](long long k) { int c = (int)((k * chunks) / ne); while (k >= bounds[(size_t)c + 1]) c++; while (k < bounds[(size_t)c]) c--; return c; };
-    std::vector<int> ready((size_t)chunks);
-    for (int c = 0; c < chunks; c++) {
-        long long hi = bounds[(size_t)c];
-        for (long long k = bounds[(size_t)c]; k < bounds[(size_t)c + 1]; k++) hi = std::max(hi, h->nbr_hi[(size_t)k]);
-        ready[(size_t)c] = std::max(c, owner(hi));
+    if (h->plan_chunks != chunks) {
+        // upload order and, for every range, the upload position after which its pass B may run (all ranges holding one of
+        // its face neighbours are through pass A).  With exact neighbour lists the last range goes first: on a periodic
+        // slab-ordered mesh range 0 otherwise waits for the wrap-around neighbour until the very end.
+        auto owner = [&](long long k) { int c = (int)((k * chunks) / ne); while (k >= bounds[(size_t)c + 1]) c++; while (k < bounds[(size_t)c]) c--; return c; };
+        const bool exact = !h->nbr.empty();
+        const int nfac = h->cfg.N_fac;
+        h->plan_order.resize((size_t)chunks);
+        std::vector<int> pos((size_t)chunks);
+        for (int i = 0; i < chunks; i++) h->plan_order[(size_t)i] = exact ? (i == 0 ? chunks - 1 : i - 1) : i;
+        for (int i = 0; i < chunks; i++) pos[(size_t)h->plan_order[(size_t)i]] = i;
+        h->plan_ready.assign((size_t)chunks, 0);
+        for (int c = 0; c < chunks; c++) {
+            int r = pos[(size_t)c];
+            if (exact) {
+                for (long long k = bounds[(size_t)c]; k < bounds[(size_t)c + 1]; k++)
+                    for (int q = 0; q < nfac; q++) {
+                        const long long nb = h->nbr[(size_t)k * nfac + q];
+                        if (nb >= 0) r = std::max(r, pos[(size_t)owner(nb)]);
+                    }
+            } else {
+                long long hi = bounds[(size_t)c];
+                for (long long k = bounds[(size_t)c]; k < bounds[(size_t)c + 1]; k++) hi = std::max(hi, h->nbr_hi[(size_t)k]);
+                r = std::max(r, owner(hi));
+            }
+            h->plan_ready[(size_t)c] = r;
+        }
+        h->plan_chunks = chunks;
     }
+    const std::vector<int>&order = h->plan_order, &ready = h->plan_ready;
     cudaEvent_t e_start = h->events[(size_t)(2 * chunks)], e_done = h->events[(size_t)(2 * chunks + 1)];
     CU(cudaEventRecord(e_start, h->stream));
     CU(cudaStreamWaitEvent(h->s_in, e_start, 0));
     CU(cudaStreamWaitEvent(h->s_out, e_start, 0));
     for (int i = 0; i < chunks; i++) {
-        const long long a = bounds[(size_t)i], b = bounds[(size_t)i + 1];
+        const long long a = bounds[(size_t)order[(size_t)i]], b = bounds[(size_t)order[(size_t)i] + 1];
         CU(cudaMemcpyAsync(d_u + per * (size_t)a, h_u + per * (size_t)a, per * (size_t)(b - a) * sizeof(double), cudaMemcpyHostToDevice, h->s_in));
         CU(cudaEventRecord(h->events[(size_t)i], h->s_in));
         CU(cudaStreamWaitEvent(h->stream, h->events[(size_t)i], 0));

@@ -8,6 +8,7 @@ namespace sse {
 
 struct CtDev {
     const double* C;        // C[a3 + N*(b1 + N*(b2 + N*b3))]
+    const double* C3;       // the same in the kernels' order: C3[l * N + a3], l the canonical modal index (tet_l)
     const double* W;        // volume quadrature weights
     SpMat R, Rt;
     long long Ne;

@@ -175,6 +175,16 @@ static int32_t set_attrs(sse_handle* h) {
 extern "C" int32_t sse_abi_version(void) { return SSE_ABI_VERSION; }
 extern "C" const char* sse_last_error_string(void) { return g_err.c_str(); }
 
+// C tensor of the collapsed tet in the order of the compile-time kernels: C3[l * N + a3], l = canonical modal index
+static int32_t upload_c3(sse_handle* h, const sse_arrays* a, int N) {
+    std::vector<double> c3;
+    for (int b1 = 0; b1 < N; b1++)
+        for (int b2 = 0; b1 + b2 < N; b2++)
+            for (int b3 = 0; b1 + b2 + b3 < N; b3++)
+                for (int a3 = 0; a3 < N; a3++) c3.push_back(a->C[a3 + N * (b1 + N * (b2 + N * b3))]);
+    return upload(h, c3, &h->ct.dev.C3);
+}
+
 static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) {
     const int d = cfg->d, NC = cfg->N_c, Np = cfg->N_p, Nq = cfg->N_q, Nf = cfg->N_f, Nfac = cfg->N_fac;
     const long long Ne = cfg->N_e;
@@ -389,6 +399,7 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
             h->ct.B.assign(a->B, a->B + N * N * N);
             h->ct.dev.C = o.C; h->ct.dev.W = o.W; h->ct.dev.R = o.R; h->ct.dev.Rt = o.Rt; h->ct.dev.Ne = Ne;
             h->ct.dev.Bf = o.Bf;
+            if ((rc = upload_c3(h, a, N))) return rc;
             {   // power-of-two scalings of the pair weights (exact): see ec_finish_scaled in kernels_ct.cuh
                 std::vector<double> vS(h->tp.v_S), fC(h->tp.f_C);
                 for (double& x : vS) x *= 0.25;
@@ -415,6 +426,7 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
             h->ct.A.assign(a->A, a->A + N * N);
             h->ct.B.assign(a->B, a->B + N * N * N);
             h->ct.dev.C = o.C; h->ct.dev.W = o.W; h->ct.dev.R = o.R; h->ct.dev.Rt = o.Rt; h->ct.dev.Ne = Ne; h->ct.dev.Bf = o.Bf;
+            if ((rc = upload_c3(h, a, N))) return rc;
             if ((rc = upload(h, h->ct.fR, &h->ct.dev.fR))) return rc;
             if (ct_set_attrs(N) != cudaSuccess) return fail(SSE_ERR_CUDA, "cudaFuncSetAttribute (compile-time kernels) failed");
             h->ct.ok = 1;

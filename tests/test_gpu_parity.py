@@ -243,6 +243,35 @@ def test_pipelined_host_residual_is_bitwise_the_device_residual(chunks):
     s.close()
 
 
+@pytest.mark.parametrize("case", [lambda: cases.euler_tgv_3d(M=2, flux="lf"), lambda: cases.euler_tgv_3d(M=2, p=3, flux="ec"),
+                                  lambda: cases.advection_3d(M=2, flux="lf"), lambda: cases.euler_vortex_2d(M=4, p=4, flux="ec")])
+def test_ragged_and_empty_element_ranges(case):
+    """The range entry points (the pipelined host call and the multi-GPU driver use them) on ragged splits: counts that
+    are not multiples of the 6 / 8 / 24 elements a projection CTA batches, single elements and empty ranges must
+    reproduce the whole-mesh residual bit for bit."""
+    c = case()
+    img, u = c.image(), c.u0(seed=5)
+    s = Solver(img, 0)
+    ud = torch.from_numpy(u).cuda()
+    ref = s.new_state()
+    s.rhs(ref, ud)
+    s.synchronize()
+    ne = c.sd.N_e
+    cuts = sorted({0, 1, 1, 6, 13, 13, 20, 37, ne - 7, ne - 1, ne})          # includes empty ranges
+    cuts = [x for x in cuts if 0 <= x <= ne]
+    du = s.new_state()
+    du.fill_(float("nan"))
+    s.pass_a_range(ud, 0, 0)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        s.pass_a_range(ud, a, b - a)
+    s.pass_b(du, 0, 0)
+    for a, b in reversed(list(zip(cuts[:-1], cuts[1:]))):
+        s.pass_b(du, a, b - a)
+    s.synchronize()
+    assert torch.equal(du, ref)
+    s.close()
+
+
 def test_bad_arguments_fail_loudly():
     from sse_b200._lib import SSEError
     c = cases.advection_2d(M=2)

@@ -9,10 +9,12 @@
 //
 // Sum factorisation (warped_product_3d.jl:47-136) is mapped as one thread per (element, variable, a3):
 // the thread owns the N x N slab y[a1][a2] of its eta_3 index in registers, the A and B tensors arrive as
-// kernel parameters (constant bank, free FMA operands after full unrolling), the C tensor slice of the
-// thread's a3 lives in registers, and the only cross-thread step of V' (the sum over a3) goes through
-// shared memory.  V -> diag(W/J) -> V' of the weight-adjusted mass solve never leaves registers.
-// A warp holds floor(32/N) groups of N lanes; a CTA of NC warps processes EPB = floor(32/N) elements.
+// kernel parameters (constant bank, free FMA operands after full unrolling), the C tensor sits in a shared
+// table [modal index][a3], and the only cross-thread step of V' (the sum over a3) goes through shared memory
+// in a bank-conflict-free layout.  V -> diag(W/J) -> V' of the weight-adjusted mass solve never leaves registers.
+// A warp holds floor(32/N) groups of N lanes; a CTA of NC warps processes EPB = floor(32/N) elements.  Every tile
+// between two pointwise (entropy-variable) phases belongs to the N lanes of one group, so those phases are
+// ordered by __syncwarp and only the pointwise phases need CTA barriers.
 #pragma once
 #include "common.cuh"
 #include "kernels_tensor.cuh"
@@ -170,16 +172,6 @@ __device__ __forceinline__ void load_c3_shared_ref(const CtDev& t, double* s_c3)
         while (ll >= N - b1 - b2) { ll -= N - b1 - b2; b2++; }
         s_c3[i] = t.C[a3 + N * (b1 + N * (b2 + N * ll))];
     }
-}
-
-template <int N>
-__device__ __forceinline__ void load_c3(const CtDev& t, int a3, double (&c3)[Tet<N>::Np]) {
-#pragma unroll
-    for (int b1 = 0; b1 < N; b1++)
-#pragma unroll
-        for (int b2 = 0; b2 < N - b1; b2++)
-#pragma unroll
-            for (int b3 = 0; b3 < N - b1 - b2; b3++) c3[tet_l<N>(b1, b2, b3)] = t.C[a3 + N * (b1 + N * (b2 + N * b3))];
 }
 
 // 1-D factors of the facet extrapolation R on the collapsed tet (tensor_simplex.jl:265-268), extracted from Matrix(R)

@@ -17,6 +17,7 @@ struct CtDev {
     const double* fC;       // [facet sub-round][Nq]  C[i, partner] / 8
     const double* fR;       // [facet sub-round][Nq]  R[partner, i]
     const double* Bf;       // [Nf]
+    const double* facR;     // 1-D factors of R: r0, r1, r2, r3 (N each), I3[y + N b] (FacetR order); Euler path only
     double nref[12];        // d x N_fac reference normals
 };
 

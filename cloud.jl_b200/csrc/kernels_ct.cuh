@@ -943,6 +943,40 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
     }
     __syncthreads();
     // ---- lift: r_q -= R' f_f (flux_differencing_form.jl:341-342); r_q goes to k_project_ct through the u_q scratch
+#ifndef SSE_FD_LIFT_PLAIN
+    if constexpr (DUAL) {
+        // The slanted face through its 1-D factors, R[(a, y), (a, b, c)] = I3[y, b] r3[c] (FacetR): the N^2 N_c sums
+        // G[e][a][b] = sum_y I3[y, b] f_f[e][(a, y)] are shared by the N nodes c of a line, one per thread; a node then
+        // needs 5 + 15 facet values instead of 40.  The stages are free by now and hold G.
+        double* s_G = s_stage;
+        const double* fac = t.facR;
+        if (node) {
+            const int re = tid / NN, rjj = tid - re * NN, rx = rjj / N, ry = rjj - rx * N;
+            double gs = 0.0;
+#pragma unroll
+            for (int y = 0; y < N; y++) gs = fma(ld_tab(fac + 4 * N + y + N * ry), s_ff[re * Nf + 3 * NN + rx * N + y], gs);
+            s_G[tid] = gs;
+        }
+        double rw[3];
+#pragma unroll
+        for (int fr = 0; fr < 3; fr++) rw[fr] = ld_tab(t.fR + (fr * Nq + tn));
+        const double r3c = ld_tab(fac + 3 * N + cc % N);
+        __syncthreads();
+        if (node) {
+#pragma unroll
+            for (int fr = 0; fr < 3; fr++) {
+                const int j = facet_partner<N>(fr, ca, cb, cc);
+#pragma unroll
+                for (int e = 0; e < NC; e++) r[e] = fma(-rw[fr], s_ff[e * Nf + j], r[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < NC; e++) r[e] = fma(-r3c, s_G[e * NN + ca * N + cb], r[e]);
+#pragma unroll
+            for (int e = 0; e < NC; e++) u_q[((size_t)k * NC + e) * Nq + tid] = r[e];
+        }
+        return;
+    }
+#endif
     if (node) {
         double rw[NFR];
 #pragma unroll

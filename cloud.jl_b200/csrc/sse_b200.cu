@@ -400,6 +400,7 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
             h->ct.dev.C = o.C; h->ct.dev.W = o.W; h->ct.dev.R = o.R; h->ct.dev.Rt = o.Rt; h->ct.dev.Ne = Ne;
             h->ct.dev.Bf = o.Bf;
             if ((rc = upload_c3(h, a, N))) return rc;
+            if ((rc = upload(h, h->ct.facetR, &h->ct.dev.facR))) return rc;
             {   // power-of-two scalings of the pair weights (exact): see ec_finish_scaled in kernels_ct.cuh
                 std::vector<double> vS(h->tp.v_S), fC(h->tp.f_C);
                 for (double& x : vS) x *= 0.25;

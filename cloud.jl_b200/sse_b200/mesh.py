@@ -149,13 +149,18 @@ def _cartesian_simplex_cells(d: int, M: Tuple[int, ...], cells: np.ndarray):
         ur, ul = vid(base + [1, 1]), vid(base + [0, 1])
         EtoV = np.stack([np.stack([ll, lr, ur], axis=1), np.stack([ur, ul, ll], axis=1)], axis=1).reshape(-1, 3)
         return EtoV, n1
+    # StartUpDG's uniform_mesh(Tet(), Kx, Ky, Kz), identified through the reference's tetrahedral golden (runtests.jl:123-129):
+    # six tets per cube around the body diagonal from (0, 0, 1) to (1, 1, 0).  With this diagonal the golden L2 error
+    # 0.1876141674772107 is reproduced to 4e-5 (the rest is the error quadrature: the un-vendored Jaskowiec-Sukumar rule
+    # against a converged collapsed Gauss rule, tests/test_oracle_goldens.py); the other three diagonals are off by 1-3e-2.
+    start = np.array([0, 0, 1])
     tets = []
     for perm in permutations(range(d)):
-        c = base.copy()
+        c = base + start[None, :]
         verts = [vid(c)]
         for ax in perm:
             c = c.copy()
-            c[:, ax] += 1
+            c[:, ax] += 1 - 2 * start[ax]
             verts.append(vid(c))
         tets.append(np.stack(verts, axis=1))
     EtoV = np.stack(tets, axis=1).reshape(-1, d + 1)       # element = cell * d! + t

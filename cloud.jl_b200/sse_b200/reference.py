@@ -277,6 +277,63 @@ def _warp_blend_nodes_tri(N: int):
     return [-L2 + L3 - L1, -L2 - L3 + L1]
 
 
+def _warp_blend_nodes_tet(N: int):
+    """Interpolation nodes of the tetrahedron mapping element: Hesthaven & Warburton's warp-and-blend construction (Nodes3D)
+    with alpha = 0, the 3-D counterpart of _warp_blend_nodes_tri — Gauss-Lobatto nodes on the edges, the triangle set on
+    every face, symmetric under all vertex permutations (tests/test_reference_operators.py)."""
+    if N == 1:
+        return [np.array([-1.0, 1.0, -1.0, -1.0]), np.array([-1.0, -1.0, 1.0, -1.0]), np.array([-1.0, -1.0, -1.0, 1.0])]
+    gll, _ = quadrature_line(GaussLobattoQuadrature(N))
+    gx = np.sort(gll)[::-1]
+    xeq = np.array([-1.0 + 2.0 * (N - i) / N for i in range(N + 1)])       # descending, like gx
+
+    def evalwarp(xout):                         # interpolant of (gx - xeq) divided by (1 - x^2)
+        warp = np.zeros_like(xout)
+        for i in range(N + 1):
+            dd = (gx[i] - xeq[i]) * np.ones_like(xout)
+            for j in range(1, N):
+                if i != j:
+                    dd = dd * (xout - xeq[j]) / (xeq[i] - xeq[j])
+            if i != 0:
+                dd = -dd / (xeq[i] - xeq[0])
+            if i != N:
+                dd = dd / (xeq[i] - xeq[N])
+            warp = warp + dd
+        return warp
+
+    def evalshift(L1, L2, L3):
+        w1, w2, w3 = (L2 * L3 * 4.0 * evalwarp(L3 - L2), L1 * L3 * 4.0 * evalwarp(L1 - L3), L1 * L2 * 4.0 * evalwarp(L2 - L1))
+        return (w1 + np.cos(2 * np.pi / 3) * w2 + np.cos(4 * np.pi / 3) * w3,
+                np.sin(2 * np.pi / 3) * w2 + np.sin(4 * np.pi / 3) * w3)
+
+    r, s, t = _lattice_nodes(3, N)
+    L1, L2, L3, L4 = (1 + t) / 2, (1 + s) / 2, -(1 + r + s + t) / 2, (1 + r) / 2
+    v1 = np.array([-1.0, -1 / np.sqrt(3), -1 / np.sqrt(6)])
+    v2 = np.array([1.0, -1 / np.sqrt(3), -1 / np.sqrt(6)])
+    v3 = np.array([0.0, 2 / np.sqrt(3), -1 / np.sqrt(6)])
+    v4 = np.array([0.0, 0.0, 3 / np.sqrt(6)])
+    t1 = [v2 - v1, v2 - v1, v3 - v2, v3 - v1]
+    t2 = [v3 - 0.5 * (v1 + v2), v4 - 0.5 * (v1 + v2), v4 - 0.5 * (v2 + v3), v4 - 0.5 * (v1 + v3)]
+    t1 = [a / np.linalg.norm(a) for a in t1]
+    t2 = [a / np.linalg.norm(a) for a in t2]
+    XYZ = np.outer(L3, v1) + np.outer(L4, v2) + np.outer(L2, v3) + np.outer(L1, v4)
+    shift = np.zeros_like(XYZ)
+    tol = 1e-10
+    for face, (La, Lb, Lc, Ld) in enumerate([(L1, L2, L3, L4), (L2, L1, L3, L4), (L3, L1, L4, L2), (L4, L1, L3, L2)]):
+        w1, w2 = evalshift(Lb, Lc, Ld)
+        blend = Lb * Lc * Ld
+        denom = (Lb + 0.5 * La) * (Lc + 0.5 * La) * (Ld + 0.5 * La)
+        ok = denom > tol
+        blend[ok] = blend[ok] / denom[ok]
+        shift = shift + np.outer(blend * w1, t1[face]) + np.outer(blend * w2, t2[face])
+        onface = (La < tol) & (((Lb > tol).astype(int) + (Lc > tol).astype(int) + (Ld > tol).astype(int)) < 3)
+        shift[onface] = np.outer(w1[onface], t1[face]) + np.outer(w2[onface], t2[face])
+    XYZ = XYZ + shift
+    A = np.stack([0.5 * (v2 - v1), 0.5 * (v3 - v1), 0.5 * (v4 - v1)], axis=1)
+    RST = np.linalg.solve(A, XYZ.T - (0.5 * (v2 + v3 + v4 - v1))[:, None])
+    return [RST[0].copy(), RST[1].copy(), RST[2].copy()]
+
+
 def _tensor_nodes(d: int, N: int):
     """Tensor-product Gauss-Lobatto interpolation nodes of the Quad / Hex mapping element (NodesAndModes' nodes(Quad/Hex, N)
     are the tensor product of the 1-D Lobatto nodes), first coordinate slowest."""
@@ -341,7 +398,8 @@ class GeometryElement:
 
 
 def geometry_element(d: int, N: int, rstq, rstf, tensor: bool = False) -> GeometryElement:
-    rst = _tensor_nodes(d, N) if tensor else (_warp_blend_nodes_tri(N) if d == 2 else _lattice_nodes(d, N))
+    rst = _tensor_nodes(d, N) if tensor else (_warp_blend_nodes_tri(N) if d == 2 else
+                                              (_warp_blend_nodes_tet(N) if d == 3 else _lattice_nodes(d, N)))
     VDM, G = _poly_basis(d, N, rst, grad=True, tensor=tensor)
     Drst = [np.linalg.solve(VDM.T, g.T).T for g in G]
     ge = GeometryElement(d, N, rst, VDM, Drst, None, None, tensor)

@@ -85,3 +85,25 @@ def test_affine_curl_metrics_equal_exact():
     mesh = uniform_periodic_mesh(ra, ((0.0, 1.0),) * 3, (2,) * 3)
     a, b = geometric_factors(mesh, ra, "exact"), geometric_factors(mesh, ra, "curl")
     assert np.abs(a.Lambda_q - b.Lambda_q).max() < 1e-12 and np.abs(a.nJf - b.nJf).max() < 1e-12
+
+
+def test_tet_mapping_nodes_are_symmetric_with_lobatto_edges_and_triangle_faces():
+    """nodes(Tet(), N) of the mapping element (NodesAndModes, un-vendored): warp-and-blend without alpha optimisation —
+    invariant under the 24 vertex permutations, Gauss-Lobatto nodes on every edge, the triangle node set on every face."""
+    import itertools
+    from sse_b200 import reference as R
+    from sse_b200.quadrature import GaussLobattoQuadrature, quadrature_line
+    for N in (2, 3, 4, 5):
+        r, s, t = R._warp_blend_nodes_tet(N)
+        assert r.size == (N + 1) * (N + 2) * (N + 3) // 6
+        lam = np.stack([-(1 + r + s + t) / 2, (1 + r) / 2, (1 + s) / 2, (1 + t) / 2], axis=1)
+        for perm in itertools.permutations(range(4)):
+            for q in lam[:, perm]:
+                assert np.min(np.linalg.norm(lam - q, axis=1)) < 1e-12
+        gll, _ = quadrature_line(GaussLobattoQuadrature(N))
+        edge = lam[(np.abs(lam[:, 2]) < 1e-12) & (np.abs(lam[:, 3]) < 1e-12)]
+        assert np.abs(np.sort(2 * edge[:, 1] - 1) - np.sort(gll)).max() < 1e-13
+        tri = R._warp_blend_nodes_tri(N)
+        tl = np.stack([-(tri[0] + tri[1]) / 2, (1 + tri[0]) / 2, (1 + tri[1]) / 2], axis=1)
+        for q in lam[np.abs(lam[:, 3]) < 1e-12][:, :3]:
+            assert np.min(np.linalg.norm(tl - q, axis=1)) < 1e-13

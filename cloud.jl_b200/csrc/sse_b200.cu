@@ -175,6 +175,70 @@ static int32_t set_attrs(sse_handle* h) {
 extern "C" int32_t sse_abi_version(void) { return SSE_ABI_VERSION; }
 extern "C" const char* sse_last_error_string(void) { return g_err.c_str(); }
 
+// ---- schedule of the pipelined host-buffer residual (sse_rhs_host); pure host logic, exported as sse_host_range_plan so
+//      that it is testable without a device
+// local face neighbours of every element from mapP: the highest one (nbr_hi) and, when no element has more than N_fac
+// distinct ones, the exact list (nbr, -1 padded; cleared otherwise).  Ghost slots lie beyond the local elements.
+static void collect_neighbours(const int64_t* mapP, long long Ne, int Nf, int Nfac, std::vector<long long>& nbr_hi, std::vector<long long>& nbr) {
+    nbr_hi.assign((size_t)Ne, 0);
+    nbr.assign((size_t)Ne * Nfac, -1);
+    bool few = true;
+    for (long long k = 0; k < Ne; k++) {
+        long long hi = k;
+        int cnt = 0;
+        for (int j = 0; j < Nf; j++) {
+            const long long nb = (mapP[(size_t)k * Nf + j] - 1) / Nf;
+            if (nb >= Ne) continue;
+            if (nb > hi) hi = nb;
+            if (!few || nb == k) continue;
+            bool seen = false;
+            for (int q = 0; q < cnt; q++) seen = seen || nbr[(size_t)k * Nfac + q] == nb;
+            if (!seen) { if (cnt < Nfac) nbr[(size_t)k * Nfac + cnt++] = nb; else few = false; }
+        }
+        nbr_hi[(size_t)k] = hi;
+    }
+    if (!few) nbr.clear();
+}
+// ranges c = [ne c / chunks, ne (c + 1) / chunks): upload order and, for every range, the upload position after which its
+// pass B may run (all ranges holding one of its face neighbours are through pass A).  With exact neighbour lists the last
+// range goes first: on a periodic slab-ordered mesh range 0 otherwise waits for the wrap-around neighbour until the very end.
+static void make_range_plan(long long ne, int chunks, int nfac, const std::vector<long long>& nbr, const std::vector<long long>& nbr_hi,
+                            std::vector<int>& order, std::vector<int>& ready) {
+    std::vector<long long> bounds((size_t)chunks + 1);
+    for (int c = 0; c <= chunks; c++) bounds[(size_t)c] = ne * c / chunks;
+    auto owner = [&](long long k) { int c = (int)((k * chunks) / ne); while (k >= bounds[(size_t)c + 1]) c++; while (k < bounds[(size_t)c]) c--; return c; };
+    const bool exact = !nbr.empty();
+    order.resize((size_t)chunks);
+    std::vector<int> pos((size_t)chunks);
+    for (int i = 0; i < chunks; i++) order[(size_t)i] = exact ? (i == 0 ? chunks - 1 : i - 1) : i;
+    for (int i = 0; i < chunks; i++) pos[(size_t)order[(size_t)i]] = i;
+    ready.assign((size_t)chunks, 0);
+    for (int c = 0; c < chunks; c++) {
+        int r = pos[(size_t)c];
+        if (exact) {
+            for (long long k = bounds[(size_t)c]; k < bounds[(size_t)c + 1]; k++)
+                for (int q = 0; q < nfac; q++) {
+                    const long long nb = nbr[(size_t)k * nfac + q];
+                    if (nb >= 0) r = std::max(r, pos[(size_t)owner(nb)]);
+                }
+        } else {
+            long long hi = bounds[(size_t)c];
+            for (long long k = bounds[(size_t)c]; k < bounds[(size_t)c + 1]; k++) hi = std::max(hi, nbr_hi[(size_t)k]);
+            r = std::max(r, owner(hi));
+        }
+        ready[(size_t)c] = r;
+    }
+}
+extern "C" int32_t sse_host_range_plan(const int64_t* mapP, int64_t N_e, int32_t N_f, int32_t N_fac, int32_t chunks, int32_t* order, int32_t* ready) {
+    if (!mapP || !order || !ready || N_e <= 0 || N_f <= 0 || N_fac <= 0 || chunks <= 0 || N_e < chunks) return fail(SSE_ERR_BAD_ARGUMENT, "bad argument");
+    std::vector<long long> hi, nbr;
+    collect_neighbours(mapP, N_e, N_f, N_fac, hi, nbr);
+    std::vector<int> o, r;
+    make_range_plan(N_e, chunks, N_fac, nbr, hi, o, r);
+    for (int c = 0; c < chunks; c++) { order[c] = o[(size_t)c]; ready[c] = r[(size_t)c]; }
+    return SSE_OK;
+}
+
 // C tensor of the collapsed tet in the order of the compile-time kernels: C3[l * N + a3], l = canonical modal index
 static int32_t upload_c3(sse_handle* h, const sse_arrays* a, int N) {
     std::vector<double> c3;
@@ -310,24 +374,7 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
         const long long lim = g.NFT;
         for (size_t t = 0; t < (size_t)Nf * Ne; t++)
             if (a->mapP[t] < 1 || a->mapP[t] > lim) return fail(SSE_ERR_BAD_ARGUMENT, "mapP[%zu] = %lld out of range (BoundsError)", t, (long long)a->mapP[t]);
-        h->nbr_hi.assign((size_t)Ne, 0);
-        h->nbr.assign((size_t)Ne * Nfac, -1);
-        bool few = true;
-        for (long long k = 0; k < Ne; k++) {
-            long long hi = k;
-            int cnt = 0;
-            for (int j = 0; j < Nf; j++) {
-                const long long nb = (a->mapP[(size_t)k * Nf + j] - 1) / Nf;        // ghost slots lie beyond the local elements
-                if (nb >= Ne) continue;
-                if (nb > hi) hi = nb;
-                if (!few || nb == k) continue;
-                bool seen = false;
-                for (int q = 0; q < cnt; q++) seen = seen || h->nbr[(size_t)k * Nfac + q] == nb;
-                if (!seen) { if (cnt < Nfac) h->nbr[(size_t)k * Nfac + cnt++] = nb; else few = false; }
-            }
-            h->nbr_hi[(size_t)k] = hi;
-        }
-        if (!few) h->nbr.clear();
+        collect_neighbours(a->mapP, Ne, Nf, Nfac, h->nbr_hi, h->nbr);
         const long long* mp = nullptr;
         if ((rc = upload_raw(h, (const long long*)a->mapP, (size_t)Nf * Ne, &mp))) return rc;
         g.mapP = mp;
@@ -654,32 +701,7 @@ extern "C" int32_t sse_rhs_host(sse_handle* h, const double* h_u, double* h_dudt
     std::vector<long long> bounds((size_t)chunks + 1);
     for (int c = 0; c <= chunks; c++) bounds[(size_t)c] = ne * c / chunks;
     if (h->plan_chunks != chunks) {
-        // upload order and, for every range, the upload position after which its pass B may run (all ranges holding one of
-        // its face neighbours are through pass A).  With exact neighbour lists the last range goes first: on a periodic
-        // slab-ordered mesh range 0 otherwise waits for the wrap-around neighbour until the very end.
-        auto owner = [&](long long k) { int c = (int)((k * chunks) / ne); while (k >= bounds[(size_t)c + 1]) c++; while (k < bounds[(size_t)c]) c--; return c; };
-        const bool exact = !h->nbr.empty();
-        const int nfac = h->cfg.N_fac;
-        h->plan_order.resize((size_t)chunks);
-        std::vector<int> pos((size_t)chunks);
-        for (int i = 0; i < chunks; i++) h->plan_order[(size_t)i] = exact ? (i == 0 ? chunks - 1 : i - 1) : i;
-        for (int i = 0; i < chunks; i++) pos[(size_t)h->plan_order[(size_t)i]] = i;
-        h->plan_ready.assign((size_t)chunks, 0);
-        for (int c = 0; c < chunks; c++) {
-            int r = pos[(size_t)c];
-            if (exact) {
-                for (long long k = bounds[(size_t)c]; k < bounds[(size_t)c + 1]; k++)
-                    for (int q = 0; q < nfac; q++) {
-                        const long long nb = h->nbr[(size_t)k * nfac + q];
-                        if (nb >= 0) r = std::max(r, pos[(size_t)owner(nb)]);
-                    }
-            } else {
-                long long hi = bounds[(size_t)c];
-                for (long long k = bounds[(size_t)c]; k < bounds[(size_t)c + 1]; k++) hi = std::max(hi, h->nbr_hi[(size_t)k]);
-                r = std::max(r, owner(hi));
-            }
-            h->plan_ready[(size_t)c] = r;
-        }
+        make_range_plan(ne, chunks, h->cfg.N_fac, h->nbr, h->nbr_hi, h->plan_order, h->plan_ready);
         h->plan_chunks = chunks;
     }
     const std::vector<int>&order = h->plan_order, &ready = h->plan_ready;

@@ -29,6 +29,7 @@ SYMBOLS = {
     "sse_state_download": (C.c_int32, [_h, C.c_void_p, C.c_void_p]),
     "sse_rhs": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_double]),
     "sse_rhs_host": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_double, C.c_int32]),
+    "sse_host_range_plan": (C.c_int32, [_pi64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "sse_host_pin": (C.c_int32, [C.c_void_p, C.c_int64]),
     "sse_host_unpin": (C.c_int32, [C.c_void_p]),
     "sse_rhs_pass_a": (C.c_int32, [_h, C.c_void_p]),

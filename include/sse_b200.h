@@ -154,6 +154,9 @@ int32_t sse_rhs(sse_handle* h, const double* d_u, double* d_dudt, double t);
  * semi_discrete_residual!, Solvers.jl:474-483): upload, both passes and download are pipelined over `chunks` element
  * ranges (<= 0: default) on three streams.  Synchronous; page-lock the arrays with sse_host_pin for full overlap. */
 int32_t sse_rhs_host(sse_handle* h, const double* h_u, double* h_dudt, double t, int32_t chunks);
+/* the schedule sse_rhs_host follows, from mapP alone (no device needed): order[i] = range uploaded i-th, ready[c] = upload
+ * position after which pass B of range c may run (every range holding one of its face neighbours is through pass A) */
+int32_t sse_host_range_plan(const int64_t* mapP, int64_t N_e, int32_t N_f, int32_t N_fac, int32_t chunks, int32_t* order, int32_t* ready);
 int32_t sse_host_pin(void* p, int64_t bytes);
 int32_t sse_host_unpin(void* p);
 /* Split form used by the multi-GPU driver.  Pass A (nodal_values!, Solvers.jl:505-507)

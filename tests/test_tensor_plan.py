@@ -71,3 +71,29 @@ def test_host_pipeline_chunk_plan():
                 assert need <= done, "pass B released before pass A covered its neighbours"
         if chunks == 8:                      # one cube layer per range: a range depends on its two neighbours
             assert len(after[-1]) == 3 and all(len(a) <= 1 for a in after[:-1])
+
+
+@pytest.mark.parametrize("chunks", [3, 8, 16])
+def test_library_range_plan_of_the_host_buffer_residual(chunks):
+    """sse_host_range_plan is the schedule sse_rhs_host follows (no device needed): the wrap-around range is uploaded first,
+    every range is uploaded once, and pass B of a range is released exactly when pass A has covered the ranges holding its
+    face neighbours — the same answer as the NumPy restatement `range_plan` for the same upload order."""
+    import ctypes as C
+    from sse_b200 import _lib
+    from sse_b200.solver import range_plan
+    for c in (cases.euler_tgv_3d(M=4, flux="lf"), cases.euler_vortex_2d(M=8, p=3, flux="lf")):
+        img = c.image()
+        mapP = np.ascontiguousarray(np.asarray(img.arrays["mapP"]).reshape(-1), dtype=np.int64)
+        ne, nf, nfac = c.sd.N_e, int(img.cfg.N_f), int(img.cfg.N_fac)
+        order, ready = (C.c_int32 * chunks)(), (C.c_int32 * chunks)()
+        rc = _lib.load().sse_host_range_plan(mapP.ctypes.data_as(C.POINTER(C.c_int64)), ne, nf, nfac, chunks, order, ready)
+        assert rc == 0
+        order, ready = list(order), list(ready)
+        assert sorted(order) == list(range(chunks)) and order[0] == chunks - 1
+        bounds = [ne * k // chunks for k in range(chunks + 1)]
+        after = range_plan(mapP, ne, nf, [(bounds[k], bounds[k + 1]) for k in order])
+        want = [None] * chunks
+        for i, ks in enumerate(after):
+            for k in ks:
+                want[order[k]] = i
+        assert ready == want

@@ -97,3 +97,24 @@ def test_library_range_plan_of_the_host_buffer_residual(chunks):
             for k in ks:
                 want[order[k]] = i
         assert ready == want
+
+
+def test_compile_time_path_is_refused_for_operators_without_its_structure():
+    """The compile-time kernels hard-code structure that sse_create verifies on the host before selecting them (ct_eligible,
+    ct_facet_factors, c_tensor_symmetric): R must be the Kronecker product of its 1-D factors entry by entry, and the C tensor
+    of the collapsed tet must depend on (i + j, k) only.  An operator image that breaks either falls back to a general path."""
+    def perturbed(case, name, where, delta):
+        img = case.image()
+        a = np.array(img.arrays[name], dtype=np.float64, copy=True)
+        flat = a.reshape(-1)
+        flat[where(flat)] += delta
+        img.arrays[name] = a
+        return img
+    nonzero = lambda f: int(np.flatnonzero(f)[7])
+    zero = lambda f: int(np.flatnonzero(f == 0.0)[11])
+    euler, adv = cases.euler_tgv_3d(M=2, p=4), cases.advection_3d(M=2)
+    assert selfcheck(euler.image())[0][0] == 2 and selfcheck(adv.image())[0][0] == 3
+    assert selfcheck(perturbed(euler, "R", nonzero, 1e-9))[0][0] != 2          # an entry off its structured value
+    assert selfcheck(perturbed(euler, "R", zero, 1e-13))[0][0] != 2            # a structural zero that is not zero
+    assert selfcheck(perturbed(adv, "R", nonzero, 1e-9))[0][0] != 3
+    assert selfcheck(perturbed(euler, "C", nonzero, 1e-15))[0][0] != 2         # C[a3, i, j, k] no longer a function of (i + j, k)

@@ -82,3 +82,13 @@ def test_burgers_1d_fluxdiff_reference_testset():
             assert np.abs(analysis.conservation_residual(img, du)).max() < 1e-10      # runtests.jl:85
             assert abs(analysis.energy_residual(img, u, du)) < 1e-10                  # runtests.jl:86
     assert np.all(np.isfinite(u))
+
+
+def test_oracle_is_independent_of_its_thread_count():
+    """The OpenMP element loops of the oracle (Threads.@threads in the reference, Solvers.jl:505-511) only partition
+    independent elements: one thread and several threads must return the same bits — the CPU baseline of bench.py and the
+    checker of the parity tests are the same function."""
+    for c in (cases.euler_tgv_3d(M=2, flux="lf"), cases.advection_diffusion_2d(M=3)):
+        img, u = c.image(), c.u0(seed=4)
+        a, b = oracle.rhs(img, u, nthreads=1), oracle.rhs(img, u, nthreads=4)
+        assert np.array_equal(a, b)

@@ -26,7 +26,11 @@ METRIC = "FP64 RHS DOF/s (3D Euler p=4 tets, flux-diff)"
 ALG_BYTES_RHS = 23200.0          # compulsory HBM traffic of one RHS
 ALG_BYTES_PASS_B = 26800.0       # time_derivative kernel alone: u_q 5000 + own/nbr u_f 8000 + Λ 9000 + J_q 1000 + nJf 2400 + dudt 1400
 ALG_FLOPS_RHS = 476000.0         # FMA = 2
-NCU_DRAM_BYTES_PASS_B = 32750.0  # measured DRAM bytes / element of pass B (ncu, profiles/r1_ncu_final2_kernels.csv): 25.7 kB pair kernel + 7.0 kB projection
+ALG_FLOPS_PAIR = 359000.0        # the dominant kernel (k_fluxdiff_ct): volume + facet correction + interface flux + lift
+# measured DRAM bytes / element (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum at 24 576 elements,
+# profiles/r2_ncu_kernels.csv): pass A 9.02 kB, pair kernel 25.67 kB, projection 6.95 kB
+NCU_DRAM_BYTES = {"k_nodal_ct": 9017.0, "k_fluxdiff_ct": 25665.0, "k_project_ct": 6949.0}
+NCU_DRAM_BYTES_PASS_B = NCU_DRAM_BYTES["k_fluxdiff_ct"] + NCU_DRAM_BYTES["k_project_ct"]
 
 
 def parse():
@@ -103,6 +107,13 @@ def build_case(cells, flux, part, device=None):
     return c, u0
 
 
+def _cpu_sample_note(cells, case, reps, t, used):
+    return (f"same workload on a {cells}^3-cube sample ({case.sd.N_e} elements, {case.dof} DOF; the full 56^3 mesh needs ~15 s per "
+            f"RHS on the host), {reps} RHS, {t:.3f} s each, {used} OpenMP threads = every host thread of this process's affinity "
+            "mask; C/OpenMP restatement of the reference algorithm as written (Threads.@threads over elements, "
+            "Solvers.jl:505-511), built -O3 -march=native on this box (the Julia reference cannot run in this image)")
+
+
 def cpu_baseline(cells, flux, budget_s=12.0):
     """The reference algorithm (oracle port, OpenMP over elements like Threads.@threads) on a bounded
     sample of the same workload, on this box's host cores: about `budget_s` seconds of CPU work."""
@@ -110,43 +121,105 @@ def cpu_baseline(cells, flux, budget_s=12.0):
     import oracle
     c, u0 = build_case(cells, flux, None)
     img = c.image()
-    t1, used, _ = oracle.time_rhs(img, u0, 0, 1)                       # warm-up and cost estimate
+    nt = oracle.host_threads()
+    t1, used, _ = oracle.time_rhs(img, u0, nt, 1, perf=True)                 # warm-up and cost estimate
     reps = int(min(max(budget_s / max(t1, 1e-6), 3), 60))
-    t, used, _ = oracle.time_rhs(img, u0, 0, reps)
-    return {"value": c.dof / t, "unit": "DOF/s", "cores": used, "kind": "port",
-            "sample": f"same workload on {cells}^3 cubes ({c.sd.N_e} elements, {c.dof} DOF), best of {reps} RHS, "
-                      f"{t:.3f} s each ({reps * t:.1f} s of CPU work); C/OpenMP restatement of the reference "
-                      "algorithm (Julia cannot run here)"}
+    t, used, _ = oracle.time_rhs(img, u0, nt, reps, perf=True)
+    return {"value": c.dof / t, "unit": "DOF/s", "cores": used, "kind": "port", "same_config": False,
+            "sample": _cpu_sample_note(cells, c, reps, t, used) + f" (best of {reps})"}
 
 
 def run_reference(a):
+    """--impl reference: the reference's own CPU algorithm for the path, all host threads, on a bounded sample of the workload.
+    Under torchrun only rank 0 works (and it ignores OMP_NUM_THREADS=1, which torchrun exports: the thread count is explicit)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
-    cells = 12
+    cells = a.cpu_cells
     c, u0 = build_case(cells, a.flux, None)
     img = c.image()
+    nt = oracle.host_threads()
     for _ in range(max(a.warmup, 1)):
-        t, used, _ = oracle.time_rhs(img, u0, 0, 1)
+        t, used, _ = oracle.time_rhs(img, u0, nt, 1, perf=True)
     ts = []
     for _ in range(a.steps):
-        t, used, _ = oracle.time_rhs(img, u0, 0, 1)
+        t, used, _ = oracle.time_rhs(img, u0, nt, 1, perf=True)
         ts.append(t)
     t = float(np.mean(ts))
     val = c.dof / t
     n_e_full = 6 * a.cells ** 3
-    sample = (f"each step = one RHS over a {cells}^3-cube sample ({c.sd.N_e} elements, {c.dof} DOF) of the workload; "
-              "C/OpenMP restatement of the reference algorithm as written (the Julia reference cannot run in this image)")
+    sample = "each step = one RHS: " + _cpu_sample_note(cells, c, a.steps, t, used)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "DOF/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a.cells, n_e_full, n_e_full * 175, a.flux), "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": used, "kind": "port", "sample": sample},
+        "config": {"workload": workload_name(a.cells, n_e_full, n_e_full * 175, a.flux), "sample": sample, "same_config": False},
+        "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": used, "kind": "port", "same_config": False, "sample": sample},
         "e2e": {"value": val, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the host cores NVML reports as local to the GPU (what numactl does for a production run): the
+    pinned staging buffers of the end-to-end path are then first-touched on the GPU's NUMA node.  Returns the previous mask."""
+    try:
+        old = os.sched_getaffinity(0)
+    except AttributeError:
+        return None
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 64
+        words = nv.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= old
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+    return old
+
+
+def dist_parity(rank, world, local):
+    """Element-partitioned residual on `world` GPUs against the single-domain oracle (rank 0 checks): config 5 and config 4
+    at M = 4, through the same DistributedSolver.rhs the timed region used.  Returns the worst relative difference."""
+    import torch
+    import torch.distributed as dist
+    from sse_b200 import cases
+    from sse_b200.dist import DistributedSolver
+    from sse_b200.solver import Solver
+    worst = 0.0
+    M = 4 if world <= 4 else 8
+    for name, kw in (("euler_tgv_3d", dict(M=M, flux="lf")), ("advection_3d", dict(M=M, flux="lf"))):
+        full = cases.BUILDERS[name](**kw)
+        u_full = full.u0(seed=0)
+        part = cases.BUILDERS[name](part=(rank, world), **kw)
+        gid = part.sd.mesh.elem_gid
+        s = Solver(part.image(), local)
+        s.use_current_stream()
+        ds = DistributedSolver(s, part.sd.mesh)
+        u = torch.from_numpy(np.ascontiguousarray(u_full[gid])).cuda()
+        du = s.new_state()
+        for _ in range(2):
+            ds.rhs(du, u)
+        s.synchronize()
+        got = [None] * world
+        dist.all_gather_object(got, (gid, du.cpu().numpy()))
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle
+            ref = oracle.rhs(full.image(), u_full, oracle.host_threads())
+            out = np.empty_like(ref)
+            for g, d in got:
+                out[g] = d
+            worst = max(worst, float(np.abs(out - ref).max() / np.abs(ref).max()))
+        s.close()
+    t = torch.tensor([worst], dtype=torch.float64, device="cuda")
+    dist.broadcast(t, 0)
+    return float(t.item())
 
 
 def main():
@@ -166,6 +239,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libsse_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    old_affinity = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 
@@ -190,35 +264,27 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step(ev=None):
-        if ds is not None:
-            ds.rhs(du, u)
-            return
-        solver.pass_a(u)
-        if ev is not None:
-            ev[0].record()
-        solver.pass_b(du, 0, n_e_local)
-        if ev is not None:
-            ev[1].record()
+    def step():
+        ds.rhs(du, u) if ds is not None else solver.rhs(du, u)      # one sse_rhs: the call a Julia residual makes
 
     for _ in range(max(a.warmup, 3)):
         step()
     sync_all()
     sampler = ClockSampler(local)
     sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = solver.launches
     sync_all()
     e0.record()
     for i in range(a.steps):
-        step(evs[i])
+        step()
     e1.record()
     sync_all()
     clocks = sampler.result()
     ms = e0.elapsed_time(e1)
     launches = solver.launches - launches0
-    pass_b_ms = float(np.mean([x.elapsed_time(y) for x, y in evs])) if ds is None else None
+    # per-kernel durations of the same residual (CUDA events between the kernels, on the stream they are launched on)
+    kernel_ms = solver.profile_rhs(du, u, reps=min(max(a.steps, 3), 10)) if ds is None else None
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -278,6 +344,12 @@ def main():
             checks["host_buffer_result_equals_device"] = bool(okt.item() == 1.0)
     except Exception as e:
         checks["error"] = str(e)
+    if world > 1:
+        # parity of the partitioned path on this very communicator layout, against the single-domain oracle
+        checks["dist_parity_rel"] = dist_parity(rank, world, local)
+        checks["dist_parity_cases"] = "euler_tgv_3d and advection_3d (lf), M = %d, %d ranks, vs the oracle on the whole mesh" % (4 if world <= 4 else 8, world)
+    if old_affinity:
+        os.sched_setaffinity(0, old_affinity)            # the CPU baseline below uses every host thread again
     if rank == 0:
         peaks = {}
         try:
@@ -291,7 +363,8 @@ def main():
             "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a.cells, n_e, dof, a.flux),
-                       "partition": f"{world} slab(s) along z, facet-trace halos over NCCL" if world > 1 else "single GPU",
+                       "partition": (f"{world} slabs along z, facet-trace halos by ncclSend/ncclRecv inside sse_rhs "
+                                     f"(NCCL {solver.comm_info()[2]})") if world > 1 else "single GPU",
                        "l2": "no flush: per-step inputs (metrics + state, ~24 kB/element) are far larger than the 126 MB L2",
                        "kernel_variant": solver.kernel_variant(), "setup_s": round(t_setup, 1)},
             "clocks": clocks,
@@ -300,27 +373,39 @@ def main():
                     "ms_min_max": e2e_spread},
             "gpu_launches": launches,
         }
-        if pass_b_ms is not None:
-            ach = ALG_BYTES_PASS_B * n_e_local / (pass_b_ms * 1e-3) / 1e9
-            out["roofline"] = {"bound": "hbm", "kernel": "time_derivative (pass B: k_fluxdiff_ct + k_project_ct)",
-                               "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                               "traffic": NCU_DRAM_BYTES_PASS_B * n_e_local, "peak_source": hbm_src, "kernel_ms": pass_b_ms,
-                               "algorithmic_bytes_per_element": ALG_BYTES_PASS_B,
-                               "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per element from the ncu --set full "
-                                                 "capture profiles/r1_ncu_final2_kernels.csv (24 576 "
-                                                 "elements), scaled to this launch",
-                               "note": "this path is bound by the FP64 vector pipe, see roofline_fp64"}
-            try:
-                fpeak = fp64_peak(local)
-                fl = ALG_FLOPS_RHS * n_e / (ms_per_step * 1e-3)
-                out["roofline_fp64"] = {"bound": "fp64 vector pipe (binding roofline of this path)", "achieved": fl / 1e12,
-                                        "peak": fpeak / 1e12, "unit": "TFLOP/s", "frac": fl / fpeak,
-                                        "peak_source": "measured in this run: register-resident DFMA microbenchmark (sse_fp64_peak)",
-                                        "algorithmic_flops_per_element": ALG_FLOPS_RHS,
-                                        "hbm_whole_rhs": {"achieved_gbs": ALG_BYTES_RHS * n_e / (ms_per_step * 1e-3) / 1e9,
-                                                          "algorithmic_bytes_per_element": ALG_BYTES_RHS}}
-            except Exception as e:
-                out["roofline_fp64"] = {"error": str(e)}
+        try:
+            fpeak = fp64_peak(local)
+        except Exception as e:
+            fpeak = None
+            out["roofline_error"] = str(e)
+        fp_src = "measured in this run: register-resident DFMA microbenchmark (sse_fp64_peak); MEASURED_PEAKS.json has no FP64 figure"
+        if fpeak:
+            fl = ALG_FLOPS_RHS * n_e / (ms_per_step * 1e-3)
+            # the binding bound of this path, for the whole residual (the figure BASELINE.json's >= 50 % target is about)
+            out["roofline_rhs"] = {"bound": "fp64", "what": "whole residual (k_nodal_ct + k_fluxdiff_ct + k_project_ct" +
+                                   (" + halo pack / unpack)" if world > 1 else ")"), "achieved": fl / 1e12,
+                                   "peak": world * fpeak / 1e12, "unit": "TFLOP/s", "frac": fl / (world * fpeak),
+                                   "algorithmic_flops_per_element": ALG_FLOPS_RHS, "peak_source": fp_src}
+            out["roofline_hbm"] = {"bound": "hbm (not binding: 20 flop/B)", "achieved": ALG_BYTES_RHS * n_e / (ms_per_step * 1e-3) / 1e9,
+                                   "peak": world * hbm_peak, "unit": "GB/s",
+                                   "frac": ALG_BYTES_RHS * n_e / (ms_per_step * 1e-3) / 1e9 / (world * hbm_peak),
+                                   "algorithmic_bytes_per_element": ALG_BYTES_RHS, "peak_source": hbm_src,
+                                   "traffic": sum(NCU_DRAM_BYTES.values()) * n_e}
+        if kernel_ms is not None and fpeak:
+            flops = {"k_nodal_ct": ALG_FLOPS_RHS - ALG_FLOPS_PAIR - 36200.0, "k_fluxdiff_ct": ALG_FLOPS_PAIR, "k_project_ct": 36200.0}
+            kms = {"k_nodal_ct": float(kernel_ms[0]), "k_fluxdiff_ct": float(kernel_ms[2]), "k_project_ct": float(kernel_ms[3])}
+            ach = ALG_FLOPS_PAIR * n_e_local / (kms["k_fluxdiff_ct"] * 1e-3)
+            out["roofline"] = {"bound": "fp64", "kernel": "k_fluxdiff_ct (dominant kernel: interface flux, volume flux differencing, "
+                                                          "facet correction, lift)",
+                               "achieved": ach / 1e12, "peak": fpeak / 1e12, "unit": "TFLOP/s", "frac": ach / fpeak,
+                               "traffic": NCU_DRAM_BYTES["k_fluxdiff_ct"] * n_e_local, "kernel_ms": kms["k_fluxdiff_ct"],
+                               "algorithmic_flops_per_element": ALG_FLOPS_PAIR, "peak_source": fp_src,
+                               "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per element of this kernel from the "
+                                                 "ncu --set full capture profiles/r2_ncu_kernels.csv (24 576 elements), scaled to "
+                                                 "this launch",
+                               "kernels": {k: {"ms": kms[k], "algorithmic_flops_per_element": flops[k],
+                                               "frac_of_fp64_peak": flops[k] * n_e_local / (kms[k] * 1e-3) / fpeak,
+                                               "share_of_step": kms[k] / sum(kms.values())} for k in kms}}
         out["checks"] = checks
         if not a.no_cpu_baseline and world == 1:
             try:
@@ -331,6 +416,8 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+        if checks.get("dist_parity_rel", 0.0) > 1e-12:
+            raise SystemExit(f"partitioned residual differs from the oracle: {checks['dist_parity_rel']:.3e} > 1e-12")
 
 
 if __name__ == "__main__":

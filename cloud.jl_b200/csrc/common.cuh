@@ -47,8 +47,14 @@ struct Geo {
     long long Ne;
     long long NFT;           // Nf*Ne + N_ghost: stride between variables of u_f / q_f
     int mass_solver;
+    int* flag;               // set to 1 by the kernels that write dudt when a value is not finite (SSE_ERR_NONFINITE)
     const double* chol;      // CholeskySolver: upper factors U_k, Np x Np column-major per element (mass_matrix.jl:30-39)
 };
+
+// a residual entry that is NaN or infinite raises the handle's flag (one predicated store, never taken on physical states)
+__device__ __forceinline__ void flag_nonfinite(int* flag, double v) {
+    if (!(fabs(v) <= 1.7976931348623157e308)) *flag = 1;
+}
 
 #define SSE_FOR(t, n) for (int t = threadIdx.x; t < (n); t += blockDim.x)
 

@@ -45,7 +45,7 @@ bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& t
 // advection + StandardForm + ReferenceOperators on ModalTensor tets; fills D1 and fR (host images) on success
 bool ct_eligible_standard(const sse_config& cfg, const sse_arrays& a, int* Nout, std::vector<double>& D1, std::vector<double>& fR);
 void ct_standard(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
-                 double* dudt, cudaStream_t s, RkStage rk = RkStage());
+                 double* dudt, cudaStream_t s, RkStage rk = RkStage(), cudaEvent_t mid = nullptr);
 bool ct_facet_factors(const sse_config& cfg, const sse_arrays& a, int N, std::vector<double>& out);
 // true when the generic tables of tp equal the closed-form schedule k_fluxdiff_ct hard-codes
 bool ct_schedule_matches(const TensorPlan& tp, int N);
@@ -53,6 +53,7 @@ cudaError_t ct_set_attrs(int N);
 void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q, double* u_f,
               cudaStream_t s);
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
-                 double* u_q, const double* u_f, double* dudt, cudaStream_t s, RkStage rk = RkStage());
+                 double* u_q, const double* u_f, double* dudt, cudaStream_t s, RkStage rk = RkStage(), cudaEvent_t mid = nullptr);
+// mid: recorded between the two kernels of pass B (sse_profile_rhs times them separately)
 
 }  // namespace sse

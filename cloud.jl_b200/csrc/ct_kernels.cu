@@ -140,7 +140,7 @@ void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long
 
 template <int N>
 static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
-                       double* u_q, const double* u_f, double* dudt, cudaStream_t s, RkStage rk) {
+                       double* u_q, const double* u_f, double* dudt, cudaStream_t s, RkStage rk, cudaEvent_t mid) {
     constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
     (void)tp; (void)o;
     bool done = false;
@@ -148,13 +148,14 @@ static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, cons
         if (p.dual) { k_fluxdiff_ct<N, 4, true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); done = true; }
     }
     if (!done) k_fluxdiff_ct<N, 4, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
+    if (mid) cudaEventRecord(mid, s);
     const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
     k_project_ct<N, 5, 3><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt, rk);
 }
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
-                 double* u_q, const double* u_f, double* dudt, cudaStream_t s, RkStage rk) {
-    if (p.N == 5) fluxdiff_n<5>(p, tp, o, g, L, first, count, u_q, u_f, dudt, s, rk);
-    else fluxdiff_n<4>(p, tp, o, g, L, first, count, u_q, u_f, dudt, s, rk);
+                 double* u_q, const double* u_f, double* dudt, cudaStream_t s, RkStage rk, cudaEvent_t mid) {
+    if (p.N == 5) fluxdiff_n<5>(p, tp, o, g, L, first, count, u_q, u_f, dudt, s, rk, mid);
+    else fluxdiff_n<4>(p, tp, o, g, L, first, count, u_q, u_f, dudt, s, rk, mid);
 }
 
 
@@ -210,17 +211,18 @@ bool ct_eligible_standard(const sse_config& cfg, const sse_arrays& a, int* Nout,
 
 template <int N>
 static void standard_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
-                       double* dudt, cudaStream_t s, RkStage rk) {
+                       double* dudt, cudaStream_t s, RkStage rk, cudaEvent_t mid) {
     constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
     AdvTabs<N> tabs;
     for (int m = 0; m < 3; m++) for (int i = 0; i < N * N; i++) tabs.D1[m][i] = p.D1[m * N * N + i];
     k_standard_adv_ct<N, 8><<<(unsigned)count, NT, 0, s>>>(tabs, p.dev, g, L, first, u_q, u_f);
+    if (mid) cudaEventRecord(mid, s);
     const unsigned grid = (unsigned)((count + ProjSmem<N, 1>::EPB - 1) / ProjSmem<N, 1>::EPB);
     k_project_ct<N, 1, 3><<<grid, 128, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt, rk);
 }
 void ct_standard(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
-                 double* dudt, cudaStream_t s, RkStage rk) {
-    if (p.N == 5) standard_n<5>(p, g, L, first, count, u_q, u_f, dudt, s, rk); else standard_n<4>(p, g, L, first, count, u_q, u_f, dudt, s, rk);
+                 double* dudt, cudaStream_t s, RkStage rk, cudaEvent_t mid) {
+    if (p.N == 5) standard_n<5>(p, g, L, first, count, u_q, u_f, dudt, s, rk, mid); else standard_n<4>(p, g, L, first, count, u_q, u_f, dudt, s, rk, mid);
 }
 
 }  // namespace sse

@@ -531,6 +531,7 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
             if (l < Np) {
                 const size_t idx = (size_t)e0 * NC * Np + grp * Np + l;
                 dudt[idx] = out[q];
+                flag_nonfinite(g.flag, out[q]);
                 if (rk.u) {                        // fused 2N-storage RK stage (Carpenter & Kennedy 1994)
                     const double tm = fma(rk.A, rk.tmp[idx], rk.dt * out[q]);
                     rk.tmp[idx] = tm;

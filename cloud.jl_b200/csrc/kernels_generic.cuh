@@ -439,7 +439,7 @@ __global__ void k_time_fluxdiff_generic(Ops o, Geo g, Law L, long long first, co
     __syncthreads();
     apply_Vt<NC>(o, s_r, s_m, s_z, s_w);
     mass_solve<NC>(o, g, k, s_m, s_uq, s_z, s_w);
-    SSE_FOR(t, Np * NC) dudt[(size_t)Np * NC * k + t] = s_m[t];
+    SSE_FOR(t, Np * NC) { dudt[(size_t)Np * NC * k + t] = s_m[t]; flag_nonfinite(g.flag, s_m[t]); }
 }
 
 // physical_flux! into a shared Nq x NC x D tile
@@ -544,7 +544,7 @@ __global__ void k_time_standard_reference(Ops o, Geo g, Law L, long long first, 
     __syncthreads();
     apply_Vt<NC>(o, s_r, s_m, s_z, s_w);
     mass_solve<NC>(o, g, k, s_m, s_uq, s_z, s_w);
-    SSE_FOR(t, Np * NC) dudt[(size_t)Np * NC * k + t] = s_m[t];
+    SSE_FOR(t, Np * NC) { dudt[(size_t)Np * NC * k + t] = s_m[t]; flag_nonfinite(g.flag, s_m[t]); }
 }
 
 // ------------------------------------------------------------------ PhysicalOperators paths
@@ -649,6 +649,7 @@ __global__ void k_time_physical(Ops o, Geo g, Law L, long long first, int second
         double sf = 0.0;
         for (int f = 0; f < Nf; f++) sf = fma(FAC[a + (size_t)Np * f], s_ff[f + Nf * e], sf);
         dudt[(size_t)Np * NC * k + t] = s + sf;
+        flag_nonfinite(g.flag, s + sf);
     }
 }
 

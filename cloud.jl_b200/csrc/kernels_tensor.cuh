@@ -314,7 +314,7 @@ k_fluxdiff_tensor(TensorDev t, Ops o, Geo g, Law L, long long first, const doubl
     double* s_m = sm + lay.post_m;
     apply_Vt<NC>(o, s_r, s_m, sm + lay.post_z, sm + lay.post_w);
     mass_solve<NC>(o, g, k, s_m, sm + lay.post_tq, sm + lay.post_z, sm + lay.post_w);
-    SSE_FOR(x, Np * NC) dudt[(size_t)Np * NC * k + x] = s_m[x];
+    SSE_FOR(x, Np * NC) { dudt[(size_t)Np * NC * k + x] = s_m[x]; flag_nonfinite(g.flag, s_m[x]); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -537,7 +537,7 @@ template <int D, int NC>
 inline cudaError_t tensor_set_attrs(const TensorPlan& tp) {
     if (!tp.ok) return cudaSuccess;
     if constexpr (D >= 2) {
-        return cudaFuncSetAttribute(k_fluxdiff_tensor<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp.smem_fluxdiff);
+        return cudaFuncSetAttribute(k_fluxdiff_tensor<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // per kernel, never lowered by a later handle
     }
     return cudaSuccess;
 }

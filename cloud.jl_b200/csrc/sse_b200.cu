@@ -22,9 +22,11 @@
 
 using namespace sse;
 
+#include "handle.h"
+
 // ------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
-static int32_t fail(int32_t code, const char* fmt, ...) {
+int32_t sse::fail(int32_t code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -33,45 +35,6 @@ static int32_t fail(int32_t code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
-#define CU(x)                                                                                        \
-    do {                                                                                             \
-        cudaError_t e_ = (x);                                                                        \
-        if (e_ != cudaSuccess) return fail(SSE_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-
-// ------------------------------------------------------------------------------ handle
-struct sse_handle {
-    sse_config cfg;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    std::vector<void*> owned;       // device allocations freed in sse_destroy
-    Ops ops;
-    Geo geo;
-    Law law;
-    TensorPlan tp;                  // tensor-line specialisation (kernels_tensor.cuh); tp.ok == 0 -> generic only
-    CtPlan ct;                      // compile-time-sized kernels (kernels_ct.cuh): Euler on p = 3, 4 ModalTensor tets
-    int variant = 1;
-    int project = 0;                // 0 none, 1 nodal, 2 general entropy projection
-    int second_order = 0;
-    double *u_q = nullptr, *u_f = nullptr, *q_q = nullptr, *q_f = nullptr;
-    size_t smem_nodal = 0, smem_time = 0, smem_aux = 0;
-    int threads = 128;
-    int sm_count = 148;
-    // halo
-    long long n_send = 0;
-    long long* d_send_idx = nullptr;
-    double *d_send = nullptr, *d_recv = nullptr;
-    int halo_vars = 0;
-    // host-buffer residual (sse_rhs_host): highest local face neighbour of every element (from mapP), device staging
-    // states, copy streams and events, all created on first use
-    std::vector<long long> nbr_hi;
-    std::vector<long long> nbr;     // up to N_fac distinct local face neighbours per element (-1: none); empty if some element has more
-    int plan_chunks = 0;            // cached schedule of sse_rhs_host for this many ranges
-    std::vector<int> plan_order, plan_ready;
-    double *h2d_u = nullptr, *d2h_du = nullptr;
-    cudaStream_t s_in = nullptr, s_out = nullptr;
-    std::vector<cudaEvent_t> events;
-};
 
 template <class T>
 static int32_t upload(sse_handle* h, const std::vector<T>& v, const T** out) {
@@ -161,13 +124,16 @@ static size_t smem_aux_bytes(const Ops& o) {
     return sizeof(double) * (size_t)(2 * o.Nq * NC + 2 * o.Nf * NC + D * o.Nf + o.Np * NC + warp_z_size(o, NC) + warp_w_size(o, NC));
 }
 
+// The attribute is a property of the kernel template, not of a handle: a later handle with smaller elements must not lower the
+// cap under an earlier one, so every runtime-sized kernel is opted in to the device maximum once (launches pass their own size).
+static const int SMEM_OPT_IN_MAX = 227 * 1024;
 template <int D, int NC>
 static int32_t set_attrs(sse_handle* h) {
-    CU(cudaFuncSetAttribute(k_nodal_generic<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_nodal));
-    CU(cudaFuncSetAttribute(k_time_fluxdiff_generic<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_time));
-    CU(cudaFuncSetAttribute(k_time_standard_reference<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_time));
-    CU(cudaFuncSetAttribute(k_time_physical<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_time));
-    CU(cudaFuncSetAttribute(k_aux_physical<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_aux));
+    CU(cudaFuncSetAttribute(k_nodal_generic<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN_MAX));
+    CU(cudaFuncSetAttribute(k_time_fluxdiff_generic<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN_MAX));
+    CU(cudaFuncSetAttribute(k_time_standard_reference<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN_MAX));
+    CU(cudaFuncSetAttribute(k_time_physical<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN_MAX));
+    CU(cudaFuncSetAttribute(k_aux_physical<D, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN_MAX));
     return tensor_set_attrs<D, NC>(h->tp) == cudaSuccess ? SSE_OK : fail(SSE_ERR_CUDA, "cudaFuncSetAttribute (tensor kernels) failed");
 }
 
@@ -227,6 +193,27 @@ static void make_range_plan(long long ne, int chunks, int nfac, const std::vecto
             r = std::max(r, owner(hi));
         }
         ready[(size_t)c] = r;
+    }
+}
+// the same for an arbitrary list of contiguous ranges given in upload order (the multi-GPU host-buffer residual uploads the
+// halo-adjacent elements first): ready[i] = upload position after which pass B of range i may run
+void sse::make_range_plan_general(const std::vector<std::pair<long long, long long>>& ranges, long long ne, int nfac,
+                                  const std::vector<long long>& nbr, const std::vector<long long>& nbr_hi, std::vector<int>& ready) {
+    (void)nbr_hi;
+    const int n = (int)ranges.size();
+    std::vector<int> pos_of((size_t)ne, 0);
+    for (int i = 0; i < n; i++)
+        for (long long k = ranges[(size_t)i].first; k < ranges[(size_t)i].second; k++) pos_of[(size_t)k] = i;
+    ready.assign((size_t)n, n - 1);                      // without exact neighbour lists: after the last upload
+    if (nbr.empty()) return;
+    for (int i = 0; i < n; i++) {
+        int r = i;
+        for (long long k = ranges[(size_t)i].first; k < ranges[(size_t)i].second; k++)
+            for (int q = 0; q < nfac; q++) {
+                const long long nb = nbr[(size_t)k * nfac + q];
+                if (nb >= 0) r = std::max(r, pos_of[(size_t)nb]);
+            }
+        ready[(size_t)i] = r;
     }
 }
 extern "C" int32_t sse_host_range_plan(const int64_t* mapP, int64_t N_e, int32_t N_f, int32_t N_fac, int32_t chunks, int32_t* order, int32_t* ready) {
@@ -318,6 +305,13 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
     Geo& g = h->geo;
     memset(&g, 0, sizeof(g));
     g.Ne = Ne; g.NFT = (long long)Nf * Ne + cfg->N_ghost; g.mass_solver = cfg->mass_solver;
+    {
+        int* hf = nullptr;
+        CU(cudaHostAlloc((void**)&hf, sizeof(int), cudaHostAllocMapped));
+        *hf = 0;
+        h->h_flag = hf;
+        CU(cudaHostGetDevicePointer((void**)&g.flag, hf, 0));
+    }
     if (cfg->mass_solver != SSE_MASS_WEIGHT_ADJUSTED && cfg->mass_solver != SSE_MASS_DIAGONAL && cfg->mass_solver != SSE_MASS_CHOLESKY)
         return fail(SSE_ERR_BAD_ARGUMENT, "unknown mass_solver %d", cfg->mass_solver);
     // CholeskySolver with V = I is the DiagonalSolver (mass_matrix.jl:26-28)
@@ -375,6 +369,11 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
         for (size_t t = 0; t < (size_t)Nf * Ne; t++)
             if (a->mapP[t] < 1 || a->mapP[t] > lim) return fail(SSE_ERR_BAD_ARGUMENT, "mapP[%zu] = %lld out of range (BoundsError)", t, (long long)a->mapP[t]);
         collect_neighbours(a->mapP, Ne, Nf, Nfac, h->nbr_hi, h->nbr);
+        h->nbr_ghost.assign((size_t)Ne, 0);
+        if (cfg->N_ghost)
+            for (long long k = 0; k < Ne; k++)
+                for (int j = 0; j < Nf; j++)
+                    if (a->mapP[(size_t)k * Nf + j] > (long long)Nf * Ne) { h->nbr_ghost[(size_t)k] = 1; break; }
         const long long* mp = nullptr;
         if ((rc = upload_raw(h, (const long long*)a->mapP, (size_t)Nf * Ne, &mp))) return rc;
         g.mapP = mp;
@@ -389,7 +388,7 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
         CU(cudaMemset(bad, 0, sizeof(int)));
         const size_t smem = sizeof(double) * (size_t)(Np * Np + Np + Nq + warp_z_size(o, 1) + warp_w_size(o, 1));
         if (smem > 227 * 1024) return fail(SSE_ERR_UNSUPPORTED, "element mass matrix exceeds 227 KB of shared memory");
-        CU(cudaFuncSetAttribute(k_cholesky_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(k_cholesky_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         k_cholesky_factor<<<(unsigned)Ne, 128, smem, h->stream>>>(o, g, chol, bad);
         int hbad = 0;
         CU(cudaMemcpy(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost));
@@ -523,7 +522,9 @@ extern "C" int32_t sse_destroy(sse_handle* h) {
     if (!h) return SSE_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    comm_release(h);
     for (void* p : h->owned) cudaFree(p);
+    if (h->h_flag) cudaFreeHost((void*)h->h_flag);
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
@@ -544,6 +545,18 @@ extern "C" int32_t sse_set_kernel_variant(sse_handle* h, int32_t v) {
 extern "C" int32_t sse_get_kernel_variant(const sse_handle* h, int32_t* v) {
     if (!h || !v) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
     *v = (h->variant == 1 && h->ct.ok) ? 2 : ((h->variant == 1 && h->tp.ok) ? 1 : 0);
+    return SSE_OK;
+}
+
+// Non-physical states: the reference raises a DomainError from log / sqrt.  The kernels that write dudt set a
+// flag in mapped host memory when a value is not finite (log_nobranch returns NaN for a non-positive argument, so a
+// negative density or pressure always ends up there); the blocking entry points report it once and clear it.
+int32_t sse::check_flag(sse_handle* h) {
+    if (h->h_flag && *h->h_flag) {
+        *h->h_flag = 0;
+        return fail(SSE_ERR_NONFINITE, "non-finite residual: the state left the physical domain (DomainError in the reference: log / sqrt of a "
+                                       "negative density or pressure)");
+    }
     return SSE_OK;
 }
 
@@ -573,13 +586,13 @@ extern "C" int32_t sse_state_download(sse_handle* h, double* h_dst, const double
     CU(cudaSetDevice(h->device));
     CU(cudaMemcpyAsync(h_dst, d_src, state_len(h) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    return SSE_OK;
+    return check_flag(h);
 }
 extern "C" int32_t sse_synchronize(sse_handle* h) {
     if (!h) return fail(SSE_ERR_BAD_ARGUMENT, "null handle");
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
-    return SSE_OK;
+    return check_flag(h);
 }
 
 // ------------------------------------------------------------------------------ the hot path
@@ -598,6 +611,7 @@ extern "C" int32_t sse_rhs_pass_a_range(sse_handle* h, const double* d_u, int64_
         DISPATCH_DNC(h, LA);
 #undef LA
     }
+    h->launches += 1;
     CU(cudaGetLastError());
     return SSE_OK;
 }
@@ -615,16 +629,16 @@ extern "C" int32_t sse_rhs_pass_aux(sse_handle* h, double* d_dudt, int64_t first
 #define LA(D_, NC_) k_aux_physical<D_, NC_><<<(unsigned)count, h->threads, h->smem_aux, h->stream>>>(h->ops, h->geo, h->law, first, h->u_q, h->u_f, h->q_q, h->q_f)
     DISPATCH_DNC(h, LA);
 #undef LA
+    h->launches += 1;
     CU(cudaGetLastError());
     return SSE_OK;
 }
 
-static int32_t pass_b_impl(sse_handle* h, double* d_dudt, int64_t first, int64_t count, RkStage rk);
 extern "C" int32_t sse_rhs_pass_b(sse_handle* h, double* d_dudt, int64_t first, int64_t count) {
-    return pass_b_impl(h, d_dudt, first, count, RkStage());
+    return pass_b_stage(h, d_dudt, first, count, RkStage());
 }
 // rk.u != nullptr: the caller asks for the 2N-storage stage update to be fused; *fused reports whether it was
-static int32_t pass_b_impl(sse_handle* h, double* d_dudt, int64_t first, int64_t count, RkStage rk) {
+int32_t sse::pass_b_stage(sse_handle* h, double* d_dudt, int64_t first, int64_t count, RkStage rk, cudaEvent_t mid) {
     if (!h || !d_dudt) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
     if (count <= 0) return SSE_OK;
     if (first < 0 || first + count > h->cfg.N_e) return fail(SSE_ERR_BAD_ARGUMENT, "element range out of bounds");
@@ -632,7 +646,8 @@ static int32_t pass_b_impl(sse_handle* h, double* d_dudt, int64_t first, int64_t
     const unsigned n = (unsigned)count;
     if (h->cfg.form == SSE_FORM_FLUX_DIFFERENCING) {
         if (h->variant == 1 && h->ct.ok) {
-            ct_fluxdiff(h->ct, h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream, rk);
+            ct_fluxdiff(h->ct, h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream, rk, mid);
+            h->launches += 1;       // pair kernel + projection kernel
         } else if (use_tensor(h) && h->tp.has_fluxdiff) {
 #define LA(D_, NC_) tensor_launch_fluxdiff<D_, NC_>(h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->sm_count, h->stream)
             DISPATCH_DNC(h, LA);
@@ -643,7 +658,8 @@ static int32_t pass_b_impl(sse_handle* h, double* d_dudt, int64_t first, int64_t
 #undef LA
         }
     } else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE && h->variant == 1 && h->ct.ok && h->ct.kind == 1) {
-        ct_standard(h->ct, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream, rk);
+        ct_standard(h->ct, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream, rk, mid);
+        h->launches += 1;
     } else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE) {
 #define LA(D_, NC_) k_time_standard_reference<D_, NC_><<<n, h->threads, h->smem_time, h->stream>>>(h->ops, h->geo, h->law, first, h->u_q, h->u_f, d_dudt)
         DISPATCH_DNC(h, LA);
@@ -653,6 +669,7 @@ static int32_t pass_b_impl(sse_handle* h, double* d_dudt, int64_t first, int64_t
         DISPATCH_DNC(h, LA);
 #undef LA
     }
+    h->launches += 1;
     CU(cudaGetLastError());
     return SSE_OK;
 }
@@ -660,7 +677,7 @@ static int32_t pass_b_impl(sse_handle* h, double* d_dudt, int64_t first, int64_t
 extern "C" int32_t sse_rhs(sse_handle* h, const double* d_u, double* d_dudt, double t) {
     (void)t;   // no method of the reference uses t (Solvers.jl:474-564)
     if (!h) return fail(SSE_ERR_BAD_ARGUMENT, "null handle");
-    if (h->cfg.N_ghost != 0) return fail(SSE_ERR_COMM, "handle has ghost facets: drive pass_a / halo exchange / pass_b explicitly");
+    if (h->cfg.N_ghost != 0) return dist_rhs(h, d_u, d_dudt, RkStage());      // element-partitioned handle: comm.cu
     int32_t rc;
     if ((rc = sse_rhs_pass_a(h, d_u))) return rc;
     if ((rc = sse_rhs_pass_aux(h, d_dudt, 0, h->cfg.N_e))) return rc;
@@ -685,13 +702,14 @@ extern "C" int32_t sse_rhs_host(sse_handle* h, const double* h_u, double* h_dudt
         CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
     }
     double *d_u = h->h2d_u, *d_du = h->d2h_du;
+    if (h->cfg.N_ghost != 0 && !h->second_order && h->comm.planned) return dist_rhs_host(h, h_u, h_dudt, d_u, d_du, chunks);
     if (chunks <= 0) chunks = 48;        // measured on B200 + PCIe 5: 35.4 ms at 48 ranges against 39.8 (16) and 37.3 (64 and up) for 1 053 696 elements
     if (h->second_order || h->cfg.N_ghost || chunks == 1 || ne < 4 * (long long)chunks) {
         CU(cudaMemcpyAsync(d_u, h_u, total * sizeof(double), cudaMemcpyHostToDevice, h->stream));
         if ((rc = sse_rhs(h, d_u, d_du, t))) return rc;
         CU(cudaMemcpyAsync(h_dudt, d_du, total * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        return SSE_OK;
+        return check_flag(h);
     }
     while (h->events.size() < (size_t)(2 * chunks + 2)) {
         cudaEvent_t e;
@@ -727,7 +745,7 @@ extern "C" int32_t sse_rhs_host(sse_handle* h, const double* h_u, double* h_dudt
     CU(cudaEventRecord(e_done, h->s_out));
     CU(cudaStreamWaitEvent(h->stream, e_done, 0));
     CU(cudaStreamSynchronize(h->stream));
-    return SSE_OK;
+    return check_flag(h);
 }
 // page-lock / release a host array for the asynchronous copies of sse_rhs_host (cudaHostRegister)
 extern "C" int32_t sse_host_pin(void* p, int64_t bytes) {
@@ -766,6 +784,7 @@ extern "C" int32_t sse_halo_pack(sse_handle* h, int32_t which) {
     const int nv = halo_nvar(h, which);
     const long long n = h->n_send * nv;
     k_halo_pack<<<(unsigned)std::min<long long>((n + 255) / 256, 4096), 256, 0, h->stream>>>(h->n_send, nv, h->geo.NFT, h->d_send_idx, which ? h->q_f : h->u_f, h->d_send);
+    h->launches += 1;
     CU(cudaGetLastError());
     return SSE_OK;
 }
@@ -776,6 +795,7 @@ extern "C" int32_t sse_halo_unpack(sse_handle* h, int32_t which) {
     const int nv = halo_nvar(h, which);
     const long long n = h->cfg.N_ghost * nv;
     k_halo_unpack<<<(unsigned)std::min<long long>((n + 255) / 256, 4096), 256, 0, h->stream>>>(h->cfg.N_ghost, nv, h->geo.NFT, (long long)h->cfg.N_f * h->cfg.N_e, h->d_recv, which ? h->q_f : h->u_f);
+    h->launches += 1;
     CU(cudaGetLastError());
     return SSE_OK;
 }
@@ -796,6 +816,7 @@ extern "C" int32_t sse_axpby(sse_handle* h, double a, const double* d_x, double 
     CU(cudaSetDevice(h->device));
     const long long n = (long long)state_len(h);
     k_axpby<<<(unsigned)std::min<long long>((n + 255) / 256, 8 * h->sm_count), 256, 0, h->stream>>>(n, a, d_x, b, d_y);
+    h->launches += 1;
     CU(cudaGetLastError());
     return SSE_OK;
 }
@@ -804,6 +825,7 @@ extern "C" int32_t sse_lsrk_stage(sse_handle* h, double* d_u, double* d_tmp, con
     CU(cudaSetDevice(h->device));
     const long long n = (long long)state_len(h);
     k_lsrk_stage<<<(unsigned)std::min<long long>((n + 255) / 256, 8 * h->sm_count), 256, 0, h->stream>>>(n, d_u, d_tmp, d_dudt, A, B, dt);
+    h->launches += 1;
     CU(cudaGetLastError());
     return SSE_OK;
 }
@@ -820,14 +842,17 @@ static const double CK_C[5] = {0.0, 1432997174477.0 / 9575080441755.0, 252626934
 extern "C" int32_t sse_rhs_lsrk(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double A, double B, double dt, double t) {
     (void)t;
     if (!h || !d_u || !d_tmp || !d_dudt) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
-    if (h->cfg.N_ghost != 0) return fail(SSE_ERR_COMM, "handle has ghost facets: drive pass_a / halo exchange / pass_b explicitly");
     int32_t rc;
-    if ((rc = sse_rhs_pass_a(h, d_u))) return rc;
-    if ((rc = sse_rhs_pass_aux(h, d_dudt, 0, h->cfg.N_e))) return rc;
     const bool fused = h->variant == 1 && h->ct.ok;
     RkStage rk;
     if (fused) { rk.u = d_u; rk.tmp = d_tmp; rk.A = A; rk.B = B; rk.dt = dt; }
-    if ((rc = pass_b_impl(h, d_dudt, 0, h->cfg.N_e, rk))) return rc;
+    if (h->cfg.N_ghost != 0) {
+        if ((rc = dist_rhs(h, d_u, d_dudt, rk))) return rc;
+    } else {
+        if ((rc = sse_rhs_pass_a(h, d_u))) return rc;
+        if ((rc = sse_rhs_pass_aux(h, d_dudt, 0, h->cfg.N_e))) return rc;
+        if ((rc = pass_b_stage(h, d_dudt, 0, h->cfg.N_e, rk))) return rc;
+    }
     if (!fused) return sse_lsrk_stage(h, d_u, d_tmp, d_dudt, A, B, dt);
     return SSE_OK;
 }
@@ -944,11 +969,15 @@ extern "C" int32_t sse_functionals(sse_handle* h, const double* d_u, const doubl
     unsigned grid = (unsigned)std::min<long long>(h->cfg.N_e, 4LL * h->sm_count);
 #define LA(D_, NC_)                                                                                                  \
     do {                                                                                                             \
-        cudaFuncSetAttribute(k_functionals<D_, NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+        cudaFuncSetAttribute(k_functionals<D_, NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN_MAX);  \
         k_functionals<D_, NC_><<<grid, 128, smem, h->stream>>>(h->ops, h->geo, h->law, d_u, d_dudt, d_out);           \
     } while (0)
     DISPATCH_DNC(h, LA);
 #undef LA
+    h->launches += 1;
+    // element-partitioned handles: the functionals are sums over all ranks (every rank calls, every rank gets the total)
+    const int32_t rc_red = dist_allreduce_sum(h, d_out, NC + 2);
+    if (rc_red) { cudaFree(d_out); return rc_red; }
     cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(double) * (NC + 2), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(d_out);
@@ -1032,6 +1061,38 @@ extern "C" int32_t sse_geometric_factors(const sse_geom_config* c, const sse_geo
     return SSE_OK;
 }
 
+// One residual with a CUDA event between every kernel, `reps` times: ms[0] pass A, ms[1] auxiliary pass (BR1), ms[2] first
+// kernel of pass B (on the compile-time paths the pair / derivative kernel), ms[3] second kernel of pass B (the projection
+// kernel; 0 where pass B is one kernel).  Averages over the repetitions; blocking.  bench.py's per-kernel roofline uses it.
+extern "C" int32_t sse_profile_rhs(sse_handle* h, const double* d_u, double* d_dudt, int32_t reps, double* ms) {
+    if (!h || !d_u || !d_dudt || !ms || reps < 1) return fail(SSE_ERR_BAD_ARGUMENT, "bad argument");
+    if (h->cfg.N_ghost != 0) return fail(SSE_ERR_UNSUPPORTED, "sse_profile_rhs times the kernels of a single-GPU handle");
+    CU(cudaSetDevice(h->device));
+    cudaEvent_t e[5];
+    for (int i = 0; i < 5; i++) CU(cudaEventCreate(&e[i]));
+    for (int i = 0; i < 4; i++) ms[i] = 0.0;
+    int32_t rc = SSE_OK;
+    const bool two = h->variant == 1 && h->ct.ok;
+    for (int r = 0; r < reps && rc == SSE_OK; r++) {
+        cudaEventRecord(e[0], h->stream);
+        if ((rc = sse_rhs_pass_a(h, d_u))) break;
+        cudaEventRecord(e[1], h->stream);
+        if ((rc = sse_rhs_pass_aux(h, d_dudt, 0, h->cfg.N_e))) break;
+        cudaEventRecord(e[2], h->stream);
+        if ((rc = pass_b_stage(h, d_dudt, 0, h->cfg.N_e, RkStage(), two ? e[3] : nullptr))) break;
+        if (!two) cudaEventRecord(e[3], h->stream);
+        cudaEventRecord(e[4], h->stream);
+        if (cudaEventSynchronize(e[4]) != cudaSuccess) { rc = fail(SSE_ERR_CUDA, "profile run failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+        for (int i = 0; i < 4; i++) { float t = 0; cudaEventElapsedTime(&t, e[i], e[i + 1]); ms[i] += t / reps; }
+    }
+    for (int i = 0; i < 5; i++) cudaEventDestroy(e[i]);
+    return rc;
+}
+extern "C" int32_t sse_launch_count(const sse_handle* h, int64_t* n) {
+    if (!h || !n) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    *n = h->launches;
+    return SSE_OK;
+}
 extern "C" int32_t sse_debug_views(sse_handle* h, double** d_u_q, double** d_u_f) {
     if (!h) return fail(SSE_ERR_BAD_ARGUMENT, "null handle");
     if (d_u_q) *d_u_q = h->u_q;

@@ -41,6 +41,15 @@ SYMBOLS = {
     "sse_halo_send_buffer": (C.c_int32, [_h, _ppd, _pi64]),
     "sse_halo_recv_buffer": (C.c_int32, [_h, C.c_int32, _ppd, _pi64]),
     "sse_halo_unpack": (C.c_int32, [_h, C.c_int32]),
+    "sse_comm_unique_id": (C.c_int32, [C.c_void_p]),
+    "sse_comm_init": (C.c_int32, [_h, C.c_void_p, C.c_int32, C.c_int32]),
+    "sse_comm_init_all": (C.c_int32, [C.POINTER(_h), C.c_int32]),
+    "sse_comm_init_local": (C.c_int32, [C.POINTER(_h), C.c_int32]),
+    "sse_comm_info": (C.c_int32, [_h, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "sse_halo_plan": (C.c_int32, [_h, C.c_int32, C.POINTER(C.c_int32), _pi64, _pi64, _pi64, C.c_int64]),
+    "sse_rhs_multi": (C.c_int32, [C.POINTER(_h), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double]),
+    "sse_step_ck54_multi": (C.c_int32, [C.POINTER(_h), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), C.c_double, C.c_double]),
     "sse_axpby": (C.c_int32, [_h, C.c_double, C.c_void_p, C.c_double, C.c_void_p]),
     "sse_lsrk_stage": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double]),
     "sse_rhs_lsrk": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]),
@@ -49,6 +58,8 @@ SYMBOLS = {
     "sse_synchronize": (C.c_int32, [_h]),
     "sse_last_error_string": (C.c_char_p, []),
     "sse_abi_version": (C.c_int32, []),
+    "sse_profile_rhs": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_int32, _pd]),
+    "sse_launch_count": (C.c_int32, [_h, _pi64]),
     "sse_debug_views": (C.c_int32, [_h, _ppd, _ppd]),
     "sse_plan_selfcheck": (C.c_int32, [C.POINTER(_abi.sse_config), C.POINTER(_abi.sse_arrays), C.POINTER(C.c_int32), _pd]),
     "sse_fp64_peak": (C.c_int32, [C.c_int32, _pd]),

@@ -2,11 +2,10 @@
 
 The reference has no distributed path; the only cross-element coupling of
 `semi_discrete_residual!` is the gather of neighbour facet states through `mesh.mapP`
-between the two element loops (Solvers.jl:505-511), so the exchange step is: pack the cut
-faces' `u_f` after pass A, point-to-point send/recv to the slab neighbours (NCCL over
-NVLink via torch.distributed; gloo in the CPU tests), unpack into the ghost slots, run
-pass B.  Pass B on interior elements is enqueued before the receive completes so the
-transfer hides behind it.
+between the two element loops (Solvers.jl:505-511).  On the GPU the whole exchange runs inside
+libsse_b200.so (csrc/comm.cu); `DistributedSolver` is the thin caller.  `HaloExchanger` is the
+same neighbour exchange on torch tensors, kept for the CPU (gloo) tests of the partition logic
+and for callers that run their own exchange through the split entry points.
 """
 from __future__ import annotations
 
@@ -53,118 +52,35 @@ def exchanger_from_mesh(mesh, group=None) -> HaloExchanger:
 
 
 class DistributedSolver:
-    """Rank-local Solver + halo exchange.  `solver` must be built from a partitioned mesh
+    """Rank-local Solver of an element partition.  The exchange itself lives in the library (csrc/comm.cu: NCCL send/recv on a
+    side stream inside sse_rhs / sse_rhs_lsrk / sse_step_ck54 / sse_rhs_host, all-reduce inside sse_functionals); this class
+    only forms the communicator -- the NCCL unique id of rank 0 travels through torch.distributed, the host's own launcher --
+    and hands the mesh's halo plan to the handle.  `solver` must be built from a partitioned mesh
     (uniform_periodic_mesh(..., part=(rank, world)))."""
 
     def __init__(self, solver, mesh, group=None):
-        import torch
+        import torch.distributed as dist
         self.s, self.mesh, self.group = solver, mesh, group
-        send_idx = np.concatenate(mesh.send_idx) if mesh.send_idx else np.zeros(0, dtype=np.int64)
-        solver.halo_configure(send_idx + 1)
-        self.ex = exchanger_from_mesh(mesh, group)
-        self.second = bool(solver.image.law.second_order)
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world > 1:
+            box = [solver.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            solver.comm_init(box[0], rank, world)
+        solver.halo_plan(mesh)
         self.n_int = mesh.N_e - mesh.n_boundary
-        self.comm_stream = torch.cuda.Stream(device=solver.device)
-        self.nc = int(solver.cfg.N_c)
-        self.d = int(solver.cfg.d)
-
-    def _exchange(self, which: int):
-        """pack on the compute stream, send/recv on the comm stream; returns an event that marks
-        ghost data ready in the recv staging buffer."""
-        import torch
-        s = self.s
-        s.halo_pack(which)
-        send, recv = s.halo_buffers(which)
-        cur = torch.cuda.current_stream(s.device)
-        packed = torch.cuda.Event()
-        packed.record(cur)
-        with torch.cuda.stream(self.comm_stream):
-            self.comm_stream.wait_event(packed)
-            reqs = self.ex.start(send, recv, self.nc * (self.d if which else 1))
-            HaloExchanger.finish(reqs)
-            done = torch.cuda.Event()
-            done.record(self.comm_stream)
-        return done
 
     def rhs(self, dudt, u, t: float = 0.0):
-        import torch
-        s = self.s
-        cur = torch.cuda.current_stream(s.device)
-        s.pass_a(u)
-        done = self._exchange(0)
-        if self.second:
-            s.pass_aux(dudt, 0, self.n_int)
-            cur.wait_event(done)
-            s.halo_unpack(0)
-            s.pass_aux(dudt, self.n_int, self.mesh.n_boundary)
-            done = self._exchange(1)
-            s.pass_b(dudt, 0, self.n_int)
-            cur.wait_event(done)
-            s.halo_unpack(1)
-            s.pass_b(dudt, self.n_int, self.mesh.n_boundary)
-        else:
-            s.pass_b(dudt, 0, self.n_int)                 # interior elements overlap the transfer
-            cur.wait_event(done)
-            s.halo_unpack(0)
-            s.pass_b(dudt, self.n_int, self.mesh.n_boundary)
-        return dudt
+        return self.s.rhs(dudt, u, t)
 
-    def rhs_host(self, dudt_host, u_host, t: float = 0.0, chunks: int = 8):
-        """Residual on this rank's HOST buffers (pinned torch CPU tensors): the boundary elements are uploaded and put
-        through pass A first so that the facet halos travel while the interior ranges are uploaded; pass B of an
-        interior range starts as soon as pass A has covered its face neighbours (mapP) and its dudt is downloaded while
-        later ranges are still arriving; the boundary elements finish after the halo has been unpacked."""
-        import torch
-        from .solver import range_plan
-        s, ne, nb, n_int = self.s, self.mesh.N_e, self.mesh.n_boundary, self.n_int
-        if self.second or nb == 0 or n_int < 4 * chunks:
-            d_u, d_du = self._host_state()
-            d_u.copy_(u_host, non_blocking=True)
-            self.rhs(d_du, d_u, t)
-            dudt_host.copy_(d_du, non_blocking=True)
-            torch.cuda.current_stream(s.device).synchronize()
-            return dudt_host
-        d_u, d_du = self._host_state()
-        if getattr(self, "_plan", None) is None or self._plan[0] != chunks:
-            ranges = [(n_int, ne)] + [(n_int * c // chunks, n_int * (c + 1) // chunks) for c in range(chunks)]
-            self._plan = (chunks, ranges, range_plan(s.image.arrays["mapP"], ne, int(s.cfg.N_f), ranges))
-            self._copy_in, self._copy_out = torch.cuda.Stream(device=s.device), torch.cuda.Stream(device=s.device)
-        _, ranges, after = self._plan
-        cur = torch.cuda.current_stream(s.device)
-        cin, cout = self._copy_in, self._copy_out
-        cin.wait_stream(cur)
-        cout.wait_stream(cur)
+    def rhs_host(self, dudt_host, u_host, t: float = 0.0, chunks: int = 0):
+        """Residual on this rank's HOST buffers (pinned torch CPU tensors): one sse_rhs_host; the library uploads the
+        halo-adjacent elements first so that the halos travel while the interior ranges are uploaded."""
+        return self.s.rhs_host(dudt_host, u_host, t, chunks)
 
-        def pass_b_and_download(a, b):
-            s.pass_b(d_du, a, b - a)
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            with torch.cuda.stream(cout):
-                cout.wait_event(ev)
-                dudt_host[a:b].copy_(d_du[a:b], non_blocking=True)
+    def step_ck54(self, u, tmp, dudt, t, dt):
+        return self.s.step_ck54(u, tmp, dudt, t, dt)
 
-        done = None
-        for i, (a, b) in enumerate(ranges):
-            with torch.cuda.stream(cin):
-                d_u[a:b].copy_(u_host[a:b], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(cin)
-            cur.wait_event(ev)
-            s.pass_a_range(d_u, a, b - a)
-            if i == 0:
-                done = self._exchange(0)                 # boundary facets are complete: halos travel from here on
-            for k in after[i]:
-                if k:
-                    pass_b_and_download(*ranges[k])
-        cur.wait_event(done)
-        s.halo_unpack(0)
-        pass_b_and_download(*ranges[0])
-        cur.wait_stream(cout)
-        cur.wait_stream(cin)
-        cur.synchronize()
-        return dudt_host
-
-    def _host_state(self):
-        if getattr(self, "_hs", None) is None:
-            self._hs = (self.s.new_state(), self.s.new_state())
-        return self._hs
+    def functionals(self, u, dudt):
+        """Global conservation / energy / entropy residuals (all-reduced inside the library)."""
+        return self.s.functionals(u, dudt)

@@ -58,8 +58,6 @@ class Solver:
         arr = image.c_arrays()
         _lib.check(self._lib.sse_create(C.byref(image.cfg), C.byref(arr), device, C.byref(self._h)))
         self._pinned = {}
-        self.launches = 0      # kernels launched through this handle (for bench accounting)
-        self._refresh_launch_counts()
 
     # -- plumbing ------------------------------------------------------------------------
     def close(self):
@@ -90,14 +88,15 @@ class Solver:
         s = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self._lib.sse_set_stream(self._h, C.c_void_p(s)))
 
-    def _refresh_launch_counts(self):
-        # the compile-time path runs pass B as two kernels (pair kernel + projection)
-        self._pass_b = 2 if self.kernel_variant() == 2 else 1
-        self._per_rhs = 1 + self._pass_b + (1 if self.image.law.second_order else 0)
+    @property
+    def launches(self) -> int:
+        """Kernels launched through this handle, counted by the library at its launch sites (bench accounting)."""
+        n = C.c_int64(0)
+        _lib.check(self._lib.sse_launch_count(self._h, C.byref(n)))
+        return int(n.value)
 
     def set_kernel_variant(self, v: int):
         _lib.check(self._lib.sse_set_kernel_variant(self._h, v))
-        self._refresh_launch_counts()
 
     def kernel_variant(self) -> int:
         v = C.c_int32(0)
@@ -115,24 +114,19 @@ class Solver:
     # -- the path ------------------------------------------------------------------------
     def rhs(self, dudt, u, t: float = 0.0):
         _lib.check(self._lib.sse_rhs(self._h, self._check_state(u, "u"), self._check_state(dudt, "dudt"), float(t)))
-        self.launches += self._per_rhs
         return dudt
 
     def pass_a(self, u):
         _lib.check(self._lib.sse_rhs_pass_a(self._h, self._check_state(u, "u")))
-        self.launches += 1
 
     def pass_aux(self, dudt, first, count):
         _lib.check(self._lib.sse_rhs_pass_aux(self._h, self._check_state(dudt, "dudt"), first, count))
-        self.launches += 1 if (count > 0 and self.image.law.second_order) else 0
 
     def pass_b(self, dudt, first, count):
         _lib.check(self._lib.sse_rhs_pass_b(self._h, self._check_state(dudt, "dudt"), first, count))
-        self.launches += self._pass_b if count > 0 else 0
 
     def pass_a_range(self, u, first, count):
         _lib.check(self._lib.sse_rhs_pass_a_range(self._h, self._check_state(u, "u"), first, count))
-        self.launches += 1 if count > 0 else 0
 
     def _chunk_plan(self, chunks: int):
         key = ("plan", chunks)
@@ -161,35 +155,32 @@ class Solver:
             if x.is_cuda or x.dtype != torch.float64 or tuple(x.shape) != tuple(self.state_shape) or not x.is_contiguous():
                 raise ValueError(f"{name}: expected a contiguous float64 CPU tensor of shape {self.state_shape}")
         _lib.check(self._lib.sse_rhs_host(self._h, C.c_void_p(src.data_ptr()), C.c_void_p(dst.data_ptr()), float(t), int(chunks)))
-        ne = self.state_shape[0]
-        used = int(chunks) if chunks > 0 else 48
-        if self.image.law.second_order or int(self.cfg.N_ghost) or used == 1 or ne < 4 * used:
-            self.launches += self._per_rhs
-        else:
-            self.launches += used * (1 + self._pass_b)
         if isinstance(u_host, np.ndarray):
             dudt_host[...] = dst.numpy()
         return dudt_host
 
     def axpby(self, a, x, b, y):
         _lib.check(self._lib.sse_axpby(self._h, a, self._check_state(x, "x"), b, self._check_state(y, "y")))
-        self.launches += 1
 
     def lsrk_stage(self, u, tmp, dudt, A, B, dt):
         _lib.check(self._lib.sse_lsrk_stage(self._h, self._check_state(u, "u"), self._check_state(tmp, "tmp"),
                                             self._check_state(dudt, "dudt"), A, B, dt))
-        self.launches += 1
 
     def rhs_lsrk(self, u, tmp, dudt, A, B, dt, t=0.0):
         """Residual + one 2N-storage RK stage (fused on the compile-time kernel path)."""
         _lib.check(self._lib.sse_rhs_lsrk(self._h, self._check_state(u, "u"), self._check_state(tmp, "tmp"),
                                           self._check_state(dudt, "dudt"), A, B, dt, float(t)))
-        self.launches += self._per_rhs + (0 if self.kernel_variant() == 2 else 1)
 
     def step_ck54(self, u, tmp, dudt, t, dt):
         _lib.check(self._lib.sse_step_ck54(self._h, self._check_state(u, "u"), self._check_state(tmp, "tmp"),
                                            self._check_state(dudt, "dudt"), t, dt))
-        self.launches += 5 * (self._per_rhs + (0 if self.kernel_variant() == 2 else 1))
+
+    def profile_rhs(self, dudt, u, reps: int = 5) -> np.ndarray:
+        """Milliseconds of [pass A, auxiliary pass, pass B first kernel, pass B second kernel] (CUDA events between the kernels)."""
+        ms = np.zeros(4)
+        _lib.check(self._lib.sse_profile_rhs(self._h, self._check_state(u, "u"), self._check_state(dudt, "dudt"), int(reps),
+                                             ms.ctypes.data_as(C.POINTER(C.c_double))))
+        return ms
 
     def functionals(self, u, dudt) -> np.ndarray:
         out = np.zeros(int(self.cfg.N_c) + 2)
@@ -212,7 +203,63 @@ class Solver:
         uf = torch.as_tensor(_DevView(C.cast(pf, C.c_void_p).value, nft * int(c.N_c)), device=f"cuda:{self.device}")
         return uq.view(int(c.N_e), int(c.N_c), int(c.N_q)), uf.view(int(c.N_c), nft)
 
-    # -- halo buffers (multi-GPU) ----------------------------------------------------------
+    # -- multi-GPU: the exchange lives in the library (csrc/comm.cu) --------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        _lib.check(_lib.load().sse_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _lib.check(self._lib.sse_comm_init(self._h, buf, int(rank), int(world)))
+
+    @staticmethod
+    def comm_init_all(solvers):
+        hs = (C.c_void_p * len(solvers))(*[s._h for s in solvers])
+        _lib.check(_lib.load().sse_comm_init_all(hs, len(solvers)))
+
+    @staticmethod
+    def comm_init_local(solvers):
+        hs = (C.c_void_p * len(solvers))(*[s._h for s in solvers])
+        _lib.check(_lib.load().sse_comm_init_local(hs, len(solvers)))
+
+    def comm_info(self):
+        r, w, v = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        _lib.check(self._lib.sse_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        return int(r.value), int(w.value), int(v.value)
+
+    def halo_plan(self, mesh):
+        """The halo plan of a partitioned mesh (mesh.nbr_ranks / send_idx / recv_off / n_boundary)."""
+        nbr = np.asarray(mesh.nbr_ranks or [], dtype=np.int32)
+        sc = np.asarray([int(x.size) for x in (mesh.send_idx or [])], dtype=np.int64)
+        offs = list(mesh.recv_off or []) + [int(mesh.n_ghost)]
+        rc = np.asarray([offs[i + 1] - offs[i] for i in range(nbr.size)], dtype=np.int64)
+        idx = (np.concatenate(mesh.send_idx) if nbr.size else np.zeros(0, dtype=np.int64)) + 1
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        p32, p64 = C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        _lib.check(self._lib.sse_halo_plan(self._h, int(nbr.size), nbr.ctypes.data_as(p32), sc.ctypes.data_as(p64),
+                                           rc.ctypes.data_as(p64), idx.ctypes.data_as(p64),
+                                           int(mesh.N_e - mesh.n_boundary)))
+
+    @staticmethod
+    def rhs_multi(solvers, dudts, us, t: float = 0.0):
+        """One process driving several GPUs: the residual on all partitions (sse_rhs_multi)."""
+        n = len(solvers)
+        hs = (C.c_void_p * n)(*[s._h for s in solvers])
+        pu = (C.c_void_p * n)(*[s._check_state(u, "u").value for s, u in zip(solvers, us)])
+        pd = (C.c_void_p * n)(*[s._check_state(d, "dudt").value for s, d in zip(solvers, dudts)])
+        _lib.check(_lib.load().sse_rhs_multi(hs, n, pu, pd, float(t)))
+        return dudts
+
+    @staticmethod
+    def step_ck54_multi(solvers, us, tmps, dudts, t, dt):
+        n = len(solvers)
+        hs = (C.c_void_p * n)(*[s._h for s in solvers])
+        arr = lambda xs, nm: (C.c_void_p * n)(*[s._check_state(x, nm).value for s, x in zip(solvers, xs)])
+        _lib.check(_lib.load().sse_step_ck54_multi(hs, n, arr(us, "u"), arr(tmps, "tmp"), arr(dudts, "dudt"), float(t), float(dt)))
+
+    # -- halo buffers (split form: a caller that runs its own exchange) -----------------------------
     def halo_configure(self, send_index_1based: np.ndarray):
         idx = np.ascontiguousarray(send_index_1based, dtype=np.int64)
         _lib.check(self._lib.sse_halo_configure(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size))
@@ -231,11 +278,9 @@ class Solver:
 
     def halo_pack(self, which: int = 0):
         _lib.check(self._lib.sse_halo_pack(self._h, which))
-        self.launches += 1
 
     def halo_unpack(self, which: int = 0):
         _lib.check(self._lib.sse_halo_unpack(self._h, which))
-        self.launches += 1
 
 
 def range_plan(mapP_1based, ne: int, nf: int, ranges):

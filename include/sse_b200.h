@@ -147,7 +147,11 @@ int32_t sse_state_upload(sse_handle* h, double* d_dst, const double* h_src);
 int32_t sse_state_download(sse_handle* h, double* h_dst, const double* d_src);
 
 /* -- the hot path ------------------------------------------------------------------------------ */
-/* semi_discrete_residual!(dudt, u, solver, t)  (Solvers.jl:474-564).  Single GPU: all passes. */
+/* semi_discrete_residual!(dudt, u, solver, t)  (Solvers.jl:474-564): all passes.  On an element-partitioned handle
+   (N_ghost > 0, after sse_comm_init + sse_halo_plan) the same call also runs the facet-trace halo exchange of its rank
+   (NCCL send/recv on a side stream, overlapped with pass B of the interior elements); every rank calls it.
+   Non-physical states: a residual entry that is NaN / Inf raises a device flag; the next blocking call on the handle
+   (sse_synchronize, sse_state_download, sse_rhs_host) returns SSE_ERR_NONFINITE once -- the reference's DomainError. */
 int32_t sse_rhs(sse_handle* h, const double* d_u, double* d_dudt, double t);
 
 /* The same call on HOST arrays (`Array{Float64,3}` arguments, as OrdinaryDiffEq passes CPU state to
@@ -159,10 +163,13 @@ int32_t sse_rhs_host(sse_handle* h, const double* h_u, double* h_dudt, double t,
 int32_t sse_host_range_plan(const int64_t* mapP, int64_t N_e, int32_t N_f, int32_t N_fac, int32_t chunks, int32_t* order, int32_t* ready);
 int32_t sse_host_pin(void* p, int64_t bytes);
 int32_t sse_host_unpin(void* p);
-/* Split form used by the multi-GPU driver.  Pass A (nodal_values!, Solvers.jl:505-507)
+/* Split form (what sse_rhs is made of; also lets a caller run its own exchange).  Pass A (nodal_values!, Solvers.jl:505-507)
    fills u_q and the owned part of u_f and packs the halo send buffer; the caller exchanges halos
    (NCCL) into sse_halo_recv_buffer; pass B (time_derivative!, Solvers.jl:509-511) runs on the
    element range [first, first+count).  Second-order laws have an extra aux pass + exchange. */
+/* Contract of the split form: pass B of an element range consumes the u_q scratch pass A wrote for it (the compile-time
+   kernels overwrite it with r_q, as the reference reuses u_q[:,:,k], flux_differencing_form.jl:341-346).  Pass B is therefore
+   NOT idempotent: run pass A again before repeating pass B on a range; after pass B sse_debug_views shows r_q, not u_q. */
 int32_t sse_rhs_pass_a(sse_handle* h, const double* d_u);
 /* pass A on the element range [first, first+count): lets a host-buffer caller overlap the upload of u with pass A */
 int32_t sse_rhs_pass_a_range(sse_handle* h, const double* d_u, int64_t first, int64_t count);
@@ -175,6 +182,33 @@ int32_t sse_halo_send_buffer(sse_handle* h, double** d_buf, int64_t* n_doubles);
 int32_t sse_halo_recv_buffer(sse_handle* h, int32_t which, double** d_buf, int64_t* n_doubles);
 int32_t sse_halo_unpack(sse_handle* h, int32_t which);
 
+/* -- multi-GPU (SURVEY.md §8b "Threading", §8e): elements partitioned over GPUs, facet-trace halos only --------------------
+   The reference's plug-in point is the `parallelism` kwarg of semidiscretize (Solvers.jl:438) and the element loops of
+   Solvers.jl:495-514; a handle built from a partition (N_ghost > 0, elements ordered interior first, mapP rewritten to
+   local + ghost numbering) joins a communicator and then behaves like a single-GPU handle: sse_rhs, sse_rhs_lsrk,
+   sse_step_ck54, sse_rhs_host and sse_functionals (which all-reduces) are collective over the ranks.
+   (a) one process per GPU: rank 0 calls sse_comm_unique_id, the host broadcasts the 128 bytes (MPI.jl, Distributed.jl,
+       torch.distributed ...), every rank calls sse_comm_init;
+   (b) one process driving N GPUs (the Julia host stays one process): sse_comm_init_all over the N handles, then
+       sse_rhs_multi / sse_step_ck54_multi advance all of them from the single host thread.
+   NCCL is loaded at run time (libnccl.so.2, or $SSE_NCCL_LIB); a partition onto one rank needs no NCCL at all. */
+int32_t sse_comm_unique_id(uint8_t* id128);
+int32_t sse_comm_init(sse_handle* h, const uint8_t* id128, int32_t rank, int32_t world);
+int32_t sse_comm_init_all(sse_handle* const* handles, int32_t n);
+/* (b) without NCCL: the handles of one process exchange their halos by peer-to-peer copies (two partitions may share a GPU) */
+int32_t sse_comm_init_local(sse_handle* const* handles, int32_t n);
+int32_t sse_comm_info(const sse_handle* h, int32_t* rank, int32_t* world, int32_t* nccl_version);
+/* Halo plan of this rank: neighbour ranks, facet nodes sent to / received from each (the receive segments are the ghost slots
+   in order, their sum is N_ghost), the concatenated send list (1-based linear indices into the owned (N_f, N_e) facet array)
+   and the number of interior elements: elements [0, n_interior) read no ghost slot (verified against mapP). */
+int32_t sse_halo_plan(sse_handle* h, int32_t n_nbr, const int32_t* nbr_rank, const int64_t* send_count, const int64_t* recv_count,
+                      const int64_t* send_index, int64_t n_interior);
+/* (b): the residual / one CarpenterKennedy2N54 step on all handles of one process; d_u[i], d_tmp[i], d_dudt[i] live on the
+   device of handles[i].  The halo exchanges of all handles form one NCCL group. */
+int32_t sse_rhs_multi(sse_handle* const* handles, int32_t n, double* const* d_u, double* const* d_dudt, double t);
+int32_t sse_step_ck54_multi(sse_handle* const* handles, int32_t n, double* const* d_u, double* const* d_tmp, double* const* d_dudt,
+                            double t, double dt);
+
 /* -- callers either side of the path ----------------------------------------- */
 /* y = a*x + b*y on state vectors (OrdinaryDiffEq broadcast updates) */
 int32_t sse_axpby(sse_handle* h, double a, const double* d_x, double b, double* d_y);
@@ -184,17 +218,23 @@ int32_t sse_lsrk_stage(sse_handle* h, double* d_u, double* d_tmp, const double* 
 /* semi_discrete_residual! + one 2N-storage stage in one call; on the compile-time kernel path the stage update is fused
    into the epilogue of the projection kernel, so the state is updated where dudt is produced */
 int32_t sse_rhs_lsrk(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double A, double B, double dt, double t);
-/* one full CarpenterKennedy2N54 step on device (single GPU) */
+/* one full CarpenterKennedy2N54 step on device (collective on element-partitioned handles, like sse_rhs) */
 int32_t sse_step_ck54(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double t, double dt);
 /* conservation / energy / entropy residuals of Analysis/conservation.jl:145-189.
    out[0..N_c-1] = sum_k 1' WJ_k V dudt[:,e,k];  out[N_c] = sum_k u_k' M_k dudt_k (energy);
-   out[N_c+1] = sum_k (P_k w(V u_k))' M_k dudt_k (entropy; Euler only, else 0).  Blocking. */
+   out[N_c+1] = sum_k (P_k w(V u_k))' M_k dudt_k (entropy; Euler only, else 0).  Blocking.  With a communicator the sums
+   run over all ranks (NCCL all-reduce; every rank calls and receives the totals). */
 int32_t sse_functionals(sse_handle* h, const double* d_u, const double* d_dudt, double* out);
 
 /* -- misc -------------------------------------------------------------------------------------- */
 int32_t sse_synchronize(sse_handle* h);
 const char* sse_last_error_string(void);
 int32_t sse_abi_version(void);
+/* one residual with a CUDA event between every kernel, averaged over `reps` runs: ms[0] pass A, ms[1] auxiliary pass (BR1),
+   ms[2] first kernel of pass B (pair / derivative kernel), ms[3] second kernel of pass B (projection; 0 if pass B is one kernel) */
+int32_t sse_profile_rhs(sse_handle* h, const double* d_u, double* d_dudt, int32_t reps, double* ms);
+/* kernels launched through this handle so far (bench.py's gpu_launches) */
+int32_t sse_launch_count(const sse_handle* h, int64_t* n);
 /* scratch views for testing/analysis: u_q (N_q,N_c,N_e) and u_f (N_f,N_e+ghost,N_c) device pointers */
 int32_t sse_debug_views(sse_handle* h, double** d_u_q, double** d_u_f);
 /* host-only diagnostic: build the tensor-line pair schedule for (cfg, arr) and replay it against S and C.

@@ -42,6 +42,8 @@ def main():
             hdu.zero_()
             ds.rhs_host(hdu, hu, chunks=chunks)
             assert torch.equal(hdu, du.cpu()), (name, rank, chunks)
+        # the functionals are all-reduced inside the library: every rank holds the single-domain totals
+        fun = ds.functionals(u, du)
         got = [None] * world
         dist.all_gather_object(got, (gid, du.cpu().numpy()))
         if rank == 0:
@@ -52,8 +54,18 @@ def main():
                 out[g] = d
             err = float(np.abs(out - ref).max() / np.abs(ref).max())
             worst = max(worst, err)
-            print(f"dist parity {name} world={world}: max rel diff {err:.3e} (ghost facets {part.sd.mesh.n_ghost}, "
-                  f"boundary elements {part.sd.mesh.n_boundary}/{part.sd.N_e})", flush=True)
+            one = Solver(full.image(), local)
+            du1 = one.new_state()
+            u1 = torch.from_numpy(u_full).cuda()
+            one.rhs(du1, u1)
+            fun1 = one.functionals(u1, du1)
+            one.close()
+            scale = float(np.abs(ref).max()) * float(np.prod([b - a for a, b in full.sd.mesh.limits]))
+            ferr = float(np.abs(fun - fun1).max() / scale)
+            worst = max(worst, ferr if ferr > 1e-11 else 0.0)
+            print(f"dist parity {name} world={world}: max rel diff {err:.3e}, functionals (all-reduced) vs single GPU {ferr:.1e} "
+                  f"(ghost facets {part.sd.mesh.n_ghost}, boundary elements {part.sd.mesh.n_boundary}/{part.sd.N_e}, "
+                  f"NCCL {s.comm_info()[2]})", flush=True)
         s.close()
     dist.barrier()
     dist.destroy_process_group()

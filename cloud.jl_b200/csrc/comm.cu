@@ -215,6 +215,7 @@ extern "C" int32_t sse_halo_plan(sse_handle* h, int32_t n_nbr, const int32_t* nb
 // pack on the handle's stream, then hand over to the comm stream
 static int32_t exchange_pack(sse_handle* h, int which) {
     int32_t rc;
+    CU(cudaSetDevice(h->device));      // h->stream may be the default stream: it names a stream of the CURRENT device
     if ((rc = sse_halo_pack(h, which))) return rc;
     CU(cudaEventRecord(h->comm.e_packed, h->stream));
     CU(cudaStreamWaitEvent(h->comm.s_comm, h->comm.e_packed, 0));
@@ -223,6 +224,7 @@ static int32_t exchange_pack(sse_handle* h, int which) {
 // the sends / receives of one handle (inside an NCCL group opened by the caller)
 static int32_t exchange_post(sse_handle* h, int which, const NcclApi* api) {
     sse_comm& c = h->comm;
+    CU(cudaSetDevice(h->device));
     const int nv = h->cfg.N_c * (which ? h->cfg.d : 1);
     long long so = 0, ro = 0;
     for (size_t i = 0; i < c.nbr_rank.size(); i++) {
@@ -270,6 +272,7 @@ static int32_t exchange_start(sse_handle* h, int which) {
     return SSE_OK;
 }
 static int32_t exchange_finish(sse_handle* h, int which) {
+    CU(cudaSetDevice(h->device));
     CU(cudaStreamWaitEvent(h->stream, h->comm.e_done, 0));
     return sse_halo_unpack(h, which);
 }

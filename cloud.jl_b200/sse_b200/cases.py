@@ -111,6 +111,19 @@ def euler_tgv_3d(M=2, p=4, flux="lf", kind="modal", part=None) -> Case:
                 taylor_green_vortex(1.4, 0.1))
 
 
+def euler_vortex_2d_standard(M=4, p=4, flux="lf", kind="modal", strategy=REFERENCE_OPERATOR, part=None) -> Case:
+    """2-D Euler vortex in StandardForm (standard_form_first_order.jl:16-94 with the Euler physical flux,
+    euler_navierstokes.jl:58-68, 85-91): the weak-form residual the reference runs when no entropy-stable form is asked for."""
+    c = euler_vortex_2d(M, p, flux, kind, part)
+    return Case("euler_vortex_2d_standard", c.law, c.sd, StandardForm(inviscid_numerical_flux=_flux(flux)), strategy, c.ic)
+
+
+def euler_tgv_3d_standard(M=2, p=4, flux="lf", kind="modal", strategy=REFERENCE_OPERATOR, part=None) -> Case:
+    """3-D Euler Taylor-Green vortex on curved tets in StandardForm (ReferenceOperator or PhysicalOperator strategy)."""
+    c = euler_tgv_3d(M, p, flux, kind, part)
+    return Case("euler_tgv_3d_standard", c.law, c.sd, StandardForm(inviscid_numerical_flux=_flux(flux)), strategy, c.ic)
+
+
 def euler_periodic_3d_hex(M=2, p=4, flux="ec") -> Case:
     """test/euler_3d.jl (runtests.jl:131-144): 3-D Euler density wave on warped hexahedra, NodalTensor Lobatto
     collocation (diagonal-E), flux differencing, conservative-curl metrics."""
@@ -164,5 +177,6 @@ def advection_2d_quad(M=2, p=4, flux="lf", warp=0.1) -> Case:
 
 BUILDERS = {"advection_2d": advection_2d, "euler_vortex_2d": euler_vortex_2d,
             "advection_diffusion_2d": advection_diffusion_2d, "advection_3d": advection_3d,
-            "euler_tgv_3d": euler_tgv_3d,
+            "euler_tgv_3d": euler_tgv_3d, "euler_vortex_2d_standard": euler_vortex_2d_standard,
+            "euler_tgv_3d_standard": euler_tgv_3d_standard,
             "euler_periodic_3d_hex": euler_periodic_3d_hex, "burgers_1d": burgers_1d, "advection_2d_quad": advection_2d_quad}

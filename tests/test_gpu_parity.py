@@ -49,6 +49,12 @@ CASES = {
     "euler_tgv_3d_p3": lambda: cases.euler_tgv_3d(M=2, p=3, flux="lf"),
     "euler_tgv_3d_nodal": lambda: cases.euler_tgv_3d(M=2, p=3, flux="ec", kind="nodal"),
     "euler_tgv_3d_M4": lambda: cases.euler_tgv_3d(M=4, flux="lf"),
+    "euler_vortex_2d_standard_lf": lambda: cases.euler_vortex_2d_standard(M=4, p=4, flux="lf"),
+    "euler_vortex_2d_standard_nodal": lambda: cases.euler_vortex_2d_standard(M=3, p=3, flux="central", kind="nodal"),
+    "euler_vortex_2d_standard_physical": lambda: cases.euler_vortex_2d_standard(M=3, p=4, flux="lf", strategy=PHYSICAL_OPERATOR),
+    "euler_tgv_3d_standard_lf": lambda: cases.euler_tgv_3d_standard(M=2, p=4, flux="lf"),
+    "euler_tgv_3d_standard_p3_central": lambda: cases.euler_tgv_3d_standard(M=2, p=3, flux="central"),
+    "euler_tgv_3d_standard_physical": lambda: cases.euler_tgv_3d_standard(M=2, p=3, flux="lf", strategy=PHYSICAL_OPERATOR),
     "burgers_1d_ec": lambda: cases.burgers_1d(M=8, p=7, flux="ec"),
     "burgers_1d_lf": lambda: cases.burgers_1d(M=8, p=5, flux="lf"),
     "advection_2d_quad": lambda: cases.advection_2d_quad(M=3, p=4, flux="lf"),
@@ -308,3 +314,48 @@ def test_fused_rk_step_equals_unfused(name):
     assert relerr(a, b) <= 1e-14
     assert relerr(a, u0) > 1e-9          # the state really moved
     s.close()
+
+
+@pytest.mark.parametrize("name,variant", [("euler_tgv_3d", 1), ("euler_tgv_3d", 0), ("euler_vortex_2d", 1)])
+def test_nonphysical_state_is_reported(name, variant):
+    """A state outside the physical domain (negative pressure) makes the reference throw a DomainError from log / sqrt
+    (SURVEY.md §8b); the library reports SSE_ERR_NONFINITE at the next blocking call, once, and keeps working afterwards."""
+    from sse_b200._lib import SSEError
+    c = cases.BUILDERS[name](M=2 if name == "euler_tgv_3d" else 3)
+    img, good = c.image(), c.u0(seed=0)
+    bad = good.copy()
+    bad[1, -1, :] = -np.abs(bad[1, -1, :]) - 1.0          # total energy of one element negative -> p < 0
+    s = Solver(img, 0)
+    s.set_kernel_variant(variant)
+    du = s.new_state()
+    s.rhs(du, torch.from_numpy(bad).cuda())
+    with pytest.raises(SSEError) as e:
+        s.synchronize()
+    assert e.value.code == 4 and "DomainError" in str(e.value)
+    s.synchronize()                                         # reported once
+    s.rhs(du, torch.from_numpy(good).cuda())
+    s.synchronize()
+    assert relerr(du.cpu().numpy(), oracle.rhs(img, good)) <= RTOL
+    hb = torch.from_numpy(bad).pin_memory()
+    hd = torch.empty_like(hb).pin_memory()
+    with pytest.raises(SSEError) as e:                      # the synchronous host-buffer residual reports it itself
+        s.rhs_host(hd, hb)
+    assert e.value.code == 4
+    s.close()
+
+
+def test_config5_at_24576_elements_matches_oracle():
+    """BASELINE config 5 at M = 16 (24 576 curved tets, 4.3 M DOF: beyond the L2, 166 elements per SM) against the oracle on
+    the same mesh and state -- the largest size the oracle finishes in about a second; larger sizes are covered by the
+    size-independent invariants (test_invariants_at_scale_and_functionals)."""
+    c = cases.euler_tgv_3d(M=16, flux="lf")
+    img, u = c.image(), c.u0(seed=0)
+    ref = oracle.rhs(img, u)
+    got, _ = gpu_rhs(img, u, 1)
+    assert relerr(got, ref) <= RTOL
+    hu = torch.from_numpy(u).pin_memory()
+    hd = torch.empty_like(hu).pin_memory()
+    s = Solver(img, 0)
+    s.rhs_host(hd, hu, chunks=7)                      # the pipelined host-buffer residual returns the same bits
+    s.close()
+    assert np.array_equal(hd.numpy(), got)

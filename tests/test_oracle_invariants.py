@@ -15,7 +15,11 @@ from sse_b200.assembly import PHYSICAL_OPERATOR, assemble
     lambda: cases.euler_vortex_2d(M=3, p=4, flux="ec", kind="nodal"),
     lambda: cases.euler_tgv_3d(M=2, flux="ec"), lambda: cases.euler_tgv_3d(M=2, flux="lf"),
     lambda: cases.euler_tgv_3d(M=2, p=3, flux="ec", kind="nodal"),
-    lambda: cases.advection_diffusion_2d(M=3)])
+    lambda: cases.advection_diffusion_2d(M=3),
+    lambda: cases.euler_vortex_2d_standard(M=3, p=4, flux="lf"),
+    lambda: cases.euler_vortex_2d_standard(M=3, p=3, flux="central", strategy=PHYSICAL_OPERATOR),
+    lambda: cases.euler_tgv_3d_standard(M=2, p=3, flux="lf"),
+    lambda: cases.euler_tgv_3d_standard(M=2, p=4, flux="central")])
 def test_invariants(case):
     c = case()
     img, u = c.image(), c.u0(seed=0)
@@ -26,7 +30,7 @@ def test_invariants(case):
     flux = c.form.inviscid_numerical_flux
     if c.law.pde_id == 0 and flux.half_lambda == 0.0:          # energy conservation, central flux
         assert np.abs(analysis.energy_residual(img, u, du)).max() < 1e-12 * scale
-    if c.law.pde_id == 2:
+    if c.law.pde_id == 2 and int(img.cfg.form) == 2:            # entropy statements belong to the flux-differencing form
         ds = analysis.entropy_residual(img, u, du)
         if flux.flux_id == 2:
             assert abs(ds) < 1e-11 * scale                      # entropy conservation, EC interface flux
@@ -36,7 +40,9 @@ def test_invariants(case):
         assert analysis.energy_residual(img, u, du)[0] < 0      # BR1 dissipates
 
 
-@pytest.mark.parametrize("case", [lambda: cases.advection_2d(M=3, flux="lf"), lambda: cases.advection_3d(M=2, flux="lf")])
+@pytest.mark.parametrize("case", [lambda: cases.advection_2d(M=3, flux="lf"), lambda: cases.advection_3d(M=2, flux="lf"),
+                                  lambda: cases.euler_vortex_2d_standard(M=3, p=4, flux="lf"),
+                                  lambda: cases.euler_tgv_3d_standard(M=2, p=3, flux="lf")])
 def test_physical_operator_equals_reference_operator(case):
     """PhysicalOperators fold M^-1 into VOL/FAC (operators.jl:132-160): same residual."""
     c = case()
@@ -44,6 +50,39 @@ def test_physical_operator_equals_reference_operator(case):
     a = oracle.rhs(c.image(), u)
     b = oracle.rhs(assemble(c.law, c.sd, c.form, PHYSICAL_OPERATOR), u)
     assert np.abs(a - b).max() <= 1e-13 * np.abs(a).max()
+
+
+def test_euler_standard_form_physical_flux():
+    """StandardForm with the Euler physical flux (euler_navierstokes.jl:58-68, 85-91; standard_form_first_order.jl:16-63): on an
+    affine mesh with a uniform state the weak-form residual vanishes (free-stream preservation: sum_m D_m applied to constant
+    fluxes cancels against the facet terms), and the conservative two-point flux used at the interfaces
+    (ConservationLaws.jl:83, euler_navierstokes.jl:152-158) is the arithmetic mean of the two physical fluxes."""
+    from sse_b200.assembly import SpatialDiscretization, StandardForm, REFERENCE_OPERATOR
+    from sse_b200.laws import EulerEquations
+    from sse_b200.mesh import uniform_periodic_mesh
+    from sse_b200.reference import ModalTensor, reference_approximation
+    ra = reference_approximation(ModalTensor(3), "Tet", mapping_degree=1)
+    mesh = uniform_periodic_mesh(ra, ((0.0, 1.0),) * 3, (2,) * 3, None)
+    sd = SpatialDiscretization.build(mesh, ra, "exact", True)
+    law = EulerEquations(3, 1.4)
+    ic = lambda x: np.stack([c0 + 0 * x[0] for c0 in (1.1, 0.3, -0.2, 0.5, 2.7)], axis=-1)
+    c = cases.Case("uniform", law, sd, StandardForm(inviscid_numerical_flux=cases._flux("lf")), REFERENCE_OPERATOR, ic)
+    img = c.image()
+    du = oracle.rhs(img, c.u0())
+    assert np.abs(du).max() < 1e-11
+    import ctypes as C
+    L = oracle.lib()
+    uL, uR = np.array([1.0, 0.2, -0.1, 0.3, 2.5]), np.array([0.8, -0.1, 0.25, 0.1, 2.1])
+    F = np.zeros(15)
+    pd = C.POINTER(C.c_double)
+    L.sse_oracle_two_point_flux(C.byref(img.cfg), 0, uL.ctypes.data_as(pd), uR.ctypes.data_as(pd), F.ctypes.data_as(pd))
+    def phys(u):
+        rho, V, E = u[0], u[1:4] / u[0], u[4]
+        p = 0.4 * (E - 0.5 * rho * V @ V)
+        return np.array([[u[1 + n] for n in range(3)]] + [[u[1 + m] * V[n] + (p if m == n else 0.0) for n in range(3)] for m in range(3)]
+                        + [[(E + p) * V[n] for n in range(3)]])
+    ref = 0.5 * (phys(uL) + phys(uR))
+    assert np.abs(F.reshape(3, 5).T - ref).max() < 1e-14
 
 
 def test_recomputed_nJq_equals_stored():

@@ -47,6 +47,7 @@ struct Geo {
     long long Ne;
     long long NFT;           // Nf*Ne + N_ghost: stride between variables of u_f / q_f
     int mass_solver;
+    const double* iJW;       // W / J_q per volume node (Nq x Ne), built at sse_create for the compile-time Euler path; else nullptr
     int* flag;               // set to 1 by the kernels that write dudt when a value is not finite (SSE_ERR_NONFINITE)
     const double* chol;      // CholeskySolver: upper factors U_k, Np x Np column-major per element (mass_matrix.jl:30-39)
 };
@@ -55,6 +56,15 @@ struct Geo {
 __device__ __forceinline__ void flag_nonfinite(int* flag, double v) {
     if (!(fabs(v) <= 1.7976931348623157e308)) *flag = 1;
 }
+
+// asynchronous global -> shared copies (LDGSTS): the data never passes through registers, so a CTA prologue can put all of
+// its loads in flight at once and wait for them where they are first needed
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
 #define SSE_FOR(t, n) for (int t = threadIdx.x; t < (n); t += blockDim.x)
 

@@ -99,6 +99,10 @@ template <int N> static FacetR<N> make_facet(const CtPlan& p) {
     return f;
 }
 
+// resident CTAs per SM requested for the pair kernel (register cap = 65536 / (128 MINB))
+#ifndef SSE_FD_MINB_CT
+#define SSE_FD_MINB_CT 4
+#endif
 template <int N> static SFCoef<N> make_coef(const CtPlan& p) {
     SFCoef<N> c;
     for (int i = 0; i < N * N; i++) c.A[i] = p.A[i];
@@ -114,9 +118,9 @@ template <int N> static cudaError_t set_attrs_n() {
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
     if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 1, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod1))) return e;
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
-    if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
+    if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, SSE_FD_MINB_CT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
     if constexpr (N == 5) {
-        if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N, true>::total)))) return e;
+        if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, SSE_FD_MINB_CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N, true>::total)))) return e;
     }
     return cudaSuccess;
 }
@@ -145,9 +149,9 @@ static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, cons
     (void)tp; (void)o;
     bool done = false;
     if constexpr (N == 5) {
-        if (p.dual) { k_fluxdiff_ct<N, 4, true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); done = true; }
+        if (p.dual) { k_fluxdiff_ct<N, SSE_FD_MINB_CT, true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); done = true; }
     }
-    if (!done) k_fluxdiff_ct<N, 4, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
+    if (!done) k_fluxdiff_ct<N, SSE_FD_MINB_CT, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
     if (mid) cudaEventRecord(mid, s);
     const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
     k_project_ct<N, 5, 3><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt, rk);

@@ -30,7 +30,21 @@
 #define SSE_NODAL_ILP_F 2
 #endif
 
+// C-tensor symmetry in the applies of k_nodal_ct (15 instead of 35 table loads per application; measured with spills in round 1)
+#ifndef SSE_NODAL_SYM
+#define SSE_NODAL_SYM 0
+#endif
+#define SSE_NODAL_SYMB (SSE_NODAL_SYM != 0)
+
 namespace sse {
+
+// schedule-weight tables (vS, fC, fR: 34 x Nq doubles, the same for every element): kept in L1 against the streaming
+// element data with an evict-last hint (pass B 1.976 -> 1.935 ms at 82 944 elements)
+__device__ __forceinline__ double ld_tab(const double* p) {
+    double v;
+    asm("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
 
 template <int N> struct SFCoef {       // A[a1 + N*b1], B[a2 + N*(b1 + N*b2)]  (reference column-major)
     double A[N * N];
@@ -68,17 +82,22 @@ template <int N> __host__ __device__ constexpr int tet_l(int b1, int b2, int b3)
 // SYM selects it per call site: it pays in k_project_ct (pass B 1.796 -> 1.782 ms at 82 944 elements) and loses in k_nodal_ct,
 // whose transforms leave no registers for the N (N + 1) / 2 values (pass A 0.646 -> 0.707 ms with spills).
 template <int N> __host__ __device__ constexpr int c3_sym_idx(int s, int k) { return s * N - s * (s - 1) / 2 + k; }   // k <= N - 1 - s
-template <int N, int CS>
+// C3G: c3 points into the global table (read through L1 with the evict-last hint) instead of a shared copy
+template <int N, int CS, bool C3G = false>
 __device__ __forceinline__ void load_c3_sym(const double* c3, double (&cs)[N * (N + 1) / 2]) {
 #pragma unroll
     for (int sidx = 0; sidx < N; sidx++)
 #pragma unroll
-        for (int k = 0; k < N - sidx; k++) cs[c3_sym_idx<N>(sidx, k)] = c3[tet_l<N>(0, sidx, k) * CS];
+        for (int k = 0; k < N - sidx; k++) {
+            if constexpr (C3G) cs[c3_sym_idx<N>(sidx, k)] = ld_tab(c3 + tet_l<N>(0, sidx, k) * CS);
+            else cs[c3_sym_idx<N>(sidx, k)] = c3[tet_l<N>(0, sidx, k) * CS];
+        }
 }
-template <int N, int CS = 1, bool SYM = false>
+template <int N, int CS = 1, bool SYM = false, bool C3G = false>
 __device__ __forceinline__ void sf3_fwd(const SFCoef<N>& cf, const double* c3, const double* __restrict__ xs, double (&y)[N][N]) {
+    static_assert(!C3G || SYM, "the global C table is read through its (i + j, k) symmetry");
     double cs[SYM ? N * (N + 1) / 2 : 1];
-    if constexpr (SYM) load_c3_sym<N, CS>(c3, cs);
+    if constexpr (SYM) load_c3_sym<N, CS, C3G>(c3, cs);
 #pragma unroll
     for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
@@ -110,10 +129,11 @@ __device__ __forceinline__ void sf3_fwd(const SFCoef<N>& cf, const double* c3, c
 
 // partial[l][a3] = C[a3,l] * sum_{a2} B[a2,b1,b2] sum_{a1} A[a1,b1] x[a1][a2]        warped_product_3d.jl:94-136
 // written to red[l * RED_SL] (the caller passes red already offset by group and a3 * RED_SA)
-template <int N, int CS = 1, bool SYM = false>
+template <int N, int CS = 1, bool SYM = false, bool C3G = false>
 __device__ __forceinline__ void sf3_bwd_partials(const SFCoef<N>& cf, const double* c3, const double (&x)[N][N], double* __restrict__ red) {
+    static_assert(!C3G || SYM, "the global C table is read through its (i + j, k) symmetry");
     double cs[SYM ? N * (N + 1) / 2 : 1];
-    if constexpr (SYM) load_c3_sym<N, CS>(c3, cs);
+    if constexpr (SYM) load_c3_sym<N, CS, C3G>(c3, cs);
 #pragma unroll
     for (int b1 = 0; b1 < N; b1++) {
         asm volatile("" ::: "memory");
@@ -161,19 +181,6 @@ template <int N>
 __device__ __forceinline__ void load_c3_shared(const CtDev& t, double* s_c3) {
     for (int i = threadIdx.x; i < Tet<N>::Np * N; i += blockDim.x) s_c3[i] = t.C3[i];
 }
-// the same from the reference-layout tensor (index arithmetic per entry).  k_project_ct keeps this loader: with the straight copy
-// its pass B measured 1.794 instead of 1.773 ms at 82 944 elements, while pass A gains 0.647 -> 0.629 ms from the copy
-template <int N>
-__device__ __forceinline__ void load_c3_shared_ref(const CtDev& t, double* s_c3) {
-    for (int i = threadIdx.x; i < Tet<N>::Np * N; i += blockDim.x) {
-        const int l = i / N, a3 = i - l * N;
-        int b1 = 0, b2 = 0, ll = l;
-        while (ll >= (N - b1) * (N - b1 + 1) / 2) { ll -= (N - b1) * (N - b1 + 1) / 2; b1++; }
-        while (ll >= N - b1 - b2) { ll -= N - b1 - b2; b2++; }
-        s_c3[i] = t.C[a3 + N * (b1 + N * (b2 + N * ll))];
-    }
-}
-
 // 1-D factors of the facet extrapolation R on the collapsed tet (tensor_simplex.jl:265-268), extracted from Matrix(R)
 // and verified entry by entry on the host (ct_facet_factors):
 //   face 0 (eta_2 = -1), node (a1, a3): sum_a2 r0[a2] q[a1,a2,a3]      face 1 / 2 (eta_1 = +1 / -1), node (a2, a3): sum_a1 r1|r2[a1] q
@@ -271,22 +278,25 @@ k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, l
     const int nel = (int)((first + count - e0 < EPB) ? (first + count - e0) : EPB);
     const bool act = gl < T::GPW && (grp / NC) < nel;
 
-    load_c3_shared<N>(t, sm + S::c3);
-    const double* c3 = sm + S::c3 + a3;
-    for (int i = tid; i < nel * NC * Np; i += NT) s_x[i] = u[(size_t)e0 * NC * Np + i];
+    // every global load of the prologue as an asynchronous copy: the C table and u (needed by the first V) form the first
+    // group, J_q (needed by the entropy-variable phase only) the second one, which stays in flight behind the first V
+    for (int i = tid; i < Np * N; i += NT) cp_async8(sm + S::c3 + i, t.C3 + i);
+    for (int i = tid; i < nel * NC * Np; i += NT) cp_async8(s_x + i, u + (size_t)e0 * NC * Np + i);
+    cp_async_commit();
     if constexpr (PROJECT) {
-        // J_q rides along with u: one exposed memory round trip at the start of the CTA instead of a second one in the
-        // entropy-variable phase, which turns the tile into W / J
         for (int it = tid; it < nel * Nq; it += NT) {
             const int el = it / Nq, i = it - el * Nq;
-            s_wij[el * S::QS + i] = g.J_q[(size_t)(e0 + el) * Nq + i];
+            cp_async8(s_wij + el * S::QS + i, g.J_q + (size_t)(e0 + el) * Nq + i);
         }
     }
+    cp_async_commit();
+    const double* c3 = sm + S::c3 + a3;
+    cp_async_wait<1>();
     __syncthreads();
 
     double y[N][N];
     // u_q = V u
-    if (act) sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
+    if (act) sf3_fwd<N, N, SSE_NODAL_SYMB>(cf, c3, s_x + grp * Np, y);
     if constexpr (PROJECT) {
     if (act) {
 #pragma unroll
@@ -294,6 +304,7 @@ k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, l
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) s_q[grp * S::QS + (a1 * N + a2) * N + a3] = y[a1][a2];
     }
+    cp_async_wait<0>();
     __syncthreads();
     // w_q = WJ * w(u_q)                                      flux_differencing_form.jl:230-235
     // UT independent nodes per thread and trip: the branch-free maps of physics.cuh make the trip one basic block, so
@@ -343,7 +354,7 @@ k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, l
     }
     __syncthreads();                                   // the partials of a group lie over the nodal tiles of other groups
     double out[T::LPT];
-    if (act) sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
+    if (act) sf3_bwd_partials<N, N, SSE_NODAL_SYMB>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
     __syncwarp();
     if (act) {
         sf3_bwd_reduce<N>(s_red + grp * S::RS, a3, out);
@@ -353,13 +364,13 @@ k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, l
     __syncwarp();
     // w = M \ w : V, diag(W/J), V'                           mass_matrix.jl:185-196
     if (act) {
-        sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
+        sf3_fwd<N, N, SSE_NODAL_SYMB>(cf, c3, s_x + grp * Np, y);
         const double* wij = s_wij + (grp / NC) * S::QS;
 #pragma unroll
         for (int a1 = 0; a1 < N; a1++)
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= wij[(a1 * N + a2) * N + a3];
-        sf3_bwd_partials<N, N>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
+        sf3_bwd_partials<N, N, SSE_NODAL_SYMB>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
     }
     __syncwarp();
     if (act) {
@@ -369,7 +380,7 @@ k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, l
     }
     __syncwarp();
     // w_q = V w
-    if (act) sf3_fwd<N, N>(cf, c3, s_x + grp * Np, y);
+    if (act) sf3_fwd<N, N, SSE_NODAL_SYMB>(cf, c3, s_x + grp * Np, y);
     }
     // Every warp is past its partials, modal coefficients and W / J: the nodal tile (over the partials of other groups) and
     // the facet tile (over x | wij) may be written.  Facet values R w_q (R u_q for scalar laws) come from the 1-D factors
@@ -479,7 +490,16 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
     const bool act = gl < T::GPW && (grp / NC) < nel;
 
     double y[N][N], out[T::LPT];
-    // r_q slab of this thread straight from global memory (25 independent loads in flight)
+    // Prologue without a barrier: the W / J tile arrives by asynchronous copies (precomputed at sse_create, so no reciprocal
+    // sits between the load and the tile) and is waited for where it is first used; the C tensor is read from its global
+    // table through L1 (15 values per application by the (i + j, k) symmetry) instead of being staged in shared memory.
+    if constexpr (NC > 1) {
+        for (int it = tid; it < nel * Nq; it += NT) {
+            const int el = it / Nq, i = it - el * Nq;
+            cp_async8(s_wij + el * S::QS + i, g.iJW + (size_t)(e0 + el) * Nq + i);
+        }
+        cp_async_commit();
+    }
     if (act) {
         const double* src = r_q + (size_t)e0 * NC * Nq + (size_t)grp * Nq + a3;
 #pragma unroll
@@ -487,17 +507,8 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
 #pragma unroll
             for (int a2 = 0; a2 < N; a2++) y[a1][a2] = src[(a1 * N + a2) * N];
     }
-    load_c3_shared_ref<N>(t, sm + S::c3);
-    const double* c3 = sm + S::c3 + a3;
-    if constexpr (NC > 1) {
-        for (int it = tid; it < nel * Nq; it += NT) {
-            const int el = it / Nq, i = it - el * Nq;
-            s_wij[el * S::QS + i] = t.W[i] * rcp_fast(g.J_q[(size_t)(e0 + el) * Nq + i]);
-        }
-    }
-    __syncthreads();
-    // the partials and modal coefficients of a group are touched by its own N lanes only (one warp): __syncwarp suffices
-    if (act) sf3_bwd_partials<N, N, true>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
+    const double* c3 = t.C3 + a3;
+    if (act) sf3_bwd_partials<N, N, true, true>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
     __syncwarp();
     if (act) {
         sf3_bwd_reduce<N>(s_red + grp * S::RS, a3, out);
@@ -505,8 +516,12 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
         for (int q = 0; q < T::LPT; q++) { const int l = a3 * T::LPT + q; if (l < Np) s_x[grp * Np + l] = out[q]; }
     }
     __syncwarp();
+    if (act) sf3_fwd<N, N, true, true>(cf, c3, s_x + grp * Np, y);
+    if constexpr (NC > 1) {
+        cp_async_wait<0>();
+        __syncthreads();                                   // the tile of an element is filled by threads of several warps
+    }
     if (act) {
-        sf3_fwd<N, N, true>(cf, c3, s_x + grp * Np, y);
         if constexpr (NC > 1) {
             const double* wij = s_wij + (grp / NC) * S::QS;
 #pragma unroll
@@ -520,7 +535,7 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
 #pragma unroll
                 for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= t.W[(a1 * N + a2) * N + a3] * rcp_fast(Jq[(a1 * N + a2) * N]);
         }
-        sf3_bwd_partials<N, N, true>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
+        sf3_bwd_partials<N, N, true, true>(cf, c3, y, s_red + grp * S::RS + a3 * T::RED_SA);
     }
     __syncwarp();
     if (act) {
@@ -633,14 +648,6 @@ __device__ __forceinline__ int facet_partner(int fr, int ca, int cb, int cc) {
     int bp = (fr - 3) - cc;
     if (bp < 0) bp += N;
     return 3 * NN + ca * N + bp;
-}
-
-// schedule-weight tables (vS, fC, fR: 34 x Nq doubles, the same for every element): kept in L1 against the streaming
-// element data with an evict-last hint (pass B 1.976 -> 1.935 ms at 82 944 elements)
-__device__ __forceinline__ double ld_tab(const double* p) {
-    double v;
-    asm("ld.global.nc.L1::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    return v;
 }
 
 template <int N, int MINB, bool DUAL>

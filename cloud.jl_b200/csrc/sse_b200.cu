@@ -226,6 +226,12 @@ extern "C" int32_t sse_host_range_plan(const int64_t* mapP, int64_t N_e, int32_t
     return SSE_OK;
 }
 
+// W / J_q per volume node, with the very expression the projection kernel used to evaluate in its prologue (bit-identical)
+static __global__ void k_ijw(long long n, int Nq, const double* __restrict__ W, const double* __restrict__ J, double* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = W[i % Nq] * rcp_fast(J[i]);
+}
+
 // C tensor of the collapsed tet in the order of the compile-time kernels: C3[l * N + a3], l = canonical modal index
 static int32_t upload_c3(sse_handle* h, const sse_arrays* a, int N) {
     std::vector<double> c3;
@@ -462,6 +468,14 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
             if (const char* mb = getenv("SSE_PROJ_MINB")) h->ct.proj_minb = atoi(mb);
             if (const char* mb = getenv("SSE_FD_DUAL")) h->ct.dual = atoi(mb);
             if (ct_set_attrs(N) != cudaSuccess) return fail(SSE_ERR_CUDA, "cudaFuncSetAttribute (compile-time kernels) failed");
+            {   // the projection kernel copies W / J straight into its tile (cp.async): 1 kB per element, read instead of J_q
+                double* ijw = nullptr;
+                if ((rc = dalloc(h, (size_t)Nq * Ne, &ijw))) return rc;
+                const long long n = (long long)Nq * Ne;
+                k_ijw<<<(unsigned)std::min<long long>((n + 255) / 256, 8LL * h->sm_count), 256, 0, h->stream>>>(n, Nq, o.W, g.J_q, ijw);
+                CU(cudaGetLastError());
+                g.iJW = ijw;
+            }
             h->ct.ok = 1;
         }
     }

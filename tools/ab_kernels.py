@@ -69,6 +69,11 @@ def one(a):
     out["pass_a_ms"] = float(np.median([e[0].elapsed_time(e[1]) for e in ev]))
     out["pass_b_ms"] = float(np.median([e[1].elapsed_time(e[2]) for e in ev]))
     out["rhs_ms"] = float(np.median([e[0].elapsed_time(e[2]) for e in ev]))
+    try:
+        k = s.profile_rhs(du, u, reps=a.steps)
+        out["k_nodal_ms"], out["k_pair_ms"], out["k_project_ms"] = float(k[0]), float(k[2]), float(k[3])
+    except Exception as e:       # older library variants have no sse_profile_rhs
+        out["profile_error"] = str(e)[:80]
     f = s.functionals(u, du)
     out["conservation"] = float(np.abs(np.asarray(f[:5])).max())
     out["du_sha"] = hashlib.sha1(du.cpu().numpy().tobytes()).hexdigest()[:10]

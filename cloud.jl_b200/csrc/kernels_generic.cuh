@@ -658,6 +658,9 @@ static __global__ void k_axpby(long long n, double a, const double* __restrict__
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         y[i] = (b == 0.0) ? a * x[i] : fma(a, x[i], b * y[i]);
 }
+static __global__ void k_fill(long long n, double v, double* __restrict__ y) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = v;
+}
 // 2N-storage RK stage (Carpenter & Kennedy 1994): tmp = A tmp + dt dudt ; u += B tmp
 static __global__ void k_lsrk_stage(long long n, double* __restrict__ u, double* __restrict__ tmp, const double* __restrict__ dudt,
                              double A, double B, double dt) {

@@ -589,6 +589,16 @@ extern "C" int32_t sse_state_free(sse_handle* h, double* p) {
     CU(cudaFree(p));
     return SSE_OK;
 }
+extern "C" int32_t sse_state_fill(sse_handle* h, double* d_x, double value) {
+    if (!h || !d_x) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    CU(cudaSetDevice(h->device));
+    if (value == 0.0) { CU(cudaMemsetAsync(d_x, 0, state_len(h) * sizeof(double), h->stream)); return SSE_OK; }
+    const long long n = (long long)state_len(h);
+    k_fill<<<(unsigned)std::min<long long>((n + 255) / 256, 8 * h->sm_count), 256, 0, h->stream>>>(n, value, d_x);
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return SSE_OK;
+}
 extern "C" int32_t sse_state_upload(sse_handle* h, double* d_dst, const double* h_src) {
     if (!h || !d_dst || !h_src) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
     CU(cudaSetDevice(h->device));

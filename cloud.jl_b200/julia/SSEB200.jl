@@ -5,8 +5,10 @@
 # Everything else of StableSpectralElements.jl (ConservationLaws, SpatialDiscretization,
 # semidiscretize, ODEProblem, Analysis, File) is used unchanged.
 #
-# NOTE: Julia is not installed in the build image, so this file is reviewed but not executed
-# there; the same entry points are exercised through the Python ctypes mirror
+# NOTE: Julia is not installed in the build image, so this file cannot be executed there.  What IS checked mechanically
+# (tests/test_julia_binding.py, CPU suite): every `ccall` below names a symbol include/sse_b200.h declares, with the same
+# number of arguments and C-compatible argument / return types, and the two struct mirrors have the header's field order
+# and types.  The same entry points are exercised at run time through the Python ctypes mirror
 # (cloud.jl_b200/sse_b200/_lib.py), which binds the identical C ABI.
 module SSEB200
 
@@ -65,33 +67,135 @@ mutable struct CUDAB200 <: AbstractParallelism
     CUDAB200(device = 0) = new(Int32(device), C_NULL)
 end
 
-"Device-resident state: a thin `AbstractArray{Float64,3}` of size (N_p, N_c, N_e)."
-struct DeviceState <: AbstractArray{Float64, 3}
+"""
+Device-resident state: an `AbstractArray{Float64,3}` of size (N_p, N_c, N_e) whose memory lives on the GPU of its handle.
+It implements the part of the array interface a time integrator touches between residual calls -- `similar`, `zero`,
+`copyto!`, `fill!`, and broadcasts that are linear combinations of states (`@. tmp = A*tmp + dt*k`, `@. u = u + B*tmp`, the
+forms OrdinaryDiffEq's low-storage Runge-Kutta methods emit, test/test_driver.jl:77-83) -- on top of `sse_axpby`, so the
+state never returns to the host.  Scalar indexing is refused (it would be one PCIe round trip per entry); `Array(x)`
+downloads.  Memory is released by a finalizer (`sse_state_free`).
+"""
+mutable struct DeviceState <: AbstractArray{Float64, 3}
     ptr::Ptr{Float64}
     dims::NTuple{3, Int}
     par::CUDAB200
+    function DeviceState(ptr, dims, par)
+        x = new(ptr, dims, par)
+        finalizer(x) do y
+            y.ptr == C_NULL || ccall((:sse_state_free, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}), y.par.handle, y.ptr)
+            y.ptr = C_NULL
+        end
+        return x
+    end
 end
 Base.size(x::DeviceState) = x.dims
-Base.similar(x::DeviceState) = alloc_state(x.par, x.dims)
 Base.getindex(::DeviceState, I...) = error("DeviceState lives on the GPU: use Array(x)")
+Base.setindex!(::DeviceState, v, I...) = error("DeviceState lives on the GPU: use copyto!(x, host_array)")
+Base.show(io::IO, x::DeviceState) = print(io, "DeviceState", x.dims, " on GPU ", x.par.device)
+Base.show(io::IO, ::MIME"text/plain", x::DeviceState) = show(io, x)
 
 function alloc_state(par::CUDAB200, dims)
     p = Ref{Ptr{Float64}}()
     check(ccall((:sse_state_alloc, libsse), Int32, (Ptr{Cvoid}, Ptr{Ptr{Float64}}), par.handle, p))
-    x = DeviceState(p[], dims, par)
-    return x
+    return DeviceState(p[], Tuple(dims), par)
 end
+Base.similar(x::DeviceState) = alloc_state(x.par, x.dims)
+Base.similar(x::DeviceState, ::Type{Float64}) = alloc_state(x.par, x.dims)
+function Base.similar(x::DeviceState, ::Type{Float64}, dims::Dims{3})
+    dims == x.dims || error("a DeviceState has the size of its Solver: ", x.dims)
+    return alloc_state(x.par, dims)
+end
+Base.fill!(x::DeviceState, v::Real) =
+    (check(ccall((:sse_state_fill, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}, Float64), x.par.handle, x.ptr, Float64(v))); x)
+Base.zero(x::DeviceState) = fill!(similar(x), 0.0)
 upload!(x::DeviceState, h::Array{Float64, 3}) =
-    check(ccall((:sse_state_upload, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), x.par.handle, x.ptr, h))
+    (check(ccall((:sse_state_upload, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), x.par.handle, x.ptr, h)); x)
 function Base.Array(x::DeviceState)
     h = Array{Float64}(undef, x.dims)
     check(ccall((:sse_state_download, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), x.par.handle, h, x.ptr))
     return h
 end
-# broadcast-free integrator updates (OrdinaryDiffEq low-storage methods call axpby-type kernels)
+# y = a x + b y on the device
 axpby!(a, x::DeviceState, b, y::DeviceState) =
-    check(ccall((:sse_axpby, libsse), Int32, (Ptr{Cvoid}, Float64, Ptr{Float64}, Float64, Ptr{Float64}),
-        x.par.handle, a, x.ptr, b, y.ptr))
+    (check(ccall((:sse_axpby, libsse), Int32, (Ptr{Cvoid}, Float64, Ptr{Float64}, Float64, Ptr{Float64}),
+        x.par.handle, Float64(a), x.ptr, Float64(b), y.ptr)); y)
+Base.copyto!(dst::DeviceState, src::DeviceState) = dst.ptr == src.ptr ? dst : axpby!(1.0, src, 0.0, dst)
+Base.copyto!(dst::DeviceState, src::Array{Float64, 3}) = upload!(dst, src)
+Base.copyto!(dst::Array{Float64, 3}, src::DeviceState) = copyto!(dst, Array(src))
+Base.copy(x::DeviceState) = copyto!(similar(x), x)
+device_synchronize(x::DeviceState) = check(ccall((:sse_synchronize, libsse), Int32, (Ptr{Cvoid},), x.par.handle))
+
+# --- broadcasting: linear combinations of DeviceStates with scalar coefficients are lowered to sse_axpby ------------------
+struct DeviceStyle <: Broadcast.AbstractArrayStyle{3} end
+DeviceStyle(::Val{3}) = DeviceStyle()
+DeviceStyle(::Val{N}) where {N} = Broadcast.DefaultArrayStyle{N}()
+Base.BroadcastStyle(::Type{DeviceState}) = DeviceStyle()
+Base.similar(bc::Broadcast.Broadcasted{DeviceStyle}, ::Type{Float64}) = similar(first_state(bc))
+first_state(x::DeviceState) = x
+first_state(x) = nothing
+function first_state(bc::Broadcast.Broadcasted)
+    for a in bc.args
+        s = first_state(a)
+        s === nothing || return s
+    end
+    return nothing
+end
+# a broadcast expression as a list of (coefficient, state) terms; anything that is not linear in the states is refused
+const Term = Tuple{Float64, DeviceState}
+lin(x::DeviceState) = Term[(1.0, x)]
+lin(x::Ref) = lin(x[])
+lin(x) = error("unsupported operand in a DeviceState broadcast: ", typeof(x), " (only linear combinations of states)")
+scalar(x::Number) = Float64(x)
+scalar(x::Ref{<:Number}) = Float64(x[])
+scalar(x) = nothing
+function lin(bc::Broadcast.Broadcasted)
+    f, args = bc.f, bc.args
+    if f === (+)
+        return reduce(vcat, map(lin, args))
+    elseif f === (-) && length(args) == 1
+        return Term[(-c, x) for (c, x) in lin(args[1])]
+    elseif f === (-) && length(args) == 2
+        return vcat(lin(args[1]), Term[(-c, x) for (c, x) in lin(args[2])])
+    elseif f === (*)
+        k, rest = 1.0, Any[]
+        for a in args
+            s = scalar(a)
+            s === nothing ? push!(rest, a) : (k *= s)
+        end
+        length(rest) == 1 || error("a DeviceState broadcast may multiply a state by scalars only")
+        return Term[(k * c, x) for (c, x) in lin(rest[1])]
+    elseif f === (/) && length(args) == 2 && scalar(args[2]) !== nothing
+        return Term[(c / scalar(args[2]), x) for (c, x) in lin(args[1])]
+    elseif f === muladd && length(args) == 3          # muladd(a, x, y) = a x + y   (what @muladd / @.. emit)
+        s1, s2 = scalar(args[1]), scalar(args[2])
+        prod = s1 !== nothing ? Term[(s1 * c, x) for (c, x) in lin(args[2])] :
+               s2 !== nothing ? Term[(s2 * c, x) for (c, x) in lin(args[1])] :
+               error("muladd of two states is not linear")
+        return vcat(prod, lin(args[3]))
+    elseif f === identity && length(args) == 1
+        return lin(args[1])
+    end
+    error("unsupported function in a DeviceState broadcast: ", f)
+end
+function Base.copyto!(dest::DeviceState, bc::Broadcast.Broadcasted{DeviceStyle})
+    terms = lin(bc)                                              # nested Broadcasted objects are walked by `lin` itself
+    # merge the coefficients of repeated states; the destination's own term becomes the `b` of the first axpby
+    coef = Dict{Ptr{Float64}, Term}()
+    for (c, x) in terms
+        coef[x.ptr] = haskey(coef, x.ptr) ? (coef[x.ptr][1] + c, x) : (c, x)
+    end
+    b = haskey(coef, dest.ptr) ? coef[dest.ptr][1] : 0.0
+    delete!(coef, dest.ptr)
+    if isempty(coef)
+        return axpby!(b, dest, 0.0, dest)                        # dest .= b .* dest
+    end
+    for (c, x) in values(coef)
+        axpby!(c, x, b, dest)                                   # dest = c x + b dest, then accumulate with b = 1
+        b = 1.0
+    end
+    return dest
+end
+Base.copy(bc::Broadcast.Broadcasted{DeviceStyle}) = copyto!(similar(bc, Float64), bc)
 
 pde_id(::LinearAdvectionEquation) = Int32(0)
 pde_id(::LinearAdvectionDiffusionEquation) = Int32(1)
@@ -115,7 +219,7 @@ mass_id(::CholeskySolver) = Int32(2)          # the library factorises V' WJ_k V
 Uploads the Solver's operators and geometric factors (the arrays the reference constructors
 at Solvers.jl:287-376 / operators.jl:1-160 hold) and stores the opaque handle in the tag.
 """
-function attach!(solver::Solver, sd::SpatialDiscretization{d}) where {d}
+function attach!(solver::Solver, sd::SpatialDiscretization{d}; n_ghost::Integer = 0) where {d}
     par = solver.parallelism::CUDAB200
     law, ops, form = solver.conservation_law, solver.operators, solver.form
     ra, gf = sd.reference_approximation, sd.geometric_factors
@@ -158,7 +262,7 @@ function attach!(solver::Solver, sd::SpatialDiscretization{d}) where {d}
     nref = [ra.reference_element.nrstJ[m][npf * (f - 1) + 1] for m in 1:d, f in 1:nfac]
     tp = form isa FluxDifferencingForm ? two_point_id(form.two_point_flux) : Int32(0)
     a = ntuple(m -> (hasproperty(law, :a) && m <= d) ? Float64(law.a[m]) : 0.0, 3)
-    cfg = SSEConfig(1, d, N_c, N_p, ra.N_q, ra.N_f, nfac, ra.approx_type.p, N_e, 0,
+    cfg = SSEConfig(1, d, N_c, N_p, ra.N_q, ra.N_f, nfac, ra.approx_type.p, N_e, Int64(n_ghost),
         pde_id(law), form_id, flux_id(form.inviscid_numerical_flux),
         (law isa LinearAdvectionDiffusionEquation || law isa ViscousBurgersEquation) ? Int32(1) : Int32(0), tp, mass_id(solver.mass_solver), v_kind, M1d,
         halfλ(form.inviscid_numerical_flux), a, hasproperty(law, :b) ? law.b : 0.0,
@@ -194,5 +298,61 @@ function StableSpectralElements.Solvers.semi_discrete_residual!(dudt::Array{Floa
         solver.parallelism.handle, u, dudt, t, 0))
     return dudt
 end
+
+# --- device-resident time integration without the broadcast machinery ----------------------------------------------------
+"""
+    solve_ck54!(u, solver, tspan, dt; callback = nothing)
+
+`solve(ode, CarpenterKennedy2N54(); adaptive = false, dt)` (test/test_driver.jl:77-83) with the whole step on the device:
+one `sse_step_ck54` per step (five fused residual + 2N-storage stages).  `callback(u, t)` runs between steps.
+"""
+function solve_ck54!(u::DeviceState, solver::Solver{<:Any, <:Any, <:Any, <:Any, CUDAB200}, tspan, dt; callback = nothing)
+    tmp, dudt = zero(u), similar(u)
+    t, T = Float64(tspan[1]), Float64(tspan[2])
+    while t < T - 1e-12 * abs(T)
+        h = min(dt, T - t)
+        check(ccall((:sse_step_ck54, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Float64),
+            solver.parallelism.handle, u.ptr, tmp.ptr, dudt.ptr, t, h))
+        t += h
+        callback === nothing || callback(u, t)
+    end
+    device_synchronize(u)
+    return u
+end
+
+"conservation / energy / entropy residuals on the device (Analysis/conservation.jl:145-189): N_c + 2 numbers"
+function functionals(u::DeviceState, dudt::DeviceState, solver::Solver{<:Any, <:Any, <:Any, <:Any, CUDAB200})
+    out = zeros(Float64, size(solver)[2] + 2)
+    check(ccall((:sse_functionals, libsse), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        solver.parallelism.handle, u.ptr, dudt.ptr, out))
+    return out
+end
+
+# --- several GPUs driven by this one Julia process (include/sse_b200.h, "multi-GPU") ---------------------------------------
+# One Solver per partition (built from the partition's mesh: elements ordered interior first, `mapP` in local + ghost
+# numbering, `N_ghost` set in `attach!` through `n_ghost`), one GPU each.
+"join the handles of `pars` into one NCCL communicator (ncclCommInitAll)"
+comm_init_all!(pars::Vector{CUDAB200}) =
+    check(ccall((:sse_comm_init_all, libsse), Int32, (Ptr{Ptr{Cvoid}}, Int32), [p.handle for p in pars], Int32(length(pars))))
+"the same without NCCL: halos by peer-to-peer copies"
+comm_init_local!(pars::Vector{CUDAB200}) =
+    check(ccall((:sse_comm_init_local, libsse), Int32, (Ptr{Ptr{Cvoid}}, Int32), [p.handle for p in pars], Int32(length(pars))))
+"halo plan of one partition: neighbour ranks (0-based), facet nodes sent / received per neighbour, 1-based send list, interior element count"
+halo_plan!(par::CUDAB200, nbr_rank::Vector{Int32}, send_count::Vector{Int64}, recv_count::Vector{Int64},
+    send_index::Vector{Int64}, n_interior::Integer) =
+    check(ccall((:sse_halo_plan, libsse), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Int64),
+        par.handle, Int32(length(nbr_rank)), nbr_rank, send_count, recv_count, send_index, Int64(n_interior)))
+"semi_discrete_residual! on all partitions (one NCCL group for the halos of all GPUs)"
+function rhs_multi!(dudts::Vector{DeviceState}, us::Vector{DeviceState}, pars::Vector{CUDAB200}, t::Float64 = 0.0)
+    check(ccall((:sse_rhs_multi, libsse), Int32, (Ptr{Ptr{Cvoid}}, Int32, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}, Float64),
+        [p.handle for p in pars], Int32(length(pars)), [u.ptr for u in us], [d.ptr for d in dudts], t))
+    return dudts
+end
+"one CarpenterKennedy2N54 step on all partitions"
+step_ck54_multi!(us::Vector{DeviceState}, tmps::Vector{DeviceState}, dudts::Vector{DeviceState}, pars::Vector{CUDAB200}, t, dt) =
+    check(ccall((:sse_step_ck54_multi, libsse), Int32,
+        (Ptr{Ptr{Cvoid}}, Int32, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}, Ptr{Ptr{Float64}}, Float64, Float64),
+        [p.handle for p in pars], Int32(length(pars)), [u.ptr for u in us], [x.ptr for x in tmps], [d.ptr for d in dudts],
+        Float64(t), Float64(dt)))
 
 end # module

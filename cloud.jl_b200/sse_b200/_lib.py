@@ -25,6 +25,7 @@ SYMBOLS = {
     "sse_get_kernel_variant": (C.c_int32, [_h, C.POINTER(C.c_int32)]),
     "sse_state_alloc": (C.c_int32, [_h, _ppd]),
     "sse_state_free": (C.c_int32, [_h, C.c_void_p]),
+    "sse_state_fill": (C.c_int32, [_h, C.c_void_p, C.c_double]),
     "sse_state_upload": (C.c_int32, [_h, C.c_void_p, C.c_void_p]),
     "sse_state_download": (C.c_int32, [_h, C.c_void_p, C.c_void_p]),
     "sse_rhs": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_double]),

@@ -143,6 +143,7 @@ int32_t sse_get_kernel_variant(const sse_handle* h, int32_t* variant);
 /* -- state vectors (u, dudt of Solvers.jl:474-483; layout (N_p, N_c, N_e)) --------------------- */
 int32_t sse_state_alloc(sse_handle* h, double** d_out);
 int32_t sse_state_free(sse_handle* h, double* d_ptr);
+int32_t sse_state_fill(sse_handle* h, double* d_x, double value);      /* fill!(x, value), zero(x) */
 int32_t sse_state_upload(sse_handle* h, double* d_dst, const double* h_src);
 int32_t sse_state_download(sse_handle* h, double* h_dst, const double* d_src);
 

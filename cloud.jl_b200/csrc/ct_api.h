@@ -28,6 +28,15 @@ struct RkStage {
     double A = 0.0, B = 0.0, dt = 0.0;
 };
 
+// device tables of the fused 3-D advection path (kernels_adv.cuh), warp-interleaved: [task of 32/N elements][item][32 lanes]
+struct AdvDev {
+    const double* C = nullptr;      // [task][m][a1][a2][32]   c_m = sum_n (W Lambda_mn / 2) a_n at node (a1, a2, lane's a3)
+    const double* iJW = nullptr;    // [task][a1][a2][32]      W / J
+    const double* F = nullptr;      // [task][2][4 N][32]      fa = BJf (a.n)/2, fl = BJf halflambda |a.n| at the lane's facet nodes
+    const int* map = nullptr;       // [task][4 N][32]         0-based index of the neighbour's facet node in u_f
+    double* um = nullptr;           // [N_e][N_p]              modal coefficients handed from pass A to pass B
+};
+
 struct CtPlan {
     int ok = 0, N = 0;
     int kind = 0;                   // 0: Euler flux differencing; 1: linear advection, StandardForm + ReferenceOperators
@@ -39,6 +48,8 @@ struct CtPlan {
     int minb = 4;                   // resident CTAs per SM requested for k_fluxdiff_ct (tuning knob)
     int dual = 1;                   // two pairs per thread and round in k_fluxdiff_ct (N = 5; SSE_FD_DUAL=0 disables)
     int proj_minb = 3;              // same for k_nodal_ct / k_project_ct
+    AdvDev adv;                     // kind 1: tables of the fused two-kernel path; adv_ok = 0 -> the three-kernel path
+    int adv_ok = 0;
 };
 
 bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& tp, int* Nout);
@@ -50,6 +61,9 @@ bool ct_facet_factors(const sse_config& cfg, const sse_arrays& a, int N, std::ve
 // true when the generic tables of tp equal the closed-form schedule k_fluxdiff_ct hard-codes
 bool ct_schedule_matches(const TensorPlan& tp, int N);
 cudaError_t ct_set_attrs(int N);
+// builds the tables of the fused advection path on the device (allocations are appended to `owned`); false on failure
+bool ct_adv_build(CtPlan& p, const Geo& g, const Law& L, const double* W, const double* Bf, long long Ne, long long NFT,
+                  cudaStream_t s, std::vector<void*>& owned);
 void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q, double* u_f,
               cudaStream_t s);
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,

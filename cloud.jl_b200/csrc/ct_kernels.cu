@@ -1,5 +1,6 @@
 // ct_kernels.cu — instantiations of the compile-time-sized kernels (N = p + 1 = 4, 5)
 #include "kernels_ct.cuh"
+#include "kernels_adv.cuh"
 
 namespace sse {
 
@@ -110,6 +111,40 @@ template <int N> static SFCoef<N> make_coef(const CtPlan& p) {
     return c;
 }
 
+// fused advection path: warps per CTA and resident CTAs per SM requested from ptxas (register cap 65536 / (32 WARPS MINB))
+#ifndef SSE_ADV_WARPS
+#define SSE_ADV_WARPS 2
+#endif
+#ifndef SSE_ADV_MINB
+#define SSE_ADV_MINB 5
+#endif
+constexpr int ADV_WARPS = SSE_ADV_WARPS, ADV_MINB = SSE_ADV_MINB;
+template <int N> static constexpr int adv_smem() { return (int)(sizeof(double) * ADV_WARPS * AdvSmem<N>::GSLOTS * AdvSmem<N>::group); }
+
+template <int N> static bool adv_build_n(CtPlan& p, const Geo& g, const Law& L, const double* W, const double* Bf, long long Ne,
+                                         cudaStream_t s, std::vector<void*>& owned) {
+    constexpr int GPW = 32 / N, NN = N * N, NI = 4 * N, Np = Tet<N>::Np;
+    const long long tasks = (Ne + GPW - 1) / GPW;
+    double *C = nullptr, *iJW = nullptr, *F = nullptr, *um = nullptr;
+    int* map = nullptr;
+    auto al = [&](void** q, size_t bytes) { if (cudaMalloc(q, bytes) != cudaSuccess) return false; owned.push_back(*q); return cudaMemsetAsync(*q, 0, bytes, s) == cudaSuccess; };
+    if (!al((void**)&C, sizeof(double) * tasks * 3 * NN * 32) || !al((void**)&iJW, sizeof(double) * tasks * NN * 32) ||
+        !al((void**)&F, sizeof(double) * tasks * 2 * NI * 32) || !al((void**)&map, sizeof(int) * tasks * NI * 32) ||
+        !al((void**)&um, sizeof(double) * Ne * Np))
+        return false;
+    k_adv_build<N><<<(unsigned)Ne, 128, 0, s>>>(Ne, W, g.Lambda_q, g.J_q, g.J_f, g.nJf, Bf, g.mapP, L, C, iJW, F, map);
+    if (cudaGetLastError() != cudaSuccess) return false;
+    p.adv.C = C; p.adv.iJW = iJW; p.adv.F = F; p.adv.map = map; p.adv.um = um;
+    p.adv_ok = 1;
+    return true;
+}
+bool ct_adv_build(CtPlan& p, const Geo& g, const Law& L, const double* W, const double* Bf, long long Ne, long long NFT,
+                  cudaStream_t s, std::vector<void*>& owned) {
+    if (p.kind != 1 || NFT >= 2147483647LL) return false;             // neighbour indices are stored as int32
+    if (const char* e = getenv("SSE_ADV_FUSED")) if (atoi(e) == 0) return false;
+    return p.N == 5 ? adv_build_n<5>(p, g, L, W, Bf, Ne, s, owned) : adv_build_n<4>(p, g, L, W, Bf, Ne, s, owned);
+}
+
 template <int N> static cudaError_t set_attrs_n() {
     cudaError_t e;
     const int proj5 = (int)(sizeof(double) * ProjSmem<N, 5>::total), proj1 = (int)(sizeof(double) * ProjSmem<N, 1>::total);
@@ -119,6 +154,8 @@ template <int N> static cudaError_t set_attrs_n() {
     if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 1, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod1))) return e;
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
     if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, SSE_FD_MINB_CT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
+    if ((e = cudaFuncSetAttribute(k_adv_facets_ct<N, ADV_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, adv_smem<N>()))) return e;
+    if ((e = cudaFuncSetAttribute(k_adv_fused_ct<N, ADV_WARPS, ADV_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, adv_smem<N>()))) return e;
     if constexpr (N == 5) {
         if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, SSE_FD_MINB_CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N, true>::total)))) return e;
     }
@@ -132,6 +169,11 @@ static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first
     if (p.kind == 0) {
         const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
         k_nodal_ct<N, 5, 3, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5, true>::total, s>>>(make_coef<N>(p), make_facet<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
+    } else if (p.adv_ok) {
+        constexpr int GPW = 32 / N;
+        const long long tasks = (first + count - 1) / GPW - first / GPW + 1;
+        k_adv_facets_ct<N, ADV_WARPS><<<(unsigned)((tasks + ADV_WARPS - 1) / ADV_WARPS), ADV_WARPS * 32, adv_smem<N>(), s>>>(
+            make_coef<N>(p), make_facet<N>(p), p.dev, p.adv, first, count, u, u_f);
     } else {
         const unsigned grid = (unsigned)((count + ProjSmem<N, 1>::EPB - 1) / ProjSmem<N, 1>::EPB);
         k_nodal_ct<N, 1, 4, false><<<grid, 128, sizeof(double) * ProjSmem<N, 1, true>::total, s>>>(make_coef<N>(p), make_facet<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
@@ -216,6 +258,16 @@ bool ct_eligible_standard(const sse_config& cfg, const sse_arrays& a, int* Nout,
 template <int N>
 static void standard_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
                        double* dudt, cudaStream_t s, RkStage rk, cudaEvent_t mid) {
+    if (p.adv_ok) {                                   // two-kernel path: everything of pass B in one launch
+        constexpr int GPW = 32 / N;
+        AdvTabs2<N> tb;
+        for (int m = 0; m < 3; m++) for (int i = 0; i < N * N; i++) tb.D1[m][i] = p.D1[m * N * N + i];
+        const long long tasks = (first + count - 1) / GPW - first / GPW + 1;
+        if (mid) cudaEventRecord(mid, s);
+        k_adv_fused_ct<N, ADV_WARPS, ADV_MINB><<<(unsigned)((tasks + ADV_WARPS - 1) / ADV_WARPS), ADV_WARPS * 32, adv_smem<N>(), s>>>(
+            make_coef<N>(p), make_facet<N>(p), tb, p.dev, p.adv, g, first, count, u_f, dudt, rk);
+        return;
+    }
     constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
     AdvTabs<N> tabs;
     for (int m = 0; m < 3; m++) for (int i = 0; i < N * N; i++) tabs.D1[m][i] = p.D1[m * N * N + i];

@@ -490,6 +490,10 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
             if ((rc = upload_c3(h, a, N))) return rc;
             if ((rc = upload(h, h->ct.fR, &h->ct.dev.fR))) return rc;
             if (ct_set_attrs(N) != cudaSuccess) return fail(SSE_ERR_CUDA, "cudaFuncSetAttribute (compile-time kernels) failed");
+            // fused two-kernel path (kernels_adv.cuh): derived coefficient tables in the kernels' own order; falls back to the
+            // three-kernel path when the tables cannot be built (memory) or are switched off (SSE_ADV_FUSED=0)
+            ct_adv_build(h->ct, g, h->law, o.W, o.Bf, Ne, g.NFT, h->stream, h->owned);
+            cudaGetLastError();
             h->ct.ok = 1;
         }
     }
@@ -683,7 +687,7 @@ int32_t sse::pass_b_stage(sse_handle* h, double* d_dudt, int64_t first, int64_t 
         }
     } else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE && h->variant == 1 && h->ct.ok && h->ct.kind == 1) {
         ct_standard(h->ct, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream, rk, mid);
-        h->launches += 1;
+        h->launches += h->ct.adv_ok ? 0 : 1;           // derivative kernel + projection kernel, or the fused kernel alone
     } else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE) {
 #define LA(D_, NC_) k_time_standard_reference<D_, NC_><<<n, h->threads, h->smem_time, h->stream>>>(h->ops, h->geo, h->law, first, h->u_q, h->u_f, d_dudt)
         DISPATCH_DNC(h, LA);

@@ -111,12 +111,19 @@ template <int N> static SFCoef<N> make_coef(const CtPlan& p) {
     return c;
 }
 
+// resident CTAs per SM requested for the Euler projection kernels (3: 128 registers, 15 warps per SM)
+#ifndef SSE_NODAL_MINB_CT
+#define SSE_NODAL_MINB_CT 3
+#endif
+#ifndef SSE_PROJ_MINB_CT
+#define SSE_PROJ_MINB_CT 3
+#endif
 // fused advection path: warps per CTA and resident CTAs per SM requested from ptxas (register cap 65536 / (32 WARPS MINB))
 #ifndef SSE_ADV_WARPS
 #define SSE_ADV_WARPS 2
 #endif
 #ifndef SSE_ADV_MINB
-#define SSE_ADV_MINB 5
+#define SSE_ADV_MINB 4
 #endif
 constexpr int ADV_WARPS = SSE_ADV_WARPS, ADV_MINB = SSE_ADV_MINB;
 template <int N> static constexpr int adv_smem() { return (int)(sizeof(double) * ADV_WARPS * AdvSmem<N>::GSLOTS * AdvSmem<N>::group); }
@@ -149,8 +156,8 @@ template <int N> static cudaError_t set_attrs_n() {
     cudaError_t e;
     const int proj5 = (int)(sizeof(double) * ProjSmem<N, 5>::total), proj1 = (int)(sizeof(double) * ProjSmem<N, 1>::total);
     const int nod5 = (int)(sizeof(double) * ProjSmem<N, 5, true>::total), nod1 = (int)(sizeof(double) * ProjSmem<N, 1, true>::total);
-    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 5, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod5))) return e;
-    if ((e = cudaFuncSetAttribute(k_project_ct<N, 5, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
+    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 5, SSE_NODAL_MINB_CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod5))) return e;
+    if ((e = cudaFuncSetAttribute(k_project_ct<N, 5, SSE_PROJ_MINB_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
     if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 1, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod1))) return e;
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
     if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, SSE_FD_MINB_CT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
@@ -168,7 +175,7 @@ static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first
                     cudaStream_t s) {
     if (p.kind == 0) {
         const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
-        k_nodal_ct<N, 5, 3, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5, true>::total, s>>>(make_coef<N>(p), make_facet<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
+        k_nodal_ct<N, 5, SSE_NODAL_MINB_CT, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5, true>::total, s>>>(make_coef<N>(p), make_facet<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
     } else if (p.adv_ok) {
         constexpr int GPW = 32 / N;
         const long long tasks = (first + count - 1) / GPW - first / GPW + 1;
@@ -196,7 +203,7 @@ static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, cons
     if (!done) k_fluxdiff_ct<N, SSE_FD_MINB_CT, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
     if (mid) cudaEventRecord(mid, s);
     const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
-    k_project_ct<N, 5, 3><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt, rk);
+    k_project_ct<N, 5, SSE_PROJ_MINB_CT><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt, rk);
 }
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
                  double* u_q, const double* u_f, double* dudt, cudaStream_t s, RkStage rk, cudaEvent_t mid) {

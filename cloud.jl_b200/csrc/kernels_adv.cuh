@@ -95,8 +95,13 @@ k_adv_facets_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, AdvDev ad, long long first,
 
 // ---------------------------------------------------------------------------------------------------------
 // pass B, fused
+#ifdef SSE_ADV_MAXREG
+template <int N, int WARPS, int MINB>
+__global__ void __maxnreg__(SSE_ADV_MAXREG)
+#else
 template <int N, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
+#endif
 k_adv_fused_ct(SFCoef<N> cf, FacetR<N> fr, AdvTabs2<N> tb, CtDev t, AdvDev ad, Geo g, long long first, long long count,
                const double* __restrict__ u_f, double* __restrict__ dudt, RkStage rk) {
     using T = Tet<N>;

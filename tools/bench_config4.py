@@ -29,7 +29,7 @@ def main():
     small = [(cases.advection_3d(M=4, flux=f, p=p), f"p{p} {f}") for p, f in ((4, "lf"), (4, "central"), (3, "lf"))]
     big = cases.advection_3d(M=M, flux="lf")
     img_big, u_big = big.image(), big.u0(seed=0)
-    for fused in (1, 0):
+    for fused in ((1,) if os.environ.get("SSE_C4_FUSED_ONLY") else (1, 0)):
         os.environ["SSE_ADV_FUSED"] = str(fused)
         out = {"path": "fused (k_adv_facets_ct + k_adv_fused_ct)" if fused else "three kernels (k_nodal_ct + k_standard_adv_ct + k_project_ct)"}
         for c, name in small:

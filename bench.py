@@ -22,6 +22,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [os.path.join(ROOT, "cloud.jl_b200")]
 
 METRIC = "FP64 RHS DOF/s (3D Euler p=4 tets, flux-diff)"
+# BASELINE config 4 as a second workload (--workload advection_3d): HBM-bound, algorithmic 14 560 B per element;
+# the fused pass-B kernel streams everything but the u read / u_f write of pass A
+METRIC_ADV = "FP64 RHS DOF/s (3D advection p=4 tets, StandardForm)"
+ALG_BYTES_ADV = 14560.0
+ALG_BYTES_ADV_FUSED = 14560.0 - 280.0 - 800.0
+NCU_DRAM_BYTES_ADV = {"k_adv_facets_ct": 1078.0, "k_adv_fused_ct": 7735.0}    # profiles/r2_ncu_config4.csv (196 608 elements)
 # algorithmic figures per element, p=4 tet Euler
 ALG_BYTES_RHS = 23200.0          # compulsory HBM traffic of one RHS
 ALG_BYTES_PASS_B = 26800.0       # time_derivative kernel alone: u_q 5000 + own/nbr u_f 8000 + Λ 9000 + J_q 1000 + nJf 2400 + dudt 1400
@@ -39,14 +45,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cells", type=int, default=int(os.environ.get("SSE_BENCH_CELLS", "56")),
-                    help="cubes per direction (6 tets each); 56 -> 1 053 696 elements")
+    ap.add_argument("--workload", default="euler_tgv_3d", choices=["euler_tgv_3d", "advection_3d"],
+                    help="euler_tgv_3d: BASELINE config 5 (the headline metric); advection_3d: config 4")
+    ap.add_argument("--cells", type=int, default=int(os.environ.get("SSE_BENCH_CELLS", "0")),
+                    help="cubes per direction (6 tets each); default 56 -> 1 053 696 elements (config 5), 32 -> 196 608 (config 4)")
     ap.add_argument("--flux", default="lf", choices=["lf", "ec"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-cells", type=int, default=16, help="cubes per direction of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--variant", type=int, default=1)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.cells <= 0:
+        a.cells = 56 if a.workload == "euler_tgv_3d" else 32
+    return a
 
 
 class ClockSampler(threading.Thread):
@@ -72,7 +83,7 @@ class ClockSampler(threading.Thread):
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
+                time.sleep(0.01)
         except Exception as e:          # never let monitoring kill the benchmark
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -83,14 +94,32 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def workload_name(cells, n_e, dof, flux):
+def workload_name(cells, n_e, dof, flux, workload="euler_tgv_3d"):
+    if workload == "advection_3d":
+        return (f"advection_3d: 3-D linear advection a = (1,1,1), ModalTensor p=4 curved tets, {cells}^3 cubes x 6 = {n_e} elements "
+                f"({dof} DOF), StandardForm(skew-symmetric mapping, {'Lax-Friedrichs' if flux == 'lf' else 'central'} interface flux), "
+                "DelReyWarping 0.1, conservative-curl metrics")
     return (f"euler_tgv_3d: 3-D Euler Taylor-Green vortex, ModalTensor p=4 curved tets, {cells}^3 cubes x 6 = "
             f"{n_e} elements ({dof} DOF), FluxDifferencingForm(EC two-point, "
             f"{'Lax-Friedrichs' if flux == 'lf' else 'EC'} interface), ChanWarping 1/16, conservative-curl metrics")
 
 
-def build_case(cells, flux, part, device=None):
+def build_case(cells, flux, part, device=None, workload="euler_tgv_3d"):
     from sse_b200 import cases
+    if workload == "advection_3d":
+        from sse_b200.assembly import REFERENCE_OPERATOR, SpatialDiscretization, StandardForm
+        from sse_b200.laws import LinearAdvectionEquation, initial_data_cosine, project_function_reference
+        from sse_b200.mesh import DelReyWarping, uniform_periodic_mesh
+        from sse_b200.reference import ModalTensor, reference_approximation
+        ra = reference_approximation(ModalTensor(4), "Tet", mapping_degree=4)
+        mesh = uniform_periodic_mesh(ra, ((0.0, 1.0),) * 3, (cells,) * 3, DelReyWarping(0.1, (1.0,) * 3), part)
+        sd = SpatialDiscretization.build(mesh, ra, "curl", need_nJq=False, device=device)
+        ic = initial_data_cosine(1.0, (2 * np.pi,) * 3)
+        c = cases.Case("advection_3d", LinearAdvectionEquation((1.0, 1.0, 1.0)), sd,
+                       StandardForm(inviscid_numerical_flux=cases._flux(flux)), REFERENCE_OPERATOR, ic)
+        u0 = project_function_reference(ic, ra, mesh.xyzq)
+        mesh.xyzq = mesh.xyzf = None
+        return c, u0
     from sse_b200.assembly import FluxDifferencingForm, REFERENCE_OPERATOR, SpatialDiscretization
     from sse_b200.laws import EulerEquations, project_function_reference, taylor_green_vortex
     from sse_b200.mesh import ChanWarping, uniform_periodic_mesh
@@ -114,12 +143,12 @@ def _cpu_sample_note(cells, case, reps, t, used):
             "Solvers.jl:505-511), built -O3 -march=native on this box (the Julia reference cannot run in this image)")
 
 
-def cpu_baseline(cells, flux, budget_s=12.0):
+def cpu_baseline(cells, flux, budget_s=12.0, workload="euler_tgv_3d"):
     """The reference algorithm (oracle port, OpenMP over elements like Threads.@threads) on a bounded
     sample of the same workload, on this box's host cores: about `budget_s` seconds of CPU work."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
-    c, u0 = build_case(cells, flux, None)
+    c, u0 = build_case(cells, flux, None, workload=workload)
     img = c.image()
     nt = oracle.host_threads()
     t1, used, _ = oracle.time_rhs(img, u0, nt, 1, perf=True)                 # warm-up and cost estimate
@@ -138,7 +167,7 @@ def run_reference(a):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
     cells = a.cpu_cells
-    c, u0 = build_case(cells, a.flux, None)
+    c, u0 = build_case(cells, a.flux, None, workload=a.workload)
     img = c.image()
     nt = oracle.host_threads()
     for _ in range(max(a.warmup, 1)):
@@ -150,12 +179,13 @@ def run_reference(a):
     t = float(np.mean(ts))
     val = c.dof / t
     n_e_full = 6 * a.cells ** 3
+    dpe = 175 if a.workload == "euler_tgv_3d" else 35
     sample = "each step = one RHS: " + _cpu_sample_note(cells, c, a.steps, t, used)
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "DOF/s", "n_gpus": a.gpus, "steps": a.steps,
+        "impl": "reference", "metric": METRIC if a.workload == "euler_tgv_3d" else METRIC_ADV, "value": val, "unit": "DOF/s", "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a.cells, n_e_full, n_e_full * 175, a.flux), "sample": sample, "same_config": False},
+        "config": {"workload": workload_name(a.cells, n_e_full, n_e_full * dpe, a.flux, a.workload), "sample": sample, "same_config": False},
         "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": used, "kind": "port", "same_config": False, "sample": sample},
         "e2e": {"value": val, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -244,7 +274,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 
     t_setup = time.time()
-    case, u0 = build_case(a.cells, a.flux, (rank, world) if world > 1 else None, device=local)
+    case, u0 = build_case(a.cells, a.flux, (rank, world) if world > 1 else None, device=local, workload=a.workload)
+    adv = a.workload == "advection_3d"
     img = case.image()
     solver = Solver(img, local)
     solver.set_kernel_variant(a.variant)
@@ -252,7 +283,7 @@ def main():
     mesh = case.sd.mesh
     n_e_local = case.sd.N_e
     n_e = 6 * a.cells ** 3
-    dof = n_e * 175
+    dof = n_e * (35 if adv else 175)
     u = torch.from_numpy(u0).cuda()
     du = solver.new_state()
     ds = DistributedSolver(solver, mesh) if world > 1 else None
@@ -331,12 +362,12 @@ def main():
     checks = {}
     try:
         ds.rhs(du, u) if ds is not None else solver.rhs(du, u)
-        f = torch.tensor(solver.functionals(u, du)[:5], dtype=torch.float64, device="cuda")
+        f = torch.tensor(solver.functionals(u, du)[:int(solver.cfg.N_c)], dtype=torch.float64, device="cuda")
         sc = torch.tensor([float(du.abs().max())], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(f)
             dist.all_reduce(sc, op=dist.ReduceOp.MAX)
-        checks["conservation_residual_rel"] = float(f.abs().max() / (sc[0] * (2 * np.pi) ** 3))
+        checks["conservation_residual_rel"] = float(f.abs().max() / (sc[0] * (1.0 if adv else (2 * np.pi) ** 3)))
         checks["host_buffer_result_equals_device"] = bool(torch.equal(hdu, du.cpu()))
         if world > 1:
             okt = torch.tensor([1.0 if checks["host_buffer_result_equals_device"] else 0.0], dtype=torch.float64, device="cuda")
@@ -359,10 +390,10 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         out = {
-            "metric": METRIC, "value": value, "unit": "DOF/s", "n_gpus": world, "steps": a.steps,
+            "metric": METRIC_ADV if adv else METRIC, "value": value, "unit": "DOF/s", "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a.cells, n_e, dof, a.flux),
+            "config": {"workload": workload_name(a.cells, n_e, dof, a.flux, a.workload),
                        "partition": (f"{world} slabs along z, facet-trace halos by ncclSend/ncclRecv inside sse_rhs "
                                      f"(NCCL {solver.comm_info()[2]})") if world > 1 else "single GPU",
                        "l2": "no flush: per-step inputs (metrics + state, ~24 kB/element) are far larger than the 126 MB L2",
@@ -379,7 +410,25 @@ def main():
             fpeak = None
             out["roofline_error"] = str(e)
         fp_src = "measured in this run: register-resident DFMA microbenchmark (sse_fp64_peak); MEASURED_PEAKS.json has no FP64 figure"
-        if fpeak:
+        if adv:
+            gbs = ALG_BYTES_ADV * n_e / (ms_per_step * 1e-3) / 1e9
+            out["roofline_rhs"] = {"bound": "hbm", "what": "whole residual (k_adv_facets_ct + k_adv_fused_ct)", "achieved": gbs,
+                                   "peak": world * hbm_peak, "unit": "GB/s", "frac": gbs / (world * hbm_peak),
+                                   "algorithmic_bytes_per_element": ALG_BYTES_ADV, "peak_source": hbm_src,
+                                   "traffic": sum(NCU_DRAM_BYTES_ADV.values()) * n_e}
+            if kernel_ms is not None:
+                kms = {"k_adv_facets_ct": float(kernel_ms[0]), "k_adv_fused_ct": float(kernel_ms[2] + kernel_ms[3])}
+                ach = ALG_BYTES_ADV_FUSED * n_e_local / (kms["k_adv_fused_ct"] * 1e-3) / 1e9
+                out["roofline"] = {"bound": "hbm", "kernel": "k_adv_fused_ct (pass B in one kernel: V u, volume terms, interface flux, "
+                                                             "lift, V', mass solve)", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": ach / hbm_peak, "traffic": NCU_DRAM_BYTES_ADV["k_adv_fused_ct"] * n_e_local,
+                                   "kernel_ms": kms["k_adv_fused_ct"], "algorithmic_bytes_per_element": ALG_BYTES_ADV_FUSED,
+                                   "peak_source": hbm_src, "kernels": kms,
+                                   "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per element of this kernel (ncu "
+                                                     "--set full, profiles/r2_ncu_config4.csv), scaled to this launch; it is below the "
+                                                     "algorithmic figure because the kernel reads coefficient tables derived at "
+                                                     "sse_create (3 instead of 9 metric terms per node) instead of the raw metrics"}
+        elif fpeak:
             fl = ALG_FLOPS_RHS * n_e / (ms_per_step * 1e-3)
             # the binding bound of this path, for the whole residual (the figure BASELINE.json's >= 50 % target is about)
             out["roofline_rhs"] = {"bound": "fp64", "what": "whole residual (k_nodal_ct + k_fluxdiff_ct + k_project_ct" +
@@ -391,7 +440,7 @@ def main():
                                    "frac": ALG_BYTES_RHS * n_e / (ms_per_step * 1e-3) / 1e9 / (world * hbm_peak),
                                    "algorithmic_bytes_per_element": ALG_BYTES_RHS, "peak_source": hbm_src,
                                    "traffic": sum(NCU_DRAM_BYTES.values()) * n_e}
-        if kernel_ms is not None and fpeak:
+        if kernel_ms is not None and fpeak and not adv:
             flops = {"k_nodal_ct": ALG_FLOPS_RHS - ALG_FLOPS_PAIR - 36200.0, "k_fluxdiff_ct": ALG_FLOPS_PAIR, "k_project_ct": 36200.0}
             kms = {"k_nodal_ct": float(kernel_ms[0]), "k_fluxdiff_ct": float(kernel_ms[2]), "k_project_ct": float(kernel_ms[3])}
             ach = ALG_FLOPS_PAIR * n_e_local / (kms["k_fluxdiff_ct"] * 1e-3)
@@ -409,7 +458,7 @@ def main():
         out["checks"] = checks
         if not a.no_cpu_baseline and world == 1:
             try:
-                out["cpu_baseline"] = cpu_baseline(a.cpu_cells, a.flux)
+                out["cpu_baseline"] = cpu_baseline(a.cpu_cells, a.flux, workload=a.workload)
             except Exception as e:
                 out["cpu_baseline"] = {"error": str(e)}
         print(json.dumps(out))

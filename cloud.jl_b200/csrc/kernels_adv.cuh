@@ -60,6 +60,7 @@ k_adv_facets_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, AdvDev ad, long long first,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane / N, a3 = lane - gl * N;
     const long long task = first / GPW + (long long)blockIdx.x * WARPS + warp;
+    if (task > (first + count - 1) / GPW) return;              // a spare warp of the last CTA (no CTA barrier below: safe)
     const long long k = task * GPW + gl;
     const bool act = gl < GPW && k >= first && k < first + count;
     double* s_x = sm + (warp * S::GSLOTS + gl) * S::group + S::x;
@@ -111,6 +112,7 @@ k_adv_fused_ct(SFCoef<N> cf, FacetR<N> fr, AdvTabs2<N> tb, CtDev t, AdvDev ad, G
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane / N, a3 = lane - gl * N;
     const long long task = first / GPW + (long long)blockIdx.x * WARPS + warp;
+    if (task > (first + count - 1) / GPW) return;              // a spare warp of the last CTA (no CTA barrier below: safe)
     const long long k = task * GPW + gl;
     const bool act = gl < GPW && k >= first && k < first + count;
     double* s_x = sm + (warp * S::GSLOTS + gl) * S::group + S::x;
@@ -123,6 +125,28 @@ k_adv_fused_ct(SFCoef<N> cf, FacetR<N> fr, AdvTabs2<N> tb, CtDev t, AdvDev ad, G
     const double* pF = ad.F + (size_t)task * (2 * NI) * 32 + lane;
     const int* pM = ad.map + (size_t)task * NI * 32 + lane;
 
+#ifndef SSE_ADV_PREFETCH
+#define SSE_ADV_PREFETCH 150       // tasks ahead; measured at 196 608 elements: 0 -> 0.482, 32..300 -> 0.429-0.438, 600 -> 0.474, 1200 -> 0.500 ms
+#endif
+#if SSE_ADV_PREFETCH > 0
+    // The kernel is bound by the latency of its table reads at 8 warps per SM: pull the tables of a task that a later wave of
+    // CTAs will process from DRAM into L2 now (one prefetch per 128-byte line, spread over the lanes)
+    {
+        const long long pt = task + SSE_ADV_PREFETCH;
+        if (pt <= (first + count - 1) / GPW) {
+            const char* pc = (const char*)(ad.C + (size_t)pt * (3 * NN) * 32);
+            for (int i = lane; i < 3 * NN * 2; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + (size_t)i * 128));
+            const char* pw = (const char*)(ad.iJW + (size_t)pt * NN * 32);
+            for (int i = lane; i < NN * 2; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pw + (size_t)i * 128));
+            const char* pf = (const char*)(ad.F + (size_t)pt * (2 * NI) * 32);
+            for (int i = lane; i < 2 * NI * 2; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)i * 128));
+            const char* pm = (const char*)(ad.map + (size_t)pt * NI * 32);
+            for (int i = lane; i < NI; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pm + (size_t)i * 128));
+            const char* pu = (const char*)(ad.um + (size_t)pt * GPW * Np);
+            for (int i = lane; i < (GPW * Np * 8 + 127) / 128; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(pu + (size_t)i * 128));
+        }
+    }
+#endif
     // neighbour indices first: the gather of u+ depends on them (two round trips), everything else is one
     int jo[NI];
 #pragma unroll

@@ -19,7 +19,7 @@ from .laws import (CentralNumericalFlux, EntropyConservativeNumericalFlux, Euler
                    initial_data_cosine, initial_data_sine, isentropic_vortex, project_function,
                    taylor_green_vortex)
 from .mesh import ChanWarping, DelReyWarping, uniform_periodic_mesh
-from .reference import ModalTensor, NodalTensor, reference_approximation
+from .reference import ModalMulti, ModalTensor, NodalMulti, NodalTensor, reference_approximation
 
 
 @dataclass
@@ -56,7 +56,9 @@ def _flux(name: str):
 
 
 def _approx(kind: str, p: int):
-    return ModalTensor(p) if kind == "modal" else NodalTensor(p)
+    """"modal" / "nodal": the sum-factorised tensor-product schemes (tensor_simplex.jl); "modal_multi" / "nodal_multi": the
+    multidimensional schemes with dense operators (multidimensional.jl:1-75)."""
+    return {"modal": ModalTensor, "nodal": NodalTensor, "modal_multi": ModalMulti, "nodal_multi": NodalMulti}[kind](p)
 
 
 def advection_2d(M=4, p=4, flux="lf", kind="modal", warp=0.1, part=None) -> Case:

@@ -44,6 +44,11 @@ class ModalMulti:
     p: int
 
 
+@dataclass(frozen=True)
+class NodalMulti:
+    p: int
+
+
 NUM_FACES = {"Line": 2, "Tri": 3, "Tet": 4}
 DIM = {"Line": 1, "Tri": 2, "Tet": 3}
 
@@ -502,6 +507,8 @@ def reference_approximation(approx_type, element: str, mapping_degree: int = 1,
                             volume_quadrature_rule=None, facet_quadrature_rule=None
                             ) -> ReferenceApproximation:
     p = approx_type.p
+    if element in ("Tri", "Tet") and isinstance(approx_type, (ModalMulti, NodalMulti)):
+        return _ref_multi(approx_type, element, p, mapping_degree, volume_quadrature_rule, facet_quadrature_rule)
     if element == "Tri":
         return _ref_tri(approx_type, p, mapping_degree, volume_quadrature_rule,
                         facet_quadrature_rule)
@@ -513,6 +520,25 @@ def reference_approximation(approx_type, element: str, mapping_degree: int = 1,
     if element in ("Quad", "Hex"):
         return _ref_box(approx_type, element, p, mapping_degree, volume_quadrature_rule, facet_quadrature_rule)
     raise ValueError(f"unsupported element {element}")
+
+
+# multidimensional.jl:1-75 -- ModalMulti / NodalMulti: dense operators D_m = grad(VDM)_m P, R = V_f P (and V = VDM or I) with
+# P = (VDM' W VDM)^-1 VDM' W, on a simplex without a collapsed reference mapping (NoMapping).  The reference takes its volume /
+# facet nodes from StartUpDG's tabulated symmetric rules of degree 2p (not vendored); here the collapsed Gauss rules of the
+# tensor schemes stand in for them -- they are exact to degree 2p as well, so every operator identity the constructors rely
+# on holds (SBP property, exact differentiation and extrapolation of P_p), while the node SET differs from the reference's.
+def _ref_multi(approx_type, element, p, mapping_degree, vq, fq):
+    t = (_ref_tri if element == "Tri" else _ref_tet)(ModalTensor(p), p, mapping_degree, vq, fq)
+    VDM, W = t.V, t.W
+    grad = [Dm @ VDM for Dm in t.D_xi()]                      # basis gradients at the volume nodes (D_xi is exact on P_p)
+    Vf = t.R @ VDM                                            # basis at the facet nodes (R is exact on P_p)
+    P = np.linalg.solve(VDM.T @ (W[:, None] * VDM), VDM.T * W[None, :])
+    D = [g @ P for g in grad]
+    nodal = isinstance(approx_type, NodalMulti)
+    V = np.eye(W.size) if nodal else VDM
+    return ReferenceApproximation(approx_type, element, t.d, p, V.shape[1], V.shape[0], t.N_f, t.N_fac,
+                                  D, V, None, nodal, Vf @ P, W, t.B, None, None, t.rstq, t.rstf, t.nrstJ, t.geom,
+                                  is_tensor=False)
 
 
 # tensor_simplex.jl:158-219

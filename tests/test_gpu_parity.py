@@ -55,6 +55,13 @@ CASES = {
     "euler_tgv_3d_standard_lf": lambda: cases.euler_tgv_3d_standard(M=2, p=4, flux="lf"),
     "euler_tgv_3d_standard_p3_central": lambda: cases.euler_tgv_3d_standard(M=2, p=3, flux="central"),
     "euler_tgv_3d_standard_physical": lambda: cases.euler_tgv_3d_standard(M=2, p=3, flux="lf", strategy=PHYSICAL_OPERATOR),
+    # dense multidimensional operators (multidimensional.jl:1-75) through the generic kernels
+    "advection_2d_modal_multi": lambda: cases.advection_2d(M=3, flux="lf", kind="modal_multi"),
+    "advection_3d_nodal_multi": lambda: cases.advection_3d(M=2, p=3, flux="lf", kind="nodal_multi"),
+    "euler_vortex_2d_modal_multi": lambda: cases.euler_vortex_2d(M=3, p=3, flux="ec", kind="modal_multi"),
+    "euler_vortex_2d_nodal_multi": lambda: cases.euler_vortex_2d(M=3, p=4, flux="lf", kind="nodal_multi"),
+    "euler_tgv_3d_modal_multi": lambda: cases.euler_tgv_3d(M=2, p=2, flux="ec", kind="modal_multi"),
+    "euler_tgv_3d_nodal_multi": lambda: cases.euler_tgv_3d(M=2, p=2, flux="lf", kind="nodal_multi"),
     "burgers_1d_ec": lambda: cases.burgers_1d(M=8, p=7, flux="ec"),
     "burgers_1d_lf": lambda: cases.burgers_1d(M=8, p=5, flux="lf"),
     "advection_2d_quad": lambda: cases.advection_2d_quad(M=3, p=4, flux="lf"),
@@ -359,3 +366,31 @@ def test_config5_at_24576_elements_matches_oracle():
     s.rhs_host(hd, hu, chunks=7)                      # the pipelined host-buffer residual returns the same bits
     s.close()
     assert np.array_equal(hd.numpy(), got)
+
+
+@pytest.mark.parametrize("first,count", [(0, 384), (5, 100), (7, 1), (101, 283), (380, 4)])
+def test_config4_fused_path_on_element_ranges(first, count):
+    """The fused advection kernels work on tasks of 32/N elements; a pass over an arbitrary element range (the multi-GPU
+    interior / halo split, the ranges of the pipelined host-buffer residual) must touch exactly that range -- including
+    ranges that start or end inside a task and an odd number of tasks (spare warp of the last CTA)."""
+    c = cases.advection_3d(M=4, flux="lf")
+    img, u = c.image(), c.u0(seed=1)
+    ref = oracle.rhs(img, u)
+    s = Solver(img, 0)
+    assert s.kernel_variant() == 2
+    du = s.new_state()
+    du.fill_(777.0)
+    ud = torch.from_numpy(u).cuda()
+    s.pass_a(ud)
+    s.pass_b(du, first, count)
+    s.synchronize()
+    got = du.cpu().numpy()
+    assert relerr(got[first:first + count], ref[first:first + count]) <= RTOL
+    mask = np.ones(got.shape[0], dtype=bool)
+    mask[first:first + count] = False
+    assert np.all(got[mask] == 777.0)
+    hu = torch.from_numpy(u).pin_memory()
+    hd = torch.empty_like(hu).pin_memory()
+    s.rhs_host(hd, hu, chunks=7)
+    s.close()
+    assert relerr(hd.numpy(), ref) <= RTOL

@@ -19,7 +19,13 @@ from sse_b200.assembly import PHYSICAL_OPERATOR, assemble
     lambda: cases.euler_vortex_2d_standard(M=3, p=4, flux="lf"),
     lambda: cases.euler_vortex_2d_standard(M=3, p=3, flux="central", strategy=PHYSICAL_OPERATOR),
     lambda: cases.euler_tgv_3d_standard(M=2, p=3, flux="lf"),
-    lambda: cases.euler_tgv_3d_standard(M=2, p=4, flux="central")])
+    lambda: cases.euler_tgv_3d_standard(M=2, p=4, flux="central"),
+    # multidimensional schemes with dense D, S, R (and dense V or V = I): multidimensional.jl:1-75, runtests.jl:98-109
+    lambda: cases.advection_2d(M=3, flux="lf0", kind="modal_multi"),
+    lambda: cases.advection_3d(M=2, p=3, flux="central", kind="nodal_multi"),
+    lambda: cases.euler_vortex_2d(M=3, p=3, flux="ec", kind="modal_multi"),
+    lambda: cases.euler_vortex_2d(M=3, p=3, flux="lf", kind="nodal_multi"),
+    lambda: cases.euler_tgv_3d(M=2, p=2, flux="ec", kind="modal_multi")])
 def test_invariants(case):
     c = case()
     img, u = c.image(), c.u0(seed=0)
@@ -50,6 +56,24 @@ def test_physical_operator_equals_reference_operator(case):
     a = oracle.rhs(c.image(), u)
     b = oracle.rhs(assemble(c.law, c.sd, c.form, PHYSICAL_OPERATOR), u)
     assert np.abs(a - b).max() <= 1e-13 * np.abs(a).max()
+
+
+def test_multidimensional_operators():
+    """ModalMulti / NodalMulti (multidimensional.jl:1-75): D_m = grad(VDM)_m P, R = V_f P with P the W-orthogonal projection.
+    check_sbp_property (SpatialDiscretizations.jl:441-455), exact differentiation of P_p and D_m V = grad V on the nodes."""
+    from sse_b200.reference import ModalMulti, ModalTensor, NodalMulti, reference_approximation
+    for el, p in (("Tri", 4), ("Tet", 3)):
+        t = reference_approximation(ModalTensor(p), el, mapping_degree=p)
+        for T in (ModalMulti, NodalMulti):
+            ra = reference_approximation(T(p), el, mapping_degree=p)
+            assert ra.V_warped is None and ra.J_ref is None and not ra.is_tensor
+            assert (ra.N_p == ra.N_q) == (T is NodalMulti)
+            assert max(ra.check_sbp_property()) < 1e-13
+            for m, Dm in enumerate(ra.D):
+                assert np.abs(Dm @ t.V - t.D_xi()[m] @ t.V).max() < 1e-11          # both differentiate the basis exactly
+                assert np.count_nonzero(np.abs(Dm) > 1e-14) > 0.9 * Dm.size         # dense, unlike the tensor-product operators
+            S, C = ra.flux_differencing_operators()
+            assert all(np.abs(Sm + Sm.T).max() < 1e-14 for Sm in S) and C is not None
 
 
 def test_euler_standard_form_physical_flux():

@@ -69,5 +69,13 @@ void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
                  double* u_q, const double* u_f, double* dudt, cudaStream_t s, RkStage rk = RkStage(), cudaEvent_t mid = nullptr);
 // mid: recorded between the two kernels of pass B (sse_profile_rhs times them separately)
+// pair kernel of pass B alone: r_q stays in the u_q scratch for ct_project_nodal / the projection kernel
+void ct_pair(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f, cudaStream_t s);
+// projection kernel alone (pass B-2): dudt = M^-1 V' r_q with the optional fused stage update
+void ct_project(const CtPlan& p, const Geo& g, long long first, long long count, const double* r_q, double* dudt, cudaStream_t s, RkStage rk);
+// pass B-2 of one Runge-Kutta stage fused with pass A of the next (k_nodal_ct<..., FUSED>): dudt = M^-1 V' r_q, the 2N-storage
+// update of rk.u / rk.tmp, then u_q / u_f of the updated state
+void ct_project_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, double* u_f,
+                      double* dudt, cudaStream_t s, RkStage rk);
 
 }  // namespace sse

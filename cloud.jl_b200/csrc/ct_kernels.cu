@@ -157,6 +157,7 @@ template <int N> static cudaError_t set_attrs_n() {
     const int proj5 = (int)(sizeof(double) * ProjSmem<N, 5>::total), proj1 = (int)(sizeof(double) * ProjSmem<N, 1>::total);
     const int nod5 = (int)(sizeof(double) * ProjSmem<N, 5, true>::total), nod1 = (int)(sizeof(double) * ProjSmem<N, 1, true>::total);
     if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 5, SSE_NODAL_MINB_CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod5))) return e;
+    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 5, SSE_NODAL_MINB_CT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod5))) return e;
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 5, SSE_PROJ_MINB_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
     if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 1, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod1))) return e;
     if ((e = cudaFuncSetAttribute(k_project_ct<N, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
@@ -189,6 +190,37 @@ static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first
 void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q, double* u_f,
               cudaStream_t s) {
     if (p.N == 5) nodal_n<5>(p, g, L, first, count, u, u_q, u_f, s); else nodal_n<4>(p, g, L, first, count, u, u_q, u_f, s);
+}
+
+template <int N>
+static void pair_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f, cudaStream_t s) {
+    constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
+    if constexpr (N == 5) {
+        if (p.dual) { k_fluxdiff_ct<N, SSE_FD_MINB_CT, true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); return; }
+    }
+    k_fluxdiff_ct<N, SSE_FD_MINB_CT, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
+}
+void ct_pair(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f, cudaStream_t s) {
+    if (p.N == 5) pair_n<5>(p, g, L, first, count, u_q, u_f, s); else pair_n<4>(p, g, L, first, count, u_q, u_f, s);
+}
+template <int N>
+static void project_n(const CtPlan& p, const Geo& g, long long first, long long count, const double* r_q, double* dudt, cudaStream_t s, RkStage rk) {
+    const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
+    k_project_ct<N, 5, SSE_PROJ_MINB_CT><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, r_q, dudt, rk);
+}
+void ct_project(const CtPlan& p, const Geo& g, long long first, long long count, const double* r_q, double* dudt, cudaStream_t s, RkStage rk) {
+    if (p.N == 5) project_n<5>(p, g, first, count, r_q, dudt, s, rk); else project_n<4>(p, g, first, count, r_q, dudt, s, rk);
+}
+template <int N>
+static void project_nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, double* u_f,
+                            double* dudt, cudaStream_t s, RkStage rk) {
+    const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
+    k_nodal_ct<N, 5, SSE_NODAL_MINB_CT, true, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5, true>::total, s>>>(
+        make_coef<N>(p), make_facet<N>(p), p.dev, g, L, first, count, nullptr, u_q, u_f, dudt, rk);
+}
+void ct_project_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, double* u_f,
+                      double* dudt, cudaStream_t s, RkStage rk) {
+    if (p.N == 5) project_nodal_n<5>(p, g, L, first, count, u_q, u_f, dudt, s, rk); else project_nodal_n<4>(p, g, L, first, count, u_q, u_f, dudt, s, rk);
 }
 
 template <int N>

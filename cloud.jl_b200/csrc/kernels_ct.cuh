@@ -254,12 +254,16 @@ template <int N, int NC, bool FACETS = false> struct ProjSmem {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// pass A — nodal_values! with the general (modal) entropy projection
-template <int N, int NC, int MINB, bool PROJECT>
+// pass A — nodal_values! with the general (modal) entropy projection.
+// FUSED (device-resident CarpenterKennedy2N54, sse_step_ck54): the kernel starts with pass B-2 of the PREVIOUS Runge-Kutta stage
+// on the same elements -- dudt = M^-1 V' r_q (k_project_ct), the 2N-storage update u += B (tmp = A tmp + dt dudt) -- and carries
+// the new modal coefficients straight into pass A of the next stage: no second launch, no re-read of u, one W / J tile.
+template <int N, int NC, int MINB, bool PROJECT, bool FUSED = false>
 __global__ void __launch_bounds__(ProjSmem<N, NC>::WARPS * 32, MINB)
 k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, long long count, const double* __restrict__ u,
-           double* __restrict__ u_q, double* __restrict__ u_f) {
+           double* __restrict__ u_q, double* __restrict__ u_f, double* __restrict__ dudt = nullptr, RkStage rk = RkStage()) {
     constexpr int D = 3;
+    static_assert(!FUSED || PROJECT, "the fused stage kernel is the Euler kernel");
     static_assert(!PROJECT || NC == D + 2, "the entropy projection of this kernel is written for the Euler equations");
     using T = Tet<N>;
     using S = ProjSmem<N, NC, true>;
@@ -278,6 +282,67 @@ k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, l
     const int nel = (int)((first + count - e0 < EPB) ? (first + count - e0) : EPB);
     const bool act = gl < T::GPW && (grp / NC) < nel;
 
+    double y[N][N];
+    const double* c3 = sm + S::c3 + a3;
+    if constexpr (FUSED) {
+        // ---- pass B-2 of the previous stage (the body of k_project_ct): r_q sits in the u_q scratch of these elements
+        for (int i = tid; i < Np * N; i += NT) cp_async8(sm + S::c3 + i, t.C3 + i);
+        for (int it = tid; it < nel * Nq; it += NT) {
+            const int el = it / Nq, i = it - el * Nq;
+            cp_async8(s_wij + el * S::QS + i, g.iJW + (size_t)(e0 + el) * Nq + i);
+        }
+        cp_async_commit();
+        // J_q is needed much later (entropy-variable phase): pull its lines into L2 now
+        for (int i = tid; i < (nel * Nq * 8 + 127) / 128; i += NT)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)(g.J_q + (size_t)e0 * Nq) + (size_t)i * 128));
+        if (act) {
+            const double* src = u_q + (size_t)e0 * NC * Nq + (size_t)grp * Nq + a3;
+#pragma unroll
+            for (int a1 = 0; a1 < N; a1++)
+#pragma unroll
+                for (int a2 = 0; a2 < N; a2++) y[a1][a2] = src[(a1 * N + a2) * N];
+        }
+        const double* c3g = t.C3 + a3;
+        double out[T::LPT];
+        if (act) sf3_bwd_partials<N, N, true, true>(cf, c3g, y, s_red + grp * S::RS + a3 * T::RED_SA);
+        __syncwarp();
+        if (act) {
+            sf3_bwd_reduce<N>(s_red + grp * S::RS, a3, out);
+#pragma unroll
+            for (int q = 0; q < T::LPT; q++) { const int l = a3 * T::LPT + q; if (l < Np) s_x[grp * Np + l] = out[q]; }
+        }
+        __syncwarp();
+        if (act) sf3_fwd<N, N, true, true>(cf, c3g, s_x + grp * Np, y);
+        cp_async_wait<0>();
+        __syncthreads();                                   // W / J tile and the shared C table (filled by all warps)
+        if (act) {
+            const double* wij = s_wij + (grp / NC) * S::QS;
+#pragma unroll
+            for (int a1 = 0; a1 < N; a1++)
+#pragma unroll
+                for (int a2 = 0; a2 < N; a2++) y[a1][a2] *= wij[(a1 * N + a2) * N + a3];
+            sf3_bwd_partials<N, N, true, true>(cf, c3g, y, s_red + grp * S::RS + a3 * T::RED_SA);
+        }
+        __syncwarp();
+        if (act) {
+            sf3_bwd_reduce<N>(s_red + grp * S::RS, a3, out);
+#pragma unroll
+            for (int q = 0; q < T::LPT; q++) {
+                const int l = a3 * T::LPT + q;
+                if (l < Np) {
+                    const size_t idx = (size_t)e0 * NC * Np + grp * Np + l;
+                    dudt[idx] = out[q];
+                    flag_nonfinite(g.flag, out[q]);
+                    const double tm = fma(rk.A, rk.tmp[idx], rk.dt * out[q]);      // 2N-storage stage (Carpenter & Kennedy 1994)
+                    rk.tmp[idx] = tm;
+                    const double un = fma(rk.B, tm, rk.u[idx]);
+                    rk.u[idx] = un;
+                    s_x[grp * Np + l] = un;                // ... and straight into pass A of the next stage
+                }
+            }
+        }
+        __syncwarp();
+    } else {
     // every global load of the prologue as an asynchronous copy: the C table and u (needed by the first V) form the first
     // group, J_q (needed by the entropy-variable phase only) the second one, which stays in flight behind the first V
     for (int i = tid; i < Np * N; i += NT) cp_async8(sm + S::c3 + i, t.C3 + i);
@@ -290,11 +355,10 @@ k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, l
         }
     }
     cp_async_commit();
-    const double* c3 = sm + S::c3 + a3;
     cp_async_wait<1>();
     __syncthreads();
+    }
 
-    double y[N][N];
     // u_q = V u
     if (act) sf3_fwd<N, N, SSE_NODAL_SYMB>(cf, c3, s_x + grp * Np, y);
     if constexpr (PROJECT) {
@@ -324,7 +388,8 @@ k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, l
                 const int el = it / Nq, i = it - el * Nq;
                 sq[k] = el * NC * S::QS + i;
                 sw[k] = el * S::QS + i;
-                J[k] = s_wij[sw[k]];
+                if constexpr (FUSED) J[k] = g.J_q[(size_t)(e0 + el) * Nq + i];       // the tile already holds W / J
+                else J[k] = s_wij[sw[k]];
                 W[k] = t.W[i];
 #pragma unroll
                 for (int e = 0; e < NC; e++) ui[k][e] = s_q[sq[k] + e * S::QS];
@@ -335,7 +400,7 @@ k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, l
             for (int k = 0; k < UT; k++) {
                 if (ok[k]) {
                     const double wj = W[k] * J[k];
-                    s_wij[sw[k]] = W[k] * rcp_fast(J[k]);
+                    if constexpr (!FUSED) s_wij[sw[k]] = W[k] * rcp_fast(J[k]);
 #pragma unroll
                     for (int e = 0; e < NC; e++) s_q[sq[k] + e * S::QS] = wi[k][e] * wj;
                 }

@@ -885,7 +885,27 @@ extern "C" int32_t sse_rhs_lsrk(sse_handle* h, double* d_u, double* d_tmp, doubl
     return SSE_OK;
 }
 extern "C" int32_t sse_step_ck54(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double t, double dt) {
+    if (!h || !d_u || !d_tmp || !d_dudt) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
     int32_t rc;
+    static const bool fuse_stages = [] { const char* e = getenv("SSE_CK54_FUSED"); return !e || atoi(e) != 0; }();
+    if (fuse_stages && h->variant == 1 && h->ct.ok && h->ct.kind == 0 && h->cfg.N_ghost == 0) {
+        // compile-time Euler path on one GPU: 11 launches instead of 15 -- pass A once, then per stage the pair kernel and ONE
+        // kernel that finishes the stage (projection, mass solve, 2N-storage update) and starts the next (entropy projection of
+        // the updated state); the last stage ends with the plain projection kernel
+        CU(cudaSetDevice(h->device));
+        const long long ne = h->cfg.N_e;
+        if ((rc = sse_rhs_pass_a(h, d_u))) return rc;
+        for (int s = 0; s < 5; s++) {
+            RkStage rk;
+            rk.u = d_u; rk.tmp = d_tmp; rk.A = CK_A[s]; rk.B = CK_B[s]; rk.dt = dt;
+            ct_pair(h->ct, h->geo, h->law, 0, ne, h->u_q, h->u_f, h->stream);
+            if (s < 4) ct_project_nodal(h->ct, h->geo, h->law, 0, ne, h->u_q, h->u_f, d_dudt, h->stream, rk);
+            else ct_project(h->ct, h->geo, 0, ne, h->u_q, d_dudt, h->stream, rk);
+            h->launches += 2;
+        }
+        CU(cudaGetLastError());
+        return SSE_OK;
+    }
     for (int s = 0; s < 5; s++)
         if ((rc = sse_rhs_lsrk(h, d_u, d_tmp, d_dudt, CK_A[s], CK_B[s], dt, t + CK_C[s] * dt))) return rc;
     return SSE_OK;

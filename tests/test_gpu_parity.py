@@ -394,3 +394,18 @@ def test_config4_fused_path_on_element_ranges(first, count):
     s.rhs_host(hd, hu, chunks=7)
     s.close()
     assert relerr(hd.numpy(), ref) <= RTOL
+
+
+def test_ck54_stage_fused_kernels_match_the_unfused_sequence():
+    """sse_step_ck54 on the compile-time Euler path runs each stage as pair kernel + ONE kernel that finishes the stage and starts
+    the next (k_nodal_ct<FUSED>); the result must equal residual + sse_lsrk_stage per stage (solve_ck54(fused=False)) to
+    round-off, on a mesh with a partial last CTA (384 elements = 64 CTAs of 6) and one without (48 elements)."""
+    for M in (2, 4):
+        c = cases.euler_tgv_3d(M=M, flux="lf")
+        img, u = c.image(), c.u0(seed=0)
+        s = Solver(img, 0)
+        a = solve_ck54(ODEProblem(semi_discrete_residual, u, (0.0, 1.0), s), 1e-3, 3, fused=True)
+        b = solve_ck54(ODEProblem(semi_discrete_residual, u, (0.0, 1.0), s), 1e-3, 3, fused=False)
+        s.close()
+        assert np.all(np.isfinite(a))
+        assert relerr(a, b) <= 1e-13

@@ -331,6 +331,31 @@ end
 # --- several GPUs driven by this one Julia process (include/sse_b200.h, "multi-GPU") ---------------------------------------
 # One Solver per partition (built from the partition's mesh: elements ordered interior first, `mapP` in local + ghost
 # numbering, `N_ghost` set in `attach!` through `n_ghost`), one GPU each.
+"""
+    partition(mapP, N_f, owner, n_parts, rank) -> NamedTuple
+
+Local view of `rank` (0-based) of an element partition, from the mesh's global connectivity `mesh.mapP` (N_f x N_e, 1-based;
+Solvers.jl:207) and the owner rank of every element: `elem_gid` (1-based global ids, interior elements first), `mapP` in
+local + ghost numbering, `n_interior`, `n_ghost`, and the halo plan (`nbr_rank`, `send_count`, `recv_count`, `send_index`).
+Build the partition's `SpatialDiscretization` from the elements `elem_gid`, pass `n_ghost` to `attach!` and the plan to
+`halo_plan!`.  Host only; no device is touched.
+"""
+function partition(mapP::Array{Int64}, N_f::Integer, owner::Vector{Int32}, n_parts::Integer, rank::Integer)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sse_partition_create, libsse), Int32, (Ptr{Int64}, Int64, Int32, Ptr{Int32}, Int32, Int32, Ptr{Ptr{Cvoid}}),
+        mapP, Int64(length(owner)), Int32(N_f), owner, Int32(n_parts), Int32(rank), h))
+    nl, ni, ng, ns, nn = Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0), Ref{Int64}(0), Ref{Int32}(0)
+    check(ccall((:sse_partition_sizes, libsse), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Ptr{Int64}),
+        h[], nl, ni, ng, nn, ns))
+    elem_gid, mapP_local = Vector{Int64}(undef, nl[]), Matrix{Int64}(undef, N_f, nl[])
+    nbr_rank, send_count, recv_count = Vector{Int32}(undef, nn[]), Vector{Int64}(undef, nn[]), Vector{Int64}(undef, nn[])
+    send_index = Vector{Int64}(undef, ns[])
+    check(ccall((:sse_partition_fill, libsse), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+        h[], elem_gid, mapP_local, nbr_rank, send_count, recv_count, send_index))
+    check(ccall((:sse_partition_destroy, libsse), Int32, (Ptr{Cvoid},), h[]))
+    return (; elem_gid, mapP = mapP_local, n_interior = ni[], n_ghost = ng[], nbr_rank, send_count, recv_count, send_index)
+end
+
 "join the handles of `pars` into one NCCL communicator (ncclCommInitAll)"
 comm_init_all!(pars::Vector{CUDAB200}) =
     check(ccall((:sse_comm_init_all, libsse), Int32, (Ptr{Ptr{Cvoid}}, Int32), [p.handle for p in pars], Int32(length(pars))))

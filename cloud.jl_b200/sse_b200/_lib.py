@@ -51,6 +51,10 @@ SYMBOLS = {
     "sse_rhs_multi": (C.c_int32, [C.POINTER(_h), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double]),
     "sse_step_ck54_multi": (C.c_int32, [C.POINTER(_h), C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p), C.c_double, C.c_double]),
+    "sse_partition_create": (C.c_int32, [_pi64, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(_h)]),
+    "sse_partition_sizes": (C.c_int32, [_h, _pi64, _pi64, _pi64, C.POINTER(C.c_int32), _pi64]),
+    "sse_partition_fill": (C.c_int32, [_h, _pi64, _pi64, C.POINTER(C.c_int32), _pi64, _pi64, _pi64]),
+    "sse_partition_destroy": (C.c_int32, [_h]),
     "sse_axpby": (C.c_int32, [_h, C.c_double, C.c_void_p, C.c_double, C.c_void_p]),
     "sse_lsrk_stage": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double]),
     "sse_rhs_lsrk": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]),

@@ -51,6 +51,35 @@ def exchanger_from_mesh(mesh, group=None) -> HaloExchanger:
     return HaloExchanger(mesh.nbr_ranks, sc, rc, group)
 
 
+def partition(mapP_1based, N_f: int, owner, n_parts: int, rank: int) -> dict:
+    """Local view of `rank` of an element partition (sse_partition_*: host only, works for any mesh and any owner array):
+    elem_gid (0-based here), mapP (0-based, local + ghost numbering, shape (n_local, N_f)), n_interior, n_ghost, nbr_ranks,
+    send_count, recv_count, send_idx (0-based indices into the owned facet array)."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.load()
+    mp = np.ascontiguousarray(np.asarray(mapP_1based).reshape(-1), dtype=np.int64)
+    ow = np.ascontiguousarray(owner, dtype=np.int32)
+    ne = ow.size
+    h = C.c_void_p()
+    p64, p32 = C.POINTER(C.c_int64), C.POINTER(C.c_int32)
+    _lib.check(L.sse_partition_create(mp.ctypes.data_as(p64), ne, int(N_f), ow.ctypes.data_as(p32), int(n_parts), int(rank), C.byref(h)))
+    try:
+        nl, ni, ng, ns, nn = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int32()
+        _lib.check(L.sse_partition_sizes(h, C.byref(nl), C.byref(ni), C.byref(ng), C.byref(nn), C.byref(ns)))
+        gid = np.zeros(nl.value, dtype=np.int64)
+        mpl = np.zeros(nl.value * N_f, dtype=np.int64)
+        nbr = np.zeros(nn.value, dtype=np.int32)
+        sc, rc = np.zeros(nn.value, dtype=np.int64), np.zeros(nn.value, dtype=np.int64)
+        si = np.zeros(ns.value, dtype=np.int64)
+        _lib.check(L.sse_partition_fill(h, gid.ctypes.data_as(p64), mpl.ctypes.data_as(p64), nbr.ctypes.data_as(p32),
+                                        sc.ctypes.data_as(p64), rc.ctypes.data_as(p64), si.ctypes.data_as(p64)))
+    finally:
+        L.sse_partition_destroy(h)
+    return {"elem_gid": gid - 1, "mapP": (mpl - 1).reshape(nl.value, N_f), "n_interior": int(ni.value), "n_ghost": int(ng.value),
+            "nbr_ranks": nbr.tolist(), "send_count": sc.tolist(), "recv_count": rc.tolist(), "send_idx": si - 1}
+
+
 class DistributedSolver:
     """Rank-local Solver of an element partition.  The exchange itself lives in the library (csrc/comm.cu: NCCL send/recv on a
     side stream inside sse_rhs / sse_rhs_lsrk / sse_step_ck54 / sse_rhs_host, all-reduce inside sse_functionals); this class

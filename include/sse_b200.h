@@ -210,6 +210,22 @@ int32_t sse_rhs_multi(sse_handle* const* handles, int32_t n, double* const* d_u,
 int32_t sse_step_ck54_multi(sse_handle* const* handles, int32_t n, double* const* d_u, double* const* d_tmp, double* const* d_dudt,
                             double t, double dt);
 
+/* Partition helper (host only, no device): the local view of `rank` of an element partition, from the reference's global
+   connectivity mesh.mapP (N_f x N_e, 1-based; Solvers.jl:207) and the owner rank of every element (slabs, blocks, or any graph
+   partition of the face adjacency).  Local elements are ordered interior first; ghost slots are grouped by neighbour rank
+   (ascending) and ordered by global facet-node index inside a rank, which is also the order of the owner's send list -- both
+   sides agree without communicating.  sse_partition_fill returns exactly what sse_create (mapP_local, N_e = n_local,
+   N_ghost = n_ghost; the operator / metric arrays of the elements elem_gid) and sse_halo_plan take. */
+typedef struct sse_partition sse_partition;
+int32_t sse_partition_create(const int64_t* mapP, int64_t N_e, int32_t N_f, const int32_t* owner, int32_t n_parts, int32_t rank,
+                             sse_partition** out);
+int32_t sse_partition_sizes(const sse_partition* p, int64_t* n_local, int64_t* n_interior, int64_t* n_ghost, int32_t* n_nbr, int64_t* n_send);
+/* elem_gid[n_local] (1-based global element ids), mapP_local[N_f x n_local] (1-based, local + ghost numbering), nbr_rank[n_nbr],
+   send_count[n_nbr], recv_count[n_nbr], send_index[n_send] (1-based into the owned (N_f, n_local) facet array); NULL skips */
+int32_t sse_partition_fill(const sse_partition* p, int64_t* elem_gid, int64_t* mapP_local, int32_t* nbr_rank, int64_t* send_count,
+                           int64_t* recv_count, int64_t* send_index);
+int32_t sse_partition_destroy(sse_partition* p);
+
 /* -- callers either side of the path ----------------------------------------- */
 /* y = a*x + b*y on state vectors (OrdinaryDiffEq broadcast updates) */
 int32_t sse_axpby(sse_handle* h, double a, const double* d_x, double b, double* d_y);

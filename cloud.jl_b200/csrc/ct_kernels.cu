@@ -4,6 +4,17 @@
 
 namespace sse {
 
+// polynomial degrees with compile-time kernels: N = p + 1 = 3 .. 6
+#define SSE_CT_DISPATCH(N_, CALL)                                                                   \
+    switch (N_) { case 3: CALL(3); break; case 4: CALL(4); break; case 5: CALL(5); break; case 6: CALL(6); break; default: break; }
+static bool ct_size_ok(int N) { return N >= 3 && N <= 6; }
+static int tet_l_rt(int N, int b1, int b2, int b3) {          // tet_l<N> for a run-time N
+    int l = 0;
+    for (int i = 0; i < b1; i++) { const int m = N - i; l += m * (m + 1) / 2; }
+    for (int j = 0; j < b2; j++) l += N - b1 - j;
+    return l + b3;
+}
+
 // C[a3, i, j, k] depends on (i + j, k) only (kernels_ct.cuh: c3_sym)
 static bool c_tensor_symmetric(const sse_arrays& a, int N) {
     if (!a.C) return false;
@@ -19,13 +30,13 @@ bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& t
     if (cfg.form != SSE_FORM_FLUX_DIFFERENCING || cfg.two_point_flux != SSE_TWO_POINT_ENTROPY_CONSERVATIVE) return false;
     if (cfg.v_kind != SSE_V_WARPED || cfg.mass_solver != SSE_MASS_WEIGHT_ADJUSTED || !a.Cfd) return false;
     const int N = cfg.p + 1;
-    if (N != 4 && N != 5) return false;
+    if (!ct_size_ok(N)) return false;
     if (cfg.M1d[0] != N || cfg.M1d[1] != N || cfg.M1d[2] != N) return false;
     if (cfg.N_q != N * N * N || cfg.N_p != N * (N + 1) * (N + 2) / 6 || cfg.N_f != 4 * N * N || cfg.N_fac != 4) return false;
     for (int t = 0; t < N * N * N; t++) {                  // canonical orderings (tensor_simplex.jl:111-131)
         const int a1 = t % N, a2 = (t / N) % N, a3 = t / (N * N);
         if (a.sigma_o[t] - 1 != (a1 * N + a2) * N + a3) return false;
-        const long long want = (a1 + a2 + a3 <= N - 1) ? (N == 4 ? tet_l<4>(a1, a2, a3) : tet_l<5>(a1, a2, a3)) + 1 : 0;
+        const long long want = (a1 + a2 + a3 <= N - 1) ? tet_l_rt(N, a1, a2, a3) + 1 : 0;
         if (a.sigma_i[t] != want) return false;
     }
     if (!c_tensor_symmetric(a, N)) return false;
@@ -149,7 +160,11 @@ bool ct_adv_build(CtPlan& p, const Geo& g, const Law& L, const double* W, const 
                   cudaStream_t s, std::vector<void*>& owned) {
     if (p.kind != 1 || NFT >= 2147483647LL) return false;             // neighbour indices are stored as int32
     if (const char* e = getenv("SSE_ADV_FUSED")) if (atoi(e) == 0) return false;
-    return p.N == 5 ? adv_build_n<5>(p, g, L, W, Bf, Ne, s, owned) : adv_build_n<4>(p, g, L, W, Bf, Ne, s, owned);
+    bool ok = false;
+#define CALL_(N_) ok = adv_build_n<N_>(p, g, L, W, Bf, Ne, s, owned)
+    SSE_CT_DISPATCH(p.N, CALL_);
+#undef CALL_
+    return ok;
 }
 
 template <int N> static cudaError_t set_attrs_n() {
@@ -169,7 +184,13 @@ template <int N> static cudaError_t set_attrs_n() {
     }
     return cudaSuccess;
 }
-cudaError_t ct_set_attrs(int N) { return N == 5 ? set_attrs_n<5>() : set_attrs_n<4>(); }
+cudaError_t ct_set_attrs(int N) {
+    cudaError_t e = cudaErrorInvalidValue;
+#define CALL_(N_) e = set_attrs_n<N_>()
+    SSE_CT_DISPATCH(N, CALL_);
+#undef CALL_
+    return e;
+}
 
 template <int N>
 static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q, double* u_f,
@@ -189,19 +210,23 @@ static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first
 }
 void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q, double* u_f,
               cudaStream_t s) {
-    if (p.N == 5) nodal_n<5>(p, g, L, first, count, u, u_q, u_f, s); else nodal_n<4>(p, g, L, first, count, u, u_q, u_f, s);
+#define CALL_(N_) nodal_n<N_>(p, g, L, first, count, u, u_q, u_f, s)
+    SSE_CT_DISPATCH(p.N, CALL_);
+#undef CALL_
 }
 
 template <int N>
 static void pair_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f, cudaStream_t s) {
-    constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
+    constexpr int NT = Tet<N>::NT;
     if constexpr (N == 5) {
         if (p.dual) { k_fluxdiff_ct<N, SSE_FD_MINB_CT, true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); return; }
     }
     k_fluxdiff_ct<N, SSE_FD_MINB_CT, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
 }
 void ct_pair(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f, cudaStream_t s) {
-    if (p.N == 5) pair_n<5>(p, g, L, first, count, u_q, u_f, s); else pair_n<4>(p, g, L, first, count, u_q, u_f, s);
+#define CALL_(N_) pair_n<N_>(p, g, L, first, count, u_q, u_f, s)
+    SSE_CT_DISPATCH(p.N, CALL_);
+#undef CALL_
 }
 template <int N>
 static void project_n(const CtPlan& p, const Geo& g, long long first, long long count, const double* r_q, double* dudt, cudaStream_t s, RkStage rk) {
@@ -209,7 +234,9 @@ static void project_n(const CtPlan& p, const Geo& g, long long first, long long 
     k_project_ct<N, 5, SSE_PROJ_MINB_CT><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, r_q, dudt, rk);
 }
 void ct_project(const CtPlan& p, const Geo& g, long long first, long long count, const double* r_q, double* dudt, cudaStream_t s, RkStage rk) {
-    if (p.N == 5) project_n<5>(p, g, first, count, r_q, dudt, s, rk); else project_n<4>(p, g, first, count, r_q, dudt, s, rk);
+#define CALL_(N_) project_n<N_>(p, g, first, count, r_q, dudt, s, rk)
+    SSE_CT_DISPATCH(p.N, CALL_);
+#undef CALL_
 }
 template <int N>
 static void project_nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, double* u_f,
@@ -220,13 +247,15 @@ static void project_nodal_n(const CtPlan& p, const Geo& g, const Law& L, long lo
 }
 void ct_project_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, double* u_f,
                       double* dudt, cudaStream_t s, RkStage rk) {
-    if (p.N == 5) project_nodal_n<5>(p, g, L, first, count, u_q, u_f, dudt, s, rk); else project_nodal_n<4>(p, g, L, first, count, u_q, u_f, dudt, s, rk);
+#define CALL_(N_) project_nodal_n<N_>(p, g, L, first, count, u_q, u_f, dudt, s, rk)
+    SSE_CT_DISPATCH(p.N, CALL_);
+#undef CALL_
 }
 
 template <int N>
 static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
                        double* u_q, const double* u_f, double* dudt, cudaStream_t s, RkStage rk, cudaEvent_t mid) {
-    constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
+    constexpr int NT = Tet<N>::NT;
     (void)tp; (void)o;
     bool done = false;
     if constexpr (N == 5) {
@@ -239,8 +268,9 @@ static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, cons
 }
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
                  double* u_q, const double* u_f, double* dudt, cudaStream_t s, RkStage rk, cudaEvent_t mid) {
-    if (p.N == 5) fluxdiff_n<5>(p, tp, o, g, L, first, count, u_q, u_f, dudt, s, rk, mid);
-    else fluxdiff_n<4>(p, tp, o, g, L, first, count, u_q, u_f, dudt, s, rk, mid);
+#define CALL_(N_) fluxdiff_n<N_>(p, tp, o, g, L, first, count, u_q, u_f, dudt, s, rk, mid)
+    SSE_CT_DISPATCH(p.N, CALL_);
+#undef CALL_
 }
 
 
@@ -248,14 +278,14 @@ bool ct_eligible_standard(const sse_config& cfg, const sse_arrays& a, int* Nout,
     if (cfg.d != 3 || cfg.N_c != 1 || cfg.pde != SSE_PDE_ADVECTION || cfg.form != SSE_FORM_STANDARD_REFERENCE) return false;
     if (cfg.v_kind != SSE_V_WARPED || cfg.mass_solver != SSE_MASS_WEIGHT_ADJUSTED) return false;
     const int N = cfg.p + 1;
-    if (N != 4 && N != 5) return false;
+    if (!ct_size_ok(N)) return false;
     if (cfg.M1d[0] != N || cfg.M1d[1] != N || cfg.M1d[2] != N) return false;
     const int NN = N * N, Nq = N * NN, Nf = 4 * NN;
     if (cfg.N_q != Nq || cfg.N_p != N * (N + 1) * (N + 2) / 6 || cfg.N_f != Nf || cfg.N_fac != 4) return false;
     for (int t = 0; t < Nq; t++) {
         const int a1 = t % N, a2 = (t / N) % N, a3 = t / NN;
         if (a.sigma_o[t] - 1 != (a1 * N + a2) * N + a3) return false;
-        const long long want = (a1 + a2 + a3 <= N - 1) ? (N == 4 ? tet_l<4>(a1, a2, a3) : tet_l<5>(a1, a2, a3)) + 1 : 0;
+        const long long want = (a1 + a2 + a3 <= N - 1) ? tet_l_rt(N, a1, a2, a3) + 1 : 0;
         if (a.sigma_i[t] != want) return false;
     }
     // D[m] must be the Kronecker product I (x) D_1D (x) I along direction m
@@ -307,7 +337,7 @@ static void standard_n(const CtPlan& p, const Geo& g, const Law& L, long long fi
             make_coef<N>(p), make_facet<N>(p), tb, p.dev, p.adv, g, first, count, u_f, dudt, rk);
         return;
     }
-    constexpr int NT = (Tet<N>::Nq + 31) / 32 * 32;
+    constexpr int NT = Tet<N>::NT;
     AdvTabs<N> tabs;
     for (int m = 0; m < 3; m++) for (int i = 0; i < N * N; i++) tabs.D1[m][i] = p.D1[m * N * N + i];
     k_standard_adv_ct<N, 8><<<(unsigned)count, NT, 0, s>>>(tabs, p.dev, g, L, first, u_q, u_f);
@@ -317,7 +347,9 @@ static void standard_n(const CtPlan& p, const Geo& g, const Law& L, long long fi
 }
 void ct_standard(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
                  double* dudt, cudaStream_t s, RkStage rk, cudaEvent_t mid) {
-    if (p.N == 5) standard_n<5>(p, g, L, first, count, u_q, u_f, dudt, s, rk, mid); else standard_n<4>(p, g, L, first, count, u_q, u_f, dudt, s, rk, mid);
+#define CALL_(N_) standard_n<N_>(p, g, L, first, count, u_q, u_f, dudt, s, rk, mid)
+    SSE_CT_DISPATCH(p.N, CALL_);
+#undef CALL_
 }
 
 }  // namespace sse

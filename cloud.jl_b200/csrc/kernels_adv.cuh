@@ -30,7 +30,8 @@ template <int N> struct AdvSmem {
     static constexpr int QS = T::Nq + ((N - T::Nq % 16) % 16 + 16) % 16;            // nodal tile stride (= N mod 16)
     static constexpr int RSM = (N == 5) ? 15 : N;
     static constexpr int RS = T::RED_SPAN + ((RSM - T::RED_SPAN % 16) % 16 + 16) % 16;
-    static constexpr int T2 = RS > QS ? RS : QS;                                   // second tile | V' partials
+    static constexpr int T2a = RS > QS ? RS : QS;
+    static constexpr int T2 = T2a > T::Nf ? T2a : T::Nf;                            // second tile | V' partials | facet tile (pass A) | u+ gather
     static constexpr int GSLOTS = GPW + (32 % N != 0);   // groups per warp in shared memory: the idle lanes of a warp (32 mod N)
                                                          // compute along on a dummy slot instead of being masked everywhere
     static constexpr int tile = 0;                       // [QS]   u_q of the element

@@ -56,6 +56,7 @@ template <int N> struct Tet {
     static constexpr int Np = N * (N + 1) * (N + 2) / 6;
     static constexpr int npf = N * N;
     static constexpr int Nf = 4 * N * N;
+    static constexpr int NT = ((Nq > Nf ? Nq : Nf) + 31) / 32 * 32;   // threads of the node-per-thread kernels (N = 3: N_f > N_q)
     static constexpr int GPW = 32 / N;          // groups (of N lanes) per warp
     static constexpr int EPB = GPW;             // elements per CTA in the projection kernels
     static constexpr int LPT = (Np + N - 1) / N;  // modal outputs per lane in the a3-reduction
@@ -716,7 +717,7 @@ __device__ __forceinline__ int facet_partner(int fr, int ca, int cb, int cc) {
 }
 
 template <int N, int MINB, bool DUAL>
-__global__ void __launch_bounds__((Tet<N>::Nq + 31) / 32 * 32, MINB)
+__global__ void __launch_bounds__(Tet<N>::NT, MINB)
 k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, const double* __restrict__ u_f) {
     constexpr int NC = 5, D = 3, NP = 6;
     using T = Tet<N>;
@@ -738,7 +739,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
     // ---- prologue: every global load of the element is issued before any arithmetic.  Idle lanes load a clamped
     //      (valid) address so that the loads need no branch: node data, own facet data and the mapP-dependent
     //      neighbour gather are all in flight together instead of one dependent round trip after another.
-    static_assert(Nf <= (Nq + 31) / 32 * 32, "one facet node per thread");
+    static_assert(Nf <= T::NT && Nq <= T::NT, "one volume node and one facet node per thread");
     const bool fac = tid < Nf;
     const int tn = node ? tid : Nq - 1, tj = fac ? tid : Nf - 1;
     double qi[NP], lam[D][D], r[NC], sw[D];
@@ -1075,7 +1076,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
 template <int N> struct AdvTabs { double D1[3][N * N]; };     // D_1D[m][t + N*s]: row t, column s
 
 template <int N, int MINB>
-__global__ void __launch_bounds__((Tet<N>::Nq + 31) / 32 * 32, MINB)
+__global__ void __launch_bounds__(Tet<N>::NT, MINB)
 k_standard_adv_ct(AdvTabs<N> a, CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, const double* __restrict__ u_f) {
     constexpr int D = 3;
     using T = Tet<N>;
@@ -1088,7 +1089,7 @@ k_standard_adv_ct(AdvTabs<N> a, CtDev t, Geo g, Law L, long long first, double* 
     for (int i = tid; i < D * N * N; i += blockDim.x) s_D[i / (N * N)][i % (N * N)] = a.D1[i / (N * N)][i % (N * N)];
     // every global load of the element is issued before any arithmetic (idle lanes load a clamped, valid address): the
     // kernel is a few hundred instructions long, so its time is the latency of these loads unless they overlap
-    static_assert(Nf <= (Nq + 31) / 32 * 32, "one facet node per thread");
+    static_assert(Nf <= T::NT && Nq <= T::NT, "one volume node and one facet node per thread");
     const bool fac = tid < Nf;
     const int tn = node ? tid : Nq - 1, tj = fac ? tid : Nf - 1;
     const size_t jo = (size_t)(g.mapP[(size_t)k * Nf + tj] - 1);

@@ -330,7 +330,8 @@ inline void tensor_plan_build(TensorPlan& tp, const sse_config& cfg, const sse_a
     for (int m = 0; m < d; m++) chk *= N1;
     if (chk != Nq || N1 < 2 || N1 > 8) return;
     const int threads = ((std::max(Nq, 1) + 31) / 32) * 32;
-    if (threads > 128) return;                       // kernel is compiled for <= 128 threads per element
+    const bool runtime_kernel = threads <= 128;      // k_fluxdiff_tensor is compiled for <= 128 threads per element; the schedule
+                                                     // tables are still built beyond that (the compile-time kernels take them)
     int stride[3] = {1, 1, 1};
     for (int m = 0; m < d; m++) { stride[m] = 1; for (int mm = m + 1; mm < d; mm++) stride[m] *= N1; }
     auto coord = [&](int i, int m) { return (i / stride[m]) % N1; };
@@ -449,7 +450,7 @@ inline void tensor_plan_build(TensorPlan& tp, const sse_config& cfg, const sse_a
     const int NP = (cfg.N_c == d + 2) ? d + 3 : 1;
     tp.smem_fluxdiff = sizeof(double) * (size_t)fd_layout(o, d, cfg.N_c, NP).total;
     if (tp.smem_fluxdiff > 227 * 1024) return;
-    tp.has_fluxdiff = 1;
+    tp.has_fluxdiff = runtime_kernel ? 1 : 0;
     tp.ok = 1;
 }
 

@@ -562,7 +562,7 @@ extern "C" int32_t sse_set_kernel_variant(sse_handle* h, int32_t v) {
 }
 extern "C" int32_t sse_get_kernel_variant(const sse_handle* h, int32_t* v) {
     if (!h || !v) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
-    *v = (h->variant == 1 && h->ct.ok) ? 2 : ((h->variant == 1 && h->tp.ok) ? 1 : 0);
+    *v = (h->variant == 1 && h->ct.ok) ? 2 : ((h->variant == 1 && h->tp.ok && h->tp.has_fluxdiff) ? 1 : 0);
     return SSE_OK;
 }
 
@@ -624,7 +624,7 @@ extern "C" int32_t sse_synchronize(sse_handle* h) {
 }
 
 // ------------------------------------------------------------------------------ the hot path
-static bool use_tensor(const sse_handle* h) { return h->variant == 1 && h->tp.ok; }
+static bool use_tensor(const sse_handle* h) { return h->variant == 1 && h->tp.ok && h->tp.has_fluxdiff; }
 
 extern "C" int32_t sse_rhs_pass_a_range(sse_handle* h, const double* d_u, int64_t first, int64_t count) {
     if (!h || !d_u) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
@@ -1170,6 +1170,7 @@ extern "C" int32_t sse_plan_selfcheck(const sse_config* cfg, const sse_arrays* a
         else if (ct_eligible_standard(*cfg, *arr, &N, D1, fR) && ct_facet_factors(*cfg, *arr, N, fac)) { info[0] = 3; info[1] = 128; return SSE_OK; }
     }
     if (!tp.ok) return SSE_OK;
+    if (info[0] != 2 && !tp.has_fluxdiff) { info[0] = 0; return SSE_OK; }      // schedule exists, but no kernel for this size
     info[1] = tp.threads; info[2] = tp.dev.n_vrounds; info[3] = tp.dev.n_frounds;
     info[4] = tp.dev.red_items_max; info[5] = tp.dev.red_max; info[6] = (int32_t)tp.smem_fluxdiff;
     int evals = 0;

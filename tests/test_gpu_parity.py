@@ -49,6 +49,11 @@ CASES = {
     "euler_tgv_3d_p3": lambda: cases.euler_tgv_3d(M=2, p=3, flux="lf"),
     "euler_tgv_3d_nodal": lambda: cases.euler_tgv_3d(M=2, p=3, flux="ec", kind="nodal"),
     "euler_tgv_3d_M4": lambda: cases.euler_tgv_3d(M=4, flux="lf"),
+    # the compile-time kernels are instantiated for N = p + 1 = 3 .. 6
+    "euler_tgv_3d_p2": lambda: cases.euler_tgv_3d(M=2, p=2, flux="lf"),
+    "euler_tgv_3d_p5": lambda: cases.euler_tgv_3d(M=2, p=5, flux="ec"),
+    "advection_3d_p2": lambda: cases.advection_3d(M=2, p=2, flux="lf"),
+    "advection_3d_p5": lambda: cases.advection_3d(M=2, p=5, flux="central"),
     "euler_vortex_2d_standard_lf": lambda: cases.euler_vortex_2d_standard(M=4, p=4, flux="lf"),
     "euler_vortex_2d_standard_nodal": lambda: cases.euler_vortex_2d_standard(M=3, p=3, flux="central", kind="nodal"),
     "euler_vortex_2d_standard_physical": lambda: cases.euler_vortex_2d_standard(M=3, p=4, flux="lf", strategy=PHYSICAL_OPERATOR),
@@ -409,3 +414,21 @@ def test_ck54_stage_fused_kernels_match_the_unfused_sequence():
         s.close()
         assert np.all(np.isfinite(a))
         assert relerr(a, b) <= 1e-13
+
+
+@pytest.mark.parametrize("p", [2, 3, 4, 5])
+def test_compile_time_kernels_cover_p2_to_p5(p):
+    """ModalTensor(p) tets run the compile-time kernels for p = 2 .. 5 (kernel variant 2), for the Euler flux-differencing path
+    and for the fused advection path, and the device-resident CarpenterKennedy2N54 step agrees with the unfused sequence."""
+    c = cases.euler_tgv_3d(M=2, p=p, flux="lf")
+    img, u = c.image(), c.u0(seed=0)
+    s = Solver(img, 0)
+    assert s.kernel_variant() == 2
+    a = solve_ck54(ODEProblem(semi_discrete_residual, u, (0.0, 1.0), s), 1e-3, 2, fused=True)
+    b = solve_ck54(ODEProblem(semi_discrete_residual, u, (0.0, 1.0), s), 1e-3, 2, fused=False)
+    s.close()
+    assert relerr(a, b) <= 1e-13
+    c = cases.advection_3d(M=2, p=p, flux="lf")
+    s = Solver(c.image(), 0)
+    assert s.kernel_variant() == 2
+    s.close()

@@ -39,11 +39,14 @@ def test_kernel_family_selection():
     """Which kernels sse_create will pick (host-side decision, checked without a GPU)."""
     assert selfcheck(cases.euler_tgv_3d(M=2, p=4).image())[0][0] == 2       # headline: compile-time kernels
     assert selfcheck(cases.euler_tgv_3d(M=2, p=3).image())[0][0] == 2
-    assert selfcheck(cases.euler_tgv_3d(M=2, p=2).image())[0][0] == 1       # other degrees: runtime tensor-line kernel
+    assert selfcheck(cases.euler_tgv_3d(M=2, p=2).image())[0][0] == 2       # compile-time kernels exist for p = 2 .. 5
+    assert selfcheck(cases.euler_tgv_3d(M=2, p=5).image())[0][0] == 2
+    assert selfcheck(cases.euler_tgv_3d(M=2, p=1).image())[0][0] == 1       # other degrees: runtime tensor-line kernel
     assert selfcheck(cases.euler_tgv_3d(M=2, p=3, kind="nodal").image())[0][0] == 1
     assert selfcheck(cases.euler_vortex_2d(M=2, p=4).image())[0][0] == 1
     assert selfcheck(cases.advection_3d(M=2).image())[0][0] == 3            # config 4: compile-time StandardForm path
-    assert selfcheck(cases.advection_3d(M=2, p=2).image())[0][0] == 0       # generic
+    assert selfcheck(cases.advection_3d(M=2, p=2).image())[0][0] == 3
+    assert selfcheck(cases.advection_3d(M=2, p=1).image())[0][0] == 0       # generic
     assert selfcheck(cases.advection_2d(M=2).image())[0][0] == 0
     assert selfcheck(cases.advection_diffusion_2d(M=2).image())[0][0] == 0
 

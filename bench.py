@@ -34,8 +34,8 @@ ALG_BYTES_PASS_B = 26800.0       # time_derivative kernel alone: u_q 5000 + own/
 ALG_FLOPS_RHS = 476000.0         # FMA = 2
 ALG_FLOPS_PAIR = 359000.0        # the dominant kernel (k_fluxdiff_ct): volume + facet correction + interface flux + lift
 # measured DRAM bytes / element (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum at 24 576 elements,
-# profiles/r2_ncu_kernels.csv): pass A 9.02 kB, pair kernel 25.67 kB, projection 6.95 kB
-NCU_DRAM_BYTES = {"k_nodal_ct": 9017.0, "k_fluxdiff_ct": 25665.0, "k_project_ct": 6949.0}
+# profiles/r2_ncu_kernels.csv): pass A 9.05 kB, pair kernel 25.67 kB, projection 6.75 kB
+NCU_DRAM_BYTES = {"k_nodal_ct": 9051.0, "k_fluxdiff_ct": 25668.0, "k_project_ct": 6747.0}
 NCU_DRAM_BYTES_PASS_B = NCU_DRAM_BYTES["k_fluxdiff_ct"] + NCU_DRAM_BYTES["k_project_ct"]
 
 

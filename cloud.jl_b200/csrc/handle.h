@@ -66,6 +66,17 @@ struct sse_handle {
     double *h2d_u = nullptr, *d2h_du = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> events;
+    // CUDA-graph replay of sse_step_ck54 (sse_set_graph_mode)
+    struct Graph {
+        bool on = false;
+        cudaStream_t stream = nullptr;
+        cudaEvent_t e_in = nullptr, e_out = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        double *u = nullptr, *tmp = nullptr, *dudt = nullptr;
+        double dt = 0.0;
+        int variant = -1;
+        long long launches = 0;
+    } graph;
     // non-finite / non-physical state detection (SSE_ERR_NONFINITE): device flag set by the kernels, read at sse_synchronize
     volatile int* h_flag = nullptr; // mapped, page-locked; Geo.flag is its device alias
 };

@@ -541,6 +541,10 @@ extern "C" int32_t sse_destroy(sse_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     comm_release(h);
+    if (h->graph.exec) cudaGraphExecDestroy(h->graph.exec);
+    if (h->graph.stream) cudaStreamDestroy(h->graph.stream);
+    if (h->graph.e_in) cudaEventDestroy(h->graph.e_in);
+    if (h->graph.e_out) cudaEventDestroy(h->graph.e_out);
     for (void* p : h->owned) cudaFree(p);
     if (h->h_flag) cudaFreeHost((void*)h->h_flag);
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
@@ -884,8 +888,62 @@ extern "C" int32_t sse_rhs_lsrk(sse_handle* h, double* d_u, double* d_tmp, doubl
     if (!fused) return sse_lsrk_stage(h, d_u, d_tmp, d_dudt, A, B, dt);
     return SSE_OK;
 }
+static int32_t step_ck54_launches(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double t, double dt);
+
+// CUDA-graph replay of the step (sse_set_graph_mode): the 11 - 20 launches of one CarpenterKennedy2N54 step are captured once per
+// (u, tmp, dudt, dt) and replayed with one cudaGraphLaunch -- on meshes of a few thousand elements the step is bound by launch
+// latency, not by the kernels.  The capture runs on an internal stream (the caller's stream may be the legacy default stream,
+// which cannot be captured); the replay is ordered after the caller's stream and the caller's stream after the replay.
+static int32_t step_ck54_graph(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double t, double dt) {
+    CU(cudaSetDevice(h->device));
+    sse_handle::Graph& G = h->graph;
+    if (!G.stream) {
+        CU(cudaStreamCreateWithFlags(&G.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&G.e_in, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&G.e_out, cudaEventDisableTiming));
+    }
+    if (!G.exec || G.u != d_u || G.tmp != d_tmp || G.dudt != d_dudt || G.dt != dt || G.variant != h->variant) {
+        if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+        cudaStream_t user = h->stream;
+        const long long l0 = h->launches;
+        h->stream = G.stream;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(G.stream, cudaStreamCaptureModeThreadLocal);
+        int32_t rc = e == cudaSuccess ? step_ck54_launches(h, d_u, d_tmp, d_dudt, t, dt) : SSE_ERR_CUDA;
+        const cudaError_t e2 = cudaStreamEndCapture(G.stream, &graph);
+        h->stream = user;
+        G.launches = h->launches - l0;
+        h->launches = l0;
+        if (e != cudaSuccess || e2 != cudaSuccess || rc != SSE_OK || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return rc != SSE_OK ? rc : fail(SSE_ERR_CUDA, "capturing the Runge-Kutta step failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+        }
+        e = cudaGraphInstantiate(&G.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { G.exec = nullptr; return fail(SSE_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+        G.u = d_u; G.tmp = d_tmp; G.dudt = d_dudt; G.dt = dt; G.variant = h->variant;
+    }
+    CU(cudaEventRecord(G.e_in, h->stream));
+    CU(cudaStreamWaitEvent(G.stream, G.e_in, 0));
+    CU(cudaGraphLaunch(G.exec, G.stream));
+    CU(cudaEventRecord(G.e_out, G.stream));
+    CU(cudaStreamWaitEvent(h->stream, G.e_out, 0));
+    h->launches += G.launches;
+    return SSE_OK;
+}
+extern "C" int32_t sse_set_graph_mode(sse_handle* h, int32_t on) {
+    if (!h) return fail(SSE_ERR_BAD_ARGUMENT, "null handle");
+    h->graph.on = on != 0;
+    return SSE_OK;
+}
+
 extern "C" int32_t sse_step_ck54(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double t, double dt) {
     if (!h || !d_u || !d_tmp || !d_dudt) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
+    if (h->graph.on && h->cfg.N_ghost == 0) return step_ck54_graph(h, d_u, d_tmp, d_dudt, t, dt);
+    return step_ck54_launches(h, d_u, d_tmp, d_dudt, t, dt);
+}
+static int32_t step_ck54_launches(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double t, double dt) {
     int32_t rc;
     static const bool fuse_stages = [] { const char* e = getenv("SSE_CK54_FUSED"); return !e || atoi(e) != 0; }();
     if (fuse_stages && h->variant == 1 && h->ct.ok && h->ct.kind == 0 && h->cfg.N_ghost == 0) {

@@ -59,6 +59,7 @@ SYMBOLS = {
     "sse_lsrk_stage": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double]),
     "sse_rhs_lsrk": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]),
     "sse_step_ck54": (C.c_int32, [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]),
+    "sse_set_graph_mode": (C.c_int32, [_h, C.c_int32]),
     "sse_functionals": (C.c_int32, [_h, C.c_void_p, C.c_void_p, _pd]),
     "sse_synchronize": (C.c_int32, [_h]),
     "sse_last_error_string": (C.c_char_p, []),

@@ -182,6 +182,10 @@ class Solver:
                                              ms.ctypes.data_as(C.POINTER(C.c_double))))
         return ms
 
+    def set_graph_mode(self, on: bool = True):
+        """Replay sse_step_ck54 as one CUDA graph (launch-latency-bound meshes)."""
+        _lib.check(self._lib.sse_set_graph_mode(self._h, 1 if on else 0))
+
     def functionals(self, u, dudt) -> np.ndarray:
         out = np.zeros(int(self.cfg.N_c) + 2)
         _lib.check(self._lib.sse_functionals(self._h, self._check_state(u, "u"), self._check_state(dudt, "dudt"),

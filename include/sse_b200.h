@@ -237,6 +237,9 @@ int32_t sse_lsrk_stage(sse_handle* h, double* d_u, double* d_tmp, const double* 
 int32_t sse_rhs_lsrk(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double A, double B, double dt, double t);
 /* one full CarpenterKennedy2N54 step on device (collective on element-partitioned handles, like sse_rhs) */
 int32_t sse_step_ck54(sse_handle* h, double* d_u, double* d_tmp, double* d_dudt, double t, double dt);
+/* on != 0: sse_step_ck54 of a single-GPU handle captures its launches into a CUDA graph once per (u, tmp, dudt, dt) and replays
+   it with one cudaGraphLaunch -- for meshes small enough that the step is bound by launch latency (the reference's 2-D examples) */
+int32_t sse_set_graph_mode(sse_handle* h, int32_t on);
 /* conservation / energy / entropy residuals of Analysis/conservation.jl:145-189.
    out[0..N_c-1] = sum_k 1' WJ_k V dudt[:,e,k];  out[N_c] = sum_k u_k' M_k dudt_k (energy);
    out[N_c+1] = sum_k (P_k w(V u_k))' M_k dudt_k (entropy; Euler only, else 0).  Blocking.  With a communicator the sums

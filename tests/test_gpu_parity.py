@@ -432,3 +432,31 @@ def test_compile_time_kernels_cover_p2_to_p5(p):
     s = Solver(c.image(), 0)
     assert s.kernel_variant() == 2
     s.close()
+
+
+@pytest.mark.parametrize("name", ["euler_vortex_2d", "euler_tgv_3d", "advection_diffusion_2d", "advection_3d"])
+def test_graph_replay_of_the_ck54_step_is_bit_identical(name):
+    """sse_set_graph_mode: the launches of one CarpenterKennedy2N54 step captured into a CUDA graph and replayed (re-captured
+    when dt or a buffer changes) give the same bits as launching them one by one -- for the compile-time, tensor-line and
+    generic (BR1) kernel families."""
+    c = cases.BUILDERS[name](M=4 if name.endswith("2d") else 2)
+    img, u0 = c.image(), c.u0(seed=0)
+    outs = []
+    for graph in (False, True):
+        s = Solver(img, 0)
+        s.use_current_stream()
+        s.set_graph_mode(graph)
+        u, tmp, du = torch.from_numpy(u0).cuda(), s.new_state(), s.new_state()
+        t = 0.0
+        for dt in (1e-3, 1e-3, 1e-3, 5e-4, 5e-4):
+            s.step_ck54(u, tmp, du, t, dt)
+            t += dt
+        u2 = u.clone()                                     # another buffer: the graph is re-captured
+        tmp.zero_()
+        s.step_ck54(u2, tmp, du, t, 1e-3)
+        s.synchronize()
+        outs.append((u.cpu().numpy(), u2.cpu().numpy(), s.launches))
+        s.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2] == outs[1][2]                        # the replay accounts for the launches it contains
+    assert np.all(np.isfinite(outs[1][1]))

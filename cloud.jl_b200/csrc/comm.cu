@@ -83,7 +83,6 @@ static int32_t comm_streams(sse_handle* h) {
     if (!c.e_packed) CU(cudaEventCreateWithFlags(&c.e_packed, cudaEventDisableTiming));
     if (!c.e_done) CU(cudaEventCreateWithFlags(&c.e_done, cudaEventDisableTiming));
     if (!c.e_sent) CU(cudaEventCreateWithFlags(&c.e_sent, cudaEventDisableTiming));
-    if (!c.d_red) CU(cudaMalloc((void**)&c.d_red, sizeof(double) * 16));
     return SSE_OK;
 }
 
@@ -175,15 +174,14 @@ void sse::comm_release(sse_handle* h) {
     if (c.e_done) cudaEventDestroy(c.e_done);
     if (c.e_sent) cudaEventDestroy(c.e_sent);
     c.e_sent = nullptr; c.peers.clear();
-    if (c.d_red) cudaFree(c.d_red);
-    c.s_comm = nullptr; c.e_packed = c.e_done = nullptr; c.d_red = nullptr;
+    c.s_comm = nullptr; c.e_packed = c.e_done = nullptr;
 }
 
 // The halo plan of this rank: neighbour ranks, facet nodes sent to / received from each (segments of the packed buffers, in this
 // order; the receive segments are the ghost slots in order), the 1-based send list (as sse_halo_configure takes it) and the
-// number of interior elements -- elements [0, n_interior) must not read a ghost slot (checked against mapP at sse_create time
-// data is not kept, so the check is the caller's: the partitioner orders elements interior first).  A neighbour equal to this
-// rank (periodic wrap of a single-rank partition) is a device-local copy.
+// number of interior elements -- elements [0, n_interior) must not read a ghost slot, which is verified here against the
+// per-element flags sse_create derived from mapP.  A neighbour equal to this rank (periodic wrap inside one partition) is a
+// device-local copy.
 extern "C" int32_t sse_halo_plan(sse_handle* h, int32_t n_nbr, const int32_t* nbr_rank, const int64_t* send_count, const int64_t* recv_count,
                                  const int64_t* send_index, int64_t n_interior) {
     if (!h || n_nbr < 0 || (n_nbr > 0 && (!nbr_rank || !send_count || !recv_count))) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");

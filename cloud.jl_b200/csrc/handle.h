@@ -29,7 +29,6 @@ struct sse_comm {
     std::vector<int> nbr_rank;
     std::vector<long long> send_count, recv_count;     // facet nodes per neighbour (segments of the packed buffers, in order)
     long long n_interior = 0;       // elements [0, n_interior) read no ghost facet; [n_interior, N_e) do
-    double* d_red = nullptr;        // all-reduce scratch of sse_functionals
 };
 
 struct sse_handle {

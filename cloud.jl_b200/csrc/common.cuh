@@ -10,7 +10,19 @@ struct SpMat {              // compressed rows: row r owns entries [ptr[r], ptr[
     const int* ptr;
     const int* idx;
     const double* val;
+    // the same rows slot-major, padded to the longest row with column -1: entry q of row r at [q * rows + r].  Kernels map one
+    // row to one thread, so a warp reads consecutive addresses (with CSR every lane reads its own cache line: a dense R or D
+    // of the multidimensional schemes costs 32 L1 wavefronts per load).  Entries keep their CSR order: same sums, same bits.
+    // Narrow rows (w <= 16: Kronecker D, selection-like R) stay row-major (sq = 1, sr = w): a thread's row is one or two cache
+    // lines fetched by its first entry, which is what small, latency-bound meshes want.
+    int rows, w, sq, sr;        // entry q of row r at [q * sq + r * sr]
+    const int* ei;
+    const double* ev;
 };
+// s += sum_q A[r, c_q] x[c_q * 1 + off]  over the stored entries of row r
+#define SSE_ROW_FOR(A, r, c, v)                                                              \
+    for (int q_ = 0, c = 0; q_ < (A).w && (c = (A).ei[q_ * (A).sq + (r) * (A).sr]) >= 0; q_++) \
+        if (const double v = (A).ev[q_ * (A).sq + (r) * (A).sr]; true)
 
 // Reference-element operators (element independent), device pointers.
 struct Ops {
@@ -31,7 +43,21 @@ struct Ops {
     SpMat Cq;                      // C by volume-node rows  (j, C_ij)
     SpMat Cf;                      // C by facet-node rows   (i, C_ij)
     int has_C;
+    // the same three pair lists slot-major (padded to the longest row, -1 = no entry): entry q of row r at [q * rows + r], so
+    // that the threads of a warp (one row each) read consecutive addresses -- with dense operators a row has N_q - 1 / N_f entries
+    int vol_w, cq_w, cf_w;
+    const int *vol_je, *cq_je, *cf_ie;
+    const double *vol_Se;          // [(q * d + m) * Nq + i]
+    const double *cq_ve, *cf_ve;
     const double *W, *Bf, *nref;   // nref: d x Nfac column-major
+};
+
+// dense all-pairs tables of k_time_fluxdiff_dense (kernels_generic.cuh)
+struct DenseDev {
+    const double* S4;      // [(j * D + m) * Nq + i]  S_m[i, j] / 4 (skew-extended: -S_m[j, i] below the diagonal)
+    const double* C4;      // [j * Nq + i]            C[i, j] / 4
+    const double* RT;      // [j * Nq + i]            R[j, i]: the lift r_q -= R' f_f as a dense product, coalesced over i
+    int ok;
 };
 
 // Per-element geometry and scratch, device pointers (reference layouts).

@@ -41,6 +41,8 @@ struct sse_handle {
     sse::Law law;
     sse::TensorPlan tp;             // tensor-line specialisation (kernels_tensor.cuh); tp.ok == 0 -> generic only
     sse::CtPlan ct;                 // compile-time-sized kernels (kernels_ct.cuh): Euler on p = 3, 4 ModalTensor tets
+    sse::DenseDev dense{};          // dense all-pairs flux differencing (ModalMulti / NodalMulti Euler): dense.ok == 0 -> not used
+    size_t smem_dense = 0;
     int variant = 1;
     int project = 0;                // 0 none, 1 nodal, 2 general entropy projection
     int second_order = 0;

@@ -644,65 +644,6 @@ template <int N, bool DUAL = false> struct FdSmem {
     static_assert(!DUAL || 2 * NC * FS <= 4 * buf, "the two padded facet stages reuse the four volume stages");
 };
 
-// Ranocha's EC flux (euler_navierstokes.jl:171-195) contracted with g, in the scaled form of the compile-time kernels:
-// primitives are (rho, V, 2p, rho/p) and gq = g / 4, so that every factor 1/2 of the averages is a power-of-two scaling
-// folded into the tables (exact) instead of a multiplication:
-//   rho_hat (ga + gb)/2 = lm2 (gqa + gqb),  p_avg g = (2pa + 2pb) gq,  (pa gb + pb ga)/2 = 2pa gqb + 2pb gqa,
-//   mf C = (mf/2) (Va.Vb + cc2 ilm105).
-template <int D>
-__device__ __forceinline__ void ec_finish_scaled(const Law& L, const double* a, const double* b, const double* gq, double lm2, double ilm105,
-                                                 double* phi) {
-    double dot = 0.0, ga = 0.0, gb = 0.0;
-#pragma unroll
-    for (int m = 0; m < D; m++) { dot = fma(a[1 + m], b[1 + m], dot); ga = fma(gq[m], a[1 + m], ga); gb = fma(gq[m], b[1 + m], gb); }
-    const double C2 = fma(L.cc2, ilm105, dot);
-    const double mf = lm2 * (ga + gb);
-    const double mfh = 0.5 * mf;
-    const double ps = a[D + 1] + b[D + 1];
-    phi[0] = mf;
-#pragma unroll
-    for (int m = 0; m < D; m++) phi[1 + m] = fma(mfh, a[1 + m] + b[1 + m], ps * gq[m]);
-    phi[D + 1] = fma(mfh, C2, fma(a[D + 1], gb, b[D + 1] * ga));
-}
-template <int D>
-__device__ __forceinline__ void ec_contract_scaled(const Law& L, const double* a, const double* b, const double* gq, double* phi) {
-    LmPair o;
-    if (logmean_pair_scaled(L, a[0], b[0], a[D + 2], b[D + 2], o) >= 1.0e-4) {
-        const double2 v = logmean_pair_scaled_rare(a[0], b[0], a[D + 2], b[D + 2], o.s1, o.is2, o.f1, o.f2);
-        o.lm2 = v.x; o.ilm105 = v.y;
-    }
-    ec_finish_scaled<D>(L, a, b, gq, o.lm2, o.ilm105, phi);
-}
-// two pairs sharing the left state, one (rare) branch for both
-template <int D>
-__device__ __forceinline__ void ec_contract_scaled2(const Law& L, const double* a, const double* bA, const double* bB, const double* gA,
-                                                    const double* gB, double* pA, double* pB) {
-    LmPair oA, oB;
-    const double fA = logmean_pair_scaled(L, a[0], bA[0], a[D + 2], bA[D + 2], oA);
-    const double fB = logmean_pair_scaled(L, a[0], bB[0], a[D + 2], bB[D + 2], oB);
-    if (fmax(fA, fB) >= 1.0e-4) {
-        const double2 vA = logmean_pair_scaled_rare(a[0], bA[0], a[D + 2], bA[D + 2], oA.s1, oA.is2, oA.f1, oA.f2);
-        const double2 vB = logmean_pair_scaled_rare(a[0], bB[0], a[D + 2], bB[D + 2], oB.s1, oB.is2, oB.f1, oB.f2);
-        oA.lm2 = vA.x; oA.ilm105 = vA.y; oB.lm2 = vB.x; oB.ilm105 = vB.y;
-    }
-    ec_finish_scaled<D>(L, a, bA, gA, oA.lm2, oA.ilm105, pA);
-    ec_finish_scaled<D>(L, a, bB, gB, oB.lm2, oB.ilm105, pB);
-}
-
-// conservative -> (rho, V, 2p, rho/p); returns 1/rho
-template <int D>
-__device__ __forceinline__ double to_prim_fast(const Law& L, const double* u, double* q) {
-    const double ir = rcp_fast(u[0]);
-    double s = 0.0;
-    q[0] = u[0];
-#pragma unroll
-    for (int m = 0; m < D; m++) { q[1 + m] = u[1 + m] * ir; s = fma(q[1 + m], q[1 + m], s); }
-    const double p = L.gm1 * (u[D + 1] - 0.5 * u[0] * s);
-    q[D + 1] = 2.0 * p;
-    q[D + 2] = u[0] * rcp_fast(p);
-    return ir;
-}
-
 // closed-form facet partner of volume node (a,b,c) in facet sub-round fr (the rotation schedule of
 // tensor_plan_build; ct_schedule_matches() verifies it against the generic tables on the host)
 template <int N>

@@ -23,11 +23,20 @@ __device__ void apply_V(const Ops& o, const double* x, double* y, double* zb, do
         return;
     }
     if (o.v_kind == SSE_V_DENSE) {
-        SSE_FOR(t, Nq * NC) {
-            int i = t % Nq, e = t / Nq;
-            double s = 0.0;
-            for (int j = 0; j < Np; j++) s = fma(o.Vd[i + (size_t)Nq * j], x[j + Np * e], s);
-            y[t] = s;
+        // one node per thread, all variables at once: the entry of V is loaded once (coalesced over the nodes) and feeds NC
+        // independent accumulators; same summation order per (node, variable) as a plain dot product
+        SSE_FOR(i, Nq) {
+            double acc[NC];
+#pragma unroll
+            for (int e = 0; e < NC; e++) acc[e] = 0.0;
+#pragma unroll 4
+            for (int j = 0; j < Np; j++) {
+                const double v = o.Vd[i + (size_t)Nq * j];
+#pragma unroll
+                for (int e = 0; e < NC; e++) acc[e] = fma(v, x[j + Np * e], acc[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < NC; e++) y[i + Nq * e] = acc[e];
         }
         __syncthreads();
         return;
@@ -70,11 +79,20 @@ __device__ void apply_Vt(const Ops& o, const double* x, double* y, double* zb, d
         return;
     }
     if (o.v_kind == SSE_V_DENSE) {
-        SSE_FOR(t, Np * NC) {
-            int j = t % Np, e = t / Np;
-            double s = 0.0;
-            for (int i = 0; i < Nq; i++) s = fma(o.Vd[i + (size_t)Nq * j], x[i + Nq * e], s);
-            y[t] = s;
+        // one mode per thread, all variables at once (NC independent accumulators, fixed trip count: the loads pipeline)
+        SSE_FOR(j, Np) {
+            double acc[NC];
+#pragma unroll
+            for (int e = 0; e < NC; e++) acc[e] = 0.0;
+            const double* vj = o.Vd + (size_t)Nq * j;
+#pragma unroll 4
+            for (int i = 0; i < Nq; i++) {
+                const double v = vj[i];
+#pragma unroll
+                for (int e = 0; e < NC; e++) acc[e] = fma(v, x[i + Nq * e], acc[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < NC; e++) y[j + Np * e] = acc[e];
         }
         __syncthreads();
         return;
@@ -113,7 +131,7 @@ __device__ void apply_sp(const SpMat& A, int nrow, const double* x, int ldx, dou
     SSE_FOR(t, nrow * NC) {
         int i = t % nrow, e = t / nrow;
         double s = 0.0;
-        for (int q = A.ptr[i]; q < A.ptr[i + 1]; q++) s = fma(A.val[q], x[A.idx[q] + ldx * e], s);
+        SSE_ROW_FOR(A, i, c_, v_) s = fma(v_, x[c_ + ldx * e], s);
         y[i + ldy * e] = s;
     }
     __syncthreads();
@@ -320,10 +338,42 @@ __global__ void k_time_fluxdiff_generic(Ops o, Geo g, Law L, long long first, co
     double* s_m = s_lam + Nq * D * D;        // Np x NC
     double* s_z = s_m + Np * NC;
     double* s_w = s_z + warp_z_size(o, NC);
+    // Euler with the entropy-conservative two-point flux: every pair is evaluated in the contracted, scaled form of the
+    // compile-time kernels (ec_contract_scaled: primitives (rho, V, 2p, rho/p) per node, one shared reciprocal for both
+    // log-means, no flux tensor, no division per pair) -- about a third of the instructions of two_point_flux + contraction.
+    // Dense operators (ModalMulti / NodalMulti, multidimensional.jl) evaluate N_q^2 + 2 N_q N_f pairs per element, so this is
+    // what decides their speed.
+    constexpr int NPR = D + 3;
+    const bool fast_ec = (NC == D + 2) && L.pde == SSE_PDE_EULER && L.two_point == SSE_TWO_POINT_ENTROPY_CONSERVATIVE;
+    double* s_prim = s_w + warp_w_size(o, NC);   // NPR x Nq   (fast_ec only)
+    double* s_fprim = s_prim + NPR * Nq;         // NPR x Nf
+    double* s_hnf = (NC == D + 2) ? s_fprim + NPR * Nf : s_prim;   // D x Nf   halfnJf (operators.jl:78)
 
     SSE_FOR(t, Nq * NC) s_uq[t] = u_q[(size_t)Nq * NC * k + t];
     SSE_FOR(t, Nq * D * D) s_lam[t] = g.Lambda_q[(size_t)Nq * D * D * k + t];
     load_facets<D, NC>(o, g, k, u_f, s_in, s_out, s_nf);
+    SSE_FOR(t, D * Nf) s_hnf[t] = 0.5 * g.nJf[(size_t)D * Nf * k + t];
+    if constexpr (NC == D + 2) {
+        if (fast_ec) {
+            SSE_FOR(i, Nq) {
+                double ui[NC], q[NPR];
+#pragma unroll
+                for (int e = 0; e < NC; e++) ui[e] = s_uq[i + Nq * e];
+                to_prim_fast<D>(L, ui, q);
+#pragma unroll
+                for (int c = 0; c < NPR; c++) s_prim[i + Nq * c] = q[c];
+            }
+            SSE_FOR(j, Nf) {
+                double ui[NC], q[NPR];
+#pragma unroll
+                for (int e = 0; e < NC; e++) ui[e] = s_in[j + Nf * e];
+                to_prim_fast<D>(L, ui, q);
+#pragma unroll
+                for (int c = 0; c < NPR; c++) s_fprim[j + Nf * c] = q[c];
+            }
+        }
+    }
+    __syncthreads();
 
     // facet side: f_f = BJf f* - sum_i C_ij (F(u_i, u_fj) . nJ_ij)
     SSE_FOR(j, Nf) {
@@ -336,15 +386,26 @@ __global__ void k_time_fluxdiff_generic(Ops o, Geo g, Law L, long long first, co
         for (int e = 0; e < NC; e++) fs[e] *= bj;
         if (o.has_C) {
             const int f = j / o.npf;
-            double hf[D];
+            double hf[D], nr[D];
 #pragma unroll
-            for (int m = 0; m < D; m++) hf[m] = 0.5 * g.nJf[m + D * ((size_t)Nf * k + j)];
-            for (int q = o.Cf.ptr[j]; q < o.Cf.ptr[j + 1]; q++) {
-                const int i = o.Cf.idx[q];
+            for (int m = 0; m < D; m++) { hf[m] = s_hnf[m + D * j]; nr[m] = o.nref[m + D * f]; }
+            double qf[NPR];
+            if constexpr (NC == D + 2) {
+                if (fast_ec) {
+#pragma unroll
+                    for (int c = 0; c < NPR; c++) qf[c] = s_fprim[j + Nf * c];
+                }
+            }
+            const int cfw = o.cf_w < 0 ? -o.cf_w : o.cf_w, cfq = o.cf_w < 0 ? 1 : Nf, cfr = o.cf_w < 0 ? cfw : 1;
+            for (int q = 0; q < cfw; q++) {
+                const int i = o.cf_ie[q * cfq + j * cfr];
+                if (i < 0) break;
                 double uq[NC], F[NC][D], nJ[D];
+                if (!fast_ec) {
 #pragma unroll
-                for (int e = 0; e < NC; e++) uq[e] = s_uq[i + Nq * e];
-                two_point_flux<D, NC>(L, L.two_point, uq, ui, F);
+                    for (int e = 0; e < NC; e++) uq[e] = s_uq[i + Nq * e];
+                    two_point_flux<D, NC>(L, L.two_point, uq, ui, F);
+                }
 #pragma unroll
                 for (int m = 0; m < D; m++) {
                     double hq;
@@ -352,12 +413,25 @@ __global__ void k_time_fluxdiff_generic(Ops o, Geo g, Law L, long long first, co
                     else {
                         double t = 0.0;
 #pragma unroll
-                        for (int l = 0; l < D; l++) t += s_lam[i + Nq * (l + D * m)] * o.nref[l + D * f];
+                        for (int l = 0; l < D; l++) t += s_lam[i + Nq * (l + D * m)] * nr[l];
                         hq = 0.5 * t;
                     }
                     nJ[m] = hf[m] + hq;
                 }
-                const double cij = o.Cf.val[q];
+                const double cij = o.cf_ve[q * cfq + j * cfr];
+                if constexpr (NC == D + 2) {
+                    if (fast_ec) {
+                        double qi[NPR], gq[D], phi[NC];
+#pragma unroll
+                        for (int c = 0; c < NPR; c++) qi[c] = s_prim[i + Nq * c];
+#pragma unroll
+                        for (int m = 0; m < D; m++) gq[m] = (0.25 * cij) * nJ[m];
+                        ec_contract_scaled<D>(L, qi, qf, gq, phi);
+#pragma unroll
+                        for (int e = 0; e < NC; e++) fs[e] -= phi[e];
+                        continue;
+                    }
+                }
 #pragma unroll
                 for (int e = 0; e < NC; e++) {
                     double Fn = 0.0;
@@ -375,15 +449,43 @@ __global__ void k_time_fluxdiff_generic(Ops o, Geo g, Law L, long long first, co
         double ui[NC], r[NC];
 #pragma unroll
         for (int e = 0; e < NC; e++) { ui[e] = s_uq[i + Nq * e]; r[e] = 0.0; }
-        for (int q = o.vol_ptr[i]; q < o.vol_ptr[i + 1]; q++) {
-            const int j = o.vol_j[q];
+        double qi[NPR];
+        if constexpr (NC == D + 2) {
+            if (fast_ec) {
+#pragma unroll
+                for (int c = 0; c < NPR; c++) qi[c] = s_prim[i + Nq * c];
+            }
+        }
+        const int vw = o.vol_w < 0 ? -o.vol_w : o.vol_w, vq = o.vol_w < 0 ? 1 : Nq, vr = o.vol_w < 0 ? vw : 1;
+        for (int q = 0; q < vw; q++) {
+            const int j = o.vol_je[q * vq + i * vr];
+            if (j < 0) break;
+            if constexpr (NC == D + 2) {
+                if (fast_ec) {
+                    double qj[NPR], gq[D], phi[NC];
+#pragma unroll
+                    for (int c = 0; c < NPR; c++) qj[c] = s_prim[j + Nq * c];
+#pragma unroll
+                    for (int n = 0; n < D; n++) gq[n] = 0.0;
+#pragma unroll
+                    for (int m = 0; m < D; m++) {
+                        const double Sm = 0.25 * o.vol_Se[o.vol_w < 0 ? (i * vw + q) * D + m : (q * D + m) * Nq + i];
+#pragma unroll
+                        for (int n = 0; n < D; n++) gq[n] = fma(Sm, s_lam[i + Nq * (m + D * n)] + s_lam[j + Nq * (m + D * n)], gq[n]);
+                    }
+                    ec_contract_scaled<D>(L, qi, qj, gq, phi);
+#pragma unroll
+                    for (int e = 0; e < NC; e++) r[e] -= phi[e];
+                    continue;
+                }
+            }
             double uj[NC], F[NC][D];
 #pragma unroll
             for (int e = 0; e < NC; e++) uj[e] = s_uq[j + Nq * e];
             two_point_flux<D, NC>(L, L.two_point, ui, uj, F);
 #pragma unroll
             for (int m = 0; m < D; m++) {
-                const double Sm = o.vol_S[q * D + m];
+                const double Sm = o.vol_Se[o.vol_w < 0 ? (i * vw + q) * D + m : (q * D + m) * Nq + i];
                 if (Sm != 0.0) {
 #pragma unroll
                     for (int e = 0; e < NC; e++) {
@@ -396,26 +498,50 @@ __global__ void k_time_fluxdiff_generic(Ops o, Geo g, Law L, long long first, co
             }
         }
         if (o.has_C) {
-            for (int q = o.Cq.ptr[i]; q < o.Cq.ptr[i + 1]; q++) {
-                const int j = o.Cq.idx[q];
+            int f_prev = -1;
+            double hqv[D];
+#pragma unroll
+            for (int m = 0; m < D; m++) hqv[m] = 0.0;
+            const int cqw = o.cq_w < 0 ? -o.cq_w : o.cq_w, cqq = o.cq_w < 0 ? 1 : Nq, cqr = o.cq_w < 0 ? cqw : 1;
+            for (int q = 0; q < cqw; q++) {
+                const int j = o.cq_je[q * cqq + i * cqr];
+                if (j < 0) break;
                 const int f = j / o.npf;
                 double uj[NC], F[NC][D], nJ[D];
+                if (!fast_ec) {
 #pragma unroll
-                for (int e = 0; e < NC; e++) uj[e] = s_in[j + Nf * e];
-                two_point_flux<D, NC>(L, L.two_point, ui, uj, F);
-#pragma unroll
-                for (int m = 0; m < D; m++) {
-                    double hq;
-                    if (g.nJq) hq = 0.5 * g.nJq[m + D * (f + (size_t)o.Nfac * (i + (size_t)Nq * k))];
-                    else {
-                        double t = 0.0;
-#pragma unroll
-                        for (int l = 0; l < D; l++) t += s_lam[i + Nq * (l + D * m)] * o.nref[l + D * f];
-                        hq = 0.5 * t;
-                    }
-                    nJ[m] = 0.5 * g.nJf[m + D * ((size_t)Nf * k + j)] + hq;
+                    for (int e = 0; e < NC; e++) uj[e] = s_in[j + Nf * e];
+                    two_point_flux<D, NC>(L, L.two_point, ui, uj, F);
                 }
-                const double cij = o.Cq.val[q];
+                if (f != f_prev) {                     // halfnJq depends on (node, face) only: mesh.jl:262-269
+                    f_prev = f;
+#pragma unroll
+                    for (int m = 0; m < D; m++) {
+                        if (g.nJq) hqv[m] = 0.5 * g.nJq[m + D * (f + (size_t)o.Nfac * (i + (size_t)Nq * k))];
+                        else {
+                            double t = 0.0;
+#pragma unroll
+                            for (int l = 0; l < D; l++) t += s_lam[i + Nq * (l + D * m)] * o.nref[l + D * f];
+                            hqv[m] = 0.5 * t;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < D; m++) nJ[m] = s_hnf[m + D * j] + hqv[m];
+                const double cij = o.cq_ve[q * cqq + i * cqr];
+                if constexpr (NC == D + 2) {
+                    if (fast_ec) {
+                        double qj[NPR], gq[D], phi[NC];
+#pragma unroll
+                        for (int c = 0; c < NPR; c++) qj[c] = s_fprim[j + Nf * c];
+#pragma unroll
+                        for (int m = 0; m < D; m++) gq[m] = (0.25 * cij) * nJ[m];
+                        ec_contract_scaled<D>(L, qi, qj, gq, phi);
+#pragma unroll
+                        for (int e = 0; e < NC; e++) r[e] -= phi[e];
+                        continue;
+                    }
+                }
 #pragma unroll
                 for (int e = 0; e < NC; e++) {
                     double Fn = 0.0;
@@ -433,7 +559,7 @@ __global__ void k_time_fluxdiff_generic(Ops o, Geo g, Law L, long long first, co
     SSE_FOR(t, Nq * NC) {
         int i = t % Nq, e = t / Nq;
         double s = 0.0;
-        for (int q = o.Rt.ptr[i]; q < o.Rt.ptr[i + 1]; q++) s = fma(o.Rt.val[q], s_ff[o.Rt.idx[q] + Nf * e], s);
+        SSE_ROW_FOR(o.Rt, i, c_, v_) s = fma(v_, s_ff[c_ + Nf * e], s);
         s_r[t] -= s;
     }
     __syncthreads();
@@ -443,6 +569,199 @@ __global__ void k_time_fluxdiff_generic(Ops o, Geo g, Law L, long long first, co
 }
 
 // physical_flux! into a shared Nq x NC x D tile
+// ---------------------------------------------------------------------------------------------------------
+// Dense flux differencing for the multidimensional schemes (ModalMulti / NodalMulti, multidimensional.jl:1-75): S_m and C are
+// dense, so an element evaluates N_q^2 volume pairs and 2 N_q N_f facet pairs of the entropy-conservative two-point flux
+// (flux_differencing_form.jl:1-35, 91-124: the dense methods of flux_difference! / facet_correction!).  All-pairs tile, like an
+// N-body kernel: thread i keeps its node (primitives, metric terms, residual) in registers and sweeps j, whose data every lane
+// reads from the same shared address (broadcast, no bank conflicts, nothing handed back: each side of a pair evaluates it for
+// itself, as the reference does when it visits (i, j) and (j, i)); two partners per trip so their dependent chains interleave.
+// Tables are dense and slot-major ([j][m][i]: coalesced over the threads), skew-extended and pre-scaled by 1/4 (scaled pair
+// flux, physics.cuh).  Euler + EC two-point flux only; everything else of pass B (interface flux, lift, V', mass solve) is the
+// generic code.
+template <int D>
+__global__ void __launch_bounds__(128, 3)
+k_time_fluxdiff_dense(Ops o, Geo g, Law L, DenseDev dd, long long first, const double* __restrict__ u_q, const double* __restrict__ u_f,
+                      double* __restrict__ dudt) {
+    constexpr int NC = D + 2, NPR = D + 3;
+    extern __shared__ double sm[];
+    const long long k = first + blockIdx.x;
+    const int Nq = o.Nq, Np = o.Np, Nf = o.Nf, Nfac = o.Nfac, npf = o.npf;
+    double* s_uq = sm;                       // Nq x NC  (conservative; scratch of the mass solve later)
+    double* s_r = s_uq + Nq * NC;            // Nq x NC
+    double* s_in = s_r + Nq * NC;            // Nf x NC
+    double* s_out = s_in + Nf * NC;          // Nf x NC
+    double* s_ff = s_out + Nf * NC;          // Nf x NC
+    double* s_nf = s_ff + Nf * NC;           // D x Nf
+    double* s_lam = s_nf + D * Nf;           // Nq x D x D
+    double* s_m = s_lam + Nq * D * D;        // Np x NC
+    double* s_z = s_m + Np * NC;
+    double* s_w = s_z + warp_z_size(o, NC);
+    double* s_prim = s_w + warp_w_size(o, NC);   // NPR x Nq
+    double* s_fprim = s_prim + NPR * Nq;         // NPR x Nf
+    double* s_hnf = s_fprim + NPR * Nf;          // D x Nf       halfnJf / 4 ... kept unscaled, the 1/4 sits in C4
+    double* s_hq = s_hnf + D * Nf;               // Nfac x D x Nq  halfnJq (mesh.jl:262-269)
+
+    SSE_FOR(t, Nq * NC) s_uq[t] = u_q[(size_t)Nq * NC * k + t];
+    SSE_FOR(t, Nq * D * D) s_lam[t] = g.Lambda_q[(size_t)Nq * D * D * k + t];
+    load_facets<D, NC>(o, g, k, u_f, s_in, s_out, s_nf);
+    SSE_FOR(t, D * Nf) s_hnf[t] = 0.5 * g.nJf[(size_t)D * Nf * k + t];
+    SSE_FOR(i, Nq) {
+        double ui[NC], q[NPR];
+#pragma unroll
+        for (int e = 0; e < NC; e++) ui[e] = s_uq[i + Nq * e];
+        to_prim_fast<D>(L, ui, q);
+#pragma unroll
+        for (int c = 0; c < NPR; c++) s_prim[i + Nq * c] = q[c];
+        for (int f = 0; f < Nfac; f++)
+#pragma unroll
+            for (int m = 0; m < D; m++) {
+                double hq;
+                if (g.nJq) hq = 0.5 * g.nJq[m + D * (f + (size_t)Nfac * (i + (size_t)Nq * k))];
+                else {
+                    double t = 0.0;
+#pragma unroll
+                    for (int l = 0; l < D; l++) t += s_lam[i + Nq * (l + D * m)] * o.nref[l + D * f];
+                    hq = 0.5 * t;
+                }
+                s_hq[i + Nq * (m + D * f)] = hq;
+            }
+    }
+    SSE_FOR(j, Nf) {
+        double ui[NC], q[NPR];
+#pragma unroll
+        for (int e = 0; e < NC; e++) ui[e] = s_in[j + Nf * e];
+        to_prim_fast<D>(L, ui, q);
+#pragma unroll
+        for (int c = 0; c < NPR; c++) s_fprim[j + Nf * c] = q[c];
+    }
+    __syncthreads();
+
+    // ---- volume side: r_i = - sum_j F(u_i, u_j) . g_ij,  g_ij = sum_m S_m[i,j] (Lambda_i + Lambda_j)[m, :]
+    //                        - sum_j F(u_i, u_fj) . C_ij (halfnJf_j + halfnJq_i,f(j))
+    SSE_FOR(i, Nq) {
+        double qi[NPR], li[D][D], r[NC];
+#pragma unroll
+        for (int c = 0; c < NPR; c++) qi[c] = s_prim[i + Nq * c];
+#pragma unroll
+        for (int m = 0; m < D; m++)
+#pragma unroll
+            for (int n = 0; n < D; n++) li[m][n] = s_lam[i + Nq * (m + D * n)];
+#pragma unroll
+        for (int e = 0; e < NC; e++) r[e] = 0.0;
+        // the S table (N_q^2 d doubles) does not stay in L1 next to the tiles of six resident CTAs: the weights of the NEXT trip are
+        // fetched (L2) while the current one computes
+        double sA[D], sB[D];
+#pragma unroll
+        for (int m = 0; m < D; m++) { sA[m] = dd.S4[(size_t)m * Nq + i]; sB[m] = dd.S4[((size_t)(Nq > 1 ? 1 : 0) * D + m) * Nq + i]; }
+        for (int j0 = 0; j0 < Nq; j0 += 2) {
+            const int jA = j0, jB = (j0 + 1 < Nq) ? j0 + 1 : j0;       // odd N_q: the last trip repeats a partner with weight 0
+            const double wB = (j0 + 1 < Nq) ? 1.0 : 0.0;
+            const int nA = (j0 + 2 < Nq) ? j0 + 2 : jA, nB = (j0 + 3 < Nq) ? j0 + 3 : jB;
+            double tA[D], tB[D];
+#pragma unroll
+            for (int m = 0; m < D; m++) { tA[m] = dd.S4[((size_t)nA * D + m) * Nq + i]; tB[m] = dd.S4[((size_t)nB * D + m) * Nq + i]; }
+            double qA[NPR], qB[NPR], gA[D], gB[D], pA[NC], pB[NC];
+#pragma unroll
+            for (int c = 0; c < NPR; c++) { qA[c] = s_prim[jA + Nq * c]; qB[c] = s_prim[jB + Nq * c]; }
+#pragma unroll
+            for (int n = 0; n < D; n++) { gA[n] = 0.0; gB[n] = 0.0; }
+#pragma unroll
+            for (int m = 0; m < D; m++) {
+                const double wsB = wB * sB[m];
+#pragma unroll
+                for (int n = 0; n < D; n++) {
+                    gA[n] = fma(sA[m], li[m][n] + s_lam[jA + Nq * (m + D * n)], gA[n]);
+                    gB[n] = fma(wsB, li[m][n] + s_lam[jB + Nq * (m + D * n)], gB[n]);
+                }
+            }
+            ec_contract_scaled2<D>(L, qi, qA, qB, gA, gB, pA, pB);
+#pragma unroll
+            for (int e = 0; e < NC; e++) r[e] -= pA[e] + pB[e];
+#pragma unroll
+            for (int m = 0; m < D; m++) { sA[m] = tA[m]; sB[m] = tB[m]; }
+        }
+        if (o.has_C) {
+            for (int f = 0; f < Nfac; f++) {
+                double hq[D];
+#pragma unroll
+                for (int n = 0; n < D; n++) hq[n] = s_hq[i + Nq * (n + D * f)];
+                double cnA = dd.C4[(size_t)(f * npf) * Nq + i], cnB = dd.C4[(size_t)(f * npf + (npf > 1 ? 1 : 0)) * Nq + i];
+                for (int j0 = f * npf; j0 < (f + 1) * npf; j0 += 2) {
+                    const int jA = j0, jB = (j0 + 1 < (f + 1) * npf) ? j0 + 1 : j0;
+                    const double cA = cnA, cB = (jB != jA) ? cnB : 0.0;
+                    cnA = dd.C4[(size_t)((j0 + 2 < (f + 1) * npf) ? j0 + 2 : jA) * Nq + i];      // next trip's weights
+                    cnB = dd.C4[(size_t)((j0 + 3 < (f + 1) * npf) ? j0 + 3 : jB) * Nq + i];
+                    double qA[NPR], qB[NPR], gA[D], gB[D], pA[NC], pB[NC];
+#pragma unroll
+                    for (int c = 0; c < NPR; c++) { qA[c] = s_fprim[jA + Nf * c]; qB[c] = s_fprim[jB + Nf * c]; }
+#pragma unroll
+                    for (int n = 0; n < D; n++) { gA[n] = cA * (s_hnf[n + D * jA] + hq[n]); gB[n] = cB * (s_hnf[n + D * jB] + hq[n]); }
+                    ec_contract_scaled2<D>(L, qi, qA, qB, gA, gB, pA, pB);
+#pragma unroll
+                    for (int e = 0; e < NC; e++) r[e] -= pA[e] + pB[e];
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < NC; e++) s_r[i + Nq * e] = r[e];
+    }
+    // ---- facet side: f_f[j] = BJf f*(u-, u+) - sum_i F(u_i, u_fj) . C_ij (halfnJf_j + halfnJq_i,f(j))
+    SSE_FOR(j, Nf) {
+        double ui[NC], uo[NC], fs[NC], qj[NPR], hf[D];
+#pragma unroll
+        for (int e = 0; e < NC; e++) { ui[e] = s_in[j + Nf * e]; uo[e] = s_out[j + Nf * e]; }
+        numerical_flux<D, NC>(L, L.two_point, ui, uo, s_nf + D * j, fs);
+        const double bj = o.Bf[j] * g.J_f[(size_t)Nf * k + j];
+#pragma unroll
+        for (int e = 0; e < NC; e++) fs[e] *= bj;
+        if (o.has_C) {
+            const int f = j / npf;
+#pragma unroll
+            for (int c = 0; c < NPR; c++) qj[c] = s_fprim[j + Nf * c];
+#pragma unroll
+            for (int n = 0; n < D; n++) hf[n] = s_hnf[n + D * j];
+            double cnA = dd.C4[(size_t)j * Nq], cnB = dd.C4[(size_t)j * Nq + (Nq > 1 ? 1 : 0)];
+            for (int i0 = 0; i0 < Nq; i0 += 2) {
+                const int iA = i0, iB = (i0 + 1 < Nq) ? i0 + 1 : i0;
+                const double cA = cnA, cB = (iB != iA) ? cnB : 0.0;
+                cnA = dd.C4[(size_t)j * Nq + ((i0 + 2 < Nq) ? i0 + 2 : iA)];                    // next trip's weights
+                cnB = dd.C4[(size_t)j * Nq + ((i0 + 3 < Nq) ? i0 + 3 : iB)];
+                double qA[NPR], qB[NPR], gA[D], gB[D], pA[NC], pB[NC];
+#pragma unroll
+                for (int c = 0; c < NPR; c++) { qA[c] = s_prim[iA + Nq * c]; qB[c] = s_prim[iB + Nq * c]; }
+#pragma unroll
+                for (int n = 0; n < D; n++) { gA[n] = cA * (hf[n] + s_hq[iA + Nq * (n + D * f)]); gB[n] = cB * (hf[n] + s_hq[iB + Nq * (n + D * f)]); }
+                ec_contract_scaled2<D>(L, qj, qA, qB, gA, gB, pA, pB);       // the flux is symmetric in its two states
+#pragma unroll
+                for (int e = 0; e < NC; e++) fs[e] -= pA[e] + pB[e];
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < NC; e++) s_ff[j + Nf * e] = fs[e];
+    }
+    __syncthreads();
+    // ---- r_q -= R' f_f as a dense product (no index indirection, no data-dependent loop exit: the loads pipeline);
+    //      dudt = M^-1 V' r_q         flux_differencing_form.jl:341-346
+    SSE_FOR(i, Nq) {
+        double acc[NC];
+#pragma unroll
+        for (int e = 0; e < NC; e++) acc[e] = 0.0;
+#pragma unroll 4
+        for (int j = 0; j < Nf; j++) {
+            const double v = dd.RT[(size_t)j * Nq + i];
+#pragma unroll
+            for (int e = 0; e < NC; e++) acc[e] = fma(v, s_ff[j + Nf * e], acc[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < NC; e++) s_r[i + Nq * e] -= acc[e];
+    }
+    __syncthreads();
+    apply_Vt<NC>(o, s_r, s_m, s_z, s_w);
+    mass_solve<NC>(o, g, k, s_m, s_uq, s_z, s_w);
+    SSE_FOR(t, Np * NC) { dudt[(size_t)Np * NC * k + t] = s_m[t]; flag_nonfinite(g.flag, s_m[t]); }
+}
+
 template <int D, int NC>
 __device__ void physical_flux_tile(const Ops& o, const Law& L, const double* s_uq, const double* s_qq, double* s_fq) {
     const int Nq = o.Nq;
@@ -506,8 +825,8 @@ __global__ void k_time_standard_reference(Ops o, Geo g, Law L, long long first, 
             for (int m = 0; m < D; m++) {
                 const double* hl = s_lam + Nq * (m + D * n);
                 double s1 = 0.0, s2 = 0.0;
-                for (int q = o.Dt[m].ptr[i]; q < o.Dt[m].ptr[i + 1]; q++) { int j = o.Dt[m].idx[q]; s1 = fma(o.Dt[m].val[q], hl[j] * fn[j], s1); }
-                for (int q = o.D[m].ptr[i]; q < o.D[m].ptr[i + 1]; q++) s2 = fma(o.D[m].val[q], fn[o.D[m].idx[q]], s2);
+                SSE_ROW_FOR(o.Dt[m], i, j, v_) s1 = fma(v_, hl[j] * fn[j], s1);
+                SSE_ROW_FOR(o.D[m], i, c_, v_) s2 = fma(v_, fn[c_], s2);
                 r += s1;
                 r -= hl[i] * s2;
             }
@@ -526,7 +845,7 @@ __global__ void k_time_standard_reference(Ops o, Geo g, Law L, long long first, 
 #pragma unroll
             for (int e = 0; e < NC; e++) {
                 double s = 0.0;
-                for (int q = o.R.ptr[j]; q < o.R.ptr[j + 1]; q++) s = fma(o.R.val[q], s_fq[o.R.idx[q] + Nq * (e + NC * n)], s);
+                SSE_ROW_FOR(o.R, j, c_, v_) s = fma(v_, s_fq[c_ + Nq * (e + NC * n)], s);
                 fs[e] -= hn * s;
             }
         }
@@ -538,7 +857,7 @@ __global__ void k_time_standard_reference(Ops o, Geo g, Law L, long long first, 
     SSE_FOR(t, Nq * NC) {
         int i = t % Nq, e = t / Nq;
         double s = 0.0;
-        for (int q = o.Rt.ptr[i]; q < o.Rt.ptr[i + 1]; q++) s = fma(o.Rt.val[q], s_ff[o.Rt.idx[q] + Nf * e], s);
+        SSE_ROW_FOR(o.Rt, i, c_, v_) s = fma(v_, s_ff[c_ + Nf * e], s);
         s_r[t] -= s;
     }
     __syncthreads();
@@ -585,7 +904,7 @@ __global__ void k_aux_physical(Ops o, Geo g, Law L, long long first, const doubl
         SSE_FOR(t, Nf * NC) {
             int j = t % Nf, e = t / Nf;
             double s = 0.0;
-            for (int q = o.R.ptr[j]; q < o.R.ptr[j + 1]; q++) s = fma(o.R.val[q], s_qq[o.R.idx[q] + Nq * e], s);
+            SSE_ROW_FOR(o.R, j, c_, v_) s = fma(v_, s_qq[c_ + Nq * e], s);
             q_f[(size_t)Nf * k + j + (size_t)g.NFT * (e + NC * m)] = s;
         }
         __syncthreads();

@@ -298,9 +298,7 @@ k_fluxdiff_tensor(TensorDev t, Ops o, Geo g, Law L, long long first, const doubl
     // ---- phase 3: lift, project, mass solve (flux_differencing_form.jl:340-346)
     double* s_r = sm + lay.post_r;
     if (tid < Nq) {
-        for (int q = o.Rt.ptr[tid]; q < o.Rt.ptr[tid + 1]; q++) {
-            const double rv = o.Rt.val[q];
-            const int j = o.Rt.idx[q];
+        SSE_ROW_FOR(o.Rt, tid, j, rv) {
 #pragma unroll
             for (int e = 0; e < NC; e++) r[e] = fma(-rv, s_ff[e * Nf + j], r[e]);
         }

@@ -86,7 +86,21 @@ static int32_t upload_sp(sse_handle* h, const HostSp& s, SpMat* out) {
     int32_t rc;
     if ((rc = upload(h, s.ptr, &out->ptr))) return rc;
     if ((rc = upload(h, s.idx, &out->idx))) return rc;
-    return upload(h, s.val, &out->val);
+    if ((rc = upload(h, s.val, &out->val))) return rc;
+    const int rows = (int)s.ptr.size() - 1;
+    int w = 0;
+    for (int r = 0; r < rows; r++) w = std::max(w, s.ptr[(size_t)r + 1] - s.ptr[(size_t)r]);
+    std::vector<int> ei((size_t)std::max(w, 1) * std::max(rows, 1), -1);
+    std::vector<double> ev(ei.size(), 0.0);
+    const int sq = w > 16 ? rows : 1, sr = w > 16 ? 1 : std::max(w, 1);
+    for (int r = 0; r < rows; r++)
+        for (int q = s.ptr[(size_t)r]; q < s.ptr[(size_t)r + 1]; q++) {
+            ei[(size_t)(q - s.ptr[(size_t)r]) * sq + (size_t)r * sr] = s.idx[(size_t)q];
+            ev[(size_t)(q - s.ptr[(size_t)r]) * sq + (size_t)r * sr] = s.val[(size_t)q];
+        }
+    out->rows = rows; out->w = w; out->sq = sq; out->sr = sr;
+    if ((rc = upload(h, ei, &out->ei))) return rc;
+    return upload(h, ev, &out->ev);
 }
 
 // ------------------------------------------------------------------------------ dispatch
@@ -117,6 +131,8 @@ static size_t smem_time_bytes(const sse_handle* h) {
     else
         n = o.Nq * NC + 2 * o.Nq * NC * D + 3 * o.Nf * NC + D * o.Nf;
     n += warp_z_size(o, NC) + warp_w_size(o, NC);
+    if (h->cfg.form == SSE_FORM_FLUX_DIFFERENCING) n += (size_t)D * o.Nf;                                    // halfnJf
+    if (h->cfg.form == SSE_FORM_FLUX_DIFFERENCING && NC == D + 2) n += (size_t)(D + 3) * (o.Nq + o.Nf);     // primitive tables of the fast EC path
     return n * sizeof(double);
 }
 static size_t smem_aux_bytes(const Ops& o) {
@@ -352,11 +368,55 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
         if ((rc = upload(h, vptr, &o.vol_ptr))) return rc;
         if ((rc = upload(h, vj, &o.vol_j))) return rc;
         if ((rc = upload(h, vS, &o.vol_S))) return rc;
+        // slot-major copies for the generic pair kernel (coalesced row reads)
+        auto ell = [&](const std::vector<int>& ptr, const std::vector<int>& idx, const std::vector<double>& val, int rows, int nval,
+                       int* width, const int** d_idx, const double** d_val) -> int32_t {
+            int w = 0;
+            for (int r = 0; r < rows; r++) w = std::max(w, ptr[(size_t)r + 1] - ptr[(size_t)r]);
+            std::vector<int> ei((size_t)std::max(w, 1) * rows, -1);
+            std::vector<double> ev((size_t)std::max(w, 1) * rows * nval, 0.0);
+            // wide rows slot-major (coalesced across the threads of a warp), narrow rows row-major (one cache line per thread)
+            const bool wide = w > 16;
+            for (int r = 0; r < rows; r++)
+                for (int q = ptr[(size_t)r]; q < ptr[(size_t)r + 1]; q++) {
+                    const int s_ = q - ptr[(size_t)r];
+                    ei[wide ? (size_t)s_ * rows + r : (size_t)r * w + s_] = idx[(size_t)q];
+                    for (int m = 0; m < nval; m++)
+                        ev[wide ? ((size_t)s_ * nval + m) * rows + r : ((size_t)r * w + s_) * nval + m] = val[(size_t)q * nval + m];
+                }
+            *width = wide ? w : -w;               // sign = layout
+            int32_t rc_;
+            if ((rc_ = upload(h, ei, d_idx))) return rc_;
+            return upload(h, ev, d_val);
+        };
+        if ((rc = ell(vptr, vj, vS, Nq, d, &o.vol_w, &o.vol_je, &o.vol_Se))) return rc;
         o.has_C = a->Cfd != nullptr;
         if (o.has_C) {
             if (!a->nJq && !a->nref) return fail(SSE_ERR_BAD_ARGUMENT, "facet correction needs nJq or nref");
-            if ((rc = upload_sp(h, compress(a->Cfd, Nq, Nf, false), &o.Cq))) return rc;
-            if ((rc = upload_sp(h, compress(a->Cfd, Nq, Nf, true), &o.Cf))) return rc;
+            const HostSp cq = compress(a->Cfd, Nq, Nf, false), cf = compress(a->Cfd, Nq, Nf, true);
+            if ((rc = upload_sp(h, cq, &o.Cq))) return rc;
+            if ((rc = upload_sp(h, cf, &o.Cf))) return rc;
+            if ((rc = ell(cq.ptr, cq.idx, cq.val, Nq, 1, &o.cq_w, &o.cq_je, &o.cq_ve))) return rc;
+            if ((rc = ell(cf.ptr, cf.idx, cf.val, Nf, 1, &o.cf_w, &o.cf_ie, &o.cf_ve))) return rc;
+        }
+        // dense operators (multidimensional schemes): all-pairs tables for k_time_fluxdiff_dense
+        h->dense.ok = 0;
+        if (cfg->pde == SSE_PDE_EULER && cfg->two_point_flux == SSE_TWO_POINT_ENTROPY_CONSERVATIVE && NC == d + 2 && d >= 2 && o.has_C &&
+            std::abs(o.vol_w) > 16 && Nq <= 128 && Nf <= 128) {
+            std::vector<double> S4((size_t)Nq * d * Nq, 0.0), C4((size_t)Nf * Nq, 0.0);
+            for (int j = 0; j < Nq; j++)
+                for (int i = 0; i < Nq; i++) {
+                    if (i == j) continue;
+                    const int lo = std::min(i, j), hi = std::max(i, j);
+                    for (int m = 0; m < d; m++) S4[((size_t)j * d + m) * Nq + i] = 0.25 * (i < j ? 1.0 : -1.0) * a->S[m][lo + (size_t)Nq * hi];
+                }
+            for (int j = 0; j < Nf; j++)
+                for (int i = 0; i < Nq; i++) C4[(size_t)j * Nq + i] = 0.25 * a->Cfd[i + (size_t)Nq * j];
+            std::vector<double> RT((size_t)Nf * Nq);
+            for (int j = 0; j < Nf; j++)
+                for (int i = 0; i < Nq; i++) RT[(size_t)j * Nq + i] = a->R[j + (size_t)Nf * i];
+            if ((rc = upload(h, S4, &h->dense.S4)) || (rc = upload(h, C4, &h->dense.C4)) || (rc = upload(h, RT, &h->dense.RT))) return rc;
+            h->dense.ok = 1;
         }
     } else if (cfg->form == SSE_FORM_STANDARD_PHYSICAL) {
         if (!a->VOL || !a->FAC) return fail(SSE_ERR_BAD_ARGUMENT, "VOL and FAC required for PhysicalOperators");
@@ -497,8 +557,16 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
             h->ct.ok = 1;
         }
     }
+    // threads per element of the generic (one CTA per element) kernels: enough for one volume / facet node per thread, at most 128
+    h->threads = std::min(128, std::max(64, (std::max(Nq, Nf) + 31) / 32 * 32));
     h->smem_nodal = smem_nodal_bytes(o);
     h->smem_time = smem_time_bytes(h);
+    h->smem_dense = h->smem_time + sizeof(double) * (size_t)Nfac * d * Nq;
+    if (h->dense.ok && (h->tp.ok || h->ct.ok || h->smem_dense > 227 * 1024)) h->dense.ok = 0;        // structured operators have better kernels
+    if (h->dense.ok) {
+        CU(cudaFuncSetAttribute(k_time_fluxdiff_dense<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN_MAX));
+        CU(cudaFuncSetAttribute(k_time_fluxdiff_dense<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN_MAX));
+    }
     h->smem_aux = smem_aux_bytes(o);
     if (std::max(h->smem_nodal, std::max(h->smem_time, h->smem_aux)) > 227 * 1024)
         return fail(SSE_ERR_UNSUPPORTED, "element tiles exceed 227 KB of shared memory");
@@ -566,7 +634,7 @@ extern "C" int32_t sse_set_kernel_variant(sse_handle* h, int32_t v) {
 }
 extern "C" int32_t sse_get_kernel_variant(const sse_handle* h, int32_t* v) {
     if (!h || !v) return fail(SSE_ERR_BAD_ARGUMENT, "null argument");
-    *v = (h->variant == 1 && h->ct.ok) ? 2 : ((h->variant == 1 && h->tp.ok && h->tp.has_fluxdiff) ? 1 : 0);
+    *v = (h->variant == 1 && h->ct.ok) ? 2 : ((h->variant == 1 && h->dense.ok) ? 3 : ((h->variant == 1 && h->tp.ok && h->tp.has_fluxdiff) ? 1 : 0));
     return SSE_OK;
 }
 
@@ -680,6 +748,10 @@ int32_t sse::pass_b_stage(sse_handle* h, double* d_dudt, int64_t first, int64_t 
         if (h->variant == 1 && h->ct.ok) {
             ct_fluxdiff(h->ct, h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream, rk, mid);
             h->launches += 1;       // pair kernel + projection kernel
+        } else if (h->variant == 1 && h->dense.ok) {
+            const int T = std::min(128, (std::max(h->cfg.N_q, h->cfg.N_f) + 31) / 32 * 32);
+            if (h->cfg.d == 2) k_time_fluxdiff_dense<2><<<n, T, h->smem_dense, h->stream>>>(h->ops, h->geo, h->law, h->dense, first, h->u_q, h->u_f, d_dudt);
+            else k_time_fluxdiff_dense<3><<<n, T, h->smem_dense, h->stream>>>(h->ops, h->geo, h->law, h->dense, first, h->u_q, h->u_f, d_dudt);
         } else if (use_tensor(h) && h->tp.has_fluxdiff) {
 #define LA(D_, NC_) tensor_launch_fluxdiff<D_, NC_>(h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->sm_count, h->stream)
             DISPATCH_DNC(h, LA);

@@ -31,6 +31,16 @@ def main():
             ("config3 advection_diffusion_2d p4 32x32", lambda: cases.advection_diffusion_2d(M=32), True),
             ("config4 advection_3d p4 M=8", lambda: cases.advection_3d(M=8, flux="central"), True),
             ("config5 euler_tgv_3d p4 M=8", lambda: cases.euler_tgv_3d(M=8, flux="lf"), True)]
+    # the reference's own notebook configurations: dense multidimensional operators through the generic kernels
+    runs += [("euler_3d.ipynb: Euler 3-D ModalMulti p=3 tets M=4 (reference: 31.8 ms/RHS, 1 thread)",
+              lambda: cases.euler_tgv_3d(M=4, p=3, flux="ec", kind="modal_multi"), True),
+             ("euler_vortex_2d.ipynb: Euler 2-D ModalMulti p=4 tris M=4 (reference: 541 us/RHS)",
+              lambda: cases.euler_vortex_2d(M=4, p=4, flux="lf", kind="modal_multi"), True),
+             ("advection_3d.ipynb: advection 3-D ModalTensor p=7 tets M=2 (reference: 7.64 ms/RHS)",
+              lambda: cases.advection_3d(M=2, p=7, flux="lf"), True)]
+    if a.big:
+        runs += [("Euler 3-D ModalMulti p=3 tets M=16 (dense operators, generic kernels)",
+                  lambda: cases.euler_tgv_3d(M=16, p=3, flux="ec", kind="modal_multi"), False)]
     if a.big:
         runs += [("config4 advection_3d p4 M=32", lambda: cases.advection_3d(M=32, flux="central"), False),
                  ("config5 euler_tgv_3d p4 M=24", lambda: cases.euler_tgv_3d(M=24, flux="lf"), False)]

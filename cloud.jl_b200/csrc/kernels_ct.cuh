@@ -342,7 +342,7 @@ k_nodal_ct(SFCoef<N> cf, FacetR<N> fr, CtDev t, Geo g, Law L, long long first, l
                 }
             }
         }
-        __syncwarp();
+        __syncthreads();                                   // the nodal tiles written next lie over the partials of other groups
     } else {
     // every global load of the prologue as an asynchronous copy: the C table and u (needed by the first V) form the first
     // group, J_q (needed by the entropy-variable phase only) the second one, which stays in flight behind the first V

@@ -1147,11 +1147,21 @@ extern "C" int32_t sse_functionals(sse_handle* h, const double* d_u, const doubl
     unsigned grid = (unsigned)std::min<long long>(h->cfg.N_e, 4LL * h->sm_count);
 #define LA(D_, NC_)                                                                                                  \
     do {                                                                                                             \
-        cudaFuncSetAttribute(k_functionals<D_, NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_OPT_IN_MAX);  \
-        k_functionals<D_, NC_><<<grid, 128, smem, h->stream>>>(h->ops, h->geo, h->law, d_u, d_dudt, d_out);           \
+        /* the kernel also holds a few static shared scalars: the opt-in limit covers static + dynamic */          \
+        cudaFuncAttributes fa;                                                                                       \
+        e_l = cudaFuncGetAttributes(&fa, k_functionals<D_, NC_>);                                                    \
+        if (e_l == cudaSuccess)                                                                                      \
+            e_l = cudaFuncSetAttribute(k_functionals<D_, NC_>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                       SMEM_OPT_IN_MAX - (int)fa.sharedSizeBytes);                                   \
+        if (e_l == cudaSuccess) {                                                                                    \
+            k_functionals<D_, NC_><<<grid, 128, smem, h->stream>>>(h->ops, h->geo, h->law, d_u, d_dudt, d_out);       \
+            e_l = cudaGetLastError();                                                                                \
+        }                                                                                                            \
     } while (0)
+    cudaError_t e_l = cudaSuccess;
     DISPATCH_DNC(h, LA);
 #undef LA
+    if (e_l != cudaSuccess) { cudaFree(d_out); return fail(SSE_ERR_CUDA, "functionals launch failed: %s", cudaGetErrorString(e_l)); }
     h->launches += 1;
     // element-partitioned handles: the functionals are sums over all ranks (every rank calls, every rank gets the total)
     const int32_t rc_red = dist_allreduce_sum(h, d_out, NC + 2);

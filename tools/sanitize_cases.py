@@ -52,7 +52,43 @@ FAMILIES = {
     "generic2d": lambda: run("generic advection_2d", cases.advection_2d(M=3, flux="lf"), variant=0),
     "br1": lambda: run("br1 advection_diffusion_2d", cases.advection_diffusion_2d(M=3)),
     "step": lambda: run("step euler_tgv_3d p4", cases.euler_tgv_3d(M=2, flux="ec"), step=True),
+    # round 2: fused advection path at the other compile-time sizes, the stage-fused CK54 kernel at p = 2 / 5, the dense
+    # all-pairs kernel (modal and nodal multidimensional schemes), Euler under StandardForm, and the partitioned residual
+    "ct_std_p2": lambda: run("ct_std advection_3d p2", cases.advection_3d(M=2, p=2, flux="lf"), step=True),
+    "ct_std_p5": lambda: run("ct_std advection_3d p5", cases.advection_3d(M=2, p=5, flux="central")),
+    "ct_p2_step": lambda: run("ct euler_tgv_3d p2", cases.euler_tgv_3d(M=2, p=2, flux="lf"), step=True),
+    "ct_p5": lambda: run("ct euler_tgv_3d p5", cases.euler_tgv_3d(M=2, p=5, flux="ec")),
+    "dense": lambda: run("dense euler_tgv_3d ModalMulti p2", cases.euler_tgv_3d(M=2, p=2, flux="ec", kind="modal_multi")),
+    "dense_nodal": lambda: run("dense euler_vortex_2d NodalMulti p3", cases.euler_vortex_2d(M=3, p=3, flux="lf", kind="nodal_multi")),
+    "standard_euler": lambda: run("generic euler_vortex_2d StandardForm", cases.euler_vortex_2d_standard(M=3, p=3, flux="lf")),
+    "multi": lambda: run_multi(),
 }
+
+
+def run_multi():
+    """Two partitions on one GPU, halos by peer copies (sse_comm_init_local + sse_rhs_multi), against the single-domain oracle."""
+    full = cases.euler_tgv_3d(M=4, p=3, flux="lf")
+    u_full = full.u0(seed=0)
+    parts = [cases.euler_tgv_3d(M=4, p=3, flux="lf", part=(r, 2)) for r in range(2)]
+    solvers = [Solver(p.image(), 0) for p in parts]
+    Solver.comm_init_local(solvers)
+    for s, p in zip(solvers, parts):
+        s.halo_plan(p.sd.mesh)
+    us = [torch.from_numpy(np.ascontiguousarray(u_full[p.sd.mesh.elem_gid])).cuda() for p in parts]
+    dus = [s.new_state() for s in solvers]
+    for _ in range(2):
+        Solver.rhs_multi(solvers, dus, us)
+    for s in solvers:
+        s.synchronize()
+    ref = oracle.rhs(full.image(), u_full)
+    out = np.empty_like(ref)
+    for p, d in zip(parts, dus):
+        out[p.sd.mesh.elem_gid] = d.cpu().numpy()
+    err = float(np.abs(out - ref).max() / np.abs(ref).max())
+    print(f"multi (2 partitions, peer copies): rel. diff vs oracle {err:.2e}", flush=True)
+    for s in solvers:
+        s.close()
+    assert err <= 1e-12
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(FAMILIES)

@@ -23,6 +23,9 @@
 // independent entropy-variable transforms per thread and trip in k_nodal_ct: volume-node loops / facet-node loop.
 // Measured at 82 944 elements once the maps were branch-free: (1,1) 0.643, (1,2) 0.639, (2,2) 0.646, (3,3) 0.682, (5,4) 0.78 ms
 // (beyond two the idle slots of the last trip and the register pressure cost more than the interleaving hides)
+#ifndef SSE_FD_FF_PAD
+#define SSE_FD_FF_PAD 1
+#endif
 #ifndef SSE_NODAL_ILP_Q
 #define SSE_NODAL_ILP_Q 1
 #endif
@@ -632,11 +635,17 @@ template <int N, bool DUAL = false> struct FdSmem {
     static constexpr int lam = prim + NP * T::Nq;          // [D*D][Nq]
     static constexpr int fprim = lam + D * D * T::Nq;      // [NP][Nf]
     static constexpr int hnf = fprim + NP * T::Nf;         // [D][Nf]
-    static constexpr int ff = hnf + D * T::Nf;             // [NC][Nf]
-    static constexpr int stage = ff + NC * T::Nf;          // [2][NC][Nq]
+    // rows of the facet residual FFS apart with FFS = N^2 (mod 16): reducer t = (variable, facet node of one face) then
+    // updates bank t (mod 16) -- 2 instead of 3 wavefronts per access of its read-modify-write and of the lift
+    static constexpr int FFS = SSE_FD_FF_PAD ? T::Nf + ((N * N - T::Nf) % 16 + 16) % 16 : T::Nf;
+    static constexpr int ff = hnf + D * T::Nf;             // [NC][FFS]
+    static constexpr int stage = ff + NC * FFS;            // [2][NC][Nq]
     // DUAL: in the facet sub-rounds a staged vector of volume node (a, b, c) sits at a * PS + b * N + c with the planes
     // padded to PS = N (mod 16) and the variables FS = N * PS apart, which puts the (facet node, variable) reducer of
-    // thread t on bank t (mod 16) for every face: no conflicts on its N loads (they cost 3.5 - 4 wavefronts each unpadded)
+    // thread t on bank t (mod 16) for every face: no conflicts on its N loads (they cost 3.5 - 4 wavefronts each unpadded).
+    // The staging stores pay for it (3 instead of 2 wavefronts); the layout with the fewest wavefronts in total (unpadded
+    // planes, FS = N^3 + 12: 320 + 560 instead of 480 + 480 per element, tools/bank_sim.py) is 1.3 % SLOWER -- the reducer
+    // loads sit between two barriers, the stores do not.
     static constexpr int PS = N * N + ((N - (N * N) % 16) % 16 + 16) % 16;
     static constexpr int FS = N * PS;
     static constexpr int buf = NC * T::Nq;                 // doubles per stage buffer of the volume rounds
@@ -737,7 +746,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
 #pragma unroll
             for (int c = 0; c < NP; c++) s_fprim[c * Nf + tid] = qa[c];
 #pragma unroll
-            for (int e = 0; e < NC; e++) s_ff[e * Nf + tid] = bj * phi[e];
+            for (int e = 0; e < NC; e++) s_ff[e * S::FFS + tid] = bj * phi[e];
         }
     }
     __syncthreads();
@@ -849,14 +858,14 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
                     else { bA = rjj; dA = PS; bB = rx * PS + rc3; dB = N; rc3 = rc3 + 1 == N ? 0 : rc3 + 1; }
 #pragma unroll
                     for (int i = 0; i < N; i++) { sA += stA[re * FS + bA + i * dA]; sB += stB[re * FS + bB + i * dB]; }
-                    s_ff[re * Nf + fA * NN + rjj] -= sA;
-                    s_ff[re * Nf + fB * NN + rjj] -= sB;
+                    s_ff[re * S::FFS + fA * NN + rjj] -= sA;
+                    s_ff[re * S::FFS + fB * NN + rjj] -= sB;
                 } else {                    // both sub-rounds feed face 4: one reducer sums both stages
                     const int cA = rc3, cB = cA + 1 == N ? 0 : cA + 1;
                     rc3 = cB + 1 == N ? 0 : cB + 1;
 #pragma unroll
                     for (int i = 0; i < N; i++) { sA += stA[re * FS + rx * PS + cA + i * N]; sB += stB[re * FS + rx * PS + cB + i * N]; }
-                    s_ff[re * Nf + 3 * NN + rjj] -= sA + sB;
+                    s_ff[re * S::FFS + 3 * NN + rjj] -= sA + sB;
                 }
             }
             __syncthreads();      // two reducers of one iteration may hit the same facet node only across iterations
@@ -952,7 +961,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
             double s = 0.0;
 #pragma unroll
             for (int i = 0; i < N; i++) s += st[e * Nq + base + i * stride];
-            s_ff[e * Nf + f * NN + jj] -= s;
+            s_ff[e * S::FFS + f * NN + jj] -= s;
         }
     }
     }
@@ -969,7 +978,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
             const int re = tid / NN, rjj = tid - re * NN, rx = rjj / N, ry = rjj - rx * N;
             double gs = 0.0;
 #pragma unroll
-            for (int y = 0; y < N; y++) gs = fma(ld_tab(fac + 4 * N + y + N * ry), s_ff[re * Nf + 3 * NN + rx * N + y], gs);
+            for (int y = 0; y < N; y++) gs = fma(ld_tab(fac + 4 * N + y + N * ry), s_ff[re * S::FFS + 3 * NN + rx * N + y], gs);
             s_G[tid] = gs;
         }
         double rw[3];
@@ -982,7 +991,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
             for (int fr = 0; fr < 3; fr++) {
                 const int j = facet_partner<N>(fr, ca, cb, cc);
 #pragma unroll
-                for (int e = 0; e < NC; e++) r[e] = fma(-rw[fr], s_ff[e * Nf + j], r[e]);
+                for (int e = 0; e < NC; e++) r[e] = fma(-rw[fr], s_ff[e * S::FFS + j], r[e]);
             }
 #pragma unroll
             for (int e = 0; e < NC; e++) r[e] = fma(-r3c, s_G[e * NN + ca * N + cb], r[e]);
@@ -1000,7 +1009,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
         for (int fr = 0; fr < NFR; fr++) {
             const int j = facet_partner<N>(fr, ca, cb, cc);
 #pragma unroll
-            for (int e = 0; e < NC; e++) r[e] = fma(-rw[fr], s_ff[e * Nf + j], r[e]);
+            for (int e = 0; e < NC; e++) r[e] = fma(-rw[fr], s_ff[e * S::FFS + j], r[e]);
         }
 #pragma unroll
         for (int e = 0; e < NC; e++) u_q[((size_t)k * NC + e) * Nq + tid] = r[e];

@@ -26,6 +26,9 @@
 #ifndef SSE_FD_FF_PAD
 #define SSE_FD_FF_PAD 1
 #endif
+#ifndef SSE_PROJ_PREFETCH
+#define SSE_PROJ_PREFETCH 150
+#endif
 #ifndef SSE_NODAL_ILP_Q
 #define SSE_NODAL_ILP_Q 1
 #endif
@@ -559,6 +562,17 @@ k_project_ct(SFCoef<N> cf, CtDev t, Geo g, long long first, long long count, con
     const bool act = gl < T::GPW && (grp / NC) < nel;
 
     double y[N][N], out[T::LPT];
+    // r_q comes from DRAM (the pair kernel wrote 5 kB per element since): pull the tiles of the CTA that starts SSE_PROJ_PREFETCH
+    // CTAs later into L2, so that its slab loads and its W / J copy pay an L2 round trip instead of a DRAM one
+    if constexpr (SSE_PROJ_PREFETCH > 0 && NC > 1) {
+        const long long ep = e0 + (long long)SSE_PROJ_PREFETCH * EPB;
+        if (ep + EPB <= first + count) {
+            const char* pr = (const char*)(r_q + (size_t)ep * NC * Nq);
+            for (int i = tid; i < (EPB * NC * Nq * 8 + 127) / 128; i += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + (size_t)i * 128));
+            const char* pw = (const char*)(g.iJW + (size_t)ep * Nq);
+            for (int i = tid; i < (EPB * Nq * 8 + 127) / 128; i += NT) asm volatile("prefetch.global.L2 [%0];" ::"l"(pw + (size_t)i * 128));
+        }
+    }
     // Prologue without a barrier: the W / J tile arrives by asynchronous copies (precomputed at sse_create, so no reciprocal
     // sits between the load and the tile) and is waited for where it is first used; the C tensor is read from its global
     // table through L1 (15 values per application by the (i + j, k) symmetry) instead of being staged in shared memory.

@@ -30,6 +30,7 @@ struct Ops {
     int v_kind;
     int P1, M1, M2, M3;            // warped tensors (2-D embedded as M3 = 1)
     const double* Vd;              // dense V, column-major Nq x Np
+    int v_small;                   // warped V of a small element, applied through its dense matrix Vd (sse_create)
     const double *A, *B, *C;       // warped_product_3d.jl:2-35
     const int *sig_i, *sig_o;      // 0-based, -1 = unused
     int N2[8];
@@ -93,5 +94,21 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int PENDING> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
 
 #define SSE_FOR(t, n) for (int t = threadIdx.x; t < (n); t += blockDim.x)
+
+// Element packing of the one-CTA-per-element kernels (generic and tensor-line): blockDim = (threads per element, elements per
+// CTA).  Row threadIdx.y works on element first + blockIdx.x * blockDim.y + threadIdx.y in its own slice of the dynamic shared
+// memory; the host launches full CTAs only (a second launch with one row per CTA takes the remainder), so no row is idle.
+// With 32 threads per element a row is one warp and its phases are ordered by warp barriers: the rows of a CTA never wait for
+// each other.  (Small elements -- 1-D, triangles and quadrilaterals up to 32 nodes -- used 25 of 64 lanes of a CTA of their own.)
+__device__ __forceinline__ long long sse_element(long long first) { return first + (long long)blockIdx.x * blockDim.y + threadIdx.y; }
+__device__ __forceinline__ double* sse_row_smem(double* sm) {
+    unsigned bytes;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(bytes));
+    return sm + (size_t)threadIdx.y * (bytes / (8u * blockDim.y));
+}
+__device__ __forceinline__ void sse_sync() {
+    if (blockDim.x == 32) __syncwarp();
+    else __syncthreads();
+}
 
 }  // namespace sse

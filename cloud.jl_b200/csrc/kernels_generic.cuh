@@ -19,10 +19,10 @@ __device__ void apply_V(const Ops& o, const double* x, double* y, double* zb, do
     const int Nq = o.Nq, Np = o.Np;
     if (o.v_kind == SSE_V_IDENTITY) {
         SSE_FOR(t, Nq * NC) y[t] = x[t];
-        __syncthreads();
+        sse_sync();
         return;
     }
-    if (o.v_kind == SSE_V_DENSE) {
+    if (o.v_kind == SSE_V_DENSE || o.v_small) {
         // one node per thread, all variables at once: the entry of V is loaded once (coalesced over the nodes) and feeds NC
         // independent accumulators; same summation order per (node, variable) as a plain dot product
         SSE_FOR(i, Nq) {
@@ -38,7 +38,7 @@ __device__ void apply_V(const Ops& o, const double* x, double* y, double* zb, do
 #pragma unroll
             for (int e = 0; e < NC; e++) y[i + Nq * e] = acc[e];
         }
-        __syncthreads();
+        sse_sync();
         return;
     }
     const int P1 = o.P1, M1 = o.M1, M2 = o.M2, M3 = o.M3;
@@ -51,7 +51,7 @@ __device__ void apply_V(const Ops& o, const double* x, double* y, double* zb, do
             zb[t] = s;
         }
     }
-    __syncthreads();
+    sse_sync();
     SSE_FOR(t, NC * P1 * M2 * M3) {
         int a3 = t % M3, a2 = (t / M3) % M2, b1 = (t / (M3 * M2)) % P1, e = t / (M3 * M2 * P1);
         double s = 0.0;
@@ -59,14 +59,14 @@ __device__ void apply_V(const Ops& o, const double* x, double* y, double* zb, do
             s = fma(o.B[a2 + M2 * (b1 + P1 * b2)], zb[((e * P1 + b1) * P1 + b2) * M3 + a3], s);
         wb[t] = s;
     }
-    __syncthreads();
+    sse_sync();
     SSE_FOR(t, NC * M1 * M2 * M3) {
         int a3 = t % M3, a2 = (t / M3) % M2, a1 = (t / (M3 * M2)) % M1, e = t / (M3 * M2 * M1);
         double s = 0.0;
         for (int b1 = 0; b1 < P1; b1++) s = fma(o.A[a1 + M1 * b1], wb[((e * P1 + b1) * M2 + a2) * M3 + a3], s);
         y[o.sig_o[a1 + M1 * (a2 + M2 * a3)] + Nq * e] = s;
     }
-    __syncthreads();
+    sse_sync();
 }
 
 // y (Np x NC) = V^T x (Nq x NC).  warped_product_3d.jl:94-136 / warped_product_2d.jl:61-89
@@ -75,10 +75,10 @@ __device__ void apply_Vt(const Ops& o, const double* x, double* y, double* zb, d
     const int Nq = o.Nq, Np = o.Np;
     if (o.v_kind == SSE_V_IDENTITY) {
         SSE_FOR(t, Nq * NC) y[t] = x[t];
-        __syncthreads();
+        sse_sync();
         return;
     }
-    if (o.v_kind == SSE_V_DENSE) {
+    if (o.v_kind == SSE_V_DENSE || o.v_small) {
         // one mode per thread, all variables at once (NC independent accumulators, fixed trip count: the loads pipeline)
         SSE_FOR(j, Np) {
             double acc[NC];
@@ -94,7 +94,7 @@ __device__ void apply_Vt(const Ops& o, const double* x, double* y, double* zb, d
 #pragma unroll
             for (int e = 0; e < NC; e++) y[j + Np * e] = acc[e];
         }
-        __syncthreads();
+        sse_sync();
         return;
     }
     const int P1 = o.P1, M1 = o.M1, M2 = o.M2, M3 = o.M3;
@@ -104,7 +104,7 @@ __device__ void apply_Vt(const Ops& o, const double* x, double* y, double* zb, d
         for (int a1 = 0; a1 < M1; a1++) s = fma(o.A[a1 + M1 * b1], x[o.sig_o[a1 + M1 * (a2 + M2 * a3)] + Nq * e], s);
         wb[t] = s;
     }
-    __syncthreads();
+    sse_sync();
     SSE_FOR(t, NC * P1 * P1 * M3) {
         int a3 = t % M3, b2 = (t / M3) % P1, b1 = (t / (M3 * P1)) % P1, e = t / (M3 * P1 * P1);
         if (b2 < o.N2[b1]) {
@@ -113,7 +113,7 @@ __device__ void apply_Vt(const Ops& o, const double* x, double* y, double* zb, d
             zb[t] = s;
         }
     }
-    __syncthreads();
+    sse_sync();
     SSE_FOR(t, NC * P1 * P1 * P1) {
         int b3 = t % P1, b2 = (t / P1) % P1, b1 = (t / (P1 * P1)) % P1, e = t / (P1 * P1 * P1);
         if (b2 < o.N2[b1] && b3 < o.N3[b1 * 8 + b2]) {
@@ -122,7 +122,7 @@ __device__ void apply_Vt(const Ops& o, const double* x, double* y, double* zb, d
             y[o.sig_i[b1 + P1 * (b2 + P1 * b3)] + Np * e] = s;
         }
     }
-    __syncthreads();
+    sse_sync();
 }
 
 // y (nrow x NC) = A x, rows of A compressed; ldx / ldy are the leading dimensions of the tiles
@@ -134,7 +134,7 @@ __device__ void apply_sp(const SpMat& A, int nrow, const double* x, int ldx, dou
         SSE_ROW_FOR(A, i, c_, v_) s = fma(v_, x[c_ + ldx * e], s);
         y[i + ldy * e] = s;
     }
-    __syncthreads();
+    sse_sync();
 }
 
 __host__ __device__ inline int warp_z_size(const Ops& o, int NC) { return o.v_kind == SSE_V_WARPED ? NC * o.P1 * o.P1 * o.M3 : 0; }
@@ -146,7 +146,7 @@ __device__ void mass_solve(const Ops& o, const Geo& g, long long k, double* rhs,
     const double* J = g.J_q + (size_t)o.Nq * k;
     if (g.mass_solver == SSE_MASS_DIAGONAL) {
         SSE_FOR(t, o.Np * NC) { int i = t % o.Np; rhs[t] *= 1.0 / (o.W[i] * J[i]); }
-        __syncthreads();
+        sse_sync();
         return;
     }
     if (g.mass_solver == SSE_MASS_CHOLESKY) {
@@ -156,27 +156,27 @@ __device__ void mass_solve(const Ops& o, const Geo& g, long long k, double* rhs,
         const double* U = g.chol + (size_t)Np * Np * k;
         for (int j = 0; j < Np; j++) {
             if (threadIdx.x < NC) rhs[j + Np * threadIdx.x] /= U[j + (size_t)Np * j];
-            __syncthreads();
+            sse_sync();
             SSE_FOR(t, (Np - 1 - j) * NC) {
                 const int i = j + 1 + t % (Np - 1 - j), e = t / (Np - 1 - j);
                 rhs[i + Np * e] = fma(-U[j + (size_t)Np * i], rhs[j + Np * e], rhs[i + Np * e]);
             }
-            __syncthreads();
+            sse_sync();
         }
         for (int j = Np - 1; j >= 0; j--) {
             if (threadIdx.x < NC) rhs[j + Np * threadIdx.x] /= U[j + (size_t)Np * j];
-            __syncthreads();
+            sse_sync();
             SSE_FOR(t, j * NC) {
                 const int i = t % j, e = t / j;
                 rhs[i + Np * e] = fma(-U[i + (size_t)Np * j], rhs[j + Np * e], rhs[i + Np * e]);
             }
-            __syncthreads();
+            sse_sync();
         }
         return;
     }
     apply_V<NC>(o, rhs, tq, zb, wb);
     SSE_FOR(t, o.Nq * NC) { int i = t % o.Nq; tq[t] *= o.W[i] / J[i]; }
-    __syncthreads();
+    sse_sync();
     apply_Vt<NC>(o, tq, rhs, zb, wb);
 }
 
@@ -195,25 +195,25 @@ static __global__ void k_cholesky_factor(Ops o, Geo g, double* __restrict__ chol
     const double* J = g.J_q + (size_t)Nq * k;
     for (int c = 0; c < Np; c++) {
         SSE_FOR(t, Np) s_e[t] = (t == c) ? 1.0 : 0.0;
-        __syncthreads();
+        sse_sync();
         apply_V<1>(o, s_e, s_q, s_z, s_w);
         SSE_FOR(i, Nq) s_q[i] *= o.W[i] * J[i];
-        __syncthreads();
+        sse_sync();
         apply_Vt<1>(o, s_q, s_M + Np * c, s_z, s_w);
     }
     for (int j = 0; j < Np; j++) {
         const double piv = s_M[j + Np * j];
-        __syncthreads();
+        sse_sync();
         if (!(piv > 0.0)) { if (threadIdx.x == 0) *bad = 1; return; }      // PosDefException in the reference (Solvers.jl:411-412)
         const double ujj = sqrt(piv);
         SSE_FOR(i, Np - j) s_M[j + Np * (j + i)] = (i == 0) ? ujj : s_M[j + Np * (j + i)] / ujj;
-        __syncthreads();
+        sse_sync();
         const int n = Np - 1 - j;
         SSE_FOR(t, n * n) {
             const int i = j + 1 + t % n, l = j + 1 + t / n;
             if (i <= l) s_M[i + Np * l] = fma(-s_M[j + Np * i], s_M[j + Np * l], s_M[i + Np * l]);
         }
-        __syncthreads();
+        sse_sync();
     }
     SSE_FOR(t, Np * Np) chol[(size_t)Np * Np * k + t] = (t % Np <= t / Np) ? s_M[t] : 0.0;
 }
@@ -226,8 +226,9 @@ static __global__ void k_cholesky_factor(Ops o, Geo g, double* __restrict__ chol
 template <int D, int NC>
 __global__ void k_nodal_generic(Ops o, Geo g, Law L, int project, long long first, const double* __restrict__ u,
                                 double* __restrict__ u_q, double* __restrict__ u_f) {
-    extern __shared__ double sm[];
-    const long long k = first + blockIdx.x;
+    extern __shared__ double sm_cta[];
+    double* sm = sse_row_smem(sm_cta);
+    const long long k = sse_element(first);
     const int Nq = o.Nq, Np = o.Np, Nf = o.Nf;
     double* s_u = sm;                       // Np x NC
     double* s_a = s_u + Np * NC;            // Nq x NC
@@ -237,7 +238,7 @@ __global__ void k_nodal_generic(Ops o, Geo g, Law L, int project, long long firs
     double* s_w = s_z + warp_z_size(o, NC);
 
     SSE_FOR(t, Np * NC) s_u[t] = u[(size_t)Np * NC * k + t];
-    __syncthreads();
+    sse_sync();
     apply_V<NC>(o, s_u, s_a, s_z, s_w);                           // u_q = V u
     if (project == 0) {
         apply_sp<NC>(o.R, Nf, s_a, Nq, s_f, Nf);                  // u_f = R u_q
@@ -250,7 +251,7 @@ __global__ void k_nodal_generic(Ops o, Geo g, Law L, int project, long long firs
 #pragma unroll
             for (int e = 0; e < NC; e++) s_b[i + Nq * e] = wi[e];
         }
-        __syncthreads();
+        sse_sync();
         apply_sp<NC>(o.R, Nf, s_b, Nq, s_f, Nf);                  // w_f = R w_q
         SSE_FOR(i, Nf) {
             double wi[NC], ui[NC];
@@ -260,7 +261,7 @@ __global__ void k_nodal_generic(Ops o, Geo g, Law L, int project, long long firs
 #pragma unroll
             for (int e = 0; e < NC; e++) s_f[i + Nf * e] = ui[e];
         }
-        __syncthreads();
+        sse_sync();
     } else {
         const double* J = g.J_q + (size_t)Nq * k;
         SSE_FOR(i, Nq) {                                           // w_q = WJ * w(u_q)
@@ -272,7 +273,7 @@ __global__ void k_nodal_generic(Ops o, Geo g, Law L, int project, long long firs
 #pragma unroll
             for (int e = 0; e < NC; e++) s_b[i + Nq * e] = wi[e] * wj;
         }
-        __syncthreads();
+        sse_sync();
         apply_Vt<NC>(o, s_b, s_u, s_z, s_w);                       // w = V' w_q
         mass_solve<NC>(o, g, k, s_u, s_b, s_z, s_w);               // w = M \ w
         apply_V<NC>(o, s_u, s_b, s_z, s_w);                        // w_q = V w
@@ -294,7 +295,7 @@ __global__ void k_nodal_generic(Ops o, Geo g, Law L, int project, long long firs
                 for (int e = 0; e < NC; e++) s_f[j + Nf * e] = ui[e];
             }
         }
-        __syncthreads();
+        sse_sync();
     }
     SSE_FOR(t, Nq * NC) u_q[(size_t)Nq * NC * k + t] = s_a[t];
     SSE_FOR(t, Nf * NC) { int i = t % Nf, e = t / Nf; u_f[(size_t)Nf * k + i + (size_t)g.NFT * e] = s_f[t]; }
@@ -316,7 +317,7 @@ __device__ void load_facets(const Ops& o, const Geo& g, long long k, const doubl
 #pragma unroll
         for (int m = 0; m < D; m++) s_nf[m + D * i] = g.nJf[m + D * ((size_t)Nf * k + i)] / jf;   // operators.jl:19,59
     }
-    __syncthreads();
+    sse_sync();
 }
 
 // ------------------------------------------------------------------ pass B: flux differencing
@@ -325,8 +326,9 @@ __device__ void load_facets(const Ops& o, const Geo& g, long long k, const doubl
 template <int D, int NC>
 __global__ void k_time_fluxdiff_generic(Ops o, Geo g, Law L, long long first, const double* __restrict__ u_q,
                                         const double* __restrict__ u_f, double* __restrict__ dudt) {
-    extern __shared__ double sm[];
-    const long long k = first + blockIdx.x;
+    extern __shared__ double sm_cta[];
+    double* sm = sse_row_smem(sm_cta);
+    const long long k = sse_element(first);
     const int Nq = o.Nq, Np = o.Np, Nf = o.Nf;
     double* s_uq = sm;                       // Nq x NC
     double* s_r = s_uq + Nq * NC;            // Nq x NC
@@ -373,7 +375,7 @@ __global__ void k_time_fluxdiff_generic(Ops o, Geo g, Law L, long long first, co
             }
         }
     }
-    __syncthreads();
+    sse_sync();
 
     // facet side: f_f = BJf f* - sum_i C_ij (F(u_i, u_fj) . nJ_ij)
     SSE_FOR(j, Nf) {
@@ -554,7 +556,7 @@ __global__ void k_time_fluxdiff_generic(Ops o, Geo g, Law L, long long first, co
 #pragma unroll
         for (int e = 0; e < NC; e++) s_r[i + Nq * e] = r[e];
     }
-    __syncthreads();
+    sse_sync();
     // r_q -= R' f_f
     SSE_FOR(t, Nq * NC) {
         int i = t % Nq, e = t / Nq;
@@ -562,7 +564,7 @@ __global__ void k_time_fluxdiff_generic(Ops o, Geo g, Law L, long long first, co
         SSE_ROW_FOR(o.Rt, i, c_, v_) s = fma(v_, s_ff[c_ + Nf * e], s);
         s_r[t] -= s;
     }
-    __syncthreads();
+    sse_sync();
     apply_Vt<NC>(o, s_r, s_m, s_z, s_w);
     mass_solve<NC>(o, g, k, s_m, s_uq, s_z, s_w);
     SSE_FOR(t, Np * NC) { dudt[(size_t)Np * NC * k + t] = s_m[t]; flag_nonfinite(g.flag, s_m[t]); }
@@ -635,7 +637,7 @@ k_time_fluxdiff_dense(Ops o, Geo g, Law L, DenseDev dd, long long first, const d
 #pragma unroll
         for (int c = 0; c < NPR; c++) s_fprim[j + Nf * c] = q[c];
     }
-    __syncthreads();
+    sse_sync();
 
     // ---- volume side: r_i = - sum_j F(u_i, u_j) . g_ij,  g_ij = sum_m S_m[i,j] (Lambda_i + Lambda_j)[m, :]
     //                        - sum_j F(u_i, u_fj) . C_ij (halfnJf_j + halfnJq_i,f(j))
@@ -740,7 +742,7 @@ k_time_fluxdiff_dense(Ops o, Geo g, Law L, DenseDev dd, long long first, const d
 #pragma unroll
         for (int e = 0; e < NC; e++) s_ff[j + Nf * e] = fs[e];
     }
-    __syncthreads();
+    sse_sync();
     // ---- r_q -= R' f_f as a dense product (no index indirection, no data-dependent loop exit: the loads pipeline);
     //      dudt = M^-1 V' r_q         flux_differencing_form.jl:341-346
     SSE_FOR(i, Nq) {
@@ -756,7 +758,7 @@ k_time_fluxdiff_dense(Ops o, Geo g, Law L, DenseDev dd, long long first, const d
 #pragma unroll
         for (int e = 0; e < NC; e++) s_r[i + Nq * e] -= acc[e];
     }
-    __syncthreads();
+    sse_sync();
     apply_Vt<NC>(o, s_r, s_m, s_z, s_w);
     mass_solve<NC>(o, g, k, s_m, s_uq, s_z, s_w);
     SSE_FOR(t, Np * NC) { dudt[(size_t)Np * NC * k + t] = s_m[t]; flag_nonfinite(g.flag, s_m[t]); }
@@ -787,7 +789,7 @@ __device__ void physical_flux_tile(const Ops& o, const Law& L, const double* s_u
             }
         }
     }
-    __syncthreads();
+    sse_sync();
 }
 
 // ------------------------------------------------------------------ pass B: StandardForm + ReferenceOperators
@@ -795,8 +797,9 @@ __device__ void physical_flux_tile(const Ops& o, const Law& L, const double* s_u
 template <int D, int NC>
 __global__ void k_time_standard_reference(Ops o, Geo g, Law L, long long first, const double* __restrict__ u_q,
                                           const double* __restrict__ u_f, double* __restrict__ dudt) {
-    extern __shared__ double sm[];
-    const long long k = first + blockIdx.x;
+    extern __shared__ double sm_cta[];
+    double* sm = sse_row_smem(sm_cta);
+    const long long k = sse_element(first);
     const int Nq = o.Nq, Np = o.Np, Nf = o.Nf;
     double* s_uq = sm;                        // Nq x NC (later scratch)
     double* s_r = s_uq + Nq * NC;             // Nq x NC
@@ -853,14 +856,14 @@ __global__ void k_time_standard_reference(Ops o, Geo g, Law L, long long first, 
 #pragma unroll
         for (int e = 0; e < NC; e++) s_ff[j + Nf * e] = bj * fs[e];
     }
-    __syncthreads();
+    sse_sync();
     SSE_FOR(t, Nq * NC) {
         int i = t % Nq, e = t / Nq;
         double s = 0.0;
         SSE_ROW_FOR(o.Rt, i, c_, v_) s = fma(v_, s_ff[c_ + Nf * e], s);
         s_r[t] -= s;
     }
-    __syncthreads();
+    sse_sync();
     apply_Vt<NC>(o, s_r, s_m, s_z, s_w);
     mass_solve<NC>(o, g, k, s_m, s_uq, s_z, s_w);
     SSE_FOR(t, Np * NC) { dudt[(size_t)Np * NC * k + t] = s_m[t]; flag_nonfinite(g.flag, s_m[t]); }
@@ -871,8 +874,9 @@ __global__ void k_time_standard_reference(Ops o, Geo g, Law L, long long first, 
 template <int D, int NC>
 __global__ void k_aux_physical(Ops o, Geo g, Law L, long long first, const double* __restrict__ u_q,
                                const double* __restrict__ u_f, double* __restrict__ q_q, double* __restrict__ q_f) {
-    extern __shared__ double sm[];
-    const long long k = first + blockIdx.x;
+    extern __shared__ double sm_cta[];
+    double* sm = sse_row_smem(sm_cta);
+    const long long k = sse_element(first);
     const int Nq = o.Nq, Np = o.Np, Nf = o.Nf;
     double* s_uq = sm;                        // Nq x NC
     double* s_in = s_uq + Nq * NC;            // Nf x NC
@@ -898,7 +902,7 @@ __global__ void k_aux_physical(Ops o, Geo g, Law L, long long first, const doubl
             }
             s_m[t] = -s - s2;
         }
-        __syncthreads();
+        sse_sync();
         apply_V<NC>(o, s_m, s_qq, s_z, s_w);
         SSE_FOR(t, Nq * NC) q_q[(size_t)Nq * NC * (m + (size_t)D * k) + t] = s_qq[t];
         SSE_FOR(t, Nf * NC) {
@@ -907,7 +911,7 @@ __global__ void k_aux_physical(Ops o, Geo g, Law L, long long first, const doubl
             SSE_ROW_FOR(o.R, j, c_, v_) s = fma(v_, s_qq[c_ + Nq * e], s);
             q_f[(size_t)Nf * k + j + (size_t)g.NFT * (e + NC * m)] = s;
         }
-        __syncthreads();
+        sse_sync();
     }
 }
 
@@ -917,8 +921,9 @@ template <int D, int NC>
 __global__ void k_time_physical(Ops o, Geo g, Law L, long long first, int second_order, const double* __restrict__ u_q,
                                 const double* __restrict__ u_f, const double* __restrict__ q_q,
                                 const double* __restrict__ q_f, double* __restrict__ dudt) {
-    extern __shared__ double sm[];
-    const long long k = first + blockIdx.x;
+    extern __shared__ double sm_cta[];
+    double* sm = sse_row_smem(sm_cta);
+    const long long k = sse_element(first);
     const int Nq = o.Nq, Np = o.Np, Nf = o.Nf;
     double* s_uq = sm;                        // Nq x NC
     double* s_qq = s_uq + Nq * NC;            // Nq x NC x D
@@ -953,7 +958,7 @@ __global__ void k_time_physical(Ops o, Geo g, Law L, long long first, int second
 #pragma unroll
         for (int e = 0; e < NC; e++) s_ff[j + Nf * e] = fs[e];
     }
-    __syncthreads();
+    sse_sync();
     const double* FAC = g.FAC + (size_t)Np * Nf * k;
     SSE_FOR(t, Np * NC) {
         int a = t % Np, e = t / Np;

@@ -141,9 +141,10 @@ __global__ void __launch_bounds__(128, 4)
 k_fluxdiff_tensor(TensorDev t, Ops o, Geo g, Law L, long long first, const double* __restrict__ u_q,
                   const double* __restrict__ u_f, double* __restrict__ dudt) {
     constexpr int NP = PrimCount<D, NC>::value;
-    extern __shared__ double sm[];
+    extern __shared__ double sm_cta[];
+    double* sm = sse_row_smem(sm_cta);          // element packing: common.cuh
     const int tid = threadIdx.x;
-    const long long k = first + blockIdx.x;
+    const long long k = sse_element(first);
     const int Nq = o.Nq, Nf = o.Nf, Np = o.Np;
     const FdLayout lay = fd_layout(o, D, NC, NP);
     double* s_prim = sm + lay.prim;
@@ -211,7 +212,7 @@ k_fluxdiff_tensor(TensorDev t, Ops o, Geo g, Law L, long long first, const doubl
 #pragma unroll
         for (int e = 0; e < NC; e++) s_ff[e * Nf + j] = bj * phi[e];
     }
-    __syncthreads();
+    sse_sync();
 
     // ---- phase 1: volume flux differencing along tensor lines
     int buf = 0;
@@ -239,7 +240,7 @@ k_fluxdiff_tensor(TensorDev t, Ops o, Geo g, Law L, long long first, const doubl
                 for (int e = 0; e < NC; e++) { r[e] -= phi[e]; st[e * Nq + j] = phi[e]; }
             }
         }
-        __syncthreads();
+        sse_sync();
         if (tid < Nq && t.v_source[rd * Nq + tid] >= 0) {
 #pragma unroll
             for (int e = 0; e < NC; e++) r[e] += st[e * Nq + tid];
@@ -281,7 +282,7 @@ k_fluxdiff_tensor(TensorDev t, Ops o, Geo g, Law L, long long first, const doubl
             for (int e = 0; e < NC; e++) { r[e] -= phi[e]; st[e * Nq + tid] = phi[e]; }
         }
         face_prev = f;
-        __syncthreads();
+        sse_sync();
         const int nred = t.red_n[fr] * NC;
         for (int q = tid; q < nred; q += blockDim.x) {
             const int item = q / NC, e = q - item * NC;
@@ -293,7 +294,7 @@ k_fluxdiff_tensor(TensorDev t, Ops o, Geo g, Law L, long long first, const doubl
             s_ff[e * Nf + t.red_dst[base]] -= s;
         }
     }
-    __syncthreads();
+    sse_sync();
 
     // ---- phase 3: lift, project, mass solve (flux_differencing_form.jl:340-346)
     double* s_r = sm + lay.post_r;
@@ -303,12 +304,12 @@ k_fluxdiff_tensor(TensorDev t, Ops o, Geo g, Law L, long long first, const doubl
             for (int e = 0; e < NC; e++) r[e] = fma(-rv, s_ff[e * Nf + j], r[e]);
         }
     }
-    __syncthreads();                               // every read of s_ff / stage done before s_r and scratch are written
+    sse_sync();                               // every read of s_ff / stage done before s_r and scratch are written
     if (tid < Nq) {
 #pragma unroll
         for (int e = 0; e < NC; e++) s_r[e * Nq + tid] = r[e];
     }
-    __syncthreads();
+    sse_sync();
     double* s_m = sm + lay.post_m;
     apply_Vt<NC>(o, s_r, s_m, sm + lay.post_z, sm + lay.post_w);
     mass_solve<NC>(o, g, k, s_m, sm + lay.post_tq, sm + lay.post_z, sm + lay.post_w);
@@ -546,10 +547,10 @@ inline void tensor_launch_nodal(const TensorPlan&, const Ops&, const Geo&, const
                                 long long, int, cudaStream_t) {}
 
 template <int D, int NC>
-inline void tensor_launch_fluxdiff(const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
-                                   const double* u_q, const double* u_f, double* dudt, int, cudaStream_t s) {
+inline void tensor_launch_fluxdiff(const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, unsigned grid, dim3 block, size_t smem,
+                                   long long first, const double* u_q, const double* u_f, double* dudt, cudaStream_t s) {
     if constexpr (D >= 2) {
-        k_fluxdiff_tensor<D, NC><<<(unsigned)count, tp.threads, tp.smem_fluxdiff, s>>>(tp.dev, o, g, L, first, u_q, u_f, dudt);
+        k_fluxdiff_tensor<D, NC><<<grid, block, smem, s>>>(tp.dev, o, g, L, first, u_q, u_f, dudt);     // block = (tp.threads, rows)
     }
 }
 

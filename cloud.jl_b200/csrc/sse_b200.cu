@@ -313,6 +313,27 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
         if ((rc = upload(h, si, &o.sig_i))) return rc;
         if ((rc = upload(h, so, &o.sig_o))) return rc;
         if (a->V) { if ((rc = upload_raw(h, a->V, (size_t)Nq * Np, &o.Vd))) return rc; }
+        // Small elements (triangles and low-order tetrahedra of the generic / tensor-line kernels): the N_q x N_p matrix of the
+        // warped product is a few kB, and one dense row per thread -- fixed trip count, coalesced, no index arithmetic -- beats
+        // the three sum-factorised phases with their table-driven bounds (Euler on p = 4 triangles: 5 + 3 applications of
+        // V or V' per residual were 2/3 of the time).  V[sigma_o(a), sigma_i(b)] = A[a1,b1] B[a2,b1,b2] C[a3,b1,b2,b3].
+        const char* vs = getenv("SSE_V_SMALL");
+        if ((size_t)Nq * Np <= 2048 && !(vs && atoi(vs) == 0)) {
+            std::vector<double> Vs((size_t)Nq * Np, 0.0);
+            for (int b1 = 0; b1 < P1; b1++)
+                for (int b2 = 0; b2 < o.N2[b1]; b2++)
+                    for (int b3 = 0; b3 < o.N3[b1 * 8 + b2]; b3++) {
+                        const int j = si[b1 + P1 * (b2 + P1 * b3)];
+                        if (j < 0) return fail(SSE_ERR_BAD_ARGUMENT, "warped V: the valid modes of a (b1, b2) fibre must be contiguous");
+                        for (int a1 = 0; a1 < o.M1; a1++)
+                            for (int a2 = 0; a2 < o.M2; a2++)
+                                for (int a3 = 0; a3 < o.M3; a3++)
+                                    Vs[so[a1 + o.M1 * (a2 + o.M2 * a3)] + (size_t)Nq * j] =
+                                        a->A[a1 + o.M1 * b1] * a->B[a2 + o.M2 * (b1 + P1 * b2)] * C[a3 + o.M3 * (b1 + P1 * (b2 + P1 * b3))];
+                    }
+            if ((rc = upload(h, Vs, &o.Vd))) return rc;
+            o.v_small = 1;
+        }
     } else
         return fail(SSE_ERR_BAD_ARGUMENT, "unknown v_kind %d", cfg->v_kind);
     // ---- R, W, B
@@ -558,7 +579,10 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
         }
     }
     // threads per element of the generic (one CTA per element) kernels: enough for one volume / facet node per thread, at most 128
-    h->threads = std::min(128, std::max(64, (std::max(Nq, Nf) + 31) / 32 * 32));
+    {   // threads per element of the packed kernels; SSE_THREADS_MIN=64 restores the round-1 minimum (A/B)
+        const char* tm = getenv("SSE_THREADS_MIN");
+        h->threads = std::min(128, std::max(tm ? atoi(tm) : 32, (std::max(Nq, Nf) + 31) / 32 * 32));
+    }
     h->smem_nodal = smem_nodal_bytes(o);
     h->smem_time = smem_time_bytes(h);
     h->smem_dense = h->smem_time + sizeof(double) * (size_t)Nfac * d * Nq;
@@ -696,6 +720,23 @@ extern "C" int32_t sse_synchronize(sse_handle* h) {
 }
 
 // ------------------------------------------------------------------------------ the hot path
+// Element packing of the one-CTA-per-element kernels (common.cuh: sse_element / sse_row_smem / sse_sync): rows of T threads, one
+// element per row, as many rows as fit 128 threads and 96 kB of shared memory; the remainder of the range goes to a second
+// launch with one row per CTA.  SSE_PACK_ROWS=1 keeps one element per CTA (A/B).  Returns the number of launches.
+static int pack_rows(int T, size_t smem_el) {
+    static const int cap = [] { const char* e = getenv("SSE_PACK_ROWS"); return e ? std::max(1, atoi(e)) : 8; }();
+    int r = std::max(1, std::min(cap, 128 / T));
+    while (r > 1 && r * smem_el > 96 * 1024) r--;
+    return r;
+}
+template <class F>
+static int launch_rows(int T, size_t smem_el, long long first, long long count, F&& launch) {
+    const int R = pack_rows(T, smem_el);
+    const long long full = count / R, rest = count - full * R;
+    if (full) launch((unsigned)full, dim3(T, R), R * smem_el, first);
+    if (rest) launch((unsigned)rest, dim3(T, 1), smem_el, first + full * R);
+    return (full ? 1 : 0) + (rest ? 1 : 0);
+}
 static bool use_tensor(const sse_handle* h) { return h->variant == 1 && h->tp.ok && h->tp.has_fluxdiff; }
 
 extern "C" int32_t sse_rhs_pass_a_range(sse_handle* h, const double* d_u, int64_t first, int64_t count) {
@@ -703,15 +744,18 @@ extern "C" int32_t sse_rhs_pass_a_range(sse_handle* h, const double* d_u, int64_
     if (count <= 0) return SSE_OK;
     if (first < 0 || first + count > h->cfg.N_e) return fail(SSE_ERR_BAD_ARGUMENT, "element range out of bounds");
     CU(cudaSetDevice(h->device));
-    const unsigned n = (unsigned)count;
+    int nl = 1;
     if (h->variant == 1 && h->ct.ok) {
         ct_nodal(h->ct, h->geo, h->law, first, count, d_u, h->u_q, h->u_f, h->stream);
     } else {
-#define LA(D_, NC_) k_nodal_generic<D_, NC_><<<n, h->threads, h->smem_nodal, h->stream>>>(h->ops, h->geo, h->law, h->project, first, d_u, h->u_q, h->u_f)
+#define LA(D_, NC_)                                                                                                                  \
+    nl = launch_rows(h->threads, h->smem_nodal, first, count, [&](unsigned grid, dim3 block, size_t smem, long long f0) {            \
+        k_nodal_generic<D_, NC_><<<grid, block, smem, h->stream>>>(h->ops, h->geo, h->law, h->project, f0, d_u, h->u_q, h->u_f);     \
+    })
         DISPATCH_DNC(h, LA);
 #undef LA
     }
-    h->launches += 1;
+    h->launches += nl;
     CU(cudaGetLastError());
     return SSE_OK;
 }
@@ -726,10 +770,14 @@ extern "C" int32_t sse_rhs_pass_aux(sse_handle* h, double* d_dudt, int64_t first
     if (!h->second_order || count <= 0) return SSE_OK;
     if (first < 0 || first + count > h->cfg.N_e) return fail(SSE_ERR_BAD_ARGUMENT, "element range out of bounds");
     CU(cudaSetDevice(h->device));
-#define LA(D_, NC_) k_aux_physical<D_, NC_><<<(unsigned)count, h->threads, h->smem_aux, h->stream>>>(h->ops, h->geo, h->law, first, h->u_q, h->u_f, h->q_q, h->q_f)
+    int nl = 1;
+#define LA(D_, NC_)                                                                                                                  \
+    nl = launch_rows(h->threads, h->smem_aux, first, count, [&](unsigned grid, dim3 block, size_t smem, long long f0) {              \
+        k_aux_physical<D_, NC_><<<grid, block, smem, h->stream>>>(h->ops, h->geo, h->law, f0, h->u_q, h->u_f, h->q_q, h->q_f);       \
+    })
     DISPATCH_DNC(h, LA);
 #undef LA
-    h->launches += 1;
+    h->launches += nl;
     CU(cudaGetLastError());
     return SSE_OK;
 }
@@ -744,6 +792,7 @@ int32_t sse::pass_b_stage(sse_handle* h, double* d_dudt, int64_t first, int64_t 
     if (first < 0 || first + count > h->cfg.N_e) return fail(SSE_ERR_BAD_ARGUMENT, "element range out of bounds");
     CU(cudaSetDevice(h->device));
     const unsigned n = (unsigned)count;
+    int nl = 1;
     if (h->cfg.form == SSE_FORM_FLUX_DIFFERENCING) {
         if (h->variant == 1 && h->ct.ok) {
             ct_fluxdiff(h->ct, h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream, rk, mid);
@@ -753,11 +802,17 @@ int32_t sse::pass_b_stage(sse_handle* h, double* d_dudt, int64_t first, int64_t 
             if (h->cfg.d == 2) k_time_fluxdiff_dense<2><<<n, T, h->smem_dense, h->stream>>>(h->ops, h->geo, h->law, h->dense, first, h->u_q, h->u_f, d_dudt);
             else k_time_fluxdiff_dense<3><<<n, T, h->smem_dense, h->stream>>>(h->ops, h->geo, h->law, h->dense, first, h->u_q, h->u_f, d_dudt);
         } else if (use_tensor(h) && h->tp.has_fluxdiff) {
-#define LA(D_, NC_) tensor_launch_fluxdiff<D_, NC_>(h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->sm_count, h->stream)
+#define LA(D_, NC_)                                                                                                                  \
+    nl = launch_rows(h->tp.threads, h->tp.smem_fluxdiff, first, count, [&](unsigned grid, dim3 block, size_t smem, long long f0) {   \
+        tensor_launch_fluxdiff<D_, NC_>(h->tp, h->ops, h->geo, h->law, grid, block, smem, f0, h->u_q, h->u_f, d_dudt, h->stream);    \
+    })
             DISPATCH_DNC(h, LA);
 #undef LA
         } else {
-#define LA(D_, NC_) k_time_fluxdiff_generic<D_, NC_><<<n, h->threads, h->smem_time, h->stream>>>(h->ops, h->geo, h->law, first, h->u_q, h->u_f, d_dudt)
+#define LA(D_, NC_)                                                                                                                  \
+    nl = launch_rows(h->threads, h->smem_time, first, count, [&](unsigned grid, dim3 block, size_t smem, long long f0) {             \
+        k_time_fluxdiff_generic<D_, NC_><<<grid, block, smem, h->stream>>>(h->ops, h->geo, h->law, f0, h->u_q, h->u_f, d_dudt);      \
+    })
             DISPATCH_DNC(h, LA);
 #undef LA
         }
@@ -765,15 +820,22 @@ int32_t sse::pass_b_stage(sse_handle* h, double* d_dudt, int64_t first, int64_t 
         ct_standard(h->ct, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream, rk, mid);
         h->launches += h->ct.adv_ok ? 0 : 1;           // derivative kernel + projection kernel, or the fused kernel alone
     } else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE) {
-#define LA(D_, NC_) k_time_standard_reference<D_, NC_><<<n, h->threads, h->smem_time, h->stream>>>(h->ops, h->geo, h->law, first, h->u_q, h->u_f, d_dudt)
+#define LA(D_, NC_)                                                                                                                  \
+    nl = launch_rows(h->threads, h->smem_time, first, count, [&](unsigned grid, dim3 block, size_t smem, long long f0) {             \
+        k_time_standard_reference<D_, NC_><<<grid, block, smem, h->stream>>>(h->ops, h->geo, h->law, f0, h->u_q, h->u_f, d_dudt);    \
+    })
         DISPATCH_DNC(h, LA);
 #undef LA
     } else {
-#define LA(D_, NC_) k_time_physical<D_, NC_><<<n, h->threads, h->smem_time, h->stream>>>(h->ops, h->geo, h->law, first, h->second_order, h->u_q, h->u_f, h->q_q, h->q_f, d_dudt)
+#define LA(D_, NC_)                                                                                                                  \
+    nl = launch_rows(h->threads, h->smem_time, first, count, [&](unsigned grid, dim3 block, size_t smem, long long f0) {             \
+        k_time_physical<D_, NC_><<<grid, block, smem, h->stream>>>(h->ops, h->geo, h->law, f0, h->second_order, h->u_q, h->u_f,      \
+                                                                    h->q_q, h->q_f, d_dudt);                                          \
+    })
         DISPATCH_DNC(h, LA);
 #undef LA
     }
-    h->launches += 1;
+    h->launches += nl;
     CU(cudaGetLastError());
     return SSE_OK;
 }

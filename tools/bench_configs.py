@@ -42,6 +42,10 @@ def main():
         runs += [("Euler 3-D ModalMulti p=3 tets M=16 (dense operators, generic kernels)",
                   lambda: cases.euler_tgv_3d(M=16, p=3, flux="ec", kind="modal_multi"), False)]
     if a.big:
+        runs += [("config1 advection_2d p4 256x256", lambda: cases.advection_2d(M=256, flux="lf"), False),
+                 ("config2 euler_vortex_2d p4 256x256", lambda: cases.euler_vortex_2d(M=256, p=4, flux="lf"), False),
+                 ("config3 advection_diffusion_2d p4 256x256", lambda: cases.advection_diffusion_2d(M=256), False)]
+    if a.big:
         runs += [("config4 advection_3d p4 M=32", lambda: cases.advection_3d(M=32, flux="central"), False),
                  ("config5 euler_tgv_3d p4 M=24", lambda: cases.euler_tgv_3d(M=24, flux="lf"), False)]
     for name, build, check in runs:
@@ -62,7 +66,8 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.steps
         out = {"config": name, "elements": c.sd.N_e, "dof": c.dof, "ms_per_rhs": ms, "dof_per_s": c.dof / (ms * 1e-3),
-               "kernel_variant": s.kernel_variant(), "setup_s": round(time.time() - t0, 1)}
+               "kernel_variant": s.kernel_variant(), "setup_s": round(time.time() - t0, 1),
+               "kernel_ms_passA_aux_B1_B2": [round(float(x), 5) for x in s.profile_rhs(du, u)]}
         if check:
             import oracle
             ref = oracle.rhs(img, u0)

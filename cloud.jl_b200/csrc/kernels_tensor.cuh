@@ -108,10 +108,13 @@ __device__ __forceinline__ void ec_flux_contract(const double* a, const double* 
     phi[D + 1] = fma(mf, Cc, 0.5 * fma(a[D + 1], gb, b[D + 1] * ga));
 }
 
+// Euler: the power-of-two-scaled form of the compile-time kernels (physics.cuh: primitives (rho, V, 2p, rho/p), branch-free
+// log-means and reciprocals); PAIR_G_SCALE is folded into the weight g by the caller
+template <int D, int NC> struct PairScale { static constexpr double g = (NC == D + 2) ? 0.25 : 1.0; };
 template <int D, int NC>
 __device__ __forceinline__ void pair_flux(const Law& L, const double* a, const double* b, const double* g, double* phi) {
     if constexpr (NC == D + 2) {
-        ec_flux_contract<D>(a, b, g, L.igm1, phi);
+        ec_contract_scaled<D>(L, a, b, g, phi);
     } else {   // linear advection (linear_advection_diffusion.jl:113-119)
         double ag = 0.0;
 #pragma unroll
@@ -122,16 +125,12 @@ __device__ __forceinline__ void pair_flux(const Law& L, const double* a, const d
 
 // conservative state -> primitives used by the pair kernels
 template <int D, int NC>
-__device__ __forceinline__ void to_prim(const Law& L, const double* u, double* q) {
+__device__ __forceinline__ double to_prim(const Law& L, const double* u, double* q) {
     if constexpr (NC == D + 2) {
-        double s = 0.0;
-        q[0] = u[0];
-#pragma unroll
-        for (int m = 0; m < D; m++) { q[1 + m] = u[1 + m] / u[0]; s = fma(q[1 + m], q[1 + m], s); }
-        q[D + 1] = L.gm1 * (u[D + 1] - 0.5 * u[0] * s);
-        q[D + 2] = u[0] / q[D + 1];
+        return to_prim_fast<D>(L, u, q);           // (rho, V, 2p, rho/p); returns 1/rho
     } else {
         q[0] = u[0];
+        return 1.0;
     }
 }
 
@@ -186,18 +185,21 @@ k_fluxdiff_tensor(TensorDev t, Ops o, Geo g, Law L, long long first, const doubl
             hn[m] = 0.5 * nj;                      // halfnJf, operators.jl:78
             s_hnf[m * Nf + j] = hn[m];
         }
-        to_prim<D, NC>(L, ui, qa);
-        to_prim<D, NC>(L, uo, qb);
+        const double ira = to_prim<D, NC>(L, ui, qa);
+        const double irb = to_prim<D, NC>(L, uo, qb);
 #pragma unroll
         for (int c = 0; c < NP; c++) s_fprim[c * Nf + j] = qa[c];
-        pair_flux<D, NC>(L, qa, qb, nf, phi);      // F#(u-, u+) . n   (ConservationLaws.jl:75-128)
+        double nfs[D];
+#pragma unroll
+        for (int m = 0; m < D; m++) nfs[m] = PairScale<D, NC>::g * nf[m];
+        pair_flux<D, NC>(L, qa, qb, nfs, phi);     // F#(u-, u+) . n   (ConservationLaws.jl:75-128)
         if (L.inviscid == SSE_FLUX_LAX_FRIEDRICHS) {
             double a;
             if constexpr (NC == D + 2) {
                 double vni = 0.0, vno = 0.0;
 #pragma unroll
                 for (int m = 0; m < D; m++) { vni = fma(qa[1 + m], nf[m], vni); vno = fma(qb[1 + m], nf[m], vno); }
-                const double ci = sqrt(L.gamma * qa[D + 1] / qa[0]), co = sqrt(L.gamma * qb[D + 1] / qb[0]);
+                const double ci = sqrt(L.gamma * (0.5 * qa[D + 1]) * ira), co = sqrt(L.gamma * (0.5 * qb[D + 1]) * irb);   // 2p stored
                 a = L.half_lambda * (fmax(fabs(vni), fabs(vno)) + fmax(ci, co));
             } else {
                 double s = 0.0;
@@ -228,7 +230,7 @@ k_fluxdiff_tensor(TensorDev t, Ops o, Geo g, Law L, long long first, const doubl
 #pragma unroll
                 for (int m = 0; m < D; m++) {
                     if (m >= mlo) {                // uniform over the CTA: Λ_ref is upper triangular (tensor_simplex.jl:66-75)
-                        const double s = t.v_S[(rd * D + m) * Nq + tid];
+                        const double s = PairScale<D, NC>::g * t.v_S[(rd * D + m) * Nq + tid];
 #pragma unroll
                         for (int n = 0; n < D; n++) gv[n] = fma(s, lam[m][n] + s_lam[(m + D * n) * Nq + j], gv[n]);
                     }
@@ -271,7 +273,7 @@ k_fluxdiff_tensor(TensorDev t, Ops o, Geo g, Law L, long long first, const doubl
                 }
             }
             const int j = t.f_partner[fr * Nq + tid];
-            const double c = t.f_C[fr * Nq + tid];
+            const double c = PairScale<D, NC>::g * t.f_C[fr * Nq + tid];
             double gv[D], qj[NP], phi[NC];
 #pragma unroll
             for (int n = 0; n < D; n++) gv[n] = c * (s_hnf[n * Nf + j] + hq[n]);

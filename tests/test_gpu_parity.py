@@ -460,3 +460,21 @@ def test_graph_replay_of_the_ck54_step_is_bit_identical(name):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     assert outs[0][2] == outs[1][2]                        # the replay accounts for the launches it contains
     assert np.all(np.isfinite(outs[1][1]))
+
+
+def test_element_packing_is_bitwise_neutral():
+    """Small elements run several per CTA, one warp each (common.cuh: sse_element / sse_row_smem / sse_sync).  Rows are
+    independent, so the residual must not depend on the launch shape: one element per CTA, 64 threads per element (the
+    round-1 shape) and the packed default give the same bits; element counts and ranges leave one-row remainder launches."""
+    import json
+    import os
+    import subprocess
+    import sys
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "packing_worker.py")
+    outs = []
+    for extra in ({}, {"SSE_PACK_ROWS": "1"}, {"SSE_PACK_ROWS": "1", "SSE_THREADS_MIN": "64"}, {"SSE_PACK_ROWS": "3"}):
+        env = dict(os.environ, **extra)
+        p = subprocess.run([sys.executable, worker], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs.append(json.loads(p.stdout.strip().splitlines()[-1]))
+    assert outs[0] == outs[1] == outs[2] == outs[3], outs

@@ -175,7 +175,11 @@ __device__ void mass_solve(const Ops& o, const Geo& g, long long k, double* rhs,
         return;
     }
     apply_V<NC>(o, rhs, tq, zb, wb);
-    SSE_FOR(t, o.Nq * NC) { int i = t % o.Nq; tq[t] *= o.W[i] / J[i]; }
+    SSE_FOR(i, o.Nq) {                           // one quotient per node (the same W / J every variable was multiplied by)
+        const double wj = o.W[i] / J[i];
+#pragma unroll
+        for (int e = 0; e < NC; e++) tq[i + o.Nq * e] *= wj;
+    }
     sse_sync();
     apply_Vt<NC>(o, tq, rhs, zb, wb);
 }

@@ -40,6 +40,11 @@ bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& t
         if (a.sigma_i[t] != want) return false;
     }
     if (!c_tensor_symmetric(a, N)) return false;
+    if (!a.nJq) {                                          // the pair kernel forms 2 halfnJq from these normals without multiplying
+        static const double want[12] = {0, -1, 0, 1, 1, 1, -1, 0, 0, 0, 0, -1};
+        if (!a.nref) return false;
+        for (int i = 0; i < 12; i++) if (a.nref[i] != want[i]) return false;
+    }
     *Nout = N;
     return true;
 }
@@ -320,6 +325,11 @@ bool ct_eligible_standard(const sse_config& cfg, const sse_arrays& a, int* Nout,
     }
     for (size_t x = 0; x < seen.size(); x++) if (!seen[x] && a.R[x] != 0.0) return false;
     if (!c_tensor_symmetric(a, N)) return false;
+    if (!a.nJq) {                                          // the pair kernel forms 2 halfnJq from these normals without multiplying
+        static const double want[12] = {0, -1, 0, 1, 1, 1, -1, 0, 0, 0, 0, -1};
+        if (!a.nref) return false;
+        for (int i = 0; i < 12; i++) if (a.nref[i] != want[i]) return false;
+    }
     *Nout = N;
     return true;
 }

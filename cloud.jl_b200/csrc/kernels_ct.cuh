@@ -26,6 +26,9 @@
 #ifndef SSE_FD_FF_PAD
 #define SSE_FD_FF_PAD 1
 #endif
+#ifndef SSE_FD_NREF_STATIC
+#define SSE_FD_NREF_STATIC 1
+#endif
 #ifndef SSE_PROJ_PREFETCH
 #define SSE_PROJ_PREFETCH 150
 #endif
@@ -33,7 +36,7 @@
 #define SSE_NODAL_ILP_Q 1
 #endif
 #ifndef SSE_NODAL_ILP_F
-#define SSE_NODAL_ILP_F 2
+#define SSE_NODAL_ILP_F 1
 #endif
 
 // C-tensor symmetry in the applies of k_nodal_ct (15 instead of 35 table loads per application; measured with spills in round 1)
@@ -680,6 +683,14 @@ __device__ __forceinline__ int facet_partner(int fr, int ca, int cb, int cc) {
     return 3 * NN + ca * N + bp;
 }
 
+// 2 halfnJq[n, f, i] = sum_l Lambda[i, l, n] nref[l, f] (mesh.jl:262-269) for the reference normals of the collapsed tet,
+// (0,-1,0), (1,1,1), (-1,0,0), (0,0,-1) (ct_eligible checks them): a row of Lambda with its sign flipped, or the sum of the
+// three rows in the order of the reference's loop -- the same bits as the three multiply-adds with 0 / +-1, none of them
+// issued.  f is a compile-time constant once the facet loop is unrolled.
+__device__ __forceinline__ double tet_face_h(int f, const double (&lam)[3][3], int n) {
+    return f == 0 ? -lam[1][n] : (f == 1 ? (lam[0][n] + lam[1][n]) + lam[2][n] : (f == 2 ? -lam[0][n] : -lam[2][n]));
+}
+
 template <int N, int MINB, bool DUAL>
 __global__ void __launch_bounds__(Tet<N>::NT, MINB)
 k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, const double* __restrict__ u_f) {
@@ -748,8 +759,9 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
             double vni = 0.0, vno = 0.0;
 #pragma unroll
             for (int m = 0; m < D; m++) { vni = fma(qa[1 + m], nf[m], vni); vno = fma(qb[1 + m], nf[m], vno); }
-            const double ci = sqrt(L.gamma * (0.5 * qa[D + 1]) * ira), co = sqrt(L.gamma * (0.5 * qb[D + 1]) * irb);
-            const double a = L.half_lambda * (fmax(fabs(vni), fabs(vno)) + fmax(ci, co));
+            // max(c_i, c_o) = sqrt(max(c_i^2, c_o^2)) bit for bit (sqrt is monotone and correctly rounded): one square root
+            const double cm = sqrt(fmax(L.gamma * (0.5 * qa[D + 1]) * ira, L.gamma * (0.5 * qb[D + 1]) * irb));
+            const double a = L.half_lambda * (fmax(fabs(vni), fabs(vno)) + cm);
 #pragma unroll
             for (int e = 0; e < NC; e++) phi[e] = fma(a, ui[e] - uo[e], phi[e]);
         }
@@ -828,7 +840,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
         const int re = tid / NN, rjj = tid - re * NN, rx = rjj / N, ry = rjj - rx * N;
         int rc3 = ry ? N - ry : 0;          // volume column (fr - 3 - y) mod N feeding facet node (x, y) of face 4, sub-round 3
 #ifndef SSE_FD_UNROLL_F
-#define SSE_FD_UNROLL_F 2
+#define SSE_FD_UNROLL_F 4
 #endif
         constexpr int FUN = SSE_FD_UNROLL_F;
 #pragma unroll FUN
@@ -844,10 +856,14 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
                         hA[n] = g.nJq[n + D * (fA + (size_t)4 * (tid + (size_t)Nq * k))];
                         hB[n] = g.nJq[n + D * (fB + (size_t)4 * (tid + (size_t)Nq * k))];
                     } else {
+#if SSE_FD_NREF_STATIC
+                        hA[n] = tet_face_h(fA, lam, n); hB[n] = tet_face_h(fB, lam, n);
+#else
                         double sa = 0.0, sb = 0.0;
 #pragma unroll
                         for (int l = 0; l < D; l++) { sa = fma(lam[l][n], t.nref[l + D * fA], sa); sb = fma(lam[l][n], t.nref[l + D * fB], sb); }
                         hA[n] = sa; hB[n] = sb;
+#endif
                     }
                 }
                 const int jA = facet_partner<N>(fr, ca, cb, cc), jB = facet_partner<N>(fr + 1, ca, cb, cc);

@@ -26,7 +26,7 @@ def one(a):
     from sse_b200 import cases
     from sse_b200.solver import Solver
     out = {"lib": os.path.relpath(os.environ.get("SSE_B200_LIB", "in-tree"), ROOT)}
-    for name, M, flux in (("tgv_M2_ec", 2, "ec"), ("tgv_M4_lf", 4, "lf")):
+    for name, M, flux in (("tgv_M2_ec", 2, "ec"), ("tgv_M4_lf", 4, "lf")) + ((("tgv_M8_lf", 8, "lf"),) if a.m8 else ()):
         c = cases.euler_tgv_3d(M=M, flux=flux)
         img, u = c.image(), c.u0(seed=0)
         s = Solver(img, 0)
@@ -87,6 +87,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--config4", action="store_true")
     ap.add_argument("--one", action="store_true")
+    ap.add_argument("--m8", action="store_true", help="parity on the 3 072-element mesh as well")
     a = ap.parse_args()
     if a.one:
         return one(a)
@@ -97,6 +98,8 @@ def main():
         cmd = [sys.executable, os.path.abspath(__file__), "--one", "--cells", str(a.cells), "--steps", str(a.steps)]
         if a.config4:
             cmd.append("--config4")
+        if a.m8:
+            cmd.append("--m8")
         r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
         if r.returncode != 0:
             print(json.dumps({"lib": os.path.relpath(lib, ROOT), "error": r.stderr[-800:]}), flush=True)

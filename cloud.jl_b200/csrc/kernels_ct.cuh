@@ -29,6 +29,9 @@
 #ifndef SSE_FD_NREF_STATIC
 #define SSE_FD_NREF_STATIC 1
 #endif
+#ifndef SSE_FD_RED3
+#define SSE_FD_RED3 1
+#endif
 #ifndef SSE_PROJ_PREFETCH
 #define SSE_PROJ_PREFETCH 150
 #endif
@@ -832,6 +835,7 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
         static_assert(NN * NC == Nq, "reducer items = volume nodes");
         constexpr int PS = S::PS, FS = S::FS;
         const int fslot = tid + (PS - NN) * ca;               // padded slot of this thread's volume node (FdSmem)
+        const int fslot3 = fslot + (cc == 0 ? N - 1 : -1);    // ... one column to the left (cyclic), see SSE_FD_RED3
         // one pair of padded stages for all facet sub-rounds (the barrier that closes a sub-round already separates its
         // reducer loads from the next stores); they lie over the volume stages, hence the barrier here
         double* stA = s_stage;
@@ -873,8 +877,11 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
 #pragma unroll
                 for (int c = 0; c < NP; c++) { qA[c] = s_fprim[c * Nf + jA]; qB[c] = s_fprim[c * Nf + jB]; }
                 ec_contract_scaled2<D>(L, qi, qA, qB, gA, gB, pA, pB);
+                // SSE_FD_RED3: when both sub-rounds pair with the slanted face, the second stage is stored one column to the left
+                // (c -> c - 1), so that its reducer reads the same column as the reducer of the first stage
+                const int fslotB = (SSE_FD_RED3 && fA == fB) ? fslot3 : fslot;
 #pragma unroll
-                for (int e = 0; e < NC; e++) { r[e] -= pA[e] + pB[e]; stA[e * FS + fslot] = pA[e]; stB[e * FS + fslot] = pB[e]; }
+                for (int e = 0; e < NC; e++) { r[e] -= pA[e] + pB[e]; stA[e * FS + fslot] = pA[e]; stB[e * FS + fslotB] = pB[e]; }
             }
             cwA = cwnA; cwB = cwnB;
             __syncthreads();
@@ -886,16 +893,29 @@ k_fluxdiff_ct(CtDev t, Geo g, Law L, long long first, double* __restrict__ u_q, 
                     int bA, dA, bB, dB;
                     if (fr == 0) { bA = rx * PS + ry; dA = N; bB = rjj; dB = PS; }
                     else { bA = rjj; dA = PS; bB = rx * PS + rc3; dB = N; rc3 = rc3 + 1 == N ? 0 : rc3 + 1; }
+                    int tB = rjj;
+#if SSE_FD_RED3
+                    if (fr != 0) { tB = rx * N + (bB - rx * PS); bB = rx * PS + ry; }     // slanted face: own column, permuted target
+#endif
 #pragma unroll
                     for (int i = 0; i < N; i++) { sA += stA[re * FS + bA + i * dA]; sB += stB[re * FS + bB + i * dB]; }
                     s_ff[re * S::FFS + fA * NN + rjj] -= sA;
-                    s_ff[re * S::FFS + fB * NN + rjj] -= sB;
+                    s_ff[re * S::FFS + fB * NN + tB] -= sB;
                 } else {                    // both sub-rounds feed face 4: one reducer sums both stages
                     const int cA = rc3, cB = cA + 1 == N ? 0 : cA + 1;
                     rc3 = cB + 1 == N ? 0 : cB + 1;
+#if SSE_FD_RED3
+                    // The column c = (fr - 3 - y) mod N that feeds facet node (x, y) is an involution of y: this thread sums
+                    // column ry of both stages (its own bank: conflict-free loads, they sit between two barriers) and hands
+                    // the sum to facet node (rx, cA) -- the same additions in the same order for every facet node
+#pragma unroll
+                    for (int i = 0; i < N; i++) { sA += stA[re * FS + rx * PS + ry + i * N]; sB += stB[re * FS + rx * PS + ry + i * N]; }
+                    s_ff[re * S::FFS + 3 * NN + rx * N + cA] -= sA + sB;
+#else
 #pragma unroll
                     for (int i = 0; i < N; i++) { sA += stA[re * FS + rx * PS + cA + i * N]; sB += stB[re * FS + rx * PS + cB + i * N]; }
                     s_ff[re * S::FFS + 3 * NN + rjj] -= sA + sB;
+#endif
                 }
             }
             __syncthreads();      // two reducers of one iteration may hit the same facet node only across iterations

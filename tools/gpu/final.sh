@@ -1,7 +1,7 @@
 #!/bin/bash
 # end-of-round evidence on one B200: GPU tests, smoke(), the default bench line, the reference arm, the ncu launch list
-mkdir -p gpurun_out/r2z
-O=gpurun_out/r2z
+mkdir -p gpurun_out/s3z
+O=gpurun_out/s3z
 ( time python -m pytest tests -m gpu -x -q ) > $O/gputests.log 2>&1
 tail -n 4 $O/gputests.log
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -n 2 $O/smoke.log
@@ -15,3 +15,4 @@ r=json.loads([l for l in open("$O/bench_ref.json") if l.startswith("{")][-1]); p
 PY
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $O/bench_under_ncu.log 2>&1
 grep -c "k_" $O/launches.csv
+timeout 800 ncu --set full --clock-control none --import-source on -k regex:"k_nodal_ct|k_fluxdiff_ct|k_project_ct" -s 9 -c 3 -o $O/s3z_prof -f python bench.py --cells 16 --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1 > $O/ncu_headline.log 2>&1

@@ -37,9 +37,25 @@ struct AdvDev {
     double* um = nullptr;           // [N_e][N_p]              modal coefficients handed from pass A to pass B
 };
 
+// device tables of the warp-per-element 2-D Euler path (kernels_tri.cuh); all of them element independent
+struct TriDev {
+    const double* V = nullptr;      // dense warped V, column-major N_q x N_p (node a1 N + a2, canonical modal index)
+    const double* vS = nullptr;     // [round][2][N_q]  skew-extended S_m[i, partner] / 4, round = line direction * (N/2) + shift - 1
+    const double* fC = nullptr;     // [3][N_q]         C[i, partner] / 8
+    const double* fR = nullptr;     // [3][N_q]         R[partner, i]
+    const double* rfac = nullptr;   // [N_f][N]         the N non-zeros of row j of R, along the facet node's tensor line
+    const double* W = nullptr;      // [N_q]
+    const double* Bf = nullptr;     // [N_f]
+    double nref[6] = {0, 0, 0, 0, 0, 0};   // 2 x 3 reference normals, column-major
+};
+
 struct CtPlan {
     int ok = 0, N = 0;
-    int kind = 0;                   // 0: Euler flux differencing; 1: linear advection, StandardForm + ReferenceOperators
+    int kind = 0;                   // 0: 3-D Euler flux differencing; 1: 3-D linear advection, StandardForm + ReferenceOperators;
+                                    // 2: 2-D Euler flux differencing on triangles (kernels_tri.cuh)
+    TriDev tri;                     // kind 2
+    std::vector<double> triV, trivS, trifC, trifR, triRfac;     // host images of the kind-2 tables
+    int sms = 148;                  // SMs of the device (grid of the persistent kind-2 kernels)
     std::vector<double> D1;         // kind 1: the three 1-D derivative matrices, [m][t + N*s]
     CtDev dev{};
     std::vector<double> A, B;       // host copies of the 1-D tensors handed to the kernels by value
@@ -57,6 +73,10 @@ bool ct_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& t
 bool ct_eligible_standard(const sse_config& cfg, const sse_arrays& a, int* Nout, std::vector<double>& D1, std::vector<double>& fR);
 void ct_standard(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
                  double* dudt, cudaStream_t s, RkStage rk = RkStage(), cudaEvent_t mid = nullptr);
+// kind 2: d = 2, Euler + EC two-point flux, flux differencing, warped V with M1 = M2 = p + 1 <= 5, weight-adjusted mass solver,
+// R and the pair schedule in the closed form k_tri_* hard-code; fills the host images of the tables on success
+bool tri_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& tp, CtPlan& p);
+cudaError_t tri_set_attrs(int N);
 bool ct_facet_factors(const sse_config& cfg, const sse_arrays& a, int N, std::vector<double>& out);
 // true when the generic tables of tp equal the closed-form schedule k_fluxdiff_ct hard-codes
 bool ct_schedule_matches(const TensorPlan& tp, int N);

@@ -1,6 +1,7 @@
 // ct_kernels.cu — instantiations of the compile-time-sized kernels (N = p + 1 = 4, 5)
 #include "kernels_ct.cuh"
 #include "kernels_adv.cuh"
+#include "kernels_tri.cuh"
 
 namespace sse {
 
@@ -106,6 +107,121 @@ bool ct_facet_factors(const sse_config& cfg, const sse_arrays& a, int N, std::ve
             if (want == 0.0 ? got != 0.0 : std::fabs(got - want) > 1e-14 * scale) return false;
         }
     return true;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// kind 2: 2-D Euler flux differencing on collapsed triangles (kernels_tri.cuh)
+#ifndef SSE_TRI_WARPS
+#define SSE_TRI_WARPS 4
+#endif
+#ifndef SSE_TRI_MINB
+#define SSE_TRI_MINB 4
+#endif
+constexpr int TRI_WARPS = SSE_TRI_WARPS, TRI_MINB = SSE_TRI_MINB;
+#define SSE_TRI_DISPATCH(N_, CALL) \
+    switch (N_) { case 3: CALL(3); break; case 4: CALL(4); break; case 5: CALL(5); break; default: break; }
+
+bool tri_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& tp, CtPlan& p) {
+    if (const char* e = getenv("SSE_TRI_CT")) if (atoi(e) == 0) return false;
+    if (!tp.ok || cfg.d != 2 || cfg.N_c != 4 || cfg.pde != SSE_PDE_EULER) return false;
+    if (cfg.form != SSE_FORM_FLUX_DIFFERENCING || cfg.two_point_flux != SSE_TWO_POINT_ENTROPY_CONSERVATIVE) return false;
+    if (cfg.v_kind != SSE_V_WARPED || cfg.mass_solver != SSE_MASS_WEIGHT_ADJUSTED || !a.Cfd || !a.A || !a.B || !a.R) return false;
+    if (!a.sigma_i || !a.sigma_o || !a.W || !a.Bf) return false;
+    const int N = cfg.p + 1;
+    if (N < 3 || N > 5) return false;
+    if (cfg.M1d[0] != N || cfg.M1d[1] != N) return false;
+    const int Nq = N * N, Np = N * (N + 1) / 2, Nf = 3 * N, NSH = N / 2;
+    if (cfg.N_q != Nq || cfg.N_p != Np || cfg.N_f != Nf || cfg.N_fac != 3) return false;
+    if (!a.nJq && !a.nref) return false;
+    // node ordering: tensor index (a1, a2) -> node a1 N + a2 (tensor_simplex.jl:111-112); every mode used exactly once
+    std::vector<char> seen(Np, 0);
+    for (int t = 0; t < Nq; t++) {
+        const int a1 = t % N, a2 = t / N;
+        if (a.sigma_o[t] - 1 != a1 * N + a2) return false;
+        const long long l = a.sigma_i[t];
+        if (l < 0 || l > Np) return false;
+        if ((l > 0) != (a1 + a2 <= N - 1)) return false;
+        if (l > 0) { if (seen[l - 1]) return false; seen[l - 1] = 1; }
+    }
+    // dense V[node, l] = A[a1, b1] B[a2, b1, b2] (warped_product_2d; the expression of sse_create's small-element V)
+    p.triV.assign((size_t)Nq * Np, 0.0);
+    for (int b1 = 0; b1 < N; b1++)
+        for (int b2 = 0; b1 + b2 < N; b2++) {
+            const int l = (int)a.sigma_i[b1 + N * b2] - 1;
+            for (int a1 = 0; a1 < N; a1++)
+                for (int a2 = 0; a2 < N; a2++) p.triV[(a1 * N + a2) + (size_t)Nq * l] = a.A[a1 + N * b1] * a.B[a2 + N * (b1 + N * b2)];
+        }
+    // R: facet node (0, a1) <- the a2-line of a1; facet nodes (1, a2), (2, a2) <- the a1-line of a2; nothing else
+    p.triRfac.assign((size_t)Nf * N, 0.0);
+    for (int j = 0; j < Nf; j++) {
+        const int f = j / N, q = j % N;
+        for (int i = 0; i < Nq; i++) {
+            const int a1 = i / N, a2 = i % N;
+            const bool on = f == 0 ? a1 == q : a2 == q;
+            const double v = a.R[j + (size_t)Nf * i];
+            if (on) p.triRfac[(size_t)j * N + (f == 0 ? a2 : a1)] = v;
+            else if (v != 0.0) return false;
+        }
+    }
+    // pair schedule: the closed form of the kernel against the generic tables
+    if (tp.dev.n_vrounds != 2 * NSH || tp.dev.n_frounds != 3) return false;
+    for (int fr = 0; fr < 3; fr++) if (tp.f_face[fr] != fr) return false;
+    for (int i = 0; i < Nq; i++) {
+        const int c[2] = {i / N, i % N}, stride[2] = {N, 1};
+        for (int rd = 0; rd < 2 * NSH; rd++) {
+            const int l = rd / NSH, sh = rd % NSH + 1;
+            const bool half = 2 * sh == N;
+            const int cj = (c[l] + sh) % N, cs = (c[l] - sh + N) % N;
+            const int want_p = (half && c[l] >= sh) ? -1 : i + (cj - c[l]) * stride[l];
+            const int want_s = (half && cs >= sh) ? -1 : i + (cs - c[l]) * stride[l];
+            if (tp.v_partner[(size_t)rd * Nq + i] != want_p || tp.v_source[(size_t)rd * Nq + i] != want_s) return false;
+            if (l == 1 && tp.v_S[((size_t)rd * 2 + 0) * Nq + i] != 0.0) return false;      // a2-lines carry S_2 only
+        }
+        const int want_f[3] = {c[0], N + c[1], 2 * N + c[1]};
+        for (int fr = 0; fr < 3; fr++) if (tp.f_partner[(size_t)fr * Nq + i] != want_f[fr]) return false;
+    }
+    // power-of-two scalings of the pair weights (exact): ec_finish_scaled in physics.cuh
+    p.trivS = tp.v_S; for (double& x : p.trivS) x *= 0.25;
+    p.trifC = tp.f_C; for (double& x : p.trifC) x *= 0.125;
+    p.trifR.assign((size_t)3 * Nq, 0.0);
+    for (int fr = 0; fr < 3; fr++)
+        for (int i = 0; i < Nq; i++) p.trifR[(size_t)fr * Nq + i] = a.R[tp.f_partner[(size_t)fr * Nq + i] + (size_t)Nf * i];
+    for (int i = 0; i < 6; i++) p.tri.nref[i] = a.nref ? a.nref[i] : 0.0;
+    p.N = N;
+    return true;
+}
+
+template <int N> static cudaError_t tri_set_attrs_n() {
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_tri_nodal<N, TRI_WARPS, TRI_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(double) * TriT<N>::template smem_doubles<false>(TRI_WARPS))))) return e;
+    return cudaFuncSetAttribute(k_tri_fluxdiff<N, TRI_WARPS, TRI_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(sizeof(double) * TriT<N>::template smem_doubles<true>(TRI_WARPS)));
+}
+cudaError_t tri_set_attrs(int N) {
+    cudaError_t e = cudaErrorInvalidValue;
+#define CALL_(N_) e = tri_set_attrs_n<N_>()
+    SSE_TRI_DISPATCH(N, CALL_);
+#undef CALL_
+    return e;
+}
+// persistent warps: one resident wave of CTAs, each warp strides over the elements of the range
+static unsigned tri_grid(const CtPlan& p, long long count) {
+    const long long want = (count + TRI_WARPS - 1) / TRI_WARPS, wave = (long long)p.sms * TRI_MINB;
+    return (unsigned)std::max<long long>(1, std::min(want, wave));
+}
+template <int N>
+static void tri_nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q,
+                        double* u_f, cudaStream_t s) {
+    k_tri_nodal<N, TRI_WARPS, TRI_MINB><<<tri_grid(p, count), TRI_WARPS * 32, sizeof(double) * TriT<N>::template smem_doubles<false>(TRI_WARPS), s>>>(
+        p.tri, g, L, first, count, u, u_q, u_f);
+}
+template <int N>
+static void tri_fluxdiff_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u_q,
+                           const double* u_f, double* dudt, cudaStream_t s, RkStage rk) {
+    k_tri_fluxdiff<N, TRI_WARPS, TRI_MINB><<<tri_grid(p, count), TRI_WARPS * 32, sizeof(double) * TriT<N>::template smem_doubles<true>(TRI_WARPS), s>>>(
+        p.tri, g, L, first, count, u_q, u_f, dudt, rk);
 }
 
 template <int N> static FacetR<N> make_facet(const CtPlan& p) {
@@ -215,6 +331,12 @@ static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first
 }
 void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q, double* u_f,
               cudaStream_t s) {
+    if (p.kind == 2) {
+#define CALL_(N_) tri_nodal_n<N_>(p, g, L, first, count, u, u_q, u_f, s)
+        SSE_TRI_DISPATCH(p.N, CALL_);
+#undef CALL_
+        return;
+    }
 #define CALL_(N_) nodal_n<N_>(p, g, L, first, count, u, u_q, u_f, s)
     SSE_CT_DISPATCH(p.N, CALL_);
 #undef CALL_
@@ -273,6 +395,13 @@ static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, cons
 }
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
                  double* u_q, const double* u_f, double* dudt, cudaStream_t s, RkStage rk, cudaEvent_t mid) {
+    if (p.kind == 2) {                                // all of pass B in one launch
+        if (mid) cudaEventRecord(mid, s);
+#define CALL_(N_) tri_fluxdiff_n<N_>(p, g, L, first, count, u_q, u_f, dudt, s, rk)
+        SSE_TRI_DISPATCH(p.N, CALL_);
+#undef CALL_
+        return;
+    }
 #define CALL_(N_) fluxdiff_n<N_>(p, tp, o, g, L, first, count, u_q, u_f, dudt, s, rk, mid)
     SSE_CT_DISPATCH(p.N, CALL_);
 #undef CALL_

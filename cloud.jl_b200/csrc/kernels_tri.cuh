@@ -1,0 +1,461 @@
+// kernels_tri.cuh — compile-time-sized kernels for 2-D Euler, flux differencing, ModalTensor(p) on collapsed triangles
+// (BASELINE config 2: test/euler_vortex_2d_modal.jl), N = p + 1 = 3 .. 5 nodes per direction.
+//
+//   k_tri_nodal    pass A: entropy projection                      (flux_differencing_form.jl:214-292)
+//   k_tri_fluxdiff pass B: interface flux, volume flux differencing, facet correction, lift, V', mass solve
+//                          in ONE launch (flux_differencing_form.jl:294-347, mass_matrix.jl:185-196)
+//
+// A p = 4 triangle has 25 volume nodes, 15 facet nodes and 15 modes per variable: one WARP owns one element (lane = volume
+// node (a1, a2) = a1 N + a2; lanes 0 .. 3N-1 double as the facet nodes), a CTA is a set of independent warps that walk over
+// the elements with a grid stride.  Nothing in the element loop is a CTA barrier; the phases of an element are ordered by
+// __syncwarp.  What the one-CTA-per-element kernels re-read for every element lives here for the lifetime of the warp:
+//   * the pair weights of the lane's node (S_m[i, partner] / 4 of both line directions, C[i, partner] / 8 and R[partner, i]
+//     of the three faces) in registers -- every partner is closed-form (tri_schedule_matches verifies the tables);
+//   * the warped V as a dense 25 x 15 matrix (tensor_simplex.jl:84-140 collapses to A[a1,b1] B[a2,b1,b2] in 2-D) in shared
+//     memory in the two orders its applications read it: V[:, l] across the lanes (V x: lane = node) and V[i, :] across
+//     16 lanes (V' t: lane = (mode, variable pair), so all 32 lanes carry 2 of the 4 x 15 sums).
+// Volume term: both nodes of a pair sit in the same warp, so the +phi of a unique pair goes to the partner by warp shuffles
+// along the tensor line (the cyclic schedule of kernels_tensor.cuh: node c evaluates (c, c + s mod N), s = 1 .. N/2, and
+// receives from c - s) -- no staging buffer and no barrier between the two halves of a pair.  The facet correction stages
+// its three -phi per node once and the facet lanes sum their N entries.
+// The loads of the next element (state, metrics, facet data, mapP) are issued before the arithmetic of the current one;
+// the mapP-dependent neighbour gather is issued at the top of an element and consumed after its volume term.
+#pragma once
+#include "common.cuh"
+#include "ct_api.h"
+
+namespace sse {
+
+template <int N> struct TriT {
+    static constexpr int D = 2, NC = 4, NP = 5;
+    static constexpr int Nq = N * N, Np = N * (N + 1) / 2, Nf = 3 * N, NSH = N / 2;
+    static_assert(Nq <= 32 && Np <= 16 && Nf <= 32, "one volume node per lane, one (mode, variable pair) per lane");
+    // CTA-wide tables (doubles)
+    static constexpr int vt = 0;                      // V[i, l] at l * 32 + i      (lane = node)
+    static constexpr int vc = vt + Np * 32;           // V[i, l] at i * 16 + l      (lane & 15 = mode)
+    static constexpr int tables = vc + Nq * 16;
+    // per-warp tiles (doubles); every tile is [item][slots] with the variables of an item adjacent (128-bit accesses)
+    static constexpr int PS = 6;                      // primitives (rho, V1, V2, 2p, rho/p) padded to 6
+    static constexpr int x = 0;                       // [16][NC]   modal coefficients
+    static constexpr int t = x + 16 * NC;             // [32][NC]   nodal values
+    static constexpr int a_warp = t + 32 * NC;        // pass A ends here
+    static constexpr int prim = a_warp;               // [32][PS]
+    static constexpr int lam = prim + 32 * PS;        // [32][4]    Lambda[m][n] at m + 2 n
+    static constexpr int fprim = lam + 32 * 4;        // [32][PS]   facet nodes
+    static constexpr int hnf = fprim + 32 * PS;       // [32][2]
+    static constexpr int ff = hnf + 32 * 2;           // [32][NC]
+    static constexpr int stage = ff + 32 * NC;        // [3][32][NC]
+    static constexpr int b_warp = stage + 3 * 32 * NC;
+    template <bool PASS_B> static constexpr int smem_doubles(int warps) { return tables + warps * (PASS_B ? b_warp : a_warp); }
+};
+
+__device__ __forceinline__ void ld4(const double* p, double (&v)[4]) {
+    const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4(double* p, const double (&v)[4]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+
+// copy of the dense V into the two shared orders (all threads of the CTA; followed by __syncthreads)
+template <int N>
+__device__ __forceinline__ void tri_fill_tables(const TriDev& t, double* sm) {
+    using T = TriT<N>;
+    for (int i = threadIdx.x; i < T::Np * 32; i += blockDim.x) { const int l = i >> 5, n = i & 31; sm[T::vt + i] = n < T::Nq ? t.V[n + T::Nq * l] : 0.0; }
+    for (int i = threadIdx.x; i < T::Nq * 16; i += blockDim.x) { const int n = i >> 4, l = i & 15; sm[T::vc + i] = l < T::Np ? t.V[n + T::Nq * l] : 0.0; }
+}
+// y[e] = sum_l V[lane, l] x[l][e]            (lanes >= N_q read zeros)
+template <int N>
+__device__ __forceinline__ void tri_V(const double* s_vt, const double* s_x, int lane, double (&y)[4]) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) y[e] = 0.0;
+#pragma unroll
+    for (int l = 0; l < TriT<N>::Np; l++) {
+        const double v = s_vt[l * 32 + lane];
+        double xv[4];
+        ld4(s_x + l * 4, xv);
+#pragma unroll
+        for (int e = 0; e < 4; e++) y[e] = fma(v, xv[e], y[e]);
+    }
+}
+// lane = (l, h): c[q] = sum_i V[i, l] t[i][2 h + q]            (lanes with l >= N_p read zeros)
+template <int N>
+__device__ __forceinline__ void tri_Vt(const double* s_vc, const double* s_t, int lane, double (&c)[2]) {
+    const int l = lane & 15, h = lane >> 4;
+    c[0] = 0.0; c[1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < TriT<N>::Nq; i++) {
+        const double v = s_vc[i * 16 + l];
+        const double2 tv = *reinterpret_cast<const double2*>(s_t + i * 4 + 2 * h);
+        c[0] = fma(v, tv.x, c[0]);
+        c[1] = fma(v, tv.y, c[1]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pass A — nodal_values! with the modal entropy projection: u_q = u(V M^-1 V' WJ w(V u)), u_f = u(R V ...)
+template <int N, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_tri_nodal(TriDev t, Geo g, Law L, long long first, long long count, const double* __restrict__ u, double* __restrict__ u_q,
+            double* __restrict__ u_f) {
+    using T = TriT<N>;
+    constexpr int D = 2, NC = 4, Nq = T::Nq, Np = T::Np, Nf = T::Nf;
+    extern __shared__ __align__(16) double sm[];
+    tri_fill_tables<N>(t, sm);
+    __syncthreads();
+    const double* s_vt = sm + T::vt;
+    const double* s_vc = sm + T::vc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* s_x = sm + T::tables + warp * T::a_warp + T::x;
+    double* s_t = sm + T::tables + warp * T::a_warp + T::t;
+    const bool node = lane < Nq, fac = lane < Nf;
+    const int tn = node ? lane : Nq - 1, tj = fac ? lane : Nf - 1;
+    const int ml = lane & 15, mh = lane >> 4;
+    const bool mode = ml < Np;
+    // facet node tj = (face f, position q) extrapolates the N volume nodes fb + c fs (tensor_simplex.jl:265-268 in 2-D)
+    const int ff_ = tj / N, fq = tj - ff_ * N;
+    const int fb = ff_ == 0 ? fq * N : fq, fs = ff_ == 0 ? 1 : N;
+    double rf[N];
+#pragma unroll
+    for (int c = 0; c < N; c++) rf[c] = t.rfac[tj * N + c];
+    const double Wn = t.W[tn];
+    // modal coefficients of an element: NC * Np values, two per lane, (variable e, mode l) at x = e Np + l
+    const int xa = lane, xb = lane + 32;
+    const bool ha = xa < NC * Np, hb = xb < NC * Np;
+    const int xac = ha ? xa : 0, xbc = hb ? xb : 0;
+    const int sa = (xac % Np) * 4 + xac / Np, sb = (xbc % Np) * 4 + xbc / Np;
+
+    const long long stride = (long long)gridDim.x * WARPS, end = first + count;
+    long long k = first + (long long)blockIdx.x * WARPS + warp;
+    if (k >= end) return;
+    double ua = u[(size_t)k * NC * Np + xac], ub = u[(size_t)k * NC * Np + xbc];
+    double J = g.J_q[(size_t)k * Nq + tn], ijw = g.iJW[(size_t)k * Nq + tn];
+    for (;;) {
+        const long long kn = k + stride, kl = kn < end ? kn : k;
+        if (ha) s_x[sa] = ua;
+        if (hb) s_x[sb] = ub;
+        const double Jc = J, ijwc = ijw;
+        ua = u[(size_t)kl * NC * Np + xac]; ub = u[(size_t)kl * NC * Np + xbc];
+        J = g.J_q[(size_t)kl * Nq + tn]; ijw = g.iJW[(size_t)kl * Nq + tn];
+        __syncwarp();
+        double y[NC], w[NC], c2[2];
+        tri_V<N>(s_vt, s_x, lane, y);                                     // u_q = V u
+        if (!node) { y[0] = 1.0; y[1] = 0.0; y[2] = 0.0; y[3] = 1.0; }      // idle lanes: any physical state
+        euler_cons_to_entropy_nb<D>(L.gamma, L.gm1, L.igm1, y, w);        // w_q = WJ w(u_q)   flux_differencing_form.jl:230-235
+        {
+            const double wj = Wn * Jc;
+#pragma unroll
+            for (int e = 0; e < NC; e++) w[e] *= wj;
+        }
+        if (node) st4(s_t + lane * 4, w);
+        __syncwarp();
+        tri_Vt<N>(s_vc, s_t, lane, c2);                                   // w = V' w_q
+        if (mode) *reinterpret_cast<double2*>(s_x + ml * 4 + 2 * mh) = make_double2(c2[0], c2[1]);
+        __syncwarp();
+        tri_V<N>(s_vt, s_x, lane, y);                                     // w = M \ w: V, diag(W / J), V'   mass_matrix.jl:185-196
+#pragma unroll
+        for (int e = 0; e < NC; e++) y[e] *= ijwc;
+        if (node) st4(s_t + lane * 4, y);
+        __syncwarp();
+        tri_Vt<N>(s_vc, s_t, lane, c2);
+        if (mode) *reinterpret_cast<double2*>(s_x + ml * 4 + 2 * mh) = make_double2(c2[0], c2[1]);
+        __syncwarp();
+        tri_V<N>(s_vt, s_x, lane, y);                                     // w_q = V w
+        if (node) st4(s_t + lane * 4, y);
+        __syncwarp();
+        double wf[NC], uq[NC], uf[NC];                                    // w_f = R w_q
+#pragma unroll
+        for (int e = 0; e < NC; e++) wf[e] = 0.0;
+#pragma unroll
+        for (int c = 0; c < N; c++) {
+            double tv[4];
+            ld4(s_t + (fb + c * fs) * 4, tv);
+#pragma unroll
+            for (int e = 0; e < NC; e++) wf[e] = fma(rf[c], tv[e], wf[e]);
+        }
+        if (!node) {
+#pragma unroll
+            for (int e = 0; e < NC; e++) y[e] = wf[e];                    // idle lanes: a valid entropy vector
+        }
+        // u_q = u(w_q), u_f = u(R w_q)                                   flux_differencing_form.jl:240-249
+        euler_entropy_to_cons_nb<D>(L.gamma, L.gm1, L.igm1, L.log_gm1, y, uq);
+        euler_entropy_to_cons_nb<D>(L.gamma, L.gm1, L.igm1, L.log_gm1, wf, uf);
+        if (node) {
+#pragma unroll
+            for (int e = 0; e < NC; e++) u_q[((size_t)k * NC + e) * Nq + lane] = uq[e];
+        }
+        if (fac) {
+#pragma unroll
+            for (int e = 0; e < NC; e++) u_f[(size_t)k * Nf + lane + (size_t)g.NFT * e] = uf[e];
+        }
+        if (kn >= end) break;
+        k = kn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// pass B — everything between the facet states of pass A and dudt of one element, in one warp
+template <int N, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_tri_fluxdiff(TriDev t, Geo g, Law L, long long first, long long count, const double* __restrict__ u_q,
+               const double* __restrict__ u_f, double* __restrict__ dudt, RkStage rk) {
+    using T = TriT<N>;
+    constexpr int D = 2, NC = 4, NP = 5, Nq = T::Nq, Np = T::Np, Nf = T::Nf, NSH = T::NSH, PS = T::PS;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) double sm[];
+    tri_fill_tables<N>(t, sm);
+    __syncthreads();
+    const double* s_vt = sm + T::vt;
+    const double* s_vc = sm + T::vc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* sw_ = sm + T::tables + warp * T::b_warp;
+    double* s_x = sw_ + T::x;
+    double* s_t = sw_ + T::t;
+    double* s_prim = sw_ + T::prim;
+    double* s_lam = sw_ + T::lam;
+    double* s_fprim = sw_ + T::fprim;
+    double* s_hnf = sw_ + T::hnf;
+    double* s_ff = sw_ + T::ff;
+    double* s_stage = sw_ + T::stage;
+    const bool node = lane < Nq, fac = lane < Nf;
+    const int tn = node ? lane : Nq - 1, tj = fac ? lane : Nf - 1;
+    const int a1 = tn / N, a2 = tn - a1 * N;
+    const int ml = lane & 15, mh = lane >> 4;
+    const bool mode = ml < Np;
+
+    // ---- per-lane constants of the schedule (the same for every element)
+    double sw0[NSH][D], sw1[NSH], cw[3], rw[3];
+    int jp0[NSH], js0[NSH], jp1[NSH], js1[NSH];
+    bool ac0[NSH], ac1[NSH];
+#pragma unroll
+    for (int s = 0; s < NSH; s++) {
+        const int sh = s + 1;
+        const bool half = 2 * sh == N;
+#pragma unroll
+        for (int m = 0; m < D; m++) sw0[s][m] = t.vS[((size_t)(0 * NSH + s) * D + m) * Nq + tn];
+        sw1[s] = t.vS[((size_t)(1 * NSH + s) * D + 1) * Nq + tn];
+        int cj = a1 + sh; if (cj >= N) cj -= N;
+        int cs = a1 - sh; if (cs < 0) cs += N;
+        jp0[s] = tn + (cj - a1) * N; js0[s] = tn + (cs - a1) * N; ac0[s] = !(half && a1 >= sh);
+        cj = a2 + sh; if (cj >= N) cj -= N;
+        cs = a2 - sh; if (cs < 0) cs += N;
+        jp1[s] = tn + (cj - a2); js1[s] = tn + (cs - a2); ac1[s] = !(half && a2 >= sh);
+    }
+    const int jf_[3] = {a1, N + a2, 2 * N + a2};              // facet partner of the lane's volume node on each face
+#pragma unroll
+    for (int f = 0; f < 3; f++) { cw[f] = t.fC[f * Nq + tn]; rw[f] = t.fR[f * Nq + tn]; }
+    const double bf = t.Bf[tj];
+    const int ff_ = tj / N, fq = tj - ff_ * N;                // facet lane: its N volume nodes fb + c fs
+    const int fb = ff_ == 0 ? fq * N : fq, fs = ff_ == 0 ? 1 : N;
+
+    const long long stride = (long long)gridDim.x * WARPS, end = first + count;
+    long long k = first + (long long)blockIdx.x * WARPS + warp;
+    if (k >= end) return;
+
+    // ---- loads of the first element
+    double un[NC], lam[D][D], ui[NC], jf, njf[D], ijw;
+    long long mp;
+#define SSE_TRI_LOAD(K_)                                                                                                  \
+    do {                                                                                                                  \
+        _Pragma("unroll") for (int e = 0; e < NC; e++) un[e] = __ldcs(u_q + ((size_t)(K_) * NC + e) * Nq + tn);           \
+        _Pragma("unroll") for (int n = 0; n < D; n++)                                                                     \
+            _Pragma("unroll") for (int m = 0; m < D; m++) lam[m][n] = __ldcs(g.Lambda_q + ((size_t)(K_) * D * D + (m + D * n)) * Nq + tn); \
+        _Pragma("unroll") for (int e = 0; e < NC; e++) ui[e] = u_f[(size_t)(K_) * Nf + tj + (size_t)g.NFT * e];           \
+        jf = __ldcs(g.J_f + (size_t)(K_) * Nf + tj);                                                                      \
+        _Pragma("unroll") for (int m = 0; m < D; m++) njf[m] = __ldcs(g.nJf + m + D * ((size_t)(K_) * Nf + tj));          \
+        mp = g.mapP[(size_t)(K_) * Nf + tj];                                                                              \
+        ijw = __ldcs(g.iJW + (size_t)(K_) * Nq + tn);                                                                     \
+    } while (0)
+    SSE_TRI_LOAD(k);
+
+    for (;;) {
+        const long long kn = k + stride, kl = kn < end ? kn : k;
+        // ---- neighbour gather of this element, then the current values move aside and the next element's loads go out
+        double uo[NC];
+        {
+            const size_t jo = (size_t)(mp - 1);
+#pragma unroll
+            for (int e = 0; e < NC; e++) uo[e] = u_f[jo + (size_t)g.NFT * e];
+        }
+        double cu[NC], cl[D][D], ci[NC], cnj[D];
+#pragma unroll
+        for (int e = 0; e < NC; e++) { cu[e] = un[e]; ci[e] = ui[e]; }
+#pragma unroll
+        for (int m = 0; m < D; m++) { cnj[m] = njf[m]; cl[m][0] = lam[m][0]; cl[m][1] = lam[m][1]; }
+        const double cjf = jf, cijw = ijw;
+        SSE_TRI_LOAD(kl);
+
+        // ---- node primitives and metrics into the warp's tiles
+        double qi[NP], r[NC];
+        to_prim_fast<D>(L, cu, qi);
+        if (node) {
+            double* p = s_prim + lane * PS;
+            *reinterpret_cast<double2*>(p) = make_double2(qi[0], qi[1]);
+            *reinterpret_cast<double2*>(p + 2) = make_double2(qi[2], qi[3]);
+            p[4] = qi[4];
+            double* q = s_lam + lane * 4;
+            *reinterpret_cast<double2*>(q) = make_double2(cl[0][0], cl[1][0]);
+            *reinterpret_cast<double2*>(q + 2) = make_double2(cl[0][1], cl[1][1]);
+        }
+#pragma unroll
+        for (int e = 0; e < NC; e++) r[e] = 0.0;
+        __syncwarp();
+
+        // ---- volume term (flux_difference!, flux_differencing_form.jl:37-75): line direction 0 (a1, both S_m), then 1 (a2, S_2 only)
+#pragma unroll
+        for (int l = 0; l < D; l++) {
+            double gv[NSH][D], qj[NSH][NP], ph[NSH][NC];
+#pragma unroll
+            for (int s = 0; s < NSH; s++) {
+                const int j = l == 0 ? jp0[s] : jp1[s];
+                const double* p = s_prim + j * PS;
+                const double2 p01 = *reinterpret_cast<const double2*>(p), p23 = *reinterpret_cast<const double2*>(p + 2);
+                qj[s][0] = p01.x; qj[s][1] = p01.y; qj[s][2] = p23.x; qj[s][3] = p23.y; qj[s][4] = p[4];
+                if (l == 0) {
+                    double lj[4];
+                    ld4(s_lam + j * 4, lj);
+#pragma unroll
+                    for (int n = 0; n < D; n++)
+                        gv[s][n] = fma(sw0[s][1], cl[1][n] + lj[1 + 2 * n], sw0[s][0] * (cl[0][n] + lj[0 + 2 * n]));
+                } else {
+                    const double l10 = s_lam[j * 4 + 1], l11 = s_lam[j * 4 + 3];
+                    gv[s][0] = sw1[s] * (cl[1][0] + l10);
+                    gv[s][1] = sw1[s] * (cl[1][1] + l11);
+                }
+            }
+            if constexpr (NSH == 2) ec_contract_scaled2<D>(L, qi, qj[0], qj[1], gv[0], gv[1], ph[0], ph[1]);
+            else ec_contract_scaled<D>(L, qi, qj[0], gv[0], ph[0]);
+#pragma unroll
+            for (int s = 0; s < NSH; s++) {
+                const bool ac = l == 0 ? ac0[s] : ac1[s];
+                const int src = l == 0 ? js0[s] : js1[s];
+#pragma unroll
+                for (int e = 0; e < NC; e++) {
+                    const double pz = ac ? ph[s][e] : 0.0;                // even N: the half-way pairs once only
+                    r[e] += __shfl_sync(FULL, pz, src) - pz;               // -phi stays, +phi goes to the partner along the line
+                }
+            }
+        }
+
+        // ---- interface flux (numerical_flux!, ConservationLaws.jl:75-128) on the facet lanes
+        double ffv[NC];
+        {
+            double qa[NP], qb[NP], nf[D], nfq[D], phi[NC];
+            const double ijf = rcp_fast(cjf);
+#pragma unroll
+            for (int m = 0; m < D; m++) { nf[m] = cnj[m] * ijf; nfq[m] = 0.25 * nf[m]; }        // n_f = nJf / J_f   operators.jl:59
+            const double ira = to_prim_fast<D>(L, ci, qa);
+            const double irb = to_prim_fast<D>(L, uo, qb);
+            ec_contract_scaled<D>(L, qa, qb, nfq, phi);
+            if (L.inviscid == SSE_FLUX_LAX_FRIEDRICHS) {
+                double vni = 0.0, vno = 0.0;
+#pragma unroll
+                for (int m = 0; m < D; m++) { vni = fma(qa[1 + m], nf[m], vni); vno = fma(qb[1 + m], nf[m], vno); }
+                const double cm = sqrt(fmax(L.gamma * (0.5 * qa[D + 1]) * ira, L.gamma * (0.5 * qb[D + 1]) * irb));
+                const double a = L.half_lambda * (fmax(fabs(vni), fabs(vno)) + cm);
+#pragma unroll
+                for (int e = 0; e < NC; e++) phi[e] = fma(a, ci[e] - uo[e], phi[e]);
+            }
+            const double bj = bf * cjf;                                   // BJf               operators.jl:58
+#pragma unroll
+            for (int e = 0; e < NC; e++) ffv[e] = bj * phi[e];
+            if (fac) {
+                double* p = s_fprim + lane * PS;
+                *reinterpret_cast<double2*>(p) = make_double2(qa[0], qa[1]);
+                *reinterpret_cast<double2*>(p + 2) = make_double2(qa[2], qa[3]);
+                p[4] = qa[4];
+                *reinterpret_cast<double2*>(s_hnf + lane * 2) = make_double2(cnj[0], cnj[1]);      // 2 halfnJf (operators.jl:78); the 1/2 lives in fC
+            }
+        }
+        __syncwarp();
+
+        // ---- facet correction (facet_correction!, flux_differencing_form.jl:126-168): one pair per node and face
+        {
+            double gv[3][D], qj[3][NP], ph[3][NC];
+#pragma unroll
+            for (int f = 0; f < 3; f++) {
+                const int j = jf_[f];
+                double hq[D];
+                if (g.nJq) {
+#pragma unroll
+                    for (int n = 0; n < D; n++) hq[n] = g.nJq[n + D * (f + (size_t)3 * (tn + (size_t)Nq * k))];
+                } else {
+#pragma unroll
+                    for (int n = 0; n < D; n++) hq[n] = fma(cl[1][n], t.nref[1 + D * f], cl[0][n] * t.nref[0 + D * f]);   // mesh.jl:262-269
+                }
+                const double2 hn = *reinterpret_cast<const double2*>(s_hnf + j * 2);
+                gv[f][0] = cw[f] * (hn.x + hq[0]);
+                gv[f][1] = cw[f] * (hn.y + hq[1]);
+                const double* p = s_fprim + j * PS;
+                const double2 p01 = *reinterpret_cast<const double2*>(p), p23 = *reinterpret_cast<const double2*>(p + 2);
+                qj[f][0] = p01.x; qj[f][1] = p01.y; qj[f][2] = p23.x; qj[f][3] = p23.y; qj[f][4] = p[4];
+            }
+            ec_contract_scaled2<D>(L, qi, qj[0], qj[1], gv[0], gv[1], ph[0], ph[1]);
+            ec_contract_scaled<D>(L, qi, qj[2], gv[2], ph[2]);
+#pragma unroll
+            for (int f = 0; f < 3; f++) {
+#pragma unroll
+                for (int e = 0; e < NC; e++) r[e] -= ph[f][e];
+                if (node) st4(s_stage + (f * 32 + lane) * 4, ph[f]);
+            }
+        }
+        __syncwarp();
+        {   // facet lanes: f_f = BJf f* - sum of the staged vectors of the facet node's N volume nodes
+            double s[NC];
+#pragma unroll
+            for (int e = 0; e < NC; e++) s[e] = 0.0;
+#pragma unroll
+            for (int c = 0; c < N; c++) {
+                double v[4];
+                ld4(s_stage + (ff_ * 32 + fb + c * fs) * 4, v);
+#pragma unroll
+                for (int e = 0; e < NC; e++) s[e] += v[e];
+            }
+#pragma unroll
+            for (int e = 0; e < NC; e++) ffv[e] -= s[e];
+            if (fac) st4(s_ff + lane * 4, ffv);
+        }
+        __syncwarp();
+        // ---- lift: r_q -= R' f_f (flux_differencing_form.jl:341-342)
+#pragma unroll
+        for (int f = 0; f < 3; f++) {
+            double v[4];
+            ld4(s_ff + jf_[f] * 4, v);
+#pragma unroll
+            for (int e = 0; e < NC; e++) r[e] = fma(-rw[f], v[e], r[e]);
+        }
+        // ---- dudt = M^-1 V' r_q: V', V, diag(W / J), V' (flux_differencing_form.jl:345-346, mass_matrix.jl:185-196)
+        if (node) st4(s_t + lane * 4, r);
+        __syncwarp();
+        double c2[2], y[NC];
+        tri_Vt<N>(s_vc, s_t, lane, c2);
+        if (mode) *reinterpret_cast<double2*>(s_x + ml * 4 + 2 * mh) = make_double2(c2[0], c2[1]);
+        __syncwarp();
+        tri_V<N>(s_vt, s_x, lane, y);
+#pragma unroll
+        for (int e = 0; e < NC; e++) y[e] *= cijw;
+        if (node) st4(s_t + lane * 4, y);
+        __syncwarp();
+        tri_Vt<N>(s_vc, s_t, lane, c2);
+        if (mode) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const size_t idx = ((size_t)k * NC + 2 * mh + q) * Np + ml;
+                dudt[idx] = c2[q];
+                flag_nonfinite(g.flag, c2[q]);
+                if (rk.u) {                        // fused 2N-storage RK stage (Carpenter & Kennedy 1994)
+                    const double tm = fma(rk.A, rk.tmp[idx], rk.dt * c2[q]);
+                    rk.tmp[idx] = tm;
+                    rk.u[idx] = fma(rk.B, tm, rk.u[idx]);
+                }
+            }
+        }
+        if (kn >= end) break;
+        k = kn;
+        __syncwarp();
+    }
+#undef SSE_TRI_LOAD
+}
+
+}  // namespace sse

@@ -578,6 +578,24 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
             h->ct.ok = 1;
         }
     }
+    {   // 2-D Euler flux differencing on collapsed triangles: warp-per-element kernels (kernels_tri.cuh)
+        if (!h->ct.ok && tri_eligible(*cfg, *a, h->tp, h->ct)) {
+            CtPlan& c = h->ct;
+            c.kind = 2; c.sms = h->sm_count > 0 ? h->sm_count : 148;
+            if ((rc = upload(h, c.triV, &c.tri.V)) || (rc = upload(h, c.trivS, &c.tri.vS)) || (rc = upload(h, c.trifC, &c.tri.fC)) ||
+                (rc = upload(h, c.trifR, &c.tri.fR)) || (rc = upload(h, c.triRfac, &c.tri.rfac)))
+                return rc;
+            c.tri.W = o.W; c.tri.Bf = o.Bf;
+            if (tri_set_attrs(c.N) != cudaSuccess) return fail(SSE_ERR_CUDA, "cudaFuncSetAttribute (triangle kernels) failed");
+            double* ijw = nullptr;
+            if ((rc = dalloc(h, (size_t)Nq * Ne, &ijw))) return rc;
+            const long long n = (long long)Nq * Ne;
+            k_ijw<<<(unsigned)std::min<long long>((n + 255) / 256, 8LL * std::max(h->sm_count, 1)), 256, 0, h->stream>>>(n, Nq, o.W, g.J_q, ijw);
+            CU(cudaGetLastError());
+            g.iJW = ijw;
+            c.ok = 1;
+        }
+    }
     // threads per element of the generic (one CTA per element) kernels: enough for one volume / facet node per thread, at most 128
     {   // threads per element of the packed kernels; SSE_THREADS_MIN=64 restores the round-1 minimum (A/B)
         const char* tm = getenv("SSE_THREADS_MIN");
@@ -796,7 +814,7 @@ int32_t sse::pass_b_stage(sse_handle* h, double* d_dudt, int64_t first, int64_t 
     if (h->cfg.form == SSE_FORM_FLUX_DIFFERENCING) {
         if (h->variant == 1 && h->ct.ok) {
             ct_fluxdiff(h->ct, h->tp, h->ops, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream, rk, mid);
-            h->launches += 1;       // pair kernel + projection kernel
+            h->launches += h->ct.kind == 2 ? 0 : 1;       // pair kernel + projection kernel (one fused kernel on triangles)
         } else if (h->variant == 1 && h->dense.ok) {
             const int T = std::min(128, (std::max(h->cfg.N_q, h->cfg.N_f) + 31) / 32 * 32);
             if (h->cfg.d == 2) k_time_fluxdiff_dense<2><<<n, T, h->smem_dense, h->stream>>>(h->ops, h->geo, h->law, h->dense, first, h->u_q, h->u_f, d_dudt);
@@ -1370,6 +1388,7 @@ extern "C" int32_t sse_plan_selfcheck(const sse_config* cfg, const sse_arrays* a
         std::vector<double> D1, fR, fac;
         if (tp.ok && ct_eligible(*cfg, *arr, tp, &N) && ct_schedule_matches(tp, N) && ct_facet_factors(*cfg, *arr, N, fac)) info[0] = 2;
         else if (ct_eligible_standard(*cfg, *arr, &N, D1, fR) && ct_facet_factors(*cfg, *arr, N, fac)) { info[0] = 3; info[1] = 128; return SSE_OK; }
+        else if (tp.ok) { CtPlan tri; if (tri_eligible(*cfg, *arr, tp, tri)) info[0] = 4; }      // 4: warp-per-element triangle kernels
     }
     if (!tp.ok) return SSE_OK;
     if (info[0] != 2 && !tp.has_fluxdiff) { info[0] = 0; return SSE_OK; }      // schedule exists, but no kernel for this size

@@ -39,6 +39,8 @@ struct AdvDev {
 
 // device tables of the warp-per-element 2-D Euler path (kernels_tri.cuh); all of them element independent
 struct TriDev {
+    const double* A = nullptr;      // 1-D tensors of the warped V: A[a1 + N b1], B[a2 + N (b1 + N b2)]   (tensor_simplex.jl:84-140)
+    const double* B = nullptr;
     const double* V = nullptr;      // dense warped V, column-major N_q x N_p (node a1 N + a2, canonical modal index)
     const double* vS = nullptr;     // [round][2][N_q]  skew-extended S_m[i, partner] / 4, round = line direction * (N/2) + shift - 1
     const double* fC = nullptr;     // [3][N_q]         C[i, partner] / 8

@@ -115,10 +115,20 @@ bool ct_facet_factors(const sse_config& cfg, const sse_arrays& a, int N, std::ve
 #ifndef SSE_TRI_WARPS
 #define SSE_TRI_WARPS 4
 #endif
+// resident CTAs per SM requested from ptxas: 3 = 168 registers, 12 warps per SM.  Both kernels want more registers than
+// the 128 of 16 warps per SM (pass B spills 300 bytes there, and its spill traffic competes for the shared-memory pipe):
+// measured at 131 072 triangles, pass A 0.276 (4) / 0.271 ms (3) with the V row in registers, pass B 0.515 (4) / 0.508 ms (3)
 #ifndef SSE_TRI_MINB
-#define SSE_TRI_MINB 4
+#define SSE_TRI_MINB 3
 #endif
-constexpr int TRI_WARPS = SSE_TRI_WARPS, TRI_MINB = SSE_TRI_MINB;
+// pass B with asynchronous copies into the warp's tiles (k_tri_fluxdiff_async) or with register prefetch (k_tri_fluxdiff)
+#ifndef SSE_TRI_ASYNC
+#define SSE_TRI_ASYNC 0
+#endif
+#ifndef SSE_TRI_MINB_A
+#define SSE_TRI_MINB_A SSE_TRI_MINB
+#endif
+constexpr int TRI_WARPS = SSE_TRI_WARPS, TRI_MINB = SSE_TRI_MINB, TRI_MINB_A = SSE_TRI_MINB_A;
 #define SSE_TRI_DISPATCH(N_, CALL) \
     switch (N_) { case 3: CALL(3); break; case 4: CALL(4); break; case 5: CALL(5); break; default: break; }
 
@@ -142,6 +152,7 @@ bool tri_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& 
         const long long l = a.sigma_i[t];
         if (l < 0 || l > Np) return false;
         if ((l > 0) != (a1 + a2 <= N - 1)) return false;
+        if (l > 0 && l - 1 != a1 * N - a1 * (a1 - 1) / 2 + a2) return false;      // canonical modal index (tri_l in kernels_tri.cuh)
         if (l > 0) { if (seen[l - 1]) return false; seen[l - 1] = 1; }
     }
     // dense V[node, l] = A[a1, b1] B[a2, b1, b2] (warped_product_2d; the expression of sse_create's small-element V)
@@ -194,8 +205,10 @@ bool tri_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& 
 
 template <int N> static cudaError_t tri_set_attrs_n() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_tri_nodal<N, TRI_WARPS, TRI_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if ((e = cudaFuncSetAttribute(k_tri_nodal<N, TRI_WARPS, TRI_MINB_A>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(sizeof(double) * TriT<N>::template smem_doubles<false>(TRI_WARPS))))) return e;
+    if ((e = cudaFuncSetAttribute(k_tri_fluxdiff_async<N, TRI_WARPS, TRI_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(sizeof(double) * TriB<N>::smem_doubles(TRI_WARPS))))) return e;
     return cudaFuncSetAttribute(k_tri_fluxdiff<N, TRI_WARPS, TRI_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(sizeof(double) * TriT<N>::template smem_doubles<true>(TRI_WARPS)));
 }
@@ -207,21 +220,26 @@ cudaError_t tri_set_attrs(int N) {
     return e;
 }
 // persistent warps: one resident wave of CTAs, each warp strides over the elements of the range
-static unsigned tri_grid(const CtPlan& p, long long count) {
-    const long long want = (count + TRI_WARPS - 1) / TRI_WARPS, wave = (long long)p.sms * TRI_MINB;
+static unsigned tri_grid(const CtPlan& p, long long count, int minb = TRI_MINB) {
+    const long long want = (count + TRI_WARPS - 1) / TRI_WARPS, wave = (long long)p.sms * minb;
     return (unsigned)std::max<long long>(1, std::min(want, wave));
 }
 template <int N>
 static void tri_nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q,
                         double* u_f, cudaStream_t s) {
-    k_tri_nodal<N, TRI_WARPS, TRI_MINB><<<tri_grid(p, count), TRI_WARPS * 32, sizeof(double) * TriT<N>::template smem_doubles<false>(TRI_WARPS), s>>>(
+    k_tri_nodal<N, TRI_WARPS, TRI_MINB_A><<<tri_grid(p, count, TRI_MINB_A), TRI_WARPS * 32, sizeof(double) * TriT<N>::template smem_doubles<false>(TRI_WARPS), s>>>(
         p.tri, g, L, first, count, u, u_q, u_f);
 }
 template <int N>
 static void tri_fluxdiff_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u_q,
                            const double* u_f, double* dudt, cudaStream_t s, RkStage rk) {
+#if SSE_TRI_ASYNC
+    k_tri_fluxdiff_async<N, TRI_WARPS, TRI_MINB><<<tri_grid(p, count), TRI_WARPS * 32, sizeof(double) * TriB<N>::smem_doubles(TRI_WARPS), s>>>(
+        p.tri, g, L, first, count, u_q, u_f, dudt, rk);
+#else
     k_tri_fluxdiff<N, TRI_WARPS, TRI_MINB><<<tri_grid(p, count), TRI_WARPS * 32, sizeof(double) * TriT<N>::template smem_doubles<true>(TRI_WARPS), s>>>(
         p.tri, g, L, first, count, u_q, u_f, dudt, rk);
+#endif
 }
 
 template <int N> static FacetR<N> make_facet(const CtPlan& p) {

@@ -585,7 +585,7 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
             if ((rc = upload(h, c.triV, &c.tri.V)) || (rc = upload(h, c.trivS, &c.tri.vS)) || (rc = upload(h, c.trifC, &c.tri.fC)) ||
                 (rc = upload(h, c.trifR, &c.tri.fR)) || (rc = upload(h, c.triRfac, &c.tri.rfac)))
                 return rc;
-            c.tri.W = o.W; c.tri.Bf = o.Bf;
+            c.tri.W = o.W; c.tri.Bf = o.Bf; c.tri.A = o.A; c.tri.B = o.B;
             if (tri_set_attrs(c.N) != cudaSuccess) return fail(SSE_ERR_CUDA, "cudaFuncSetAttribute (triangle kernels) failed");
             double* ijw = nullptr;
             if ((rc = dalloc(h, (size_t)Nq * Ne, &ijw))) return rc;

@@ -167,7 +167,7 @@ GOLDEN_RUNS = {
     "advection_2d_tri": (lambda: cases.advection_2d(M=2, p=4, flux="lf0", warp=0.1), 1.0, 100, "ADVECTION_2D_TRI_GOLDEN", 0),
     "advection_2d_quad": (lambda: cases.advection_2d_quad(M=2, p=4, flux="lf", warp=0.1), 1.0, 100, "ADVECTION_2D_QUAD_GOLDEN", None),
     "euler_vortex_2d_modal_tri": (lambda: cases.euler_vortex_2d(M=4, p=3, flux="lf"), 2.5, 1000,
-                                  "EULER_VORTEX_2D_MODAL_GOLDEN", 1),
+                                  "EULER_VORTEX_2D_MODAL_GOLDEN", 2),
     "euler_3d_hex": (lambda: cases.euler_periodic_3d_hex(M=2, p=4, flux="ec"), 2.0, 2500, "EULER_3D_HEX_GOLDEN", None),
 }
 

@@ -49,15 +49,19 @@ struct TriDev {
     const double* W = nullptr;      // [N_q]
     const double* Bf = nullptr;     // [N_f]
     double nref[6] = {0, 0, 0, 0, 0, 0};   // 2 x 3 reference normals, column-major
+    const double* D1 = nullptr;     // kind 3: the two 1-D derivative matrices, [m][row + N col]
+    const double* RV = nullptr;     // kind 3: R V, column-major N_f x N_p (pass A is u_f = (R V) u)
 };
 
 struct CtPlan {
     int ok = 0, N = 0;
     int kind = 0;                   // 0: 3-D Euler flux differencing; 1: 3-D linear advection, StandardForm + ReferenceOperators;
                                     // 2: 2-D Euler flux differencing on triangles (kernels_tri.cuh)
+                                    // 3: 2-D linear advection, StandardForm + ReferenceOperators on triangles (kernels_tri.cuh)
     TriDev tri;                     // kind 2
     std::vector<double> triV, trivS, trifC, trifR, triRfac;     // host images of the kind-2 tables
-    int sms = 148;                  // SMs of the device (grid of the persistent kind-2 kernels)
+    std::vector<double> triD1, triRV;                           // ... and of the kind-3 tables (with triV, trifR)
+    int sms = 148;                  // SMs of the device (grid of the persistent kind-2 / kind-3 kernels)
     std::vector<double> D1;         // kind 1: the three 1-D derivative matrices, [m][t + N*s]
     CtDev dev{};
     std::vector<double> A, B;       // host copies of the 1-D tensors handed to the kernels by value
@@ -79,6 +83,8 @@ void ct_standard(const CtPlan& p, const Geo& g, const Law& L, long long first, l
 // R and the pair schedule in the closed form k_tri_* hard-code; fills the host images of the tables on success
 bool tri_eligible(const sse_config& cfg, const sse_arrays& a, const TensorPlan& tp, CtPlan& p);
 cudaError_t tri_set_attrs(int N);
+// kind 3: d = 2, linear advection, StandardForm + ReferenceOperators, ModalTensor triangles with p + 1 <= 5, weight-adjusted mass solver
+bool tri_adv_eligible(const sse_config& cfg, const sse_arrays& a, CtPlan& p);
 bool ct_facet_factors(const sse_config& cfg, const sse_arrays& a, int N, std::vector<double>& out);
 // true when the generic tables of tp equal the closed-form schedule k_fluxdiff_ct hard-codes
 bool ct_schedule_matches(const TensorPlan& tp, int N);

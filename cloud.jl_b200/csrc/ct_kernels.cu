@@ -242,6 +242,76 @@ static void tri_fluxdiff_n(const CtPlan& p, const Geo& g, const Law& L, long lon
 #endif
 }
 
+
+// kind 3: 2-D linear advection, StandardForm + ReferenceOperators on collapsed triangles (k_tri_adv_facets / k_tri_adv)
+bool tri_adv_eligible(const sse_config& cfg, const sse_arrays& a, CtPlan& p) {
+    if (const char* e = getenv("SSE_TRI_CT")) if (atoi(e) == 0) return false;
+    if (cfg.d != 2 || cfg.N_c != 1 || cfg.pde != SSE_PDE_ADVECTION || cfg.form != SSE_FORM_STANDARD_REFERENCE) return false;
+    if (cfg.v_kind != SSE_V_WARPED || cfg.mass_solver != SSE_MASS_WEIGHT_ADJUSTED || !a.A || !a.B || !a.R || !a.D[0] || !a.D[1]) return false;
+    if (!a.sigma_i || !a.sigma_o || !a.W || !a.Bf) return false;
+    const int N = cfg.p + 1;
+    if (N < 3 || N > 5) return false;
+    if (cfg.M1d[0] != N || cfg.M1d[1] != N) return false;
+    const int Nq = N * N, Np = N * (N + 1) / 2, Nf = 3 * N;
+    if (cfg.N_q != Nq || cfg.N_p != Np || cfg.N_f != Nf || cfg.N_fac != 3) return false;
+    for (int t = 0; t < Nq; t++) {
+        const int a1 = t % N, a2 = t / N;
+        if (a.sigma_o[t] - 1 != a1 * N + a2) return false;
+        const long long want = (a1 + a2 <= N - 1) ? a1 * N - a1 * (a1 - 1) / 2 + a2 + 1 : 0;
+        if (a.sigma_i[t] != want) return false;
+    }
+    p.triV.assign((size_t)Nq * Np, 0.0);
+    for (int b1 = 0; b1 < N; b1++)
+        for (int b2 = 0; b1 + b2 < N; b2++) {
+            const int l = (int)a.sigma_i[b1 + N * b2] - 1;
+            for (int a1 = 0; a1 < N; a1++)
+                for (int a2 = 0; a2 < N; a2++) p.triV[(a1 * N + a2) + (size_t)Nq * l] = a.A[a1 + N * b1] * a.B[a2 + N * (b1 + N * b2)];
+        }
+    // R: one tensor line per facet node (as for kind 2); lift weights R[partner_f, i]
+    p.trifR.assign((size_t)3 * Nq, 0.0);
+    for (int j = 0; j < Nf; j++) {
+        const int f = j / N, q = j % N;
+        for (int i = 0; i < Nq; i++) {
+            const int a1 = i / N, a2 = i % N;
+            const bool on = f == 0 ? a1 == q : a2 == q;
+            const double v = a.R[j + (size_t)Nf * i];
+            if (on) p.trifR[(size_t)f * Nq + i] = v;
+            else if (v != 0.0) return false;
+        }
+    }
+    p.triRV.assign((size_t)Nf * Np, 0.0);
+    for (int l = 0; l < Np; l++)
+        for (int j = 0; j < Nf; j++) {
+            double s = 0.0;
+            for (int i = 0; i < Nq; i++) s = std::fma(a.R[j + (size_t)Nf * i], p.triV[i + (size_t)Nq * l], s);
+            p.triRV[j + (size_t)Nf * l] = s;
+        }
+    // D[m] must be the Kronecker product of a 1-D matrix along direction m (a1: stride N, a2: stride 1) with the identity
+    const int stride[2] = {N, 1};
+    p.triD1.assign((size_t)2 * N * N, 0.0);
+    for (int m = 0; m < 2; m++) {
+        for (int t = 0; t < N; t++) for (int s = 0; s < N; s++) p.triD1[(size_t)m * N * N + t + N * s] = a.D[m][t * stride[m] + (size_t)Nq * (s * stride[m])];
+        for (int i = 0; i < Nq; i++)
+            for (int j = 0; j < Nq; j++) {
+                const int ci[2] = {i / N, i % N}, cj[2] = {j / N, j % N};
+                const bool line = ci[1 - m] == cj[1 - m];
+                const double want = line ? p.triD1[(size_t)m * N * N + ci[m] + N * cj[m]] : 0.0;
+                if (a.D[m][i + (size_t)Nq * j] != want) return false;
+            }
+    }
+    p.N = N;
+    return true;
+}
+template <int N> static void tri_adv_facets_n(const CtPlan& p, const Geo& g, long long first, long long count, const double* u, double* u_f, double* um,
+                                              cudaStream_t s) {
+    const long long want = (count + TRI_WARPS - 1) / TRI_WARPS;
+    k_tri_adv_facets<N, TRI_WARPS><<<(unsigned)std::max<long long>(1, std::min<long long>(want, (long long)p.sms * 8)), TRI_WARPS * 32, 0, s>>>(p.tri, g, first, count, u, u_f, um);
+}
+template <int N> static void tri_adv_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, const double* u_f,
+                                       double* dudt, cudaStream_t s, RkStage rk) {
+    k_tri_adv<N, TRI_WARPS, TRI_MINB><<<tri_grid(p, count), TRI_WARPS * 32, sizeof(double) * TRI_WARPS * TriA<N>::warp, s>>>(p.tri, g, L, first, count, u, u_f, dudt, rk);
+}
+
 template <int N> static FacetR<N> make_facet(const CtPlan& p) {
     FacetR<N> f;
     const double* s = p.facetR.data();
@@ -351,6 +421,12 @@ void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long
               cudaStream_t s) {
     if (p.kind == 2) {
 #define CALL_(N_) tri_nodal_n<N_>(p, g, L, first, count, u, u_q, u_f, s)
+        SSE_TRI_DISPATCH(p.N, CALL_);
+#undef CALL_
+        return;
+    }
+    if (p.kind == 3) {
+#define CALL_(N_) tri_adv_facets_n<N_>(p, g, first, count, u, u_f, u_q, s)
         SSE_TRI_DISPATCH(p.N, CALL_);
 #undef CALL_
         return;
@@ -504,6 +580,13 @@ static void standard_n(const CtPlan& p, const Geo& g, const Law& L, long long fi
 }
 void ct_standard(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
                  double* dudt, cudaStream_t s, RkStage rk, cudaEvent_t mid) {
+    if (p.kind == 3) {                                // triangles: all of pass B in one launch, from the modal coefficients of pass A
+        if (mid) cudaEventRecord(mid, s);
+#define CALL_(N_) tri_adv_n<N_>(p, g, L, first, count, u_q, u_f, dudt, s, rk)
+        SSE_TRI_DISPATCH(p.N, CALL_);
+#undef CALL_
+        return;
+    }
 #define CALL_(N_) standard_n<N_>(p, g, L, first, count, u_q, u_f, dudt, s, rk, mid)
     SSE_CT_DISPATCH(p.N, CALL_);
 #undef CALL_

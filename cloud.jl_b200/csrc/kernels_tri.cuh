@@ -920,4 +920,184 @@ k_tri_fluxdiff_async(TriDev t, Geo g, Law L, long long first, long long count, c
     cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// BASELINE config 1: 2-D linear advection, StandardForm + ReferenceOperators on collapsed triangles
+// (standard_form_first_order.jl:16-63), the same warp-per-element mapping with one variable.  The flux is linear, so the
+// d^2 (D_m, D_m') pairs collapse to d pairs on g_m = c_m u, c_m = sum_n (W Lambda_mn / 2) a_n, and the facet difference
+// sum_n halfN_n R f_n is (a.n)/2 u_f (the collapse of kernels_adv.cuh for the tetrahedron).
+//   k_tri_adv_facets  pass A: u_f = (R V) u -- one 15-term dot product per facet lane; the modal coefficients are copied into
+//                             the u_q scratch (pass B must not depend on the caller's state staying alive and unchanged)
+//   k_tri_adv         pass B: u_q = V u (recomputed from the lane's row of V), volume terms along the two tensor lines with
+//                             the 1-D derivative rows / columns of the lane in registers, interface flux, lift, V', mass solve
+// Per lane and for the lifetime of the warp: row of V (N_p), a half column of V (V' sums split over the two half-warps and
+// joined by one shuffle), 4 N derivative coefficients, three lift weights.
+template <int N> struct TriA {
+    using T = TriT<N>;
+    static constexpr int HC = (T::Nq + 1) / 2;            // nodes per half-warp in the V' sums
+    static constexpr int x = 0;                           // [16]  modal coefficients
+    static constexpr int u = x + 16;                      // [32]  nodal values
+    static constexpr int g = u + 32;                      // [2][32]
+    static constexpr int ff = g + 64;                     // [16]
+    static constexpr int warp = ff + 16;
+};
+
+template <int N, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_tri_adv_facets(TriDev t, Geo g, long long first, long long count, const double* __restrict__ u, double* __restrict__ u_f,
+                 double* __restrict__ um) {
+    using T = TriT<N>;
+    constexpr int Np = T::Np, Nf = T::Nf;
+    __shared__ double s_x[WARPS][16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool fac = lane < Nf, md = lane < Np;
+    const int tj = fac ? lane : Nf - 1;
+    double rv[Np];
+#pragma unroll
+    for (int l = 0; l < Np; l++) rv[l] = t.RV[tj + Nf * l];
+    const long long stride = (long long)gridDim.x * WARPS, end = first + count;
+    for (long long k = first + (long long)blockIdx.x * WARPS + warp; k < end; k += stride) {
+        if (md) {
+            const double x = u[(size_t)k * Np + lane];
+            s_x[warp][lane] = x;
+            um[(size_t)k * Np + lane] = x;             // pass B reads the coefficients from the handle's scratch, not from the caller's state
+        }
+        __syncwarp();
+        double s = 0.0;
+#pragma unroll
+        for (int l = 0; l < Np; l++) s = fma(rv[l], s_x[warp][l], s);
+        if (fac) u_f[(size_t)k * Nf + lane] = s;
+        __syncwarp();
+    }
+    (void)g;
+}
+
+template <int N, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+k_tri_adv(TriDev t, Geo g, Law L, long long first, long long count, const double* u, const double* __restrict__ u_f,
+          double* __restrict__ dudt, RkStage rk) {
+    using T = TriT<N>;
+    using A = TriA<N>;
+    constexpr int D = 2, Nq = T::Nq, Np = T::Np, Nf = T::Nf, HC = A::HC;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) double sm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* sw_ = sm + warp * A::warp;
+    double* s_x = sw_ + A::x;
+    double* s_u = sw_ + A::u;
+    double* s_g = sw_ + A::g;
+    double* s_ff = sw_ + A::ff;
+    const bool node = lane < Nq, fac = lane < Nf;
+    const int tn = node ? lane : Nq - 1, tj = fac ? lane : Nf - 1;
+    const int a1 = tn / N, a2 = tn - a1 * N;
+    const int ml = lane & 15, mh = lane >> 4;
+    const bool mode = ml < Np;
+    // ---- per-lane constants
+    double vrow[Np], vcol[HC], dr[D][N], dc[D][N], rw[3];
+#pragma unroll
+    for (int l = 0; l < Np; l++) vrow[l] = t.V[tn + Nq * l];
+#pragma unroll
+    for (int q = 0; q < HC; q++) { const int i = mh * HC + q; vcol[q] = (mode && i < Nq) ? t.V[i + Nq * ml] : 0.0; }
+#pragma unroll
+    for (int q = 0; q < N; q++) {
+        dr[0][q] = t.D1[0 * N * N + a1 + N * q]; dc[0][q] = t.D1[0 * N * N + q + N * a1];     // D_1D[row, col] at row + N col
+        dr[1][q] = t.D1[1 * N * N + a2 + N * q]; dc[1][q] = t.D1[1 * N * N + q + N * a2];
+    }
+    const int jf_[3] = {a1, N + a2, 2 * N + a2};
+#pragma unroll
+    for (int f = 0; f < 3; f++) rw[f] = t.fR[f * Nq + tn];
+    const double hw = 0.5 * t.W[tn], bf = t.Bf[tj];
+    const int base0 = a2, base1 = a1 * N;                  // first node of the lane's a1-line (stride N) / a2-line (stride 1)
+
+    const long long stride = (long long)gridDim.x * WARPS, end = first + count;
+    long long k = first + (long long)blockIdx.x * WARPS + warp;
+    if (k >= end) return;
+    double xm, lam[D][D], ui, jf, njf[D], ijw;
+    long long mp;
+#define SSE_TRIA_LOAD(K_)                                                                                                 \
+    do {                                                                                                                  \
+        xm = u[(size_t)(K_) * Np + (mode ? ml : 0)];                                                                      \
+        _Pragma("unroll") for (int n = 0; n < D; n++)                                                                     \
+            _Pragma("unroll") for (int m = 0; m < D; m++) lam[m][n] = __ldcs(g.Lambda_q + ((size_t)(K_) * D * D + (m + D * n)) * Nq + tn); \
+        ui = u_f[(size_t)(K_) * Nf + tj];                                                                                 \
+        jf = __ldcs(g.J_f + (size_t)(K_) * Nf + tj);                                                                      \
+        _Pragma("unroll") for (int m = 0; m < D; m++) njf[m] = __ldcs(g.nJf + m + D * ((size_t)(K_) * Nf + tj));          \
+        mp = g.mapP[(size_t)(K_) * Nf + tj];                                                                              \
+        ijw = __ldcs(g.iJW + (size_t)(K_) * Nq + tn);                                                                     \
+    } while (0)
+    SSE_TRIA_LOAD(k);
+    for (;;) {
+        const long long kn = k + stride, kl = kn < end ? kn : k;
+        const double uo = u_f[(size_t)(mp - 1)];
+        if (lane < 16) s_x[lane] = mode ? xm : 0.0;
+        double c[D];
+#pragma unroll
+        for (int m = 0; m < D; m++) c[m] = fma(hw * lam[m][1], L.a[1], (hw * lam[m][0]) * L.a[0]);      // halfWLambda_mn a_n
+        const double ci = ui, cjf = jf, cn0 = njf[0], cn1 = njf[1], cijw = ijw;
+        SSE_TRIA_LOAD(kl);
+        __syncwarp();
+        // u_q = V u
+        double uq = 0.0;
+#pragma unroll
+        for (int l = 0; l < Np; l++) uq = fma(vrow[l], s_x[l], uq);
+        if (node) { s_u[lane] = uq; s_g[lane] = c[0] * uq; s_g[32 + lane] = c[1] * uq; }
+        {   // interface flux, f_f = BJf (f* - (a.n)/2 u_f)           standard_form_first_order.jl:48-58
+            const double ijf = rcp_fast(cjf);
+            const double an = fma(L.a[1], cn1 * ijf, L.a[0] * (cn0 * ijf));
+            double fs = (0.5 * (ci + uo)) * an;
+            if (L.inviscid == SSE_FLUX_LAX_FRIEDRICHS) fs = fma(L.half_lambda * fabs(an), ci - uo, fs);
+            if (fac) s_ff[lane] = (bf * cjf) * (fs - 0.5 * an * ci);
+        }
+        __syncwarp();
+        // volume terms: r = sum_m D_m' (c_m u) - c_m (D_m u)            standard_form_first_order.jl:38-46
+        double r = 0.0;
+        {
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int q = 0; q < N; q++) { s1 = fma(dc[0][q], s_g[base0 + q * N], s1); s2 = fma(dr[0][q], s_u[base0 + q * N], s2); }
+            r += s1 - c[0] * s2;
+            s1 = 0.0; s2 = 0.0;
+#pragma unroll
+            for (int q = 0; q < N; q++) { s1 = fma(dc[1][q], s_g[32 + base1 + q], s1); s2 = fma(dr[1][q], s_u[base1 + q], s2); }
+            r += s1 - c[1] * s2;
+        }
+#pragma unroll
+        for (int f = 0; f < 3; f++) r = fma(-rw[f], s_ff[jf_[f]], r);                               // - R' f_f
+        __syncwarp();                                      // every lane is past s_u / s_g
+        if (node) s_u[lane] = r;
+        __syncwarp();
+        // dudt = M^-1 V' r: V' (two half-warp partial sums joined by a shuffle), V, diag(W / J), V'
+        double p = 0.0;
+#pragma unroll
+        for (int q = 0; q < HC; q++) { const int i = mh * HC + q; p = fma(vcol[q], s_u[i < Nq ? i : Nq - 1], p); }
+        p += __shfl_xor_sync(FULL, p, 16);
+        if (lane < 16) s_x[lane] = mode ? p : 0.0;
+        __syncwarp();
+        double y = 0.0;
+#pragma unroll
+        for (int l = 0; l < Np; l++) y = fma(vrow[l], s_x[l], y);
+        y *= cijw;
+        __syncwarp();                                      // the first V' has read s_u everywhere (the shuffle ordered the warp)
+        if (node) s_u[lane] = y;
+        __syncwarp();
+        p = 0.0;
+#pragma unroll
+        for (int q = 0; q < HC; q++) { const int i = mh * HC + q; p = fma(vcol[q], s_u[i < Nq ? i : Nq - 1], p); }
+        p += __shfl_xor_sync(FULL, p, 16);
+        if (lane < Np) {
+            const size_t idx = (size_t)k * Np + lane;
+            dudt[idx] = p;
+            flag_nonfinite(g.flag, p);
+            if (rk.u) {
+                const double tm = fma(rk.A, rk.tmp[idx], rk.dt * p);
+                rk.tmp[idx] = tm;
+                rk.u[idx] = fma(rk.B, tm, rk.u[idx]);
+            }
+        }
+        if (kn >= end) break;
+        k = kn;
+        __syncwarp();
+    }
+#undef SSE_TRIA_LOAD
+}
+
 }  // namespace sse

@@ -596,6 +596,23 @@ static int32_t build(sse_handle* h, const sse_config* cfg, const sse_arrays* a) 
             c.ok = 1;
         }
     }
+    {   // 2-D linear advection, StandardForm + ReferenceOperators on collapsed triangles: warp-per-element kernels (kernels_tri.cuh)
+        if (!h->ct.ok && tri_adv_eligible(*cfg, *a, h->ct)) {
+            CtPlan& c = h->ct;
+            c.kind = 3; c.sms = h->sm_count > 0 ? h->sm_count : 148;
+            if ((rc = upload(h, c.triV, &c.tri.V)) || (rc = upload(h, c.trifR, &c.tri.fR)) || (rc = upload(h, c.triD1, &c.tri.D1)) ||
+                (rc = upload(h, c.triRV, &c.tri.RV)))
+                return rc;
+            c.tri.W = o.W; c.tri.Bf = o.Bf;
+            double* ijw = nullptr;
+            if ((rc = dalloc(h, (size_t)Nq * Ne, &ijw))) return rc;
+            const long long n = (long long)Nq * Ne;
+            k_ijw<<<(unsigned)std::min<long long>((n + 255) / 256, 8LL * std::max(h->sm_count, 1)), 256, 0, h->stream>>>(n, Nq, o.W, g.J_q, ijw);
+            CU(cudaGetLastError());
+            g.iJW = ijw;
+            c.ok = 1;
+        }
+    }
     // threads per element of the generic (one CTA per element) kernels: enough for one volume / facet node per thread, at most 128
     {   // threads per element of the packed kernels; SSE_THREADS_MIN=64 restores the round-1 minimum (A/B)
         const char* tm = getenv("SSE_THREADS_MIN");
@@ -834,9 +851,9 @@ int32_t sse::pass_b_stage(sse_handle* h, double* d_dudt, int64_t first, int64_t 
             DISPATCH_DNC(h, LA);
 #undef LA
         }
-    } else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE && h->variant == 1 && h->ct.ok && h->ct.kind == 1) {
+    } else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE && h->variant == 1 && h->ct.ok && (h->ct.kind == 1 || h->ct.kind == 3)) {
         ct_standard(h->ct, h->geo, h->law, first, count, h->u_q, h->u_f, d_dudt, h->stream, rk, mid);
-        h->launches += h->ct.adv_ok ? 0 : 1;           // derivative kernel + projection kernel, or the fused kernel alone
+        h->launches += (h->ct.adv_ok || h->ct.kind == 3) ? 0 : 1;           // derivative kernel + projection kernel, or the fused kernel alone
     } else if (h->cfg.form == SSE_FORM_STANDARD_REFERENCE) {
 #define LA(D_, NC_)                                                                                                                  \
     nl = launch_rows(h->threads, h->smem_time, first, count, [&](unsigned grid, dim3 block, size_t smem, long long f0) {             \
@@ -1389,6 +1406,7 @@ extern "C" int32_t sse_plan_selfcheck(const sse_config* cfg, const sse_arrays* a
         if (tp.ok && ct_eligible(*cfg, *arr, tp, &N) && ct_schedule_matches(tp, N) && ct_facet_factors(*cfg, *arr, N, fac)) info[0] = 2;
         else if (ct_eligible_standard(*cfg, *arr, &N, D1, fR) && ct_facet_factors(*cfg, *arr, N, fac)) { info[0] = 3; info[1] = 128; return SSE_OK; }
         else if (tp.ok) { CtPlan tri; if (tri_eligible(*cfg, *arr, tp, tri)) info[0] = 4; }      // 4: warp-per-element triangle kernels
+        else { CtPlan tri; if (tri_adv_eligible(*cfg, *arr, tri)) { info[0] = 5; info[1] = 128; return SSE_OK; } }   // 5: ... for 2-D advection
     }
     if (!tp.ok) return SSE_OK;
     if (info[0] != 2 && !tp.has_fluxdiff) { info[0] = 0; return SSE_OK; }      // schedule exists, but no kernel for this size

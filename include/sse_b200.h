@@ -260,7 +260,8 @@ int32_t sse_launch_count(const sse_handle* h, int64_t* n);
 int32_t sse_debug_views(sse_handle* h, double** d_u_q, double** d_u_f);
 /* host-only diagnostic: build the tensor-line pair schedule for (cfg, arr) and replay it against S and C.
    info[0..7] = {kernel family (0 generic, 1 tensor-line, 2 compile-time flux differencing, 3 compile-time advection
-   StandardForm, 4 warp-per-element 2-D Euler flux differencing on triangles), threads per CTA, volume rounds, facet sub-rounds, reducer items max, reducer
+   StandardForm, 4 warp-per-element 2-D Euler flux differencing on triangles, 5 warp-per-element 2-D advection StandardForm
+   on triangles), threads per CTA, volume rounds, facet sub-rounds, reducer items max, reducer
    sources max, shared-memory bytes, two-point flux evaluations per element}; max_err = largest deviation of
    the replayed S_m / C from the operators passed in (0 when every pair is visited exactly once). */
 int32_t sse_plan_selfcheck(const sse_config* cfg, const sse_arrays* arr, int32_t* info, double* max_err);

@@ -164,7 +164,7 @@ def test_euler_1d_reference_golden_on_gpu():
 
 GOLDEN_RUNS = {
     # name: (case builder, end time, CK54 steps, golden attribute in test_oracle_goldens, expected kernel variant)
-    "advection_2d_tri": (lambda: cases.advection_2d(M=2, p=4, flux="lf0", warp=0.1), 1.0, 100, "ADVECTION_2D_TRI_GOLDEN", 0),
+    "advection_2d_tri": (lambda: cases.advection_2d(M=2, p=4, flux="lf0", warp=0.1), 1.0, 100, "ADVECTION_2D_TRI_GOLDEN", 2),
     "advection_2d_quad": (lambda: cases.advection_2d_quad(M=2, p=4, flux="lf", warp=0.1), 1.0, 100, "ADVECTION_2D_QUAD_GOLDEN", None),
     "euler_vortex_2d_modal_tri": (lambda: cases.euler_vortex_2d(M=4, p=3, flux="lf"), 2.5, 1000,
                                   "EULER_VORTEX_2D_MODAL_GOLDEN", 2),

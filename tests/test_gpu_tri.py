@@ -135,3 +135,67 @@ def test_triangle_kernels_fused_rk_stage_and_step():
         s.close()
     assert relerr(outs[0], outs[1]) <= RTOL
     assert np.abs(outs[0] - u0).max() > 1e-6
+
+
+# ---- BASELINE config 1: 2-D linear advection, StandardForm + ReferenceOperators (k_tri_adv_facets / k_tri_adv)
+
+@pytest.mark.parametrize("p", [2, 3, 4])
+@pytest.mark.parametrize("flux", ["lf", "lf0", "central"])
+def test_triangle_advection_kernels_match_oracle(p, flux):
+    c = cases.advection_2d(M=4, p=p, flux=flux)
+    img, u = c.image(), c.u0(seed=p)
+    ref, uq_ref, uf_ref = oracle.rhs(img, u, return_scratch=True)
+    got, _, uf, used = run(img, u)
+    assert used == 2, "the warp-per-element path was not selected"
+    assert relerr(uf[:, :uf_ref.shape[1] * uf_ref.shape[2]].reshape(uf_ref.shape), uf_ref) <= RTOL, "facet states (pass A)"
+    assert relerr(got, ref) <= RTOL
+    got0, _, _, used0 = run(img, u, 0)
+    assert used0 == 0 and relerr(got0, ref) <= RTOL
+
+
+def test_triangle_advection_kernels_many_elements_and_ranges():
+    c = cases.advection_2d(M=50, p=4, flux="lf")                  # 5 000 elements: several per warp
+    img, u = c.image(), c.u0(seed=2)
+    ref = oracle.rhs(img, u)
+    s = Solver(img, 0)
+    assert s.kernel_variant() == 2
+    ud = torch.from_numpy(u).cuda()
+    du = s.new_state()
+    s.rhs(du, ud)
+    s.synchronize()
+    assert relerr(du.cpu().numpy(), ref) <= RTOL
+    first, count = 1234, 777
+    du.fill_(777.0)
+    s.pass_a(ud)
+    ud.fill_(float("nan"))                                        # pass B must not read the caller's state again
+    s.pass_b(du, first, count)
+    s.synchronize()
+    got = du.cpu().numpy()
+    assert relerr(got[first:first + count], ref[first:first + count]) <= RTOL
+    mask = np.ones(got.shape[0], dtype=bool)
+    mask[first:first + count] = False
+    assert np.all(got[mask] == 777.0)
+    hu = torch.from_numpy(u).pin_memory()
+    hd = torch.empty_like(hu).pin_memory()
+    s.rhs_host(hd, hu, chunks=5)
+    s.close()
+    assert relerr(hd.numpy(), ref) <= RTOL
+
+
+def test_triangle_advection_kernels_fused_rk_step():
+    c = cases.advection_2d(M=6, p=4, flux="lf")
+    img, u0 = c.image(), c.u0(seed=4)
+    outs = []
+    for variant in (1, 0):
+        s = Solver(img, 0)
+        s.set_kernel_variant(variant)
+        u = torch.from_numpy(u0.copy()).cuda()
+        tmp, du = s.new_state(), s.new_state()
+        tmp.zero_()
+        for _ in range(3):
+            s.step_ck54(u, tmp, du, 0.0, 1.0e-3)
+        s.synchronize()
+        outs.append(u.cpu().numpy())
+        s.close()
+    assert relerr(outs[0], outs[1]) <= RTOL
+    assert np.abs(outs[0] - u0).max() > 1e-6

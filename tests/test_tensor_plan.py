@@ -50,7 +50,10 @@ def test_kernel_family_selection():
     assert selfcheck(cases.advection_3d(M=2).image())[0][0] == 3            # config 4: compile-time StandardForm path
     assert selfcheck(cases.advection_3d(M=2, p=2).image())[0][0] == 3
     assert selfcheck(cases.advection_3d(M=2, p=1).image())[0][0] == 0       # generic
-    assert selfcheck(cases.advection_2d(M=2).image())[0][0] == 0
+    for p in (2, 3, 4):                                                     # config 1: warp-per-element triangle kernels
+        assert selfcheck(cases.advection_2d(M=2, p=p).image())[0][0] == 5
+    assert selfcheck(cases.advection_2d(M=2, p=5).image())[0][0] == 0
+    assert selfcheck(cases.advection_2d(M=2, kind="nodal").image())[0][0] == 0
     assert selfcheck(cases.advection_diffusion_2d(M=2).image())[0][0] == 0
 
 

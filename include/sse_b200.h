@@ -138,7 +138,8 @@ int32_t sse_set_stream(sse_handle* h, void* cuda_stream);
 /* 0: generic kernels only; 1 (default): use the tensor-line specialised kernels when the
    operators have the collapsed tensor-product structure */
 int32_t sse_set_kernel_variant(sse_handle* h, int32_t variant);
-/* reports the family in use: 0 generic, 1 tensor-line, 2 compile-time (p = 2..5 tets), 3 dense all-pairs (multidimensional schemes) */
+/* reports the family in use: 0 generic, 1 tensor-line, 2 compile-time (p = 2..5 tets; p = 2..4 triangles: 2-D Euler flux
+   differencing and 2-D advection StandardForm), 3 dense all-pairs (multidimensional schemes) */
 int32_t sse_get_kernel_variant(const sse_handle* h, int32_t* variant);
 
 /* -- state vectors (u, dudt of Solvers.jl:474-483; layout (N_p, N_c, N_e)) --------------------- */
@@ -171,7 +172,11 @@ int32_t sse_host_unpin(void* p);
    element range [first, first+count).  Second-order laws have an extra aux pass + exchange. */
 /* Contract of the split form: pass B of an element range consumes the u_q scratch pass A wrote for it (the compile-time
    kernels overwrite it with r_q, as the reference reuses u_q[:,:,k], flux_differencing_form.jl:341-346).  Pass B is therefore
-   NOT idempotent: run pass A again before repeating pass B on a range; after pass B sse_debug_views shows r_q, not u_q. */
+   NOT idempotent on the 3-D compile-time Euler path: run pass A again before repeating pass B on a range; after pass B
+   sse_debug_views shows r_q, not u_q.  The warp-per-element triangle kernels (2-D Euler flux differencing, 2-D advection) do
+   all of pass B in one launch and leave the scratch untouched: there pass B is a pure function of the scratch (on the 2-D
+   advection path the u_q scratch holds the modal coefficients pass A copied, not nodal values).  No path reads the caller's
+   state again after pass A. */
 int32_t sse_rhs_pass_a(sse_handle* h, const double* d_u);
 /* pass A on the element range [first, first+count): lets a host-buffer caller overlap the upload of u with pass A */
 int32_t sse_rhs_pass_a_range(sse_handle* h, const double* d_u, int64_t first, int64_t count);

@@ -895,16 +895,37 @@ __global__ void k_aux_physical(Ops o, Geo g, Law L, long long first, const doubl
     const double* FAC = g.FAC + (size_t)Np * Nf * k;
     for (int m = 0; m < D; m++) {
         const double* VOL = g.VOL + (size_t)Np * Nq * (m + (size_t)D * k);
+        if (blockDim.x == 32 && Np * NC <= 16) {
+            // small elements, one warp per element: the per-element operators stream from DRAM, so every dot product is split
+            // over the two half-warps (all 32 lanes load, twice as many independent loads in flight) and joined by a shuffle
+            const int t = threadIdx.x & 15, h = threadIdx.x >> 4;
+            const int tc = t < Np * NC ? t : 0, a = tc % Np, e = tc / Np;
+            const int q0 = h ? (Nq + 1) / 2 : 0, q1 = h ? Nq : (Nq + 1) / 2, f0 = h ? (Nf + 1) / 2 : 0, f1 = h ? Nf : (Nf + 1) / 2;
+            double s = 0.0, s2 = 0.0;
+#pragma unroll 4
+            for (int q = q0; q < q1; q++) s = fma(__ldcs(VOL + a + (size_t)Np * q), s_uq[q + Nq * e], s);
+#pragma unroll 4
+            for (int f = f0; f < f1; f++) {
+                double un = 0.5 * (s_in[f + Nf * e] + s_out[f + Nf * e]) * s_nf[m + D * f];
+                s2 = fma(__ldcs(FAC + a + (size_t)Np * f), un, s2);
+            }
+            double r = -s - s2;
+            r += __shfl_xor_sync(0xffffffffu, r, 16);
+            if (h == 0 && t < Np * NC) s_m[t] = r;
+        } else {
         SSE_FOR(t, Np * NC) {
             int a = t % Np, e = t / Np;
             double s = 0.0;
+#pragma unroll 4
             for (int q = 0; q < Nq; q++) s = fma(VOL[a + (size_t)Np * q], s_uq[q + Nq * e], s);
             double s2 = 0.0;
+#pragma unroll 4
             for (int f = 0; f < Nf; f++) {
                 double un = 0.5 * (s_in[f + Nf * e] + s_out[f + Nf * e]) * s_nf[m + D * f];
                 s2 = fma(FAC[a + (size_t)Np * f], un, s2);
             }
             s_m[t] = -s - s2;
+        }
         }
         sse_sync();
         apply_V<NC>(o, s_m, s_qq, s_z, s_w);
@@ -964,6 +985,29 @@ __global__ void k_time_physical(Ops o, Geo g, Law L, long long first, int second
     }
     sse_sync();
     const double* FAC = g.FAC + (size_t)Np * Nf * k;
+    if (blockDim.x == 32 && Np * NC <= 16) {             // as in k_aux_physical: half-warp partial sums, one shuffle
+        const int t = threadIdx.x & 15, h = threadIdx.x >> 4;
+        const int tc = t < Np * NC ? t : 0, a = tc % Np, e = tc / Np;
+        const int q0 = h ? (Nq + 1) / 2 : 0, q1 = h ? Nq : (Nq + 1) / 2, f0 = h ? (Nf + 1) / 2 : 0, f1 = h ? Nf : (Nf + 1) / 2;
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < D; m++) {
+            const double* VOL = g.VOL + (size_t)Np * Nq * (m + (size_t)D * k);
+            double sv = 0.0;
+#pragma unroll 4
+            for (int q = q0; q < q1; q++) sv = fma(__ldcs(VOL + a + (size_t)Np * q), s_fq[q + Nq * (e + NC * m)], sv);
+            s += sv;
+        }
+        double sf = 0.0;
+#pragma unroll 4
+        for (int f = f0; f < f1; f++) sf = fma(__ldcs(FAC + a + (size_t)Np * f), s_ff[f + Nf * e], sf);
+        double r = s + sf;
+        r += __shfl_xor_sync(0xffffffffu, r, 16);
+        if (h == 0 && t < Np * NC) {
+            dudt[(size_t)Np * NC * k + t] = r;
+            flag_nonfinite(g.flag, r);
+        }
+    } else {
     SSE_FOR(t, Np * NC) {
         int a = t % Np, e = t / Np;
         double s = 0.0;
@@ -971,13 +1015,16 @@ __global__ void k_time_physical(Ops o, Geo g, Law L, long long first, int second
         for (int m = 0; m < D; m++) {
             const double* VOL = g.VOL + (size_t)Np * Nq * (m + (size_t)D * k);
             double sv = 0.0;
+#pragma unroll 4
             for (int q = 0; q < Nq; q++) sv = fma(VOL[a + (size_t)Np * q], s_fq[q + Nq * (e + NC * m)], sv);
             s += sv;
         }
         double sf = 0.0;
+#pragma unroll 4
         for (int f = 0; f < Nf; f++) sf = fma(FAC[a + (size_t)Np * f], s_ff[f + Nf * e], sf);
         dudt[(size_t)Np * NC * k + t] = s + sf;
         flag_nonfinite(g.flag, s + sf);
+    }
     }
 }
 

@@ -1,14 +1,18 @@
-// ct_kernels.cu — instantiations of the compile-time-sized kernels (N = p + 1 = 4, 5)
+// ct_kernels.cu — instantiations of the compile-time-sized kernels (N = p + 1 = 3 .. 8)
 #include "kernels_ct.cuh"
 #include "kernels_adv.cuh"
 #include "kernels_tri.cuh"
 
 namespace sse {
 
-// polynomial degrees with compile-time kernels: N = p + 1 = 3 .. 6
+// polynomial degrees with compile-time kernels: N = p + 1 = 3 .. 8 (p = 7: the reference's examples/advection_3d.ipynb)
 #define SSE_CT_DISPATCH(N_, CALL)                                                                   \
-    switch (N_) { case 3: CALL(3); break; case 4: CALL(4); break; case 5: CALL(5); break; case 6: CALL(6); break; default: break; }
-static bool ct_size_ok(int N) { return N >= 3 && N <= 6; }
+    switch (N_) { case 3: CALL(3); break; case 4: CALL(4); break; case 5: CALL(5); break; case 6: CALL(6); break; case 7: CALL(7); break; case 8: CALL(8); break; default: break; }
+static bool ct_size_ok(int N) {                                // SSE_CT_NMAX: A/B switch (larger N fall back to the run-time kernels)
+    int hi = 8;
+    if (const char* e = getenv("SSE_CT_NMAX")) hi = atoi(e);
+    return N >= 3 && N <= hi;
+}
 static int tet_l_rt(int N, int b1, int b2, int b3) {          // tet_l<N> for a run-time N
     int l = 0;
     for (int i = 0; i < b1; i++) { const int m = N - i; l += m * (m + 1) / 2; }
@@ -324,6 +328,13 @@ template <int N> static FacetR<N> make_facet(const CtPlan& p) {
 #ifndef SSE_FD_MINB_CT
 #define SSE_FD_MINB_CT 4
 #endif
+// Launch shapes per degree.  The values for N <= 6 are the measured ones above; for N = 7, 8 (343 / 512 nodes per element, slabs of
+// 49 / 64 doubles per thread in the projection kernels) one CTA per SM keeps the register cap of ptxas where the slab still fits:
+// k_fluxdiff_ct 352 / 512 threads -> 184 / 128 registers, the projection kernels 160 threads -> 255.
+template <int N> constexpr int fd_minb() { return N <= 6 ? SSE_FD_MINB_CT : 1; }
+template <int N> constexpr int nodal1_minb() { return N <= 6 ? 4 : 2; }       // scalar laws (128 threads)
+template <int N> constexpr int proj1_minb() { return N <= 6 ? 3 : 2; }
+template <int N> constexpr int sadv_minb() { return N <= 6 ? 8 : 2; }         // k_standard_adv_ct (N_q threads)
 template <int N> static SFCoef<N> make_coef(const CtPlan& p) {
     SFCoef<N> c;
     for (int i = 0; i < N * N; i++) c.A[i] = p.A[i];
@@ -338,6 +349,8 @@ template <int N> static SFCoef<N> make_coef(const CtPlan& p) {
 #ifndef SSE_PROJ_MINB_CT
 #define SSE_PROJ_MINB_CT 3
 #endif
+template <int N> constexpr int nodal_minb() { return N <= 6 ? SSE_NODAL_MINB_CT : 1; }
+template <int N> constexpr int proj_minb() { return N <= 6 ? SSE_PROJ_MINB_CT : 1; }
 // fused advection path: warps per CTA and resident CTAs per SM requested from ptxas (register cap 65536 / (32 WARPS MINB))
 #ifndef SSE_ADV_WARPS
 #define SSE_ADV_WARPS 2
@@ -380,16 +393,19 @@ template <int N> static cudaError_t set_attrs_n() {
     cudaError_t e;
     const int proj5 = (int)(sizeof(double) * ProjSmem<N, 5>::total), proj1 = (int)(sizeof(double) * ProjSmem<N, 1>::total);
     const int nod5 = (int)(sizeof(double) * ProjSmem<N, 5, true>::total), nod1 = (int)(sizeof(double) * ProjSmem<N, 1, true>::total);
-    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 5, SSE_NODAL_MINB_CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod5))) return e;
-    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 5, SSE_NODAL_MINB_CT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod5))) return e;
-    if ((e = cudaFuncSetAttribute(k_project_ct<N, 5, SSE_PROJ_MINB_CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
-    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 1, 4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod1))) return e;
-    if ((e = cudaFuncSetAttribute(k_project_ct<N, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
-    if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, SSE_FD_MINB_CT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
+    constexpr size_t cap = 232448;                           // 227 KB of dynamic shared memory per CTA on sm_100
+    static_assert(sizeof(double) * ProjSmem<N, 5, true>::total <= cap && sizeof(double) * ProjSmem<N, 5>::total <= cap, "projection tiles fit one SM");
+    static_assert(sizeof(double) * FdSmem<N>::total <= cap && (size_t)adv_smem<N>() <= cap, "pair-kernel tiles fit one SM");
+    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 5, nodal_minb<N>(), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod5))) return e;
+    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 5, nodal_minb<N>(), true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod5))) return e;
+    if ((e = cudaFuncSetAttribute(k_project_ct<N, 5, proj_minb<N>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj5))) return e;
+    if ((e = cudaFuncSetAttribute(k_nodal_ct<N, 1, nodal1_minb<N>(), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nod1))) return e;
+    if ((e = cudaFuncSetAttribute(k_project_ct<N, 1, proj1_minb<N>()>, cudaFuncAttributeMaxDynamicSharedMemorySize, proj1))) return e;
+    if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, fd_minb<N>(), false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N>::total)))) return e;
     if ((e = cudaFuncSetAttribute(k_adv_facets_ct<N, ADV_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, adv_smem<N>()))) return e;
     if ((e = cudaFuncSetAttribute(k_adv_fused_ct<N, ADV_WARPS, ADV_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, adv_smem<N>()))) return e;
     if constexpr (N == 5) {
-        if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, SSE_FD_MINB_CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N, true>::total)))) return e;
+        if ((e = cudaFuncSetAttribute(k_fluxdiff_ct<N, fd_minb<N>(), true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * FdSmem<N, true>::total)))) return e;
     }
     return cudaSuccess;
 }
@@ -406,7 +422,7 @@ static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first
                     cudaStream_t s) {
     if (p.kind == 0) {
         const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
-        k_nodal_ct<N, 5, SSE_NODAL_MINB_CT, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5, true>::total, s>>>(make_coef<N>(p), make_facet<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
+        k_nodal_ct<N, 5, nodal_minb<N>(), true><<<grid, 160, sizeof(double) * ProjSmem<N, 5, true>::total, s>>>(make_coef<N>(p), make_facet<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
     } else if (p.adv_ok) {
         constexpr int GPW = 32 / N;
         const long long tasks = (first + count - 1) / GPW - first / GPW + 1;
@@ -414,7 +430,7 @@ static void nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first
             make_coef<N>(p), make_facet<N>(p), p.dev, p.adv, first, count, u, u_f);
     } else {
         const unsigned grid = (unsigned)((count + ProjSmem<N, 1>::EPB - 1) / ProjSmem<N, 1>::EPB);
-        k_nodal_ct<N, 1, 4, false><<<grid, 128, sizeof(double) * ProjSmem<N, 1, true>::total, s>>>(make_coef<N>(p), make_facet<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
+        k_nodal_ct<N, 1, nodal1_minb<N>(), false><<<grid, 128, sizeof(double) * ProjSmem<N, 1, true>::total, s>>>(make_coef<N>(p), make_facet<N>(p), p.dev, g, L, first, count, u, u_q, u_f);
     }
 }
 void ct_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, const double* u, double* u_q, double* u_f,
@@ -440,9 +456,9 @@ template <int N>
 static void pair_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f, cudaStream_t s) {
     constexpr int NT = Tet<N>::NT;
     if constexpr (N == 5) {
-        if (p.dual) { k_fluxdiff_ct<N, SSE_FD_MINB_CT, true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); return; }
+        if (p.dual) { k_fluxdiff_ct<N, fd_minb<N>(), true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); return; }
     }
-    k_fluxdiff_ct<N, SSE_FD_MINB_CT, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
+    k_fluxdiff_ct<N, fd_minb<N>(), false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
 }
 void ct_pair(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f, cudaStream_t s) {
 #define CALL_(N_) pair_n<N_>(p, g, L, first, count, u_q, u_f, s)
@@ -452,7 +468,7 @@ void ct_pair(const CtPlan& p, const Geo& g, const Law& L, long long first, long 
 template <int N>
 static void project_n(const CtPlan& p, const Geo& g, long long first, long long count, const double* r_q, double* dudt, cudaStream_t s, RkStage rk) {
     const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
-    k_project_ct<N, 5, SSE_PROJ_MINB_CT><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, r_q, dudt, rk);
+    k_project_ct<N, 5, proj_minb<N>()><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, r_q, dudt, rk);
 }
 void ct_project(const CtPlan& p, const Geo& g, long long first, long long count, const double* r_q, double* dudt, cudaStream_t s, RkStage rk) {
 #define CALL_(N_) project_n<N_>(p, g, first, count, r_q, dudt, s, rk)
@@ -463,7 +479,7 @@ template <int N>
 static void project_nodal_n(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, double* u_f,
                             double* dudt, cudaStream_t s, RkStage rk) {
     const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
-    k_nodal_ct<N, 5, SSE_NODAL_MINB_CT, true, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5, true>::total, s>>>(
+    k_nodal_ct<N, 5, nodal_minb<N>(), true, true><<<grid, 160, sizeof(double) * ProjSmem<N, 5, true>::total, s>>>(
         make_coef<N>(p), make_facet<N>(p), p.dev, g, L, first, count, nullptr, u_q, u_f, dudt, rk);
 }
 void ct_project_nodal(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, double* u_f,
@@ -480,12 +496,12 @@ static void fluxdiff_n(const CtPlan& p, const TensorPlan& tp, const Ops& o, cons
     (void)tp; (void)o;
     bool done = false;
     if constexpr (N == 5) {
-        if (p.dual) { k_fluxdiff_ct<N, SSE_FD_MINB_CT, true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); done = true; }
+        if (p.dual) { k_fluxdiff_ct<N, fd_minb<N>(), true><<<(unsigned)count, NT, sizeof(double) * FdSmem<N, true>::total, s>>>(p.dev, g, L, first, u_q, u_f); done = true; }
     }
-    if (!done) k_fluxdiff_ct<N, SSE_FD_MINB_CT, false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
+    if (!done) k_fluxdiff_ct<N, fd_minb<N>(), false><<<(unsigned)count, NT, sizeof(double) * FdSmem<N>::total, s>>>(p.dev, g, L, first, u_q, u_f);
     if (mid) cudaEventRecord(mid, s);
     const unsigned grid = (unsigned)((count + ProjSmem<N, 5>::EPB - 1) / ProjSmem<N, 5>::EPB);
-    k_project_ct<N, 5, SSE_PROJ_MINB_CT><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt, rk);
+    k_project_ct<N, 5, proj_minb<N>()><<<grid, 160, sizeof(double) * ProjSmem<N, 5>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt, rk);
 }
 void ct_fluxdiff(const CtPlan& p, const TensorPlan& tp, const Ops& o, const Geo& g, const Law& L, long long first, long long count,
                  double* u_q, const double* u_f, double* dudt, cudaStream_t s, RkStage rk, cudaEvent_t mid) {
@@ -573,10 +589,10 @@ static void standard_n(const CtPlan& p, const Geo& g, const Law& L, long long fi
     constexpr int NT = Tet<N>::NT;
     AdvTabs<N> tabs;
     for (int m = 0; m < 3; m++) for (int i = 0; i < N * N; i++) tabs.D1[m][i] = p.D1[m * N * N + i];
-    k_standard_adv_ct<N, 8><<<(unsigned)count, NT, 0, s>>>(tabs, p.dev, g, L, first, u_q, u_f);
+    k_standard_adv_ct<N, sadv_minb<N>()><<<(unsigned)count, NT, 0, s>>>(tabs, p.dev, g, L, first, u_q, u_f);
     if (mid) cudaEventRecord(mid, s);
     const unsigned grid = (unsigned)((count + ProjSmem<N, 1>::EPB - 1) / ProjSmem<N, 1>::EPB);
-    k_project_ct<N, 1, 3><<<grid, 128, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt, rk);
+    k_project_ct<N, 1, proj1_minb<N>()><<<grid, 128, sizeof(double) * ProjSmem<N, 1>::total, s>>>(make_coef<N>(p), p.dev, g, first, count, u_q, dudt, rk);
 }
 void ct_standard(const CtPlan& p, const Geo& g, const Law& L, long long first, long long count, double* u_q, const double* u_f,
                  double* dudt, cudaStream_t s, RkStage rk, cudaEvent_t mid) {

@@ -49,7 +49,11 @@ CASES = {
     "euler_tgv_3d_p3": lambda: cases.euler_tgv_3d(M=2, p=3, flux="lf"),
     "euler_tgv_3d_nodal": lambda: cases.euler_tgv_3d(M=2, p=3, flux="ec", kind="nodal"),
     "euler_tgv_3d_M4": lambda: cases.euler_tgv_3d(M=4, flux="lf"),
-    # the compile-time kernels are instantiated for N = p + 1 = 3 .. 6
+    # the compile-time kernels are instantiated for N = p + 1 = 3 .. 8 (p = 7: examples/advection_3d.ipynb of the reference)
+    "euler_tgv_3d_p6": lambda: cases.euler_tgv_3d(M=2, p=6, flux="lf"),
+    "euler_tgv_3d_p7": lambda: cases.euler_tgv_3d(M=2, p=7, flux="ec"),
+    "advection_3d_p6": lambda: cases.advection_3d(M=2, p=6, flux="central"),
+    "advection_3d_p7": lambda: cases.advection_3d(M=2, p=7, flux="lf"),
     "euler_tgv_3d_p2": lambda: cases.euler_tgv_3d(M=2, p=2, flux="lf"),
     "euler_tgv_3d_p5": lambda: cases.euler_tgv_3d(M=2, p=5, flux="ec"),
     "advection_3d_p2": lambda: cases.advection_3d(M=2, p=2, flux="lf"),
@@ -416,9 +420,9 @@ def test_ck54_stage_fused_kernels_match_the_unfused_sequence():
         assert relerr(a, b) <= 1e-13
 
 
-@pytest.mark.parametrize("p", [2, 3, 4, 5])
-def test_compile_time_kernels_cover_p2_to_p5(p):
-    """ModalTensor(p) tets run the compile-time kernels for p = 2 .. 5 (kernel variant 2), for the Euler flux-differencing path
+@pytest.mark.parametrize("p", [2, 3, 4, 5, 6, 7])
+def test_compile_time_kernels_cover_p2_to_p7(p):
+    """ModalTensor(p) tets run the compile-time kernels for p = 2 .. 7 (kernel variant 2), for the Euler flux-differencing path
     and for the fused advection path, and the device-resident CarpenterKennedy2N54 step agrees with the unfused sequence."""
     c = cases.euler_tgv_3d(M=2, p=p, flux="lf")
     img, u = c.image(), c.u0(seed=0)

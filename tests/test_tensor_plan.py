@@ -39,8 +39,10 @@ def test_kernel_family_selection():
     """Which kernels sse_create will pick (host-side decision, checked without a GPU)."""
     assert selfcheck(cases.euler_tgv_3d(M=2, p=4).image())[0][0] == 2       # headline: compile-time kernels
     assert selfcheck(cases.euler_tgv_3d(M=2, p=3).image())[0][0] == 2
-    assert selfcheck(cases.euler_tgv_3d(M=2, p=2).image())[0][0] == 2       # compile-time kernels exist for p = 2 .. 5
+    assert selfcheck(cases.euler_tgv_3d(M=2, p=2).image())[0][0] == 2       # compile-time kernels exist for p = 2 .. 7
     assert selfcheck(cases.euler_tgv_3d(M=2, p=5).image())[0][0] == 2
+    assert selfcheck(cases.euler_tgv_3d(M=2, p=7).image())[0][0] == 2       # ... and up to p = 7
+    assert selfcheck(cases.advection_3d(M=2, p=7).image())[0][0] == 3       # examples/advection_3d.ipynb of the reference
     assert selfcheck(cases.euler_tgv_3d(M=2, p=1).image())[0][0] == 1       # other degrees: runtime tensor-line kernel
     assert selfcheck(cases.euler_tgv_3d(M=2, p=3, kind="nodal").image())[0][0] == 1
     for p in (2, 3, 4):                                                     # config 2: warp-per-element triangle kernels

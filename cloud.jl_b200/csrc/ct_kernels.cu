@@ -328,10 +328,19 @@ template <int N> static FacetR<N> make_facet(const CtPlan& p) {
 #ifndef SSE_FD_MINB_CT
 #define SSE_FD_MINB_CT 4
 #endif
-// Launch shapes per degree.  The values for N <= 6 are the measured ones above; for N = 7, 8 (343 / 512 nodes per element, slabs of
-// 49 / 64 doubles per thread in the projection kernels) one CTA per SM keeps the register cap of ptxas where the slab still fits:
-// k_fluxdiff_ct 352 / 512 threads -> 184 / 128 registers, the projection kernels 160 threads -> 255.
-template <int N> constexpr int fd_minb() { return N <= 6 ? SSE_FD_MINB_CT : 1; }
+// Launch shapes per degree (resident CTAs per SM requested from ptxas = its register cap).  N <= 5: the measured values above.
+// N = 6, 7 (216 / 343 nodes, slabs of 36 / 49 doubles per thread in the projection kernels): two CTAs per SM -- the pair kernel
+// gets 128 / 80 registers (four CTAs left it 72 with spills at N = 6), the projection kernels 200 without spills.  Measured on
+// Euler EC at 6 000 elements (profiles/r2_s5_highp_ab.log): p = 5 0.597 (4 / 3 CTAs) -> 0.519 ms (2 / 2), 0.541 with 3 / 3;
+// p = 6 1.082 (1 / 1) -> 1.027 ms (2 / 2).  N = 8 (512 nodes, 64-double slabs): one CTA per SM is all the shared memory allows
+// (131 kB pair tiles, 127 kB projection tiles): 128 registers for the 512-thread pair kernel, 255 for the projection kernels.
+#ifndef SSE_FD_MINB_N6
+#define SSE_FD_MINB_N6 2
+#endif
+#ifndef SSE_FD_MINB_N7
+#define SSE_FD_MINB_N7 2
+#endif
+template <int N> constexpr int fd_minb() { return N <= 5 ? SSE_FD_MINB_CT : (N == 6 ? SSE_FD_MINB_N6 : (N == 7 ? SSE_FD_MINB_N7 : 1)); }
 template <int N> constexpr int nodal1_minb() { return N <= 6 ? 4 : 2; }       // scalar laws (128 threads)
 template <int N> constexpr int proj1_minb() { return N <= 6 ? 3 : 2; }
 template <int N> constexpr int sadv_minb() { return N <= 6 ? 8 : 2; }         // k_standard_adv_ct (N_q threads)
@@ -349,8 +358,14 @@ template <int N> static SFCoef<N> make_coef(const CtPlan& p) {
 #ifndef SSE_PROJ_MINB_CT
 #define SSE_PROJ_MINB_CT 3
 #endif
-template <int N> constexpr int nodal_minb() { return N <= 6 ? SSE_NODAL_MINB_CT : 1; }
-template <int N> constexpr int proj_minb() { return N <= 6 ? SSE_PROJ_MINB_CT : 1; }
+#ifndef SSE_PROJ_MINB_N6
+#define SSE_PROJ_MINB_N6 2
+#endif
+#ifndef SSE_PROJ_MINB_N7
+#define SSE_PROJ_MINB_N7 2
+#endif
+template <int N> constexpr int nodal_minb() { return N <= 5 ? SSE_NODAL_MINB_CT : (N == 6 ? SSE_PROJ_MINB_N6 : (N == 7 ? SSE_PROJ_MINB_N7 : 1)); }
+template <int N> constexpr int proj_minb() { return N <= 5 ? SSE_PROJ_MINB_CT : (N == 6 ? SSE_PROJ_MINB_N6 : (N == 7 ? SSE_PROJ_MINB_N7 : 1)); }
 // fused advection path: warps per CTA and resident CTAs per SM requested from ptxas (register cap 65536 / (32 WARPS MINB))
 #ifndef SSE_ADV_WARPS
 #define SSE_ADV_WARPS 2

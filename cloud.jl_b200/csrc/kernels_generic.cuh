@@ -913,18 +913,23 @@ __global__ void k_aux_physical(Ops o, Geo g, Law L, long long first, const doubl
             r += __shfl_xor_sync(0xffffffffu, r, 16);
             if (h == 0 && t < Np * NC) s_m[t] = r;
         } else {
-        SSE_FOR(t, Np * NC) {
+        SSE_FOR(t, Np * NC) {                      // the same two partial sums per entry, so the bits do not depend on the launch shape
             int a = t % Np, e = t / Np;
-            double s = 0.0;
+            double r[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int q0 = h ? (Nq + 1) / 2 : 0, q1 = h ? Nq : (Nq + 1) / 2, f0 = h ? (Nf + 1) / 2 : 0, f1 = h ? Nf : (Nf + 1) / 2;
+                double s = 0.0, s2 = 0.0;
 #pragma unroll 4
-            for (int q = 0; q < Nq; q++) s = fma(VOL[a + (size_t)Np * q], s_uq[q + Nq * e], s);
-            double s2 = 0.0;
+                for (int q = q0; q < q1; q++) s = fma(VOL[a + (size_t)Np * q], s_uq[q + Nq * e], s);
 #pragma unroll 4
-            for (int f = 0; f < Nf; f++) {
-                double un = 0.5 * (s_in[f + Nf * e] + s_out[f + Nf * e]) * s_nf[m + D * f];
-                s2 = fma(FAC[a + (size_t)Np * f], un, s2);
+                for (int f = f0; f < f1; f++) {
+                    double un = 0.5 * (s_in[f + Nf * e] + s_out[f + Nf * e]) * s_nf[m + D * f];
+                    s2 = fma(FAC[a + (size_t)Np * f], un, s2);
+                }
+                r[h] = -s - s2;
             }
-            s_m[t] = -s - s2;
+            s_m[t] = r[0] + r[1];
         }
         }
         sse_sync();
@@ -1008,22 +1013,29 @@ __global__ void k_time_physical(Ops o, Geo g, Law L, long long first, int second
             flag_nonfinite(g.flag, r);
         }
     } else {
-    SSE_FOR(t, Np * NC) {
+    SSE_FOR(t, Np * NC) {                          // the same two partial sums per entry as the half-warp form above
         int a = t % Np, e = t / Np;
-        double s = 0.0;
+        double r[2];
 #pragma unroll
-        for (int m = 0; m < D; m++) {
-            const double* VOL = g.VOL + (size_t)Np * Nq * (m + (size_t)D * k);
-            double sv = 0.0;
+        for (int h = 0; h < 2; h++) {
+            const int q0 = h ? (Nq + 1) / 2 : 0, q1 = h ? Nq : (Nq + 1) / 2, f0 = h ? (Nf + 1) / 2 : 0, f1 = h ? Nf : (Nf + 1) / 2;
+            double s = 0.0;
+#pragma unroll
+            for (int m = 0; m < D; m++) {
+                const double* VOL = g.VOL + (size_t)Np * Nq * (m + (size_t)D * k);
+                double sv = 0.0;
 #pragma unroll 4
-            for (int q = 0; q < Nq; q++) sv = fma(VOL[a + (size_t)Np * q], s_fq[q + Nq * (e + NC * m)], sv);
-            s += sv;
+                for (int q = q0; q < q1; q++) sv = fma(VOL[a + (size_t)Np * q], s_fq[q + Nq * (e + NC * m)], sv);
+                s += sv;
+            }
+            double sf = 0.0;
+#pragma unroll 4
+            for (int f = f0; f < f1; f++) sf = fma(FAC[a + (size_t)Np * f], s_ff[f + Nf * e], sf);
+            r[h] = s + sf;
         }
-        double sf = 0.0;
-#pragma unroll 4
-        for (int f = 0; f < Nf; f++) sf = fma(FAC[a + (size_t)Np * f], s_ff[f + Nf * e], sf);
-        dudt[(size_t)Np * NC * k + t] = s + sf;
-        flag_nonfinite(g.flag, s + sf);
+        const double v = r[0] + r[1];
+        dudt[(size_t)Np * NC * k + t] = v;
+        flag_nonfinite(g.flag, v);
     }
     }
 }

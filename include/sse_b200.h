@@ -138,7 +138,7 @@ int32_t sse_set_stream(sse_handle* h, void* cuda_stream);
 /* 0: generic kernels only; 1 (default): use the tensor-line specialised kernels when the
    operators have the collapsed tensor-product structure */
 int32_t sse_set_kernel_variant(sse_handle* h, int32_t variant);
-/* reports the family in use: 0 generic, 1 tensor-line, 2 compile-time (p = 2..5 tets; p = 2..4 triangles: 2-D Euler flux
+/* reports the family in use: 0 generic, 1 tensor-line, 2 compile-time (p = 2..7 tets; p = 2..4 triangles: 2-D Euler flux
    differencing and 2-D advection StandardForm), 3 dense all-pairs (multidimensional schemes) */
 int32_t sse_get_kernel_variant(const sse_handle* h, int32_t* variant);
 

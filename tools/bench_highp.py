@@ -20,9 +20,10 @@ def one(a):
     import oracle
     from sse_b200 import cases
     from sse_b200.solver import Solver
-    for name, mk in (("advection_3d", lambda M, p: cases.advection_3d(M=M, p=p, flux="lf")),
-                     ("euler_tgv_3d", lambda M, p: cases.euler_tgv_3d(M=M, p=p, flux="ec"))):
-        for p in (6, 7):
+    runs = (("advection_3d", lambda M, p: cases.advection_3d(M=M, p=p, flux="lf")),
+            ("euler_tgv_3d", lambda M, p: cases.euler_tgv_3d(M=M, p=p, flux="ec")))
+    for name, mk in (runs[1:] if a.ab else runs):
+        for p in ((5, 6, 7) if a.ab else (6, 7)):
             c = mk(2, p)
             img, u = c.image(), c.u0(seed=0)
             s = Solver(img, 0)
@@ -49,7 +50,8 @@ def one(a):
             ms = e0.elapsed_time(e1) / a.steps
             print(json.dumps({"case": name, "p": p, "elements": int(c.sd.N_e), "variant": s.kernel_variant(), "parity_M2": par,
                               "ms_per_rhs": ms, "dof_per_s": c.dof / (ms * 1e-3),
-                              "ct_nmax": os.environ.get("SSE_CT_NMAX", "8")}), flush=True)
+                              "ct_nmax": os.environ.get("SSE_CT_NMAX", "8"),
+                              "lib": os.path.basename(os.environ.get("SSE_B200_LIB", "in-tree"))}), flush=True)
             s.close()
 
 
@@ -58,9 +60,17 @@ if __name__ == "__main__":
     ap.add_argument("--M", type=int, default=8)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--child", action="store_true")
+    ap.add_argument("--ab", action="store_true", help="Euler p = 5, 6, 7 with the in-tree library and every lib/variants/*.so (launch shapes)")
     a = ap.parse_args()
     if a.child:
         one(a)
+    elif a.ab:
+        import glob
+        for lib in [None] + sorted(glob.glob(os.path.join(ROOT, "cloud.jl_b200", "lib", "variants", "*.so"))):
+            env = dict(os.environ)
+            if lib:
+                env["SSE_B200_LIB"] = lib
+            subprocess.run([sys.executable, __file__, "--child", "--ab", "--M", str(a.M), "--steps", str(a.steps)], env=env, check=False)
     else:
         for nmax in ("8", "6"):
             env = dict(os.environ, SSE_CT_NMAX=nmax)

@@ -58,6 +58,11 @@ FAMILIES = {
     "ct_std_p5": lambda: run("ct_std advection_3d p5", cases.advection_3d(M=2, p=5, flux="central")),
     "ct_p2_step": lambda: run("ct euler_tgv_3d p2", cases.euler_tgv_3d(M=2, p=2, flux="lf"), step=True),
     "ct_p5": lambda: run("ct euler_tgv_3d p5", cases.euler_tgv_3d(M=2, p=5, flux="ec")),
+    # session 5: the compile-time kernels at N = 7, 8 (other shared-memory plans, one or two CTAs per SM, 352 / 512-thread pair kernel)
+    "ct_p6_step": lambda: run("ct euler_tgv_3d p6", cases.euler_tgv_3d(M=2, p=6, flux="lf"), step=True),
+    "ct_p7_step": lambda: run("ct euler_tgv_3d p7", cases.euler_tgv_3d(M=2, p=7, flux="ec"), step=True),
+    "ct_std_p6": lambda: run("ct_std advection_3d p6", cases.advection_3d(M=2, p=6, flux="central")),
+    "ct_std_p7": lambda: run("ct_std advection_3d p7", cases.advection_3d(M=2, p=7, flux="lf"), step=True),
     "dense": lambda: run("dense euler_tgv_3d ModalMulti p2", cases.euler_tgv_3d(M=2, p=2, flux="ec", kind="modal_multi")),
     "dense_nodal": lambda: run("dense euler_vortex_2d NodalMulti p3", cases.euler_vortex_2d(M=3, p=3, flux="lf", kind="nodal_multi")),
     "standard_euler": lambda: run("generic euler_vortex_2d StandardForm", cases.euler_vortex_2d_standard(M=3, p=3, flux="lf")),

@@ -59,6 +59,15 @@ def test_kernel_family_selection():
     assert selfcheck(cases.advection_diffusion_2d(M=2).image())[0][0] == 0
 
 
+def test_ct_nmax_switch_moves_high_degrees_to_the_runtime_kernels(monkeypatch):
+    """SSE_CT_NMAX (the A/B switch of tools/bench_highp.py): degrees above it leave the compile-time families."""
+    img_e, img_a = cases.euler_tgv_3d(M=2, p=7).image(), cases.advection_3d(M=2, p=7).image()
+    assert selfcheck(img_e)[0][0] == 2 and selfcheck(img_a)[0][0] == 3
+    monkeypatch.setenv("SSE_CT_NMAX", "6")
+    assert selfcheck(img_e)[0][0] in (0, 1) and selfcheck(img_a)[0][0] == 0
+    assert selfcheck(cases.euler_tgv_3d(M=2, p=4).image())[0][0] == 2       # the headline degree is not affected
+
+
 def test_host_pipeline_chunk_plan():
     """Schedule of Solver.rhs_host: every range is uploaded once, its pass B is released exactly when pass A has covered
     all ranges holding one of its face neighbours, and on the slab-ordered periodic mesh only three ranges wait for the

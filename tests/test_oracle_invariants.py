@@ -16,6 +16,9 @@ from sse_b200.assembly import PHYSICAL_OPERATOR, assemble
     lambda: cases.euler_tgv_3d(M=2, flux="ec"), lambda: cases.euler_tgv_3d(M=2, flux="lf"),
     lambda: cases.euler_tgv_3d(M=2, p=3, flux="ec", kind="nodal"),
     lambda: cases.advection_diffusion_2d(M=3),
+    # the degrees the compile-time kernels were extended to in round 2 (p = 7: examples/advection_3d.ipynb of the reference)
+    lambda: cases.advection_3d(M=2, p=7, flux="central"), lambda: cases.euler_tgv_3d(M=2, p=6, flux="ec"),
+    lambda: cases.euler_tgv_3d(M=2, p=7, flux="ec"),
     lambda: cases.euler_vortex_2d_standard(M=3, p=4, flux="lf"),
     lambda: cases.euler_vortex_2d_standard(M=3, p=3, flux="central", strategy=PHYSICAL_OPERATOR),
     lambda: cases.euler_tgv_3d_standard(M=2, p=3, flux="lf"),
@@ -31,6 +34,10 @@ def test_invariants(case):
     img, u = c.image(), c.u0(seed=0)
     du = oracle.rhs(img, u)
     scale = max(1.0, np.abs(du).max())
+    # round-off of the collapsed-coordinate modal basis grows about tenfold per degree (3-D Euler EC on 48 curved tets, this
+    # restatement: conservation 1.2e-11, 2.6e-10, 1.8e-9, 1.5e-8 and entropy 6.9e-13, 1.2e-12, 7.8e-11, 6.2e-10 at p = 4, 5, 6, 7);
+    # the reference's own assertions stop at p = 4, so the tolerances written for it are widened by that factor above it
+    scale *= 10.0 ** max(0, int(img.cfg.p) - 4)
     assert np.all(np.isfinite(du))
     assert np.abs(analysis.conservation_residual(img, du)).max() < 1e-12 * scale * 100
     flux = c.form.inviscid_numerical_flux

@@ -875,8 +875,18 @@ __global__ void k_time_standard_reference(Ops o, Geo g, Law L, long long first, 
 
 // ------------------------------------------------------------------ PhysicalOperators paths
 // BR1 auxiliary variable: standard_form_second_order.jl:3-34, linear_advection_diffusion.jl:75-86
+// resident CTAs per SM requested for the scalar 2-D instantiation (BASELINE config 3: rows of one warp, 4 per CTA): without
+// bounds ptxas assumes 1 024 threads per CTA, i.e. 64 registers = 8 CTAs of 128 threads per SM; the kernels are bound by the
+// chain of global round trips of a warp (profiles/r2_s5_ncu_config3.csv), so resident warps are what hides it
+// Measured at 131 072 triangles (profiles/r2_s5_config3_bounds_ab.log), aux / pass B: unbounded (96 / 71 registers) 0.675 / 0.414 ms,
+// 10 CTAs (48 registers) 0.512 / 0.328, 12 CTAs (40) 0.458 / 0.302, 16 CTAs (32) 0.511 / 0.280.  The other instantiations are held
+// at 64 registers (1 024-thread bound), which is what they used before the two-partial-sum form of the wide rows.
+#ifndef SSE_PHYS_MINB
+#define SSE_PHYS_MINB 12
+#endif
+#define SSE_PHYS_BOUNDS __launch_bounds__((D == 2 && NC == 1 && SSE_PHYS_MINB > 1) ? 128 : 1024, (D == 2 && NC == 1) ? SSE_PHYS_MINB : 1)
 template <int D, int NC>
-__global__ void k_aux_physical(Ops o, Geo g, Law L, long long first, const double* __restrict__ u_q,
+__global__ void SSE_PHYS_BOUNDS k_aux_physical(Ops o, Geo g, Law L, long long first, const double* __restrict__ u_q,
                                const double* __restrict__ u_f, double* __restrict__ q_q, double* __restrict__ q_f) {
     extern __shared__ double sm_cta[];
     double* sm = sse_row_smem(sm_cta);
@@ -948,7 +958,7 @@ __global__ void k_aux_physical(Ops o, Geo g, Law L, long long first, const doubl
 // first-order (standard_form_first_order.jl:65-94) and second-order (standard_form_second_order.jl:38-75)
 // time derivative with per-element VOL / FAC; viscous flux linear_advection_diffusion.jl:90-102
 template <int D, int NC>
-__global__ void k_time_physical(Ops o, Geo g, Law L, long long first, int second_order, const double* __restrict__ u_q,
+__global__ void SSE_PHYS_BOUNDS k_time_physical(Ops o, Geo g, Law L, long long first, int second_order, const double* __restrict__ u_q,
                                 const double* __restrict__ u_f, const double* __restrict__ q_q,
                                 const double* __restrict__ q_f, double* __restrict__ dudt) {
     extern __shared__ double sm_cta[];
